@@ -1,0 +1,203 @@
+/*
+ * shapes_b200.h -- C ABI of the B200 collision pipeline for ublubu/shapes.
+ *
+ * The reference (Haskell, /root/reference) has no FFI boundary of its own
+ * (no `foreign import` anywhere).  The boundary is therefore defined by the
+ * three expressions this library replaces inside
+ * Physics.Engine.Main.updateWorld (shapes/src/Physics/Engine/Main.hs:71-86):
+ *
+ *   keys      <- G.culledKeys <$> G.toGrid gridAxes world      (Main.hs:75)
+ *                 == Aabb.culledKeys world                      (Broadphase/Aabb.hs:168-183)
+ *   kContacts <- prepareFrame keys world                        (Main.hs:77, Solvers/Contact.hs:40-52)
+ *   constraintGen beh dt fContact ab   -- per contact, inside applyCachedSlns
+ *                                                               (Solvers/Contact.hs:93,107;
+ *                                                                Constraints/Contact.hs:60-72)
+ *
+ * One shapes_frame() call returns all three results for one frame as
+ * structure-of-arrays FP64/int32 buffers, in the reference's order
+ * (descending ObjectFeatureKey).  The sequential solver, warm starting and
+ * integration stay in the host engine.  INTEGRATION.md shows the
+ * `foreign import ccall` binding a maintainer of the reference would add.
+ *
+ * Conventions: plain C, no CUDA or torch types.  Every function returns 0 on
+ * success or a negative SHAPES_E_* code, never aborts, never throws.  A ctx is
+ * single-caller and blocking; distinct ctxs may be used from distinct threads.
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * SHAPES_E_CUDA.
+ */
+#ifndef SHAPES_B200_H
+#define SHAPES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHAPES_OK          0
+#define SHAPES_E_ARG      (-1) /* bad argument / call order */
+#define SHAPES_E_CUDA     (-2) /* CUDA runtime error (text in shapes_last_error) */
+#define SHAPES_E_NCCL     (-3) /* NCCL error */
+#define SHAPES_E_CAPACITY (-4) /* max_pairs / max_contacts too small: required
+                                  sizes are in the frame's n_pairs / n_contacts;
+                                  nothing else was written; grow and retry */
+
+#define SHAPES_NCCL_ID_BYTES 128
+
+typedef struct shapes_ctx shapes_ctx;
+
+/* Per-frame results.  Every array pointer is caller-owned and may be NULL
+ * (= not wanted, nothing is copied).  Non-NULL pair arrays must hold
+ * max_pairs elements and contact arrays max_contacts elements (the capacities
+ * given to shapes_create).  Row k of every contact array describes the same
+ * contact.
+ *
+ * For shapes_frame the pointers are HOST memory (pinned recommended:
+ * shapes_host_alloc); for shapes_frame_device they are ignored and results
+ * stay in HBM (shapes_device_view). */
+typedef struct shapes_frame_out {
+    /* Aabb.culledKeys / Grid.culledKeys: pairs (i, j), i > j, descending
+     * lexicographic (Broadphase/Aabb.hs:155-183). */
+    int64_t  n_pairs;
+    int32_t *pair_i, *pair_j;
+
+    /* prepareFrame: (ObjectFeatureKey (i,j) (featA,featB), Flipping Contact)
+     * (Constraints/Contact.hs:36-57, Contact/Types.hs:28-35), descending. */
+    int64_t  n_contacts;
+    int32_t *key_i, *key_j, *feat_a, *feat_b;
+    uint8_t *flip;                         /* 0 = Same, 1 = Flip (Utils/Utils.hs:147) */
+    double  *normal_x, *normal_y;          /* _contactNormal */
+    double  *center_x, *center_y;          /* _contactCenter */
+    double  *depth;                        /* _contactDepth  */
+
+    /* constraintGen: ContactConstraint (Constraints/Types.hs:41-51). */
+    double  *j_np[6], *b_np;               /* _ccNonPen      (NonPenetration.hs:16-55) */
+    double  *ra_x, *ra_y, *rb_x, *rb_y;    /* _ccRestitution radii (Restitution.hs:21-31) */
+    double  *rn_x, *rn_y;                  /* _ccRestitution normal */
+    double  *j_f[6], *b_f;                 /* _ccFriction    (Friction.hs:18-44); b_f is always 0 */
+    /* effMassM2 of both constraints (Constraint.hs:173-179); velocity independent,
+     * the reference recomputes it in every lagrangian2 call. Optional. */
+    double  *inv_eff_np, *inv_eff_f;
+
+    /* optional debug outputs, n_slots / n_verts elements */
+    double  *aabb_min_x, *aabb_max_x, *aabb_min_y, *aabb_max_y; /* toAabb (Aabb.hs:81-110) */
+    double  *world_x, *world_y;            /* _hullVertices after moveShapes (World.hs:136-140) */
+
+    /* stats of this frame */
+    int64_t  n_big;        /* shapes that took the big-shape path */
+    int32_t  grid_w, grid_h;
+    double   cell_size;
+    float    device_ms;    /* kernels only, CUDA events on the ctx stream */
+    float    total_ms;     /* device_ms + H2D + D2H (shapes_frame only) */
+} shapes_frame_out;
+
+/* Device-resident view of the last frame's results (pointers into ctx-owned
+ * HBM, valid until the next frame / destroy).  Same meaning as above. */
+typedef struct shapes_device_view {
+    int64_t  n_pairs, n_contacts;
+    const int32_t *pair_i, *pair_j;
+    const int32_t *key_i, *key_j, *feat_a, *feat_b;
+    const uint8_t *flip;
+    const double  *normal_x, *normal_y, *center_x, *center_y, *depth;
+    const double  *j_np[6], *b_np;
+    const double  *ra_x, *ra_y, *rb_x, *rb_y, *rn_x, *rn_y;
+    const double  *j_f[6];
+    const double  *inv_eff_np, *inv_eff_f;
+    const double  *aabb;   /* n_slots x (min_x, max_x, min_y, max_y) */
+} shapes_device_view;
+
+/* ---- lifetime ------------------------------------------------------- */
+
+/* One ctx per GPU.  Owns all device memory, one stream and (world_size > 1)
+ * one NCCL communicator.  max_* are capacities: slots, vertices, broadphase
+ * pairs and contacts owned by THIS rank. */
+int  shapes_create(shapes_ctx **out, int device_id,
+                   int64_t max_shapes, int64_t max_verts,
+                   int64_t max_pairs, int64_t max_contacts);
+
+/* Rank `rank` of `world_size` cooperating ctxs (one process or thread per GPU
+ * of one NVSwitch box).  nccl_id: SHAPES_NCCL_ID_BYTES from
+ * shapes_nccl_unique_id() on rank 0, distributed by the host's own plumbing. */
+int  shapes_create_ranked(shapes_ctx **out, int device_id, int rank, int world_size,
+                          const void *nccl_id,
+                          int64_t max_shapes, int64_t max_verts,
+                          int64_t max_pairs, int64_t max_contacts);
+int  shapes_nccl_unique_id(void *out_id /* SHAPES_NCCL_ID_BYTES */);
+void shapes_destroy(shapes_ctx *);
+const char *shapes_last_error(const shapes_ctx *);   /* NULL ctx: last create error */
+
+/* ---- static geometry: once per world, and after append/delete -------- */
+
+/* Mirrors World.append / listToHull (World.hs:77-84, ConvexHull.hs:151-167).
+ * alive      n_slots  EmptiesVector filled flags (NULL = all filled)
+ * vert_offset n_slots+1  CSR offsets into local_x / local_y
+ * local_x/y  CCW local-space vertices (_hullLocalVertices)
+ * ext_min/max per edge: _hullExtents (hull-relative vertex index); NULL => the
+ *            library computes them with the listToHull rule.
+ * Host pointers. Every rank registers the whole world. */
+int  shapes_set_hulls(shapes_ctx *, int64_t n_slots, const uint8_t *alive,
+                      const int32_t *vert_offset,
+                      const double *local_x, const double *local_y,
+                      const int32_t *ext_min, const int32_t *ext_max);
+
+/* Broadphase cell edge; <= 0 restores the automatic choice made by
+ * shapes_set_hulls.  Performance only: results do not depend on it. */
+int  shapes_set_cell_size(shapes_ctx *, double cell_size);
+
+/* ---- per frame -------------------------------------------------------- */
+
+/* Inputs are the reference's own SoA columns of _wPhysObjs (World.hs:47,
+ * Constraint.hs:52-63): position, rotation, inverse masses.
+ * cos_rot/sin_rot: cos/sin of rot as the host's libm computes them
+ * (Linear.hs:353-357) for bit-exact parity; both NULL => the device computes
+ * sincos(rot) (<= 2 ulp from libm, flagged not bit-exact).  rot may be NULL
+ * when cos/sin are given.  static <=> inv_lin == 0 && inv_rot == 0
+ * (Constraint.hs:123-125).  dt, baumgarte, slop: EngineConfig / ContactBehavior
+ * (Engine/Main.hs:34-37, Contact/Types.hs:20-25).
+ * Blocking: returns after the requested outputs are in `out`. */
+int  shapes_frame(shapes_ctx *, int64_t n_slots,
+                  const double *pos_x, const double *pos_y,
+                  const double *rot, const double *cos_rot, const double *sin_rot,
+                  const double *inv_lin, const double *inv_rot,
+                  double dt, double baumgarte, double slop,
+                  shapes_frame_out *out);
+
+/* Same, with DEVICE input pointers (on the ctx's GPU); results stay in HBM.
+ * out->n_* and stats are filled, array pointers in `out` are ignored. */
+int  shapes_frame_device(shapes_ctx *, int64_t n_slots,
+                         const double *pos_x, const double *pos_y,
+                         const double *rot, const double *cos_rot, const double *sin_rot,
+                         const double *inv_lin, const double *inv_rot,
+                         double dt, double baumgarte, double slop,
+                         shapes_frame_out *out);
+
+int  shapes_device_view_get(shapes_ctx *, shapes_device_view *view);
+
+/* Copy the last frame's results from HBM into the non-NULL arrays of `out`
+ * (what shapes_frame does after the kernels). */
+int  shapes_fetch(shapes_ctx *, shapes_frame_out *out);
+
+/* ---- multi-GPU (world_size > 1) --------------------------------------- */
+
+/* Rank r owns the pairs/contacts whose larger key i lies in
+ * [own_lo, own_hi); the global descending order is rank world_size-1's rows,
+ * then world_size-2's, ...  After a frame, all_pairs/all_contacts hold every
+ * rank's counts (all-gathered), each world_size long. */
+int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
+                      int64_t *all_pairs, int64_t *all_contacts);
+
+/* ---- helpers ----------------------------------------------------------- */
+
+void *shapes_host_alloc(size_t bytes);     /* pinned host memory, NULL on failure */
+void  shapes_host_free(void *);
+/* CUDA stream handle (cudaStream_t) the ctx launches on, for event timing. */
+void *shapes_stream(shapes_ctx *);
+/* Number of kernels the library launched on the ctx stream so far. */
+int64_t shapes_launch_count(const shapes_ctx *);
+const char *shapes_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHAPES_B200_H */

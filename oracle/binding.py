@@ -1,0 +1,191 @@
+"""ctypes binding of oracle/libshapes_oracle.so (test infrastructure only).
+
+PARITY UNPINNED by reference outputs (no GHC here); see shapes_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libshapes_oracle.so")
+
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_f64p = C.POINTER(C.c_double)
+
+CONTACT_F64 = (["normal_x", "normal_y", "center_x", "center_y", "depth"]
+               + [f"j_np{q}" for q in range(6)] + ["b_np", "ra_x", "ra_y", "rb_x", "rb_y", "rn_x", "rn_y"]
+               + [f"j_f{q}" for q in range(6)] + ["b_f", "inv_eff_np", "inv_eff_f"])
+CONTACT_I32 = ["key_i", "key_j", "feat_a", "feat_b"]
+
+
+class ContactsOut(C.Structure):
+    _fields_ = [
+        ("cap", C.c_int64),
+        ("key_i", _i32p), ("key_j", _i32p), ("feat_a", _i32p), ("feat_b", _i32p),
+        ("flip", _u8p),
+        ("normal_x", _f64p), ("normal_y", _f64p), ("center_x", _f64p), ("center_y", _f64p), ("depth", _f64p),
+        ("j_np", _f64p * 6), ("b_np", _f64p),
+        ("ra_x", _f64p), ("ra_y", _f64p), ("rb_x", _f64p), ("rb_y", _f64p), ("rn_x", _f64p), ("rn_y", _f64p),
+        ("j_f", _f64p * 6), ("b_f", _f64p),
+        ("inv_eff_np", _f64p), ("inv_eff_f", _f64p),
+    ]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_DIR, "shapes_oracle.c")
+    hdr = os.path.join(_DIR, "shapes_oracle.h")
+    if force or not os.path.exists(LIB_PATH) or \
+            max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(LIB_PATH):
+        subprocess.run(["make", "-C", _DIR, "-B", "libshapes_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_culled_keys_aabb.restype = C.c_int64
+        _lib.orc_culled_keys_grid.restype = C.c_int64
+        _lib.orc_culled_keys_sweep.restype = C.c_int64
+        _lib.orc_unordered_pairs.restype = C.c_int64
+        _lib.orc_contacts.restype = C.c_int64
+        _lib.orc_dot_v2.restype = C.c_double
+        _lib.orc_dot_v2.argtypes = [C.c_double] * 4
+    return _lib
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(ty) if a is not None else None
+
+
+def _f(a):
+    return _p(a, _f64p)
+
+
+def cos_sin(rot: np.ndarray):
+    c = np.empty_like(rot); s = np.empty_like(rot)
+    lib().orc_cos_sin(C.c_int64(rot.shape[0]), _f(rot), _f(c), _f(s))
+    return c, s
+
+
+def hull_extents(world):
+    emin = np.zeros(world.n_verts, np.int32); emax = np.zeros(world.n_verts, np.int32)
+    lib().orc_hull_extents(C.c_int64(world.n_slots), _p(world.vert_offset, _i32p), _f(world.local_x),
+                           _f(world.local_y), _p(emin, _i32p), _p(emax, _i32p))
+    return emin, emax
+
+
+def move_shapes(world, cos_rot, sin_rot):
+    nv = world.n_verts
+    wx = np.zeros(nv); wy = np.zeros(nv); nx = np.zeros(nv); ny = np.zeros(nv)
+    lib().orc_move_shapes(C.c_int64(world.n_slots), _p(world.alive, _u8p), _p(world.vert_offset, _i32p),
+                          _f(world.local_x), _f(world.local_y), _f(world.pos_x), _f(world.pos_y),
+                          _f(cos_rot), _f(sin_rot), _f(wx), _f(wy), _f(nx), _f(ny))
+    return wx, wy, nx, ny
+
+
+def aabbs(world, wx, wy):
+    n = world.n_slots
+    out = [np.zeros(n) for _ in range(4)]
+    lib().orc_aabbs(C.c_int64(n), _p(world.alive, _u8p), _p(world.vert_offset, _i32p), _f(wx), _f(wy),
+                    *[_f(a) for a in out])
+    return out
+
+
+def is_static(world):
+    st = np.zeros(world.n_slots, np.uint8)
+    lib().orc_is_static(C.c_int64(world.n_slots), _f(world.inv_lin), _f(world.inv_rot), _p(st, _u8p))
+    return st
+
+
+def _culled(fn, world, boxes, static, extra=()):
+    n = world.n_slots
+    args = [C.c_int64(n), _p(world.alive, _u8p)] + [_f(b) for b in boxes] + [_p(static, _u8p)] + list(extra)
+    cap = max(1024, 16 * n)
+    while True:
+        pi = np.zeros(cap, np.int32); pj = np.zeros(cap, np.int32)
+        k = fn(*args, C.c_int64(cap), _p(pi, _i32p), _p(pj, _i32p))
+        if k <= cap:
+            return pi[:k].copy(), pj[:k].copy()
+        cap = int(k)
+
+
+def culled_keys_aabb(world, boxes, static):
+    return _culled(lib().orc_culled_keys_aabb, world, boxes, static)
+
+
+def culled_keys_sweep(world, boxes, static):
+    return _culled(lib().orc_culled_keys_sweep, world, boxes, static)
+
+
+def culled_keys_grid(world, boxes, static, x_axis=(20, 1.0, -10.0), y_axis=(20, 1.0, -10.0)):
+    """Grid.culledKeys with gridAxes of Engine/Main.hs:40-41 by default."""
+    extra = [C.c_int32(x_axis[0]), C.c_double(x_axis[1]), C.c_double(x_axis[2]),
+             C.c_int32(y_axis[0]), C.c_double(y_axis[1]), C.c_double(y_axis[2])]
+    return _culled(lib().orc_culled_keys_grid, world, boxes, static, extra)
+
+
+def unordered_pairs(n: int):
+    cap = max(1, n * (n - 1) // 2)
+    xs = np.zeros(cap, np.int32); ys = np.zeros(cap, np.int32)
+    k = lib().orc_unordered_pairs(C.c_int64(n), C.c_int64(cap), _p(xs, _i32p), _p(ys, _i32p))
+    return xs[:k], ys[:k]
+
+
+def contacts(world, pair_i, pair_j, wx, wy, nx, ny, ext_min, ext_max, dt, baumgarte, slop):
+    """prepareFrame + constraintGen over the given pairs -> dict of columns."""
+    cap = max(16, 2 * int(pair_i.shape[0]))
+    cols = {k: np.zeros(cap, np.int32) for k in CONTACT_I32}
+    cols["flip"] = np.zeros(cap, np.uint8)
+    for k in CONTACT_F64:
+        cols[k] = np.zeros(cap, np.float64)
+    out = ContactsOut()
+    out.cap = cap
+    for k in CONTACT_I32:
+        setattr(out, k, _p(cols[k], _i32p))
+    out.flip = _p(cols["flip"], _u8p)
+    for k in CONTACT_F64:
+        if k.startswith("j_np"):
+            out.j_np[int(k[4:])] = _f(cols[k])
+        elif k.startswith("j_f"):
+            out.j_f[int(k[3:])] = _f(cols[k])
+        else:
+            setattr(out, k, _f(cols[k]))
+    pi = np.ascontiguousarray(pair_i, np.int32); pj = np.ascontiguousarray(pair_j, np.int32)
+    n = lib().orc_contacts(C.c_int64(pi.shape[0]), _p(pi, _i32p), _p(pj, _i32p), _p(world.vert_offset, _i32p),
+                           _f(wx), _f(wy), _f(nx), _f(ny), _p(ext_min, _i32p), _p(ext_max, _i32p),
+                           _f(world.pos_x), _f(world.pos_y), _f(world.inv_lin), _f(world.inv_rot),
+                           C.c_double(dt), C.c_double(baumgarte), C.c_double(slop), C.byref(out))
+    assert n <= cap
+    return {k: v[:n].copy() for k, v in cols.items()}
+
+
+def frame(world, cos_rot=None, sin_rot=None, dt=0.01, baumgarte=0.01, slop=0.02, broadphase="auto",
+          ext=None):
+    """Whole hot path on the CPU: moveShapes -> culledKeys -> prepareFrame -> constraintGen."""
+    if cos_rot is None:
+        cos_rot, sin_rot = cos_sin(world.rot)
+    emin, emax = ext if ext is not None else hull_extents(world)
+    wx, wy, nx, ny = move_shapes(world, cos_rot, sin_rot)
+    boxes = aabbs(world, wx, wy)
+    static = is_static(world)
+    if broadphase == "auto":
+        broadphase = "aabb" if world.n_slots <= 3000 else "sweep"
+    fn = {"aabb": culled_keys_aabb, "sweep": culled_keys_sweep, "grid": culled_keys_grid}[broadphase]
+    pi, pj = fn(world, boxes, static)
+    res = contacts(world, pi, pj, wx, wy, nx, ny, emin, emax, dt, baumgarte, slop)
+    res.update(pair_i=pi, pair_j=pj, aabb_min_x=boxes[0], aabb_max_x=boxes[1], aabb_min_y=boxes[2],
+               aabb_max_y=boxes[3], world_x=wx, world_y=wy, normal_wx=nx, normal_wy=ny,
+               ext_min=emin, ext_max=emax, is_static=static)
+    return res

@@ -1,0 +1,103 @@
+"""ctypes binding of include/shapes_b200.h.
+
+Loading fails loudly when the CUDA library has not been built: there is no
+CPU or PyTorch fallback for this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_ROOT, "lib", "libshapes_b200.so")
+
+OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
+NCCL_ID_BYTES = 128
+
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_f64p = C.POINTER(C.c_double)
+
+
+class FrameOut(C.Structure):
+    """shapes_frame_out"""
+    _fields_ = [
+        ("n_pairs", C.c_int64), ("pair_i", _i32p), ("pair_j", _i32p),
+        ("n_contacts", C.c_int64),
+        ("key_i", _i32p), ("key_j", _i32p), ("feat_a", _i32p), ("feat_b", _i32p),
+        ("flip", _u8p),
+        ("normal_x", _f64p), ("normal_y", _f64p), ("center_x", _f64p), ("center_y", _f64p),
+        ("depth", _f64p),
+        ("j_np", _f64p * 6), ("b_np", _f64p),
+        ("ra_x", _f64p), ("ra_y", _f64p), ("rb_x", _f64p), ("rb_y", _f64p),
+        ("rn_x", _f64p), ("rn_y", _f64p),
+        ("j_f", _f64p * 6), ("b_f", _f64p),
+        ("inv_eff_np", _f64p), ("inv_eff_f", _f64p),
+        ("aabb_min_x", _f64p), ("aabb_max_x", _f64p), ("aabb_min_y", _f64p), ("aabb_max_y", _f64p),
+        ("world_x", _f64p), ("world_y", _f64p),
+        ("n_big", C.c_int64), ("grid_w", C.c_int32), ("grid_h", C.c_int32),
+        ("cell_size", C.c_double), ("device_ms", C.c_float), ("total_ms", C.c_float),
+    ]
+
+
+class DeviceView(C.Structure):
+    """shapes_device_view"""
+    _fields_ = [
+        ("n_pairs", C.c_int64), ("n_contacts", C.c_int64),
+        ("pair_i", C.c_void_p), ("pair_j", C.c_void_p),
+        ("key_i", C.c_void_p), ("key_j", C.c_void_p), ("feat_a", C.c_void_p), ("feat_b", C.c_void_p),
+        ("flip", C.c_void_p),
+        ("normal_x", C.c_void_p), ("normal_y", C.c_void_p), ("center_x", C.c_void_p),
+        ("center_y", C.c_void_p), ("depth", C.c_void_p),
+        ("j_np", C.c_void_p * 6), ("b_np", C.c_void_p),
+        ("ra_x", C.c_void_p), ("ra_y", C.c_void_p), ("rb_x", C.c_void_p), ("rb_y", C.c_void_p),
+        ("rn_x", C.c_void_p), ("rn_y", C.c_void_p),
+        ("j_f", C.c_void_p * 6),
+        ("inv_eff_np", C.c_void_p), ("inv_eff_f", C.c_void_p),
+        ("aabb", C.c_void_p),
+    ]
+
+
+# every symbol include/shapes_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "shapes_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "shapes_create_ranked": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "shapes_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "shapes_destroy": (None, [C.c_void_p]),
+    "shapes_last_error": (C.c_char_p, [C.c_void_p]),
+    "shapes_set_hulls": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "shapes_set_cell_size": (C.c_int, [C.c_void_p, C.c_double]),
+    "shapes_frame": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
+    "shapes_frame_device": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
+    "shapes_device_view_get": (C.c_int, [C.c_void_p, C.POINTER(DeviceView)]),
+    "shapes_fetch": (C.c_int, [C.c_void_p, C.POINTER(FrameOut)]),
+    "shapes_rank_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "shapes_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "shapes_host_free": (None, [C.c_void_p]),
+    "shapes_stream": (C.c_void_p, [C.c_void_p]),
+    "shapes_launch_count": (C.c_int64, [C.c_void_p]),
+    "shapes_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libshapes_b200.so and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m shapes_b200.build` "
+            "(or __graft_entry__.build()). There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

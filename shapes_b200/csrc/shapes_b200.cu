@@ -1,0 +1,1451 @@
+// shapes_b200.cu -- B200 (sm_100a) collision pipeline behind include/shapes_b200.h.
+//
+// Replaces, for one frame, the reference's
+//   Aabb.culledKeys / Grid.culledKeys   (shapes/src/Physics/Broadphase/Aabb.hs:168-183, Grid.hs:67-100)
+//   prepareFrame                        (shapes/src/Physics/Solvers/Contact.hs:40-52)
+//   constraintGen per contact           (shapes/src/Physics/Constraints/Contact.hs:60-72)
+// All reference paths below are relative to /root/reference/.
+//
+// Pipeline (one stream, no host round trip between kernels):
+//   K0  k_transform_aabb  moveShapes + toAabb per slot                 (World.hs:132-140, Aabb.hs:81-110)
+//   [N>1: ncclAllGather of the AABB records over NVLink]
+//   K0b k_bounds / k_plan_grid / k_cell_keys   uniform-grid cell key of each AABB's min corner
+//   K1  radix sort (key, slot)  + k_gather_sorted (sorted AABB records, per-cell ranges)
+//   K2  k_sweep<count> -> exclusive scan over slots in DESCENDING key order -> k_sweep<emit>
+//       (+ k_big<count/emit> for shapes spanning more than 2 cells or with non-finite bounds)
+//       => pairs come out in the reference's descending (i, j) order by construction.
+//   K3  k_contacts  SAT both directions + incident-edge clipping + NonPenetration / Friction /
+//       Restitution generators + inverse effective mass, one thread per pair, rows compacted in
+//       order by a single-pass decoupled look-back scan.
+//
+// Arithmetic: IEEE binary64, every operation a separately rounded __dmul_rn/__dadd_rn/... so no
+// FMA contraction can occur whatever the compiler flags; expression trees follow the reference's
+// TH-generated left folds (shapes-math/src/Shapes/Linear/Template.hs:108-110).
+//
+// There is no CPU fallback anywhere in this file.
+
+#include "shapes_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <nccl.h>   // types only: NCCL is bound at run time (see NcclApi), never at link time
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// small device math layer (Physics.Linear, shapes/src/Physics/Linear.hs)
+// ---------------------------------------------------------------------------------------------
+
+struct V2 { double x, y; };
+
+__device__ __forceinline__ double fmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double fadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double fsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double fdiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// dotV2 (Template.hs:108-110): (a0*b0)+(a1*b1)
+__device__ __forceinline__ double dot2(V2 a, V2 b) { return fadd(fmul(a.x, b.x), fmul(a.y, b.y)); }
+// minusV2 (Linear.hs:114-116)
+__device__ __forceinline__ V2 sub2(V2 a, V2 b) { return V2{ fsub(a.x, b.x), fsub(a.y, b.y) }; }
+// crossV2 (Linear.hs:118-120)
+__device__ __forceinline__ double cross2(V2 a, V2 b) { return fsub(fmul(a.x, b.y), fmul(a.y, b.x)); }
+// clockwiseV2 (Linear.hs:161-163)
+__device__ __forceinline__ V2 clockwise2(V2 a) { return V2{ a.y, -a.x }; }
+__device__ __forceinline__ V2 neg2(V2 a) { return V2{ -a.x, -a.y }; }
+
+// unitEdgeNormal (ConvexHull.hs:218-226) = normalizeV2 (clockwiseV2 (v' - v)) (Linear.hs:165-168)
+__device__ __forceinline__ V2 unit_edge_normal(V2 v, V2 vnext)
+{
+    V2 e = clockwise2(sub2(vnext, v));
+    double len = __dsqrt_rn(fadd(fmul(e.x, e.x), fmul(e.y, e.y)));
+    return V2{ fdiv(e.x, len), fdiv(e.y, len) };
+}
+
+// Forward matrix of toTransform pos ori = translate(pos) . rotate(ori)
+// (Transform.hs:34-38,73-77; Linear.hs:349-381), first two rows. Every entry is the generic
+// mul3x3x3 dot product ((t0*r0)+(t1*r1))+(t2*r2) (MatrixTemplate.hs:47-67) so that signed zeros
+// and non-finite inputs behave as in the reference.
+struct Aff { double m00, m01, m02, m10, m11, m12; };
+
+__device__ __forceinline__ Aff to_transform(double px, double py, double c, double s)
+{
+    const double ns = -s;
+    Aff m;
+    m.m00 = fadd(fadd(fmul(1.0, c), fmul(0.0, s)), fmul(px, 0.0));
+    m.m01 = fadd(fadd(fmul(1.0, ns), fmul(0.0, c)), fmul(px, 0.0));
+    m.m02 = fadd(fadd(fmul(1.0, 0.0), fmul(0.0, 0.0)), fmul(px, 1.0));
+    m.m10 = fadd(fadd(fmul(0.0, c), fmul(1.0, s)), fmul(py, 0.0));
+    m.m11 = fadd(fadd(fmul(0.0, ns), fmul(1.0, c)), fmul(py, 0.0));
+    m.m12 = fadd(fadd(fmul(0.0, 0.0), fmul(1.0, 0.0)), fmul(py, 1.0));
+    return m;
+}
+
+// afmul (Linear.hs:217-220): t `mul3x3c` (a, b, 1.0)
+__device__ __forceinline__ V2 afmul(const Aff &m, V2 p)
+{
+    return V2{ fadd(fadd(fmul(m.m00, p.x), fmul(m.m01, p.y)), fmul(m.m02, 1.0)),
+               fadd(fadd(fmul(m.m10, p.x), fmul(m.m11, p.y)), fmul(m.m12, 1.0)) };
+}
+
+// boundsOverlap (Aabb.hs:69-72): not (c > b || d < a); NaN bounds therefore "overlap".
+__device__ __forceinline__ bool bounds_overlap(double a, double b, double c, double d)
+{
+    return !((c > b) || (d < a));
+}
+
+struct __align__(32) Box { double min_x, max_x, min_y, max_y; };
+struct __align__(32) Xf { double px, py, c, s; };
+
+// aabbCheck boxA boxB (Aabb.hs:75-78); A is the shape with the larger key.
+__device__ __forceinline__ bool aabb_check(const Box &a, const Box &b)
+{
+    return bounds_overlap(a.min_x, a.max_x, b.min_x, b.max_x) &&
+           bounds_overlap(a.min_y, a.max_y, b.min_y, b.max_y);
+}
+
+__device__ __forceinline__ bool finite4(const Box &b)
+{
+    return isfinite(b.min_x) && isfinite(b.max_x) && isfinite(b.min_y) && isfinite(b.max_y);
+}
+
+// order-preserving map double -> uint64 for atomicMin/atomicMax
+__device__ __forceinline__ unsigned long long enc_ordered(double d)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_ordered(unsigned long long u)
+{
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int ERR_PAIR_CAP = 1;
+constexpr int ERR_CONTACT_CAP = 2;
+constexpr int MAX_STAGED_VERTS = 8; // hulls up to this many vertices are staged in shared memory
+
+// Device-resident per-frame state: lets every kernel be launched without a host round trip.
+struct FrameState {
+    unsigned long long bmin_x, bmin_y, bmax_x, bmax_y; // ordered encodings of the finite world bounds
+    double ox, oy, h;   // grid origin and (possibly coarsened) cell edge
+    int W, H;           // grid columns / rows
+    unsigned n_cells;
+    unsigned n_big;     // shapes on the big-shape path
+    unsigned n_small;   // shapes in the grid
+    unsigned ticket;    // tile ticket of k_contacts
+    int error;
+    long long n_pairs;
+    long long n_contacts;
+};
+
+// Everything the kernels need, passed by value.
+struct Params {
+    // static world
+    int n_slots;
+    int own_lo, own_hi;         // slots this rank owns as the larger key of a pair
+    const uint8_t *alive;
+    const int32_t *vert_offset;
+    const double2 *local;       // interleaved local vertices
+    const int32_t *ext_min, *ext_max;   // per edge (hull-relative)
+    const unsigned long long *ext_packed; // per slot, 3+3 bits per edge, hulls with <= 8 vertices
+    // per-frame inputs
+    const double *pos_x, *pos_y, *rot, *cos_rot, *sin_rot, *inv_lin, *inv_rot;
+    double dt, baumgarte, slop;
+    // per-frame derived
+    Xf *xf;                     // (px, py, cos, sin)
+    double2 *mass;              // (inv_lin, inv_rot)
+    uint8_t *is_static;
+    Box *box;                   // per slot
+    double *world_x, *world_y;  // optional debug output
+    uint32_t *keys, *keys_sorted, *idx, *idx_sorted;
+    Box *sbox;                  // AABB records in sorted order
+    uint32_t *smeta;            // slot | static << 31, sorted order
+    uint2 *cells;               // [begin, end) sorted positions per cell
+    unsigned cell_cap;
+    double cell_size;
+    uint32_t *big_idx;
+    unsigned long long *cnt, *off; // per query slot, indexed own_hi-1-i
+    int64_t max_pairs, max_contacts;
+    int32_t *pair_i, *pair_j;
+    // contacts
+    unsigned long long *tile_status;
+    unsigned epoch;
+    int32_t *key_i, *key_j, *feat_a, *feat_b;
+    uint8_t *flip;
+    double *normal_x, *normal_y, *center_x, *center_y, *depth;
+    double *j_np[6], *b_np, *ra_x, *ra_y, *rb_x, *rb_y, *rn_x, *rn_y, *j_f[6];
+    double *inv_eff_np, *inv_eff_f;
+    FrameState *st;
+};
+
+// ---------------------------------------------------------------------------------------------
+// K0: moveShapes + toAabb
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_reset_state(FrameState *st)
+{
+    st->bmin_x = st->bmin_y = ~0ull;
+    st->bmax_x = st->bmax_y = 0ull;
+    st->ox = st->oy = 0.0;
+    st->h = 1.0;
+    st->W = st->H = 1;
+    st->n_cells = 1;
+    st->n_big = 0;
+    st->n_small = 0;
+    st->ticket = 0;
+    st->error = 0;
+    st->n_pairs = 0;
+    st->n_contacts = 0;
+}
+
+// One thread per slot.  Packs the per-frame body state every later kernel gathers (xf, mass,
+// static flag) for ALL slots, and transforms + bounds the hulls of the slots in [lo, hi).
+// moveShape (World.hs:132-134) -> setHullTransform (ConvexHull.hs:184-195): world vertex =
+// afmul (toTransform pos rot) local; hullToAabb (Aabb.hs:81-84) = foldl1 mergeAabb with
+// mergeRange's `if a < c then a else c` / `if b > d then b else d` (Aabb.hs:104-110).
+__global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        double px = P.pos_x[s], py = P.pos_y[s];
+        double c, sn;
+        if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
+        else sincos(P.rot[s], &sn, &c); // not bit-exact against libm (documented at the ABI)
+        double il = P.inv_lin[s], ir = P.inv_rot[s];
+        P.xf[s] = Xf{ px, py, c, sn };
+        P.mass[s] = make_double2(il, ir);
+        P.is_static[s] = (il == 0.0 && ir == 0.0) ? 1 : 0; // isStatic (Constraint.hs:123-125)
+        if (s < lo || s >= hi || !P.alive[s]) continue;
+        const int o = P.vert_offset[s];
+        const int n = P.vert_offset[s + 1] - o;
+        const Aff m = to_transform(px, py, c, sn);
+        Box b;
+        for (int k = 0; k < n; ++k) {
+            double2 l = __ldg(&P.local[o + k]);
+            V2 w = afmul(m, V2{ l.x, l.y });
+            if (P.world_x) { P.world_x[o + k] = w.x; P.world_y[o + k] = w.y; }
+            if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+            else {
+                b.min_x = (b.min_x < w.x) ? b.min_x : w.x;
+                b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                b.min_y = (b.min_y < w.y) ? b.min_y : w.y;
+                b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+            }
+        }
+        P.box[s] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0b: world bounds, grid plan, cell keys
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double warp_min(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_bounds(Params P)
+{
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        if (!P.alive[s]) continue;
+        Box b = P.box[s];
+        if (!finite4(b)) continue;
+        mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
+        mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+    }
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
+        atomicMin(&P.st->bmin_x, enc_ordered(mnx));
+        atomicMin(&P.st->bmin_y, enc_ordered(mny));
+        atomicMax(&P.st->bmax_x, enc_ordered(mxx));
+        atomicMax(&P.st->bmax_y, enc_ordered(mxy));
+    }
+}
+
+// Single thread: choose origin, cell edge and grid extent.  The cell edge starts at the static
+// estimate (largest hull diameter outside the big set) and doubles until the table fits.
+__global__ void k_plan_grid(Params P)
+{
+    FrameState *st = P.st;
+    if (st->bmax_x == 0ull) { // no finite shape
+        st->ox = st->oy = 0.0; st->h = P.cell_size; st->W = st->H = 1; st->n_cells = 1;
+        return;
+    }
+    double ox = dec_ordered(st->bmin_x), oy = dec_ordered(st->bmin_y);
+    double ex = dec_ordered(st->bmax_x) - ox, ey = dec_ordered(st->bmax_y) - oy;
+    double h = P.cell_size;
+    double wx = 0.0, wy = 0.0;
+    bool ok = false;
+    for (int it = 0; it < 2200; ++it) {
+        wx = floor(ex / h) + 1.0;
+        wy = floor(ey / h) + 1.0;
+        if (isfinite(wx) && isfinite(wy) && wx < 1073741824.0 && wy < 1073741824.0 &&
+            wx * wy <= (double)P.cell_cap) { ok = true; break; }
+        h *= 2.0;
+    }
+    if (!ok) { wx = wy = 1.0; h = INFINITY; } // every finite shape lands in cell (0,0) or the big set
+    st->ox = ox; st->oy = oy; st->h = h;
+    st->W = (int)wx; st->H = (int)wy;
+    st->n_cells = (unsigned)(st->W * st->H);
+}
+
+// Cell of the AABB's min corner if the box spans at most 2 cells per axis ("small"); otherwise
+// (or with any non-finite bound) the shape goes to the big list and is tested against everything.
+// Monotonicity of x -> floor((x - ox) / h) alone guarantees that two overlapping small boxes have
+// min-corner cells at most 1 apart per axis, so the 3x3 neighbourhood search is exhaustive.
+__global__ void __launch_bounds__(256) k_cell_keys(Params P)
+{
+    const FrameState *st = P.st;
+    const double ox = st->ox, oy = st->oy, h = st->h;
+    const int W = st->W;
+    unsigned small = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        uint32_t key = KEY_NONE;
+        if (P.alive[s]) {
+            Box b = P.box[s];
+            bool big = true;
+            if (finite4(b)) {
+                double x0 = floor((b.min_x - ox) / h), x1 = floor((b.max_x - ox) / h);
+                double y0 = floor((b.min_y - oy) / h), y1 = floor((b.max_y - oy) / h);
+                if (isfinite(x0) && isfinite(x1) && isfinite(y0) && isfinite(y1) &&
+                    x1 - x0 <= 1.0 && y1 - y0 <= 1.0 && x0 >= 0.0 && y0 >= 0.0 &&
+                    x0 < (double)W && y0 < (double)st->H) {
+                    key = (uint32_t)y0 * (uint32_t)W + (uint32_t)x0;
+                    big = false;
+                }
+            }
+            if (big) {
+                unsigned pos = atomicAdd(&P.st->n_big, 1u);
+                P.big_idx[pos] = (uint32_t)s;
+            } else ++small;
+        }
+        P.keys[s] = key;
+        P.idx[s] = (uint32_t)s;
+    }
+    for (int o = 16; o > 0; o >>= 1) small += __shfl_xor_sync(0xffffffffu, small, o);
+    if ((threadIdx.x & 31) == 0 && small) atomicAdd(&P.st->n_small, small);
+}
+
+__global__ void __launch_bounds__(256) k_clear_cells(Params P)
+{
+    const unsigned n = P.st->n_cells;
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+        P.cells[c] = make_uint2(0u, 0u);
+}
+
+// After the sort: AABB records in sorted order (coalesced for the sweep) and per-cell ranges.
+__global__ void __launch_bounds__(256) k_gather_sorted(Params P)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_slots) return;
+    const uint32_t key = P.keys_sorted[p];
+    if (key == KEY_NONE) return;
+    const uint32_t s = P.idx_sorted[p];
+    P.sbox[p] = P.box[s];
+    P.smeta[p] = s | ((uint32_t)P.is_static[s] << 31);
+    if (p == 0 || P.keys_sorted[p - 1] != key) P.cells[key].x = (unsigned)p;
+    if (p + 1 == P.n_slots || P.keys_sorted[p + 1] != key) P.cells[key].y = (unsigned)(p + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: grid sweep.  Query = every owned small shape i; candidates = shapes j < i in the 3x3 cell
+// neighbourhood plus every big shape j < i.  Count pass, scan in descending i, emit pass that
+// also orders each i's partners descending => Aabb.culledKeys order (Aabb.hs:155-183).
+// ---------------------------------------------------------------------------------------------
+
+constexpr int EMIT_LOCAL = 24;
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_sweep(Params P)
+{
+    const FrameState *st = P.st;
+    if (EMIT && st->error) return;
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= st->n_small) return;
+    const uint32_t meta = P.smeta[p];
+    const int i = (int)(meta & 0x7fffffffu);
+    const bool si = (meta >> 31) != 0;
+    if (i < P.own_lo || i >= P.own_hi) return;
+    const Box bi = P.sbox[p];
+    const uint32_t key = P.keys_sorted[p];
+    const int W = st->W, H = st->H;
+    const int cy = (int)(key / (uint32_t)W), cx = (int)(key % (uint32_t)W);
+    const int r = P.own_hi - 1 - i;
+
+    unsigned long long count = 0;
+    int local[EMIT_LOCAL];
+    unsigned long long base = 0;
+    if (EMIT) base = P.off[r];
+
+    auto hit = [&](int j) {
+        if (EMIT) {
+            if (count < EMIT_LOCAL) local[count] = j;
+            else P.pair_j[base + count] = j;
+        }
+        ++count;
+    };
+
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int ny = cy + dy;
+        if (ny < 0 || ny >= H) continue;
+        const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
+        for (int nx = x_lo; nx <= x_hi; ++nx) {
+            const uint2 rng = __ldg(&P.cells[(size_t)ny * W + nx]);
+            for (unsigned q = rng.x; q < rng.y; ++q) {
+                const uint32_t m = __ldg(&P.smeta[q]);
+                const int j = (int)(m & 0x7fffffffu);
+                if (j >= i) continue;
+                if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
+                const Box bj = P.sbox[q];
+                if (aabb_check(bi, bj)) hit(j);
+            }
+        }
+    }
+    const unsigned n_big = st->n_big;
+    for (unsigned b = 0; b < n_big; ++b) {
+        const int j = (int)P.big_idx[b];
+        if (j >= i) continue;
+        if (si && P.is_static[j]) continue;
+        const Box bj = P.box[j];
+        if (aabb_check(bi, bj)) hit(j);
+    }
+
+    if (!EMIT) { P.cnt[r] = count; return; }
+    if (count == 0) return;
+    if (count <= EMIT_LOCAL) {
+        const int n = (int)count;
+        for (int a = 1; a < n; ++a) { // insertion sort, descending
+            int v = local[a], b2 = a - 1;
+            while (b2 >= 0 && local[b2] < v) { local[b2 + 1] = local[b2]; --b2; }
+            local[b2 + 1] = v;
+        }
+        for (int a = 0; a < n; ++a) { P.pair_i[base + a] = i; P.pair_j[base + a] = local[a]; }
+    } else {
+        for (int a = 0; a < EMIT_LOCAL; ++a) P.pair_j[base + a] = local[a];
+        int32_t *seg = P.pair_j + base;
+        for (unsigned long long a = 1; a < count; ++a) {
+            int v = seg[a];
+            long long b2 = (long long)a - 1;
+            while (b2 >= 0 && seg[b2] < v) { seg[b2 + 1] = seg[b2]; --b2; }
+            seg[b2 + 1] = v;
+        }
+        for (unsigned long long a = 0; a < count; ++a) P.pair_i[base + a] = i;
+    }
+}
+
+// Big shapes as queries: one block per big shape, all slots j < i in descending j.
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_big(Params P)
+{
+    const FrameState *st = P.st;
+    if (EMIT && st->error) return;
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned long long s_run;
+    const unsigned n_big = st->n_big;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned b = blockIdx.x; b < n_big; b += gridDim.x) {
+        const int i = (int)P.big_idx[b];
+        if (i < P.own_lo || i >= P.own_hi) continue;
+        const Box bi = P.box[i];
+        const bool si = P.is_static[i] != 0;
+        const int r = P.own_hi - 1 - i;
+        const unsigned long long base = EMIT ? P.off[r] : 0ull;
+        if (threadIdx.x == 0) s_run = 0;
+        __syncthreads();
+        for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
+            const int j = top - (int)threadIdx.x;
+            bool pred = false;
+            if (j >= 0 && P.alive[j] && !(si && P.is_static[j])) pred = aabb_check(bi, P.box[j]);
+            const unsigned bal = __ballot_sync(0xffffffffu, pred);
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (int w = 0; w < 8; ++w) { if (w < warp) before += s_warp[w]; total += s_warp[w]; }
+            const unsigned long long run = s_run;
+            if (EMIT && pred) {
+                const unsigned long long pos = base + run + before + __popc(bal & ((1u << lane) - 1u));
+                P.pair_i[pos] = i;
+                P.pair_j[pos] = j;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_run = run + total;
+            __syncthreads();
+        }
+        if (!EMIT && threadIdx.x == 0) P.cnt[r] = s_run;
+        __syncthreads();
+    }
+}
+
+__global__ void k_finish_pairs(Params P, int n_query)
+{
+    long long total = 0;
+    if (n_query > 0) total = (long long)(P.off[n_query - 1] + P.cnt[n_query - 1]);
+    P.st->n_pairs = total;
+    if (total > P.max_pairs) P.st->error |= ERR_PAIR_CAP;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: SAT + clipping + constraint generators, one thread per pair, ordered compaction
+// ---------------------------------------------------------------------------------------------
+
+constexpr int CT_THREADS = 128;
+
+// tile status word: [63:62] flag, [61:32] epoch, [31:0] value
+constexpr unsigned long long FLAG_AGG = 1ull, FLAG_INC = 2ull;
+__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, unsigned epoch, unsigned v)
+{
+    return (flag << 62) | ((unsigned long long)(epoch & 0x3fffffffu) << 32) | v;
+}
+
+struct HullAcc {
+    int slot, off, n;
+    int which;                 // 0 = a, 1 = b (selects the shared-memory plane)
+    unsigned long long ext;    // packed extents (n <= 8)
+};
+
+struct SatRes { bool sep; int edge; double depth; int pen; };
+
+struct ContactKernel {
+    const Params &P;
+    double2 (*sv)[MAX_STAGED_VERTS][CT_THREADS]; // [2][8][threads] staged world vertices
+    int tid;
+
+    __device__ __forceinline__ V2 slow_vertex(const HullAcc &h, int k) const
+    {
+        const Xf x = P.xf[h.slot];
+        const Aff m = to_transform(x.px, x.py, x.c, x.s);
+        const double2 l = __ldg(&P.local[h.off + k]);
+        return afmul(m, V2{ l.x, l.y });
+    }
+    __device__ __forceinline__ V2 vtx(const HullAcc &h, int k) const
+    {
+        if (h.n <= MAX_STAGED_VERTS) { const double2 v = sv[h.which][k][tid]; return V2{ v.x, v.y }; }
+        return slow_vertex(h, k);
+    }
+    __device__ __forceinline__ void ext(const HullAcc &h, int e, int &imin, int &imax) const
+    {
+        if (h.n <= MAX_STAGED_VERTS) {
+            const unsigned bits = (unsigned)(h.ext >> (6 * e));
+            imin = bits & 7; imax = (bits >> 3) & 7;
+        } else { imin = P.ext_min[h.off + e]; imax = P.ext_max[h.off + e]; }
+    }
+    __device__ __forceinline__ void stage(const HullAcc &h) const
+    {
+        if (h.n > MAX_STAGED_VERTS) return;
+        const Xf x = P.xf[h.slot];
+        const Aff m = to_transform(x.px, x.py, x.c, x.s);
+        for (int k = 0; k < h.n; ++k) {
+            const double2 l = __ldg(&P.local[h.off + k]);
+            const V2 w = afmul(m, V2{ l.x, l.y });
+            sv[h.which][k][tid] = make_double2(w.x, w.y);
+        }
+    }
+    __device__ __forceinline__ V2 normal(const HullAcc &h, int e) const
+    {
+        const int e1 = (e < h.n - 1) ? e + 1 : 0; // nextIndex (ConvexHull.hs:228-230)
+        return unit_edge_normal(vtx(h, e), vtx(h, e1));
+    }
+
+    // minOverlap' sEdge sPen (SAT.hs:121-143) with overlap (SAT.hs:103-117): the first
+    // separating edge wins (later edges cannot change the fold), else strictly smaller depth.
+    __device__ SatRes min_overlap(const HullAcc &E, const HullAcc &Pn) const
+    {
+        SatRes best{ false, 0, 0.0, 0 };
+        for (int e = 0; e < E.n; ++e) {
+            const V2 dir = normal(E, e);
+            int imin, imax;
+            ext(E, e, imin, imax);
+            // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
+            const double s_min = dot2(vtx(E, imin), dir);
+            const double s_max = dot2(vtx(E, imax), dir);
+            // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
+            double p_min = dot2(vtx(Pn, 0), dir), p_max = p_min;
+            int p_idx = 0;
+            for (int k = 1; k < Pn.n; ++k) {
+                const double d = dot2(vtx(Pn, k), dir);
+                if (d < p_min) { p_min = d; p_idx = k; }
+                if (d > p_max) p_max = d;
+            }
+            if ((p_min > s_max) || (p_max < s_min)) { best.sep = true; best.edge = e; return best; } // overlapTest (SAT.hs:74-83)
+            const double depth = fsub(s_max, p_min); // overlapAmount (SAT.hs:86-96)
+            if (e == 0 || depth < best.depth) { best.edge = e; best.depth = depth; best.pen = p_idx; }
+        }
+        return best;
+    }
+};
+
+struct Manifold {
+    int n;        // 0, 1 or 2 flattened contacts
+    int flip, edge;
+    V2 normal, ref0;
+    int pen[2];
+    V2 center[2];
+};
+
+enum { CLIP_LEFT = 0, CLIP_RIGHT = 1, CLIP_BOTH = 2, CLIP_NONE = 3 };
+
+// clipSegment (Linear.hs:327-343) with intersect2 (Linear.hs:244-251) and invM2x2 (Linear.hs:194-199).
+// The incident line (ip, in) and its offset ib = ip . in are the same for all three clips.
+__device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a, V2 b, V2 &c)
+{
+    const double b0 = dot2(bp, bn);
+    const double det = fsub(fmul(bn.x, in.y), fmul(bn.y, in.x));
+    const double inv = fdiv(1.0, det);
+    const double m00 = fmul(in.y, inv), m01 = fmul(-bn.y, inv);
+    const double m10 = fmul(-in.x, inv), m11 = fmul(bn.x, inv);
+    c.x = fadd(fmul(m00, b0), fmul(m01, ib));
+    c.y = fadd(fmul(m10, b0), fmul(m11, ib));
+    const double a1 = dot2(a, bn), b1 = dot2(b, bn), c1 = dot2(c, bn);
+    if (a1 < c1) return (b1 < c1) ? CLIP_BOTH : CLIP_LEFT;
+    if (b1 < c1) return CLIP_RIGHT;
+    return CLIP_NONE;
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_contacts(Params P)
+{
+    __shared__ double2 s_verts[2][MAX_STAGED_VERTS][CT_THREADS];
+    __shared__ unsigned s_warp_sum[CT_THREADS / 32];
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_excl;
+
+    FrameState *st = P.st;
+    if (st->error) return;
+    const long long n_pairs = st->n_pairs;
+    const unsigned n_tiles = (unsigned)((n_pairs + CT_THREADS - 1) / CT_THREADS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ContactKernel K{ P, s_verts, tid };
+
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(&st->ticket, 1u);
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= n_tiles) break;
+        const long long p = (long long)tile * CT_THREADS + tid;
+
+        Manifold m;
+        m.n = 0;
+        int i = 0, j = 0;
+        if (p < n_pairs) {
+            i = P.pair_i[p];
+            j = P.pair_j[p];
+            HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
+            A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
+            B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
+            A.ext = P.ext_packed[i];
+            B.ext = P.ext_packed[j];
+            K.stage(A);
+            K.stage(B);
+            // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
+            // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
+            const SatRes ab = K.min_overlap(A, B);
+            if (!ab.sep) {
+                const SatRes ba = K.min_overlap(B, A);
+                if (!ba.sep) {
+                    const bool same = ab.depth < ba.depth;
+                    const HullAcc &E = same ? A : B;
+                    const HullAcc &Pn = same ? B : A;
+                    const SatRes ov = same ? ab : ba;
+                    const V2 n = K.normal(E, ov.edge); // overlapNormal (SAT.hs:98-100)
+                    // penetratedEdge (SAT.hs:169-171)
+                    const int e1 = (ov.edge < E.n - 1) ? ov.edge + 1 : 0;
+                    const V2 ra = K.vtx(E, ov.edge), rb = K.vtx(E, e1);
+                    // penetratingEdge (SAT.hs:152-166)
+                    const int ib = ov.pen;
+                    const int ic = (ib < Pn.n - 1) ? ib + 1 : 0;
+                    const int ia = (ib > 0) ? ib - 1 : Pn.n - 1;
+                    const V2 va = K.vtx(Pn, ia), vb = K.vtx(Pn, ib), vc = K.vtx(Pn, ic);
+                    const double abn = fabs(dot2(sub2(vb, va), n));
+                    const double bcn = fabs(dot2(sub2(vc, vb), n));
+                    V2 q0, q1;
+                    int i0, i1;
+                    if (bcn < abn) { q0 = vb; i0 = ib; q1 = vc; i1 = ic; }
+                    else { q0 = va; i0 = ia; q1 = vb; i1 = ib; }
+                    // clipEdge (SAT.hs:190-218)
+                    const V2 inc_n = clockwise2(sub2(q1, q0)); // toLine2 c d, unclipped endpoints
+                    const double inc_b = dot2(q0, inc_n);
+                    V2 x;
+                    bool alive = true;
+                    int r = clip_segment(ra, sub2(rb, ra), inc_n, inc_b, q0, q1, x); // perpLine2 a b
+                    if (r == CLIP_BOTH) alive = false;
+                    else if (r == CLIP_LEFT) q0 = x;
+                    else if (r == CLIP_RIGHT) q1 = x;
+                    if (alive) {
+                        r = clip_segment(rb, sub2(ra, rb), inc_n, inc_b, q0, q1, x); // perpLine2 b a
+                        if (r == CLIP_BOTH) alive = false;
+                        else if (r == CLIP_LEFT) q0 = x;
+                        else if (r == CLIP_RIGHT) q1 = x;
+                    }
+                    if (alive) {
+                        r = clip_segment(ra, neg2(n), inc_n, inc_b, q0, q1, x); // Line2 a (negateV2 n)
+                        // applyClip'' (Linear.hs:285-292) removes the clipped endpoint
+                        if (r == CLIP_LEFT) { m.n = 1; m.pen[0] = i1; m.center[0] = q1; }
+                        else if (r == CLIP_RIGHT) { m.n = 1; m.pen[0] = i0; m.center[0] = q0; }
+                        else if (r == CLIP_NONE) {
+                            m.n = 2;
+                            // flattenContactPoints (SAT.hs:181-187): descending feature index
+                            if (i0 > i1) { m.pen[0] = i0; m.center[0] = q0; m.pen[1] = i1; m.center[1] = q1; }
+                            else { m.pen[0] = i1; m.center[0] = q1; m.pen[1] = i0; m.center[1] = q0; }
+                        }
+                    }
+                    m.flip = same ? 0 : 1;
+                    m.edge = ov.edge;
+                    m.normal = n;
+                    m.ref0 = ra;
+                }
+            }
+        }
+
+        // ordered compaction: block exclusive scan + decoupled look-back across tiles
+        const unsigned cnt = (unsigned)m.n;
+        unsigned incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        unsigned warp_base = 0, tile_total = 0;
+        for (int w = 0; w < CT_THREADS / 32; ++w) {
+            if (w < warp) warp_base += s_warp_sum[w];
+            tile_total += s_warp_sum[w];
+        }
+        if (warp == 0) {
+            volatile unsigned long long *status = P.tile_status;
+            unsigned excl = 0;
+            if (tile > 0) {
+                if (lane == 0) status[tile] = pack_status(FLAG_AGG, P.epoch, tile_total);
+                long long look = (long long)tile - 1 - lane;
+                while (true) {
+                    unsigned long long w = 0;
+                    bool ready;
+                    do {
+                        if (look >= 0) {
+                            w = status[look];
+                            ready = (((unsigned)(w >> 32)) & 0x3fffffffu) == (P.epoch & 0x3fffffffu) && (w >> 62) != 0;
+                        } else { w = pack_status(FLAG_INC, P.epoch, 0u); ready = true; }
+                    } while (__any_sync(0xffffffffu, !ready));
+                    const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == FLAG_INC);
+                    const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+                    unsigned v = (lane <= stop) ? (unsigned)(w & 0xffffffffu) : 0u;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    excl += v;
+                    if (inc_mask) break;
+                    look -= 32;
+                }
+            }
+            if (lane == 0) {
+                status[tile] = pack_status(FLAG_INC, P.epoch, excl + tile_total);
+                s_excl = excl;
+                if (tile == n_tiles - 1) {
+                    const long long total = (long long)excl + tile_total;
+                    st->n_contacts = total;
+                    if (total > P.max_contacts) atomicOr(&st->error, ERR_CONTACT_CAP);
+                }
+            }
+        }
+        __syncthreads();
+        const long long row0 = (long long)s_excl + warp_base + (incl - cnt);
+
+        // flattenContactResult (HullVsHull.hs:54-76) + constraintGen (Constraints/Contact.hs:60-72)
+        if (m.n > 0) {
+            const Xf xi = P.xf[i], xj = P.xf[j];
+            const double2 mi = P.mass[i], mj = P.mass[j];
+            const V2 pos_i{ xi.px, xi.py }, pos_j{ xj.px, xj.py };
+            const V2 n = m.normal;
+            const double ref_d = dot2(m.ref0, n);
+            for (int k = 0; k < m.n; ++k) {
+                const long long row = row0 + k;
+                if (row >= P.max_contacts) break;
+                const V2 c = m.center[k];
+                // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
+                const double d = fsub(ref_d, dot2(c, n));
+                P.key_i[row] = i; P.key_j[row] = j;
+                // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
+                P.feat_a[row] = m.flip ? m.pen[k] : m.edge;
+                P.feat_b[row] = m.flip ? m.edge : m.pen[k];
+                P.flip[row] = (uint8_t)m.flip;
+                P.normal_x[row] = n.x; P.normal_y[row] = n.y;
+                P.center_x[row] = c.x; P.center_y[row] = c.y;
+                P.depth[row] = d;
+                // generators run on (penetrated, penetrator) = (a,b) for Same, (b,a) for Flip, and
+                // flipExtract swaps the Jacobian halves back (Utils.hs:175-177,212-215; Constraint.hs:96-98)
+                const V2 xa = m.flip ? pos_j : pos_i;
+                const V2 xb = m.flip ? pos_i : pos_j;
+                double jn[6], jf[6];
+                // NonPenetration.jacobian (NonPenetration.hs:34-43)
+                const double np_a = cross2(sub2(xa, c), n), np_b = cross2(sub2(c, xb), n);
+                // Friction.jacobian (Friction.hs:31-44)
+                const V2 tb = clockwise2(n), ta = neg2(tb);
+                const double f_a = cross2(sub2(c, xa), ta), f_b = cross2(sub2(c, xb), tb);
+                if (!m.flip) {
+                    jn[0] = -n.x; jn[1] = -n.y; jn[2] = np_a; jn[3] = n.x; jn[4] = n.y; jn[5] = np_b;
+                    jf[0] = ta.x; jf[1] = ta.y; jf[2] = f_a; jf[3] = tb.x; jf[4] = tb.y; jf[5] = f_b;
+                } else {
+                    jn[3] = -n.x; jn[4] = -n.y; jn[5] = np_a; jn[0] = n.x; jn[1] = n.y; jn[2] = np_b;
+                    jf[3] = ta.x; jf[4] = ta.y; jf[5] = f_a; jf[0] = tb.x; jf[1] = tb.y; jf[2] = f_b;
+                }
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { P.j_np[q][row] = jn[q]; P.j_f[q][row] = jf[q]; }
+                // baumgarte (NonPenetration.hs:48-55)
+                P.b_np[row] = (d > P.slop) ? fmul(fdiv(P.baumgarte, P.dt), fsub(P.slop, d)) : 0.0;
+                // Restitution.constraintGen (Restitution.hs:21-31): radii from the unflipped pair
+                P.ra_x[row] = fsub(c.x, pos_i.x); P.ra_y[row] = fsub(c.y, pos_i.y);
+                P.rb_x[row] = fsub(c.x, pos_j.x); P.rb_y[row] = fsub(c.y, pos_j.y);
+                P.rn_x[row] = m.flip ? -n.x : n.x; P.rn_y[row] = m.flip ? -n.y : n.y;
+                // effMassM2 (Constraint.hs:173-179): left fold of (j_k * im_k) * j_k over the unflipped pair
+                const double im[6] = { mi.x, mi.x, mi.y, mj.x, mj.x, mj.y };
+                double en = fmul(fmul(jn[0], im[0]), jn[0]), ef = fmul(fmul(jf[0], im[0]), jf[0]);
+#pragma unroll
+                for (int q = 1; q < 6; ++q) {
+                    en = fadd(en, fmul(fmul(jn[q], im[q]), jn[q]));
+                    ef = fadd(ef, fmul(fmul(jf[q], im[q]), jf[q]));
+                }
+                P.inv_eff_np[row] = en; P.inv_eff_f[row] = ef;
+            }
+        }
+        __syncthreads(); // s_tile / s_warp_sum / staged vertices are reused by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// static geometry kernels
+// ---------------------------------------------------------------------------------------------
+
+// _hullExtents (ConvexHull.hs:151-167): per edge, (argmin, argmax) of the LOCAL vertices along
+// the local unit edge normal, first minimum / first maximum on ties.  One thread per edge.
+__global__ void k_hull_extents(int n_slots, const int32_t *vert_offset, const double2 *local,
+                               int32_t *ext_min, int32_t *ext_max)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int o = vert_offset[s], n = vert_offset[s + 1] - o;
+    for (int e = 0; e < n; ++e) {
+        const int e1 = (e < n - 1) ? e + 1 : 0;
+        const double2 a = local[o + e], b = local[o + e1];
+        const V2 dir = unit_edge_normal(V2{ a.x, a.y }, V2{ b.x, b.y });
+        double vmin = 0.0, vmax = 0.0;
+        int imin = 0, imax = 0;
+        for (int k = 0; k < n; ++k) {
+            const double2 v = local[o + k];
+            const double d = dot2(V2{ v.x, v.y }, dir);
+            if (k == 0) { vmin = vmax = d; }
+            else {
+                if (d < vmin) { vmin = d; imin = k; }
+                if (d > vmax) { vmax = d; imax = k; }
+            }
+        }
+        ext_min[o + e] = imin;
+        ext_max[o + e] = imax;
+    }
+}
+
+__global__ void k_pack_extents(int n_slots, const int32_t *vert_offset, const int32_t *ext_min,
+                               const int32_t *ext_max, unsigned long long *packed)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int o = vert_offset[s], n = vert_offset[s + 1] - o;
+    unsigned long long w = 0;
+    if (n <= MAX_STAGED_VERTS)
+        for (int e = 0; e < n; ++e)
+            w |= ((unsigned long long)(ext_min[o + e] & 7) | ((unsigned long long)(ext_max[o + e] & 7) << 3)) << (6 * e);
+    packed[s] = w;
+}
+
+__global__ void k_split_boxes(int n, const Box *box, double *a, double *b, double *c, double *d)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const Box x = box[s];
+    a[s] = x.min_x; b[s] = x.max_x; c[s] = x.min_y; d[s] = x.max_y;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+// NCCL is resolved with dlopen/dlsym the first time a multi-rank ctx (or a unique id) is asked
+// for.  A process that already carries an NCCL (e.g. PyTorch's bundled copy) keeps using that
+// one; single-GPU use never loads NCCL at all.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool ok = false;
+};
+
+static NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { api.error = std::string("dlopen libnccl.so.2: ") + dlerror(); return api; }
+    bool all = true;
+    auto sym = [&](const char *name) { void *p = dlsym(h, name); if (!p) { all = false; api.error = std::string("dlsym ") + name; } return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = all;
+    return api;
+}
+
+struct shapes_ctx {
+    int device = 0;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    int64_t max_shapes = 0, max_verts = 0, max_pairs = 0, max_contacts = 0;
+    int64_t n_slots = 0, n_verts = 0;
+    int64_t chunk = 0;          // slots per rank (all-gather granule)
+    bool hulls_set = false;
+    double auto_cell = 1.0, user_cell = 0.0;
+    unsigned epoch = 0;
+    int64_t launches = 0;
+    std::string err;
+    std::vector<void *> allocs;
+    // device buffers
+    uint8_t *d_alive = nullptr;
+    int32_t *d_vert_offset = nullptr, *d_ext_min = nullptr, *d_ext_max = nullptr;
+    double2 *d_local = nullptr;
+    unsigned long long *d_ext_packed = nullptr;
+    double *d_in[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    double *d_world_x = nullptr, *d_world_y = nullptr, *d_split = nullptr;
+    void *d_sort_tmp = nullptr, *d_scan_tmp = nullptr;
+    size_t sort_tmp_bytes = 0, scan_tmp_bytes = 0;
+    FrameState *h_state = nullptr; // pinned
+    int64_t *d_counts = nullptr;   // world x 2 (pairs, contacts), all-gathered
+    int64_t *h_counts = nullptr;   // pinned
+    Params P{};
+    // last frame
+    int64_t last_pairs = 0, last_contacts = 0;
+    bool have_frame = false;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CU_TRY(ctx, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                     \
+            return SHAPES_E_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+#define NCCL_TRY(ctx, expr)                                                                       \
+    do {                                                                                          \
+        ncclResult_t r__ = (expr);                                                                \
+        if (r__ != ncclSuccess) {                                                                 \
+            (ctx)->err = std::string(#expr) + ": " + nccl_api().GetErrorString(r__);                     \
+            return SHAPES_E_NCCL;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+template <typename T>
+int dev_alloc(shapes_ctx *c, T **p, size_t count)
+{
+    void *q = nullptr;
+    CU_TRY(c, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    c->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return SHAPES_OK;
+}
+
+inline int grid_for(int64_t n, int threads, int cap)
+{
+    int64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void *nccl_id,
+                int64_t max_shapes, int64_t max_verts, int64_t max_pairs, int64_t max_contacts)
+{
+    if (!out || max_shapes < 0 || max_verts < 0 || max_pairs < 0 || max_contacts < 0 ||
+        max_shapes > 0x7ffffff0ll || max_verts > 0x7ffffff0ll || max_pairs > 0x7ffffff0ll ||
+        max_contacts > 0xfffffff0ll || world < 1 || rank < 0 || rank >= world ||
+        (world > 1 && !nccl_id)) {
+        g_create_error = "shapes_create: bad argument";
+        return SHAPES_E_ARG;
+    }
+    shapes_ctx *c = new shapes_ctx();
+    c->device = device_id; c->rank = rank; c->world = world;
+    c->max_shapes = max_shapes; c->max_verts = max_verts;
+    c->max_pairs = max_pairs; c->max_contacts = max_contacts;
+    auto fail = [&](int code) { g_create_error = c->err; shapes_destroy(c); return code; };
+#define TRY_CREATE(expr) do { int rc__ = (expr); if (rc__ != SHAPES_OK) return fail(rc__); } while (0)
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e == cudaSuccess) return SHAPES_OK;
+        c->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return SHAPES_E_CUDA;
+    };
+    TRY_CREATE(cu(cudaSetDevice(device_id), "cudaSetDevice"));
+    cudaDeviceProp prop;
+    TRY_CREATE(cu(cudaGetDeviceProperties(&prop, device_id), "cudaGetDeviceProperties"));
+    c->sm_count = prop.multiProcessorCount;
+    TRY_CREATE(cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    TRY_CREATE(cu(cudaEventCreate(&c->ev0), "cudaEventCreate"));
+    TRY_CREATE(cu(cudaEventCreate(&c->ev1), "cudaEventCreate"));
+    if (world > 1) {
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) <= SHAPES_NCCL_ID_BYTES, "nccl id size");
+        std::memcpy(&id, nccl_id, sizeof(id));
+        NcclApi &api = nccl_api();
+        if (!api.ok) { c->err = "NCCL unavailable: " + api.error; return fail(SHAPES_E_NCCL); }
+        ncclResult_t r = api.CommInitRank(&c->comm, world, id, rank);
+        if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + api.GetErrorString(r); return fail(SHAPES_E_NCCL); }
+    }
+    const int64_t N = max_shapes, V = max_verts;
+    c->chunk = (N + world - 1) / world;
+    const int64_t Npad = std::max<int64_t>(c->chunk * world, 1);
+    Params &P = c->P;
+    TRY_CREATE(dev_alloc(c, &c->d_alive, N));
+    TRY_CREATE(dev_alloc(c, &c->d_vert_offset, N + 1));
+    TRY_CREATE(dev_alloc(c, &c->d_ext_min, V));
+    TRY_CREATE(dev_alloc(c, &c->d_ext_max, V));
+    TRY_CREATE(dev_alloc(c, &c->d_local, V));
+    TRY_CREATE(dev_alloc(c, &c->d_ext_packed, N));
+    for (int k = 0; k < 7; ++k) TRY_CREATE(dev_alloc(c, &c->d_in[k], N));
+    TRY_CREATE(dev_alloc(c, &P.xf, N));
+    TRY_CREATE(dev_alloc(c, &P.mass, N));
+    TRY_CREATE(dev_alloc(c, &P.is_static, N));
+    TRY_CREATE(dev_alloc(c, &P.box, Npad));
+    TRY_CREATE(dev_alloc(c, &P.keys, N));
+    TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
+    TRY_CREATE(dev_alloc(c, &P.idx, N));
+    TRY_CREATE(dev_alloc(c, &P.idx_sorted, N));
+    TRY_CREATE(dev_alloc(c, &P.sbox, N));
+    TRY_CREATE(dev_alloc(c, &P.smeta, N));
+    P.cell_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(4 * N, 1 << 16), 1ll << 28);
+    TRY_CREATE(dev_alloc(c, &P.cells, P.cell_cap));
+    TRY_CREATE(dev_alloc(c, &P.big_idx, N));
+    TRY_CREATE(dev_alloc(c, &P.cnt, N));
+    TRY_CREATE(dev_alloc(c, &P.off, N));
+    TRY_CREATE(dev_alloc(c, &P.pair_i, max_pairs));
+    TRY_CREATE(dev_alloc(c, &P.pair_j, max_pairs));
+    const int64_t n_tiles = (max_pairs + CT_THREADS - 1) / CT_THREADS + 1;
+    TRY_CREATE(dev_alloc(c, &P.tile_status, n_tiles));
+    TRY_CREATE(cu(cudaMemset(P.tile_status, 0, n_tiles * sizeof(unsigned long long)), "cudaMemset"));
+    const int64_t C = max_contacts;
+    TRY_CREATE(dev_alloc(c, &P.key_i, C)); TRY_CREATE(dev_alloc(c, &P.key_j, C));
+    TRY_CREATE(dev_alloc(c, &P.feat_a, C)); TRY_CREATE(dev_alloc(c, &P.feat_b, C));
+    TRY_CREATE(dev_alloc(c, &P.flip, C));
+    double **cols[] = { &P.normal_x, &P.normal_y, &P.center_x, &P.center_y, &P.depth, &P.b_np,
+                        &P.ra_x, &P.ra_y, &P.rb_x, &P.rb_y, &P.rn_x, &P.rn_y, &P.inv_eff_np, &P.inv_eff_f };
+    for (double **col : cols) TRY_CREATE(dev_alloc(c, col, C));
+    for (int q = 0; q < 6; ++q) { TRY_CREATE(dev_alloc(c, &P.j_np[q], C)); TRY_CREATE(dev_alloc(c, &P.j_f[q], C)); }
+    TRY_CREATE(dev_alloc(c, &P.st, 1));
+    TRY_CREATE(dev_alloc(c, &c->d_counts, 2 * world));
+    TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
+    TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 2 * world), "cudaMallocHost"));
+    // library scratch: radix sort of (cell key, slot) and the offset scan
+    size_t sb = 0, cb = 0;
+    TRY_CREATE(cu(cub::DeviceRadixSort::SortPairs(nullptr, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted,
+                                                  (int)std::max<int64_t>(N, 1), 0, 32, c->stream), "cub sort size"));
+    TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb, P.cnt, P.off, (int)std::max<int64_t>(N, 1), c->stream),
+                  "cub scan size"));
+    c->sort_tmp_bytes = sb; c->scan_tmp_bytes = cb;
+    TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_sort_tmp), sb));
+    TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_scan_tmp), cb));
+    P.max_pairs = max_pairs; P.max_contacts = max_contacts;
+    P.alive = c->d_alive; P.vert_offset = c->d_vert_offset; P.local = c->d_local;
+    P.ext_min = c->d_ext_min; P.ext_max = c->d_ext_max; P.ext_packed = c->d_ext_packed;
+#undef TRY_CREATE
+    *out = c;
+    return SHAPES_OK;
+}
+
+// Issue one frame on the ctx stream.  `in` = device pointers (pos_x, pos_y, rot, cos, sin, inv_lin, inv_rot).
+int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double dt, double baumgarte,
+              double slop, bool want_world, shapes_frame_out *out)
+{
+    if (!c->hulls_set) { c->err = "shapes_frame: shapes_set_hulls has not been called"; return SHAPES_E_ARG; }
+    if (n_slots != c->n_slots) { c->err = "shapes_frame: n_slots differs from shapes_set_hulls"; return SHAPES_E_ARG; }
+    if (!in[0] || !in[1] || !in[5] || !in[6] || (!in[2] && !(in[3] && in[4])) || ((in[3] == nullptr) != (in[4] == nullptr))) {
+        c->err = "shapes_frame: missing input column";
+        return SHAPES_E_ARG;
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    Params &P = c->P;
+    const int N = (int)n_slots;
+    P.n_slots = N;
+    P.own_lo = (int)std::min<int64_t>(c->rank * c->chunk, N);
+    P.own_hi = (int)std::min<int64_t>((c->rank + 1) * c->chunk, N);
+    const int n_query = P.own_hi - P.own_lo;
+    P.pos_x = in[0]; P.pos_y = in[1]; P.rot = in[2]; P.cos_rot = in[3]; P.sin_rot = in[4];
+    P.inv_lin = in[5]; P.inv_rot = in[6];
+    P.dt = dt; P.baumgarte = baumgarte; P.slop = slop;
+    P.cell_size = c->user_cell > 0.0 ? c->user_cell : c->auto_cell;
+    P.world_x = want_world ? c->d_world_x : nullptr;
+    P.world_y = want_world ? c->d_world_y : nullptr;
+    P.epoch = ++c->epoch;
+    if ((P.epoch & 0x3fffffffu) == 0) P.epoch = ++c->epoch; // epoch 0 means "never written"
+    cudaStream_t s = c->stream;
+    const int sms = c->sm_count;
+
+    CU_TRY(c, cudaEventRecord(c->ev0, s));
+    k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
+    if (N > 0) {
+        CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
+        k_transform_aabb<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
+        if (c->world > 1) {
+            // exchange #1: AABB records of every rank's slot range over NVLink (in place)
+            NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
+                                      sizeof(Box) * c->chunk, ncclChar, c->comm, s));
+        }
+        k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
+        k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
+        k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+        k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
+        size_t sb = c->sort_tmp_bytes;
+        CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, N, 0, 32, s));
+        k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches;
+        k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+        k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
+        if (n_query > 0) {
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+        }
+        k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+        k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+        k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
+        k_contacts<<<sms * 4, CT_THREADS, 0, s>>>(P); ++c->launches;
+    }
+    CU_TRY(c, cudaGetLastError());
+    if (c->world > 1) {
+        // exchange #2 (counts): every rank learns every rank's pair / contact counts, so the
+        // global row offset of each rank's slice is known everywhere.
+        NCCL_TRY(c, nccl_api().AllGather(&P.st->n_pairs, c->d_counts, 2, ncclInt64, c->comm, s));
+        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int64_t) * 2 * c->world, cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(c, cudaEventRecord(c->ev1, s));
+    CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    const FrameState &st = *c->h_state;
+    c->last_pairs = st.n_pairs;
+    c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
+    c->have_frame = (st.error == 0);
+    if (c->world == 1) { c->h_counts[0] = c->last_pairs; c->h_counts[1] = c->last_contacts; }
+    if (out) {
+        out->n_pairs = c->last_pairs;
+        out->n_contacts = c->last_contacts;
+        out->n_big = st.n_big;
+        out->grid_w = st.W; out->grid_h = st.H; out->cell_size = st.h;
+        float ms = 0.f;
+        CU_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        out->device_ms = ms;
+        out->total_ms = ms;
+    }
+    if (st.error) {
+        c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs)"
+                                           : "capacity: max_contacts too small (required count in n_contacts)";
+        return SHAPES_E_CAPACITY;
+    }
+    return SHAPES_OK;
+}
+
+template <typename T>
+int fetch_col(shapes_ctx *c, T *dst, const T *src, int64_t n)
+{
+    if (!dst || n <= 0) return SHAPES_OK;
+    CU_TRY(c, cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    return SHAPES_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *shapes_version(void) { return "shapes_b200 0.1 (sm_100a)"; }
+
+int shapes_create(shapes_ctx **out, int device_id, int64_t max_shapes, int64_t max_verts,
+                  int64_t max_pairs, int64_t max_contacts)
+{
+    return create_impl(out, device_id, 0, 1, nullptr, max_shapes, max_verts, max_pairs, max_contacts);
+}
+
+int shapes_create_ranked(shapes_ctx **out, int device_id, int rank, int world_size, const void *nccl_id,
+                         int64_t max_shapes, int64_t max_verts, int64_t max_pairs, int64_t max_contacts)
+{
+    return create_impl(out, device_id, rank, world_size, nccl_id, max_shapes, max_verts, max_pairs, max_contacts);
+}
+
+int shapes_nccl_unique_id(void *out_id)
+{
+    if (!out_id) return SHAPES_E_ARG;
+    NcclApi &api = nccl_api();
+    if (!api.ok) { g_create_error = "NCCL unavailable: " + api.error; return SHAPES_E_NCCL; }
+    ncclUniqueId id;
+    ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + api.GetErrorString(r); return SHAPES_E_NCCL; }
+    std::memset(out_id, 0, SHAPES_NCCL_ID_BYTES);
+    std::memcpy(out_id, &id, sizeof(id));
+    return SHAPES_OK;
+}
+
+void shapes_destroy(shapes_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *shapes_last_error(const shapes_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const int32_t *vert_offset,
+                     const double *local_x, const double *local_y, const int32_t *ext_min, const int32_t *ext_max)
+{
+    if (!c) return SHAPES_E_ARG;
+    if (n_slots < 0 || n_slots > c->max_shapes || (n_slots > 0 && (!vert_offset || !local_x || !local_y)) ||
+        ((ext_min == nullptr) != (ext_max == nullptr))) {
+        c->err = "shapes_set_hulls: bad argument";
+        return SHAPES_E_ARG;
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const int64_t n_verts = n_slots > 0 ? vert_offset[n_slots] : 0;
+    if (n_verts > c->max_verts || (n_slots > 0 && vert_offset[0] != 0)) {
+        c->err = "shapes_set_hulls: vertex count exceeds max_verts (or vert_offset[0] != 0)";
+        return SHAPES_E_ARG;
+    }
+    std::vector<uint8_t> live((size_t)n_slots, 1);
+    if (alive) std::memcpy(live.data(), alive, (size_t)n_slots);
+    // layout conversion (interleave x/y) and the static cell-size estimate: hull diameters
+    std::vector<double2> inter((size_t)n_verts);
+    std::vector<double> diam;
+    diam.reserve((size_t)n_slots);
+    for (int64_t s = 0; s < n_slots; ++s) {
+        const int32_t o = vert_offset[s], n = vert_offset[s + 1] - o;
+        if (n < 0 || (live[s] && n < 1)) { c->err = "shapes_set_hulls: a filled slot has no vertices"; return SHAPES_E_ARG; }
+        double r2 = 0.0;
+        for (int32_t k = 0; k < n; ++k) {
+            inter[o + k] = make_double2(local_x[o + k], local_y[o + k]);
+            const double d2 = local_x[o + k] * local_x[o + k] + local_y[o + k] * local_y[o + k];
+            if (d2 > r2) r2 = d2;
+        }
+        if (live[s] && std::isfinite(r2)) diam.push_back(2.0 * std::sqrt(r2));
+    }
+    // Cell edge = largest diameter outside the "obviously big" set: among the 64 largest hulls,
+    // everything above the last >= 2x gap (a floor among boxes) is left to the big-shape path.
+    double cell = 1.0;
+    if (!diam.empty()) {
+        const size_t top = std::min<size_t>(diam.size(), 65);
+        std::partial_sort(diam.begin(), diam.begin() + top, diam.end(), std::greater<double>());
+        size_t cut = 0;
+        for (size_t k = 1; k < top; ++k)
+            if (diam[k - 1] > 2.0 * diam[k]) cut = k;
+        cell = diam[cut] * (1.0 + 1e-6);
+        if (!(cell > 0.0)) cell = 1.0;
+    }
+    c->auto_cell = cell;
+    cudaStream_t s = c->stream;
+    if (n_slots > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->d_alive, live.data(), (size_t)n_slots, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, cudaMemcpyAsync(c->d_vert_offset, vert_offset, sizeof(int32_t) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, s));
+        if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+        if (ext_min) {
+            for (int64_t v = 0; v < n_verts; ++v) {
+                // _hullExtents entries index the hull's own vertices
+                if (ext_min[v] < 0 || ext_max[v] < 0) { c->err = "shapes_set_hulls: negative extent index"; return SHAPES_E_ARG; }
+            }
+            CU_TRY(c, cudaMemcpyAsync(c->d_ext_min, ext_min, sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+            CU_TRY(c, cudaMemcpyAsync(c->d_ext_max, ext_max, sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+        } else {
+            k_hull_extents<<<grid_for(n_slots, 128, 1 << 30), 128, 0, s>>>((int)n_slots, c->d_vert_offset, c->d_local, c->d_ext_min, c->d_ext_max);
+            ++c->launches;
+        }
+        k_pack_extents<<<grid_for(n_slots, 128, 1 << 30), 128, 0, s>>>((int)n_slots, c->d_vert_offset, c->d_ext_min, c->d_ext_max, c->d_ext_packed);
+        ++c->launches;
+        CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaStreamSynchronize(s));
+    c->n_slots = n_slots; c->n_verts = n_verts;
+    c->hulls_set = true;
+    c->have_frame = false;
+    return SHAPES_OK;
+}
+
+int shapes_set_cell_size(shapes_ctx *c, double cell_size)
+{
+    if (!c) return SHAPES_E_ARG;
+    c->user_cell = (cell_size > 0.0 && std::isfinite(cell_size)) ? cell_size : 0.0;
+    return SHAPES_OK;
+}
+
+int shapes_frame_device(shapes_ctx *c, int64_t n_slots, const double *pos_x, const double *pos_y,
+                        const double *rot, const double *cos_rot, const double *sin_rot,
+                        const double *inv_lin, const double *inv_rot, double dt, double baumgarte,
+                        double slop, shapes_frame_out *out)
+{
+    if (!c) return SHAPES_E_ARG;
+    const double *in[7] = { pos_x, pos_y, rot, cos_rot, sin_rot, inv_lin, inv_rot };
+    return run_frame(c, n_slots, in, dt, baumgarte, slop, false, out);
+}
+
+int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
+{
+    if (!c || !out) return SHAPES_E_ARG;
+    if (!c->have_frame) { c->err = "shapes_fetch: no completed frame"; return SHAPES_E_ARG; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const Params &P = c->P;
+    const int64_t np = c->last_pairs, nc = c->last_contacts;
+    int rc = SHAPES_OK;
+#define FETCH(dst, src, n) do { rc = fetch_col(c, dst, src, n); if (rc != SHAPES_OK) return rc; } while (0)
+    FETCH(out->pair_i, P.pair_i, np); FETCH(out->pair_j, P.pair_j, np);
+    FETCH(out->key_i, P.key_i, nc); FETCH(out->key_j, P.key_j, nc);
+    FETCH(out->feat_a, P.feat_a, nc); FETCH(out->feat_b, P.feat_b, nc);
+    FETCH(out->flip, P.flip, nc);
+    FETCH(out->normal_x, P.normal_x, nc); FETCH(out->normal_y, P.normal_y, nc);
+    FETCH(out->center_x, P.center_x, nc); FETCH(out->center_y, P.center_y, nc);
+    FETCH(out->depth, P.depth, nc);
+    for (int q = 0; q < 6; ++q) { FETCH(out->j_np[q], P.j_np[q], nc); FETCH(out->j_f[q], P.j_f[q], nc); }
+    FETCH(out->b_np, P.b_np, nc);
+    FETCH(out->ra_x, P.ra_x, nc); FETCH(out->ra_y, P.ra_y, nc);
+    FETCH(out->rb_x, P.rb_x, nc); FETCH(out->rb_y, P.rb_y, nc);
+    FETCH(out->rn_x, P.rn_x, nc); FETCH(out->rn_y, P.rn_y, nc);
+    FETCH(out->inv_eff_np, P.inv_eff_np, nc); FETCH(out->inv_eff_f, P.inv_eff_f, nc);
+    if (out->aabb_min_x || out->aabb_max_x || out->aabb_min_y || out->aabb_max_y) {
+        const int64_t N = c->n_slots;
+        if (!c->d_split) { rc = dev_alloc(c, &c->d_split, 4 * (size_t)std::max<int64_t>(c->max_shapes, 1)); if (rc) return rc; }
+        double *a = c->d_split, *b = a + c->max_shapes, *cc = b + c->max_shapes, *d = cc + c->max_shapes;
+        if (N > 0) { k_split_boxes<<<grid_for(N, 256, 1 << 30), 256, 0, c->stream>>>((int)N, P.box, a, b, cc, d); ++c->launches; }
+        FETCH(out->aabb_min_x, a, N); FETCH(out->aabb_max_x, b, N);
+        FETCH(out->aabb_min_y, cc, N); FETCH(out->aabb_max_y, d, N);
+    }
+    if (out->world_x && c->d_world_x) { FETCH(out->world_x, c->d_world_x, c->n_verts); FETCH(out->world_y, c->d_world_y, c->n_verts); }
+#undef FETCH
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (out->b_f && nc > 0) std::memset(out->b_f, 0, sizeof(double) * (size_t)nc); // Friction.toConstraint: b = 0 (Friction.hs:26-29)
+    return SHAPES_OK;
+}
+
+int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const double *pos_y,
+                 const double *rot, const double *cos_rot, const double *sin_rot,
+                 const double *inv_lin, const double *inv_rot, double dt, double baumgarte,
+                 double slop, shapes_frame_out *out)
+{
+    if (!c || !out) return SHAPES_E_ARG;
+    if (n_slots != c->n_slots || !c->hulls_set) { c->err = "shapes_frame: n_slots differs from shapes_set_hulls"; return SHAPES_E_ARG; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaEvent_t t0, t1;
+    CU_TRY(c, cudaEventCreate(&t0));
+    CU_TRY(c, cudaEventCreate(&t1));
+    CU_TRY(c, cudaEventRecord(t0, c->stream));
+    const double *host[7] = { pos_x, pos_y, rot, cos_rot, sin_rot, inv_lin, inv_rot };
+    const double *dev[7];
+    for (int k = 0; k < 7; ++k) {
+        dev[k] = nullptr;
+        if (host[k] && n_slots > 0) {
+            CU_TRY(c, cudaMemcpyAsync(c->d_in[k], host[k], sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, c->stream));
+            dev[k] = c->d_in[k];
+        } else if (host[k]) dev[k] = c->d_in[k];
+    }
+    const bool want_world = out->world_x && out->world_y;
+    if (want_world && !c->d_world_x) {
+        int rc = dev_alloc(c, &c->d_world_x, (size_t)c->max_verts); if (rc) return rc;
+        rc = dev_alloc(c, &c->d_world_y, (size_t)c->max_verts); if (rc) return rc;
+    }
+    int rc = run_frame(c, n_slots, dev, dt, baumgarte, slop, want_world, out);
+    if (rc == SHAPES_OK) rc = shapes_fetch(c, out);
+    cudaEventRecord(t1, c->stream);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    out->total_ms = ms;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    return rc;
+}
+
+int shapes_device_view_get(shapes_ctx *c, shapes_device_view *v)
+{
+    if (!c || !v) return SHAPES_E_ARG;
+    if (!c->have_frame) { c->err = "shapes_device_view_get: no completed frame"; return SHAPES_E_ARG; }
+    const Params &P = c->P;
+    v->n_pairs = c->last_pairs; v->n_contacts = c->last_contacts;
+    v->pair_i = P.pair_i; v->pair_j = P.pair_j;
+    v->key_i = P.key_i; v->key_j = P.key_j; v->feat_a = P.feat_a; v->feat_b = P.feat_b;
+    v->flip = P.flip;
+    v->normal_x = P.normal_x; v->normal_y = P.normal_y; v->center_x = P.center_x; v->center_y = P.center_y;
+    v->depth = P.depth;
+    for (int q = 0; q < 6; ++q) { v->j_np[q] = P.j_np[q]; v->j_f[q] = P.j_f[q]; }
+    v->b_np = P.b_np;
+    v->ra_x = P.ra_x; v->ra_y = P.ra_y; v->rb_x = P.rb_x; v->rb_y = P.rb_y; v->rn_x = P.rn_x; v->rn_y = P.rn_y;
+    v->inv_eff_np = P.inv_eff_np; v->inv_eff_f = P.inv_eff_f;
+    v->aabb = reinterpret_cast<const double *>(P.box);
+    return SHAPES_OK;
+}
+
+int shapes_rank_info(shapes_ctx *c, int64_t *own_lo, int64_t *own_hi, int64_t *all_pairs, int64_t *all_contacts)
+{
+    if (!c) return SHAPES_E_ARG;
+    if (own_lo) *own_lo = std::min<int64_t>(c->rank * c->chunk, c->n_slots);
+    if (own_hi) *own_hi = std::min<int64_t>((c->rank + 1) * c->chunk, c->n_slots);
+    for (int r = 0; r < c->world; ++r) {
+        if (all_pairs) all_pairs[r] = c->h_counts[2 * r];
+        if (all_contacts) all_contacts[r] = c->h_counts[2 * r + 1];
+    }
+    return SHAPES_OK;
+}
+
+void *shapes_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void shapes_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void *shapes_stream(shapes_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int64_t shapes_launch_count(const shapes_ctx *c) { return c ? c->launches : 0; }
+
+} // extern "C"

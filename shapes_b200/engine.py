@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's per-frame contact path over the C ABI.
+
+The three reference entry points this path replaces keep their names:
+
+  culledKeys     Physics.Broadphase.Aabb.culledKeys / Grid.culledKeys
+                 (shapes/src/Physics/Broadphase/Aabb.hs:168-183, Grid.hs:74-78)
+  prepareFrame   Physics.Solvers.Contact.prepareFrame (Solvers/Contact.hs:40-52)
+  constraintGen  Physics.Constraints.Contact.constraintGen (Constraints/Contact.hs:60-72)
+
+One `Engine.frame` call produces all three on the GPU; the functions at the
+bottom expose them with the reference's argument meaning.  Nothing here
+computes on the CPU: without the CUDA library or a GPU every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import FrameOut
+from .world import World
+
+PAIR_COLS = ("pair_i", "pair_j")
+CONTACT_I32 = ("key_i", "key_j", "feat_a", "feat_b")
+CONTACT_F64 = ("normal_x", "normal_y", "center_x", "center_y", "depth")
+CONSTRAINT_F64 = (tuple(f"j_np{q}" for q in range(6)) + ("b_np", "ra_x", "ra_y", "rb_x", "rb_y", "rn_x", "rn_y")
+                  + tuple(f"j_f{q}" for q in range(6)) + ("b_f", "inv_eff_np", "inv_eff_f"))
+AABB_COLS = ("aabb_min_x", "aabb_max_x", "aabb_min_y", "aabb_max_y")
+WORLD_COLS = ("world_x", "world_y")
+
+
+class ShapesError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"shapes_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CapacityError(ShapesError):
+    """SHAPES_E_CAPACITY: required sizes are in .n_pairs / .n_contacts."""
+    def __init__(self, msg: str, n_pairs: int, n_contacts: int):
+        super().__init__(_lib.E_CAPACITY, msg)
+        self.n_pairs = n_pairs
+        self.n_contacts = n_contacts
+
+
+@dataclass
+class ContactBehavior:
+    """ContactBehavior (shapes/src/Physics/Contact/Types.hs:20-25)."""
+    contactBaumgarte: float = 0.0
+    contactPenetrationSlop: float = 0.0
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class _HostBuffers:
+    """Output columns of one frame; pinned through shapes_host_alloc when asked."""
+
+    def __init__(self, lib, max_pairs, max_contacts, n_slots, n_verts, want, pinned):
+        self.lib = lib
+        self.cols: dict[str, np.ndarray] = {}
+        self._pinned_ptrs: list[int] = []
+        self.pinned = pinned
+        def alloc(n, dtype):
+            n = max(int(n), 1)
+            if not pinned:
+                return np.zeros(n, dtype)
+            nbytes = n * np.dtype(dtype).itemsize
+            p = lib.shapes_host_alloc(nbytes)
+            if not p:
+                raise ShapesError(_lib.E_CUDA, "shapes_host_alloc failed")
+            self._pinned_ptrs.append(p)
+            buf = (C.c_char * nbytes).from_address(p)
+            return np.frombuffer(buf, dtype=dtype, count=n)
+        if "pairs" in want:
+            for k in PAIR_COLS:
+                self.cols[k] = alloc(max_pairs, np.int32)
+        if "contacts" in want:
+            for k in CONTACT_I32:
+                self.cols[k] = alloc(max_contacts, np.int32)
+            self.cols["flip"] = alloc(max_contacts, np.uint8)
+            for k in CONTACT_F64:
+                self.cols[k] = alloc(max_contacts, np.float64)
+        if "constraints" in want:
+            for k in CONSTRAINT_F64:
+                self.cols[k] = alloc(max_contacts, np.float64)
+        if "aabb" in want:
+            for k in AABB_COLS:
+                self.cols[k] = alloc(n_slots, np.float64)
+        if "world" in want:
+            for k in WORLD_COLS:
+                self.cols[k] = alloc(n_verts, np.float64)
+
+    def fill(self, out: FrameOut):
+        for k, a in self.cols.items():
+            if k.startswith("j_np"):
+                out.j_np[int(k[4:])] = a.ctypes.data_as(C.POINTER(C.c_double))
+            elif k.startswith("j_f"):
+                out.j_f[int(k[3:])] = a.ctypes.data_as(C.POINTER(C.c_double))
+            else:
+                ty = dict(FrameOut._fields_)[k]
+                setattr(out, k, a.ctypes.data_as(ty))
+
+    def bytes_for(self, n_pairs, n_contacts, n_slots, n_verts) -> int:
+        total = 0
+        for k, a in self.cols.items():
+            n = (n_pairs if k in PAIR_COLS else n_slots if k in AABB_COLS else n_verts if k in WORLD_COLS
+                 else n_contacts)
+            total += n * a.dtype.itemsize
+        return total
+
+    def free(self):
+        self.cols.clear()
+        for p in self._pinned_ptrs:
+            self.lib.shapes_host_free(p)
+        self._pinned_ptrs.clear()
+
+
+class Frame:
+    """Result of one frame: numpy views trimmed to the frame's counts."""
+
+    def __init__(self, out: FrameOut, bufs: _HostBuffers, n_slots: int, n_verts: int):
+        self.n_pairs = int(out.n_pairs)
+        self.n_contacts = int(out.n_contacts)
+        self.n_big = int(out.n_big)
+        self.grid = (int(out.grid_w), int(out.grid_h), float(out.cell_size))
+        self.device_ms = float(out.device_ms)
+        self.total_ms = float(out.total_ms)
+        self.cols = {}
+        for k, a in bufs.cols.items():
+            n = (self.n_pairs if k in PAIR_COLS else n_slots if k in AABB_COLS else n_verts if k in WORLD_COLS
+                 else self.n_contacts)
+            self.cols[k] = a[:n]
+
+    def __getitem__(self, k):
+        return self.cols[k]
+
+    def __contains__(self, k):
+        return k in self.cols
+
+    @property
+    def keys(self) -> np.ndarray:
+        """Descending (i, j) pairs as an (n_pairs, 2) array -- culledKeys' result."""
+        return np.stack([self.cols["pair_i"], self.cols["pair_j"]], axis=1)
+
+
+class Engine:
+    """Owns one shapes_ctx (one GPU)."""
+
+    def __init__(self, world: World, max_pairs: Optional[int] = None, max_contacts: Optional[int] = None,
+                 device: int = 0, rank: int = 0, world_size: int = 1, nccl_id: Optional[bytes] = None,
+                 ext: Optional[tuple[np.ndarray, np.ndarray]] = None):
+        self.lib = _lib.load()
+        self.device, self.rank, self.world_size, self.nccl_id = device, rank, world_size, nccl_id
+        n = world.n_slots
+        self.max_pairs = int(max_pairs if max_pairs is not None else max(1024, 8 * n))
+        self.max_contacts = int(max_contacts if max_contacts is not None else 2 * self.max_pairs)
+        self.ctx = C.c_void_p()
+        self._bufs: Optional[_HostBuffers] = None
+        self._bufs_key = None
+        self._create(world.n_slots, world.n_verts)
+        self.world = None
+        self.set_hulls(world, ext)
+
+    # -- lifetime -------------------------------------------------------
+    def _check(self, rc: int, out: Optional[FrameOut] = None):
+        if rc == _lib.OK:
+            return
+        msg = self.lib.shapes_last_error(self.ctx if self.ctx else None)
+        msg = msg.decode() if msg else ""
+        if rc == _lib.E_CAPACITY and out is not None:
+            raise CapacityError(msg, int(out.n_pairs), int(out.n_contacts))
+        raise ShapesError(rc, msg)
+
+    def _create(self, n_slots, n_verts):
+        self.cap_slots, self.cap_verts = max(n_slots, 1), max(n_verts, 1)
+        if self.world_size > 1:
+            idbuf = C.create_string_buffer(self.nccl_id, _lib.NCCL_ID_BYTES)
+            rc = self.lib.shapes_create_ranked(C.byref(self.ctx), self.device, self.rank, self.world_size, idbuf,
+                                               self.cap_slots, self.cap_verts, self.max_pairs, self.max_contacts)
+        else:
+            rc = self.lib.shapes_create(C.byref(self.ctx), self.device, self.cap_slots, self.cap_verts,
+                                        self.max_pairs, self.max_contacts)
+        if rc != _lib.OK:
+            msg = self.lib.shapes_last_error(None)
+            self.ctx = C.c_void_p()
+            raise ShapesError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if self._bufs is not None:
+            self._bufs.free()
+            self._bufs = None
+        if self.ctx:
+            self.lib.shapes_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- static geometry -----------------------------------------------------
+    def set_hulls(self, world: World, ext=None):
+        """World.fromList / append / delete (World.hs:77-116): register the hull geometry."""
+        world.validate()
+        if world.n_slots > self.cap_slots or world.n_verts > self.cap_verts:
+            raise ShapesError(_lib.E_ARG, "world exceeds the ctx capacities")
+        emin = emax = None
+        if ext is not None:
+            emin = np.ascontiguousarray(ext[0], np.int32); emax = np.ascontiguousarray(ext[1], np.int32)
+        self._check(self.lib.shapes_set_hulls(self.ctx, world.n_slots, _ptr(world.alive), _ptr(world.vert_offset),
+                                              _ptr(world.local_x), _ptr(world.local_y), _ptr(emin), _ptr(emax)))
+        self.world = world
+
+    def set_cell_size(self, cell: float):
+        self._check(self.lib.shapes_set_cell_size(self.ctx, float(cell)))
+
+    # -- frames -----------------------------------------------------------------
+    def _buffers(self, want, pinned) -> _HostBuffers:
+        key = (tuple(sorted(want)), pinned, self.max_pairs, self.max_contacts, self.world.n_slots, self.world.n_verts)
+        if self._bufs is None or self._bufs_key != key:
+            if self._bufs is not None:
+                self._bufs.free()
+            self._bufs = _HostBuffers(self.lib, self.max_pairs, self.max_contacts, self.world.n_slots,
+                                      self.world.n_verts, want, pinned)
+            self._bufs_key = key
+        return self._bufs
+
+    def frame(self, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02,
+              cos_sin: Optional[tuple[np.ndarray, np.ndarray]] = None,
+              want=("pairs", "contacts", "constraints"), pinned: bool = False) -> Frame:
+        """One frame through shapes_frame with host buffers (H2D + kernels + D2H)."""
+        w = self.world
+        bufs = self._buffers(want, pinned)
+        out = FrameOut()
+        bufs.fill(out)
+        cos_rot = sin_rot = None
+        if cos_sin is not None:
+            cos_rot = np.ascontiguousarray(cos_sin[0], np.float64)
+            sin_rot = np.ascontiguousarray(cos_sin[1], np.float64)
+        rc = self.lib.shapes_frame(self.ctx, w.n_slots, _ptr(w.pos_x), _ptr(w.pos_y), _ptr(w.rot),
+                                   _ptr(cos_rot), _ptr(sin_rot), _ptr(w.inv_lin), _ptr(w.inv_rot),
+                                   dt, baumgarte, slop, C.byref(out))
+        self._check(rc, out)
+        return Frame(out, bufs, w.n_slots, w.n_verts)
+
+    def frame_device(self, pos_x: int, pos_y: int, rot: int, cos_rot: int, sin_rot: int, inv_lin: int,
+                     inv_rot: int, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02) -> FrameOut:
+        """One frame through shapes_frame_device: arguments are DEVICE addresses (e.g.
+        torch.Tensor.data_ptr()); results stay in HBM (see device_view)."""
+        out = FrameOut()
+        rc = self.lib.shapes_frame_device(self.ctx, self.world.n_slots, pos_x, pos_y, rot or None, cos_rot or None,
+                                          sin_rot or None, inv_lin, inv_rot, dt, baumgarte, slop, C.byref(out))
+        self._check(rc, out)
+        return out
+
+    def fetch(self, want=("pairs", "contacts", "constraints"), pinned: bool = False) -> Frame:
+        """Copy the last frame's results out of HBM (shapes_fetch)."""
+        bufs = self._buffers(want, pinned)
+        out = FrameOut()
+        bufs.fill(out)
+        self._check(self.lib.shapes_fetch(self.ctx, C.byref(out)))
+        view = self.device_view()
+        out.n_pairs, out.n_contacts = view.n_pairs, view.n_contacts
+        return Frame(out, bufs, self.world.n_slots, self.world.n_verts)
+
+    def device_view(self) -> _lib.DeviceView:
+        v = _lib.DeviceView()
+        self._check(self.lib.shapes_device_view_get(self.ctx, C.byref(v)))
+        return v
+
+    def rank_info(self):
+        lo, hi = C.c_int64(), C.c_int64()
+        pairs = (C.c_int64 * self.world_size)()
+        contacts = (C.c_int64 * self.world_size)()
+        self._check(self.lib.shapes_rank_info(self.ctx, C.byref(lo), C.byref(hi), pairs, contacts))
+        return lo.value, hi.value, list(pairs), list(contacts)
+
+    def grow(self, n_pairs: int, n_contacts: int):
+        """Re-create the ctx with larger capacities (the caller's answer to E_CAPACITY)."""
+        world = self.world
+        self.close()
+        self.max_pairs = max(self.max_pairs, int(n_pairs * 1.25) + 1024)
+        self.max_contacts = max(self.max_contacts, int(n_contacts * 1.25) + 1024)
+        self._create(world.n_slots, world.n_verts)
+        self.set_hulls(world)
+
+    def frame_grow(self, **kw) -> Frame:
+        """frame(), growing capacities and retrying on SHAPES_E_CAPACITY."""
+        for _ in range(4):
+            try:
+                return self.frame(**kw)
+            except CapacityError as e:
+                self.grow(e.n_pairs, e.n_contacts)
+        return self.frame(**kw)
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.shapes_stream(self.ctx) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.shapes_launch_count(self.ctx))
+
+
+def nccl_unique_id() -> bytes:
+    lib = _lib.load()
+    buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+    rc = lib.shapes_nccl_unique_id(buf)
+    if rc != _lib.OK:
+        raise ShapesError(rc, (lib.shapes_last_error(None) or b"").decode())
+    return buf.raw
+
+
+# ---------------------------------------------------------------------------
+# the reference's entry points, by name
+# ---------------------------------------------------------------------------
+
+def culledKeys(engine: Engine, cos_sin=None) -> np.ndarray:
+    """Aabb.culledKeys world :: Descending (Int, Int) -- (n_pairs, 2), descending."""
+    return engine.frame_grow(cos_sin=cos_sin, want=("pairs",)).keys.copy()
+
+
+def prepareFrame(engine: Engine, cos_sin=None) -> Frame:
+    """prepareFrame keys world :: Descending (ObjectFeatureKey Int, Flipping Contact).
+    The broadphase keys are produced inside the same device pass."""
+    return engine.frame_grow(cos_sin=cos_sin, want=("pairs", "contacts"))
+
+
+def constraintGen(engine: Engine, beh: ContactBehavior, dt: float, cos_sin=None) -> Frame:
+    """constraintGen beh dt fContact ab for every contact of the frame: row k of the
+    constraint columns belongs to contact k, the order applyCachedSlns walks them in."""
+    return engine.frame_grow(dt=dt, baumgarte=beh.contactBaumgarte, slop=beh.contactPenetrationSlop,
+                             cos_sin=cos_sin, want=("pairs", "contacts", "constraints"))

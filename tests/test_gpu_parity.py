@@ -1,0 +1,249 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a GPU.
+
+Pair sets and all integer columns must be bit-identical; reals are asserted bit-identical
+too (every operation is IEEE and un-fused on both sides), which is stricter than the
+north-star's 1e-9 relative bar.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_frames_match
+from shapes_b200 import scenes
+from shapes_b200.world import World, rectangle_vertices
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+WANT_ALL = ("pairs", "contacts", "constraints", "aabb", "world")
+
+
+def gpu_frame(world, cos_sin, want=WANT_ALL, ext=None, cell=None, **kw):
+    from shapes_b200.engine import Engine
+    with Engine(world, ext=ext) as eng:
+        if cell is not None:
+            eng.set_cell_size(cell)
+        fr = eng.frame_grow(cos_sin=cos_sin, want=want, **kw)
+        got = {k: np.array(v) for k, v in fr.cols.items()}
+        got["_n_big"] = fr.n_big
+        got["_launches"] = eng.launch_count
+    return got
+
+
+def check_world(oracle, world, broadphase="auto", **kw):
+    c, s = oracle.cos_sin(world.rot)
+    want = oracle.frame(world, c, s, broadphase=broadphase,
+                        **{k: v for k, v in kw.items() if k in ("dt", "baumgarte", "slop")})
+    got = gpu_frame(world, (c, s), **kw)
+    assert got["_launches"] > 0
+    assert_frames_match(got, want)
+    for k in ("aabb_min_x", "aabb_max_x", "aabb_min_y", "aabb_max_y"):
+        live = world.alive == 1
+        assert np.array_equal(got[k][live], want[k][live], equal_nan=True), k
+    for k in ("world_x", "world_y"):
+        live_v = np.repeat(world.alive == 1, np.diff(world.vert_offset))
+        assert np.array_equal(got[k][live_v], want[k][live_v], equal_nan=True), k
+    return got, want
+
+
+def test_kat1_and_kat3_through_the_abi(oracle):
+    with open(os.path.join(GOLDEN, "kat.json")) as f:
+        kat = json.load(f)
+    got, _ = check_world(oracle, scenes.test_opt_boxes())
+    k1 = kat["kat1_testOptBoxes"]
+    assert got["pair_i"].tolist() == [1] and got["pair_j"].tolist() == [0]
+    for k, c in enumerate(k1["contacts"]):
+        assert [got["feat_a"][k], got["feat_b"][k]] == c["feat"] and got["flip"][k] == c["flip"]
+        assert [got["normal_x"][k], got["normal_y"][k]] == c["normal"]
+        assert [got["center_x"][k], got["center_y"][k]] == c["center"] and got["depth"][k] == c["depth"]
+    for name, spacing in (("spacing0", 0.0), ("spacing1", 1.0)):
+        got, _ = check_world(oracle, scenes.broadphase_bench_world(spacing=spacing), broadphase="aabb")
+        want = kat["kat3_broadphase"][name]
+        assert len(got["pair_i"]) == want["n_pairs"]
+        assert [got["pair_i"][0], got["pair_j"][0]] == want["first"]
+
+
+def test_golden_fixture(oracle):
+    z = np.load(os.path.join(GOLDEN, "oracle_polygons64.npz"))
+    w = scenes.random_polygons(64, density=2.0, static_frac=0.1, config=99)
+    got = gpu_frame(w, (z["cos"], z["sin"]))
+    assert_frames_match(got, {k: z[k] for k in z.files})
+
+
+def test_config1_stacks_scene(oracle):
+    """BASELINE config 1: Stacks.makeScene (30,30) 0, frame 0; floor = big-shape path."""
+    got, want = check_world(oracle, scenes.stacks_scene(), broadphase="aabb")
+    assert got["_n_big"] >= 1 and len(want["pair_i"]) > 3000
+
+
+@pytest.mark.parametrize("dims,spacing", [((10, 10), 1.0), ((5, 40), 0.0)])
+def test_stacks_variants(oracle, dims, spacing):
+    check_world(oracle, scenes.stacks_scene(dims, spacing), broadphase="aabb")
+
+
+def test_settled_stack_touches_floor(oracle):
+    """A stack resting on (and slightly inside) the floor: floor contacts through the big path."""
+    w = scenes.stacks_scene((12, 6), 0.0)
+    w.pos_y[1:] -= 0.9 + 0.005
+    got, want = check_world(oracle, w, broadphase="aabb")
+    assert (want["key_j"] == 0).sum() >= 12
+
+
+def test_config2_polygons_10k(oracle):
+    got, want = check_world(oracle, scenes.random_polygons(10_000), broadphase="sweep")
+    assert len(want["pair_i"]) > 10_000 and len(want["key_i"]) > 3_000
+
+
+def test_polygons_dense_bruteforce_oracle(oracle):
+    """Small enough for the Theta(n^2) restatement of Aabb.culledKeys itself."""
+    check_world(oracle, scenes.random_polygons(2500, density=3.0, static_frac=0.15, config=21), broadphase="aabb")
+
+
+def test_pile_with_floor(oracle):
+    got, want = check_world(oracle, scenes.box_pile(120, 90))
+    assert (want["key_j"] == 0).sum() > 100     # bottom row rests in the floor
+
+
+def test_mixed_and_blob(oracle):
+    check_world(oracle, scenes.mixed_polygons(30_000))
+    check_world(oracle, scenes.gaussian_blob(30_000, density=1.0))
+
+
+def test_deleted_slots_and_all_static(oracle):
+    w = scenes.random_polygons(3000, density=2.5, static_frac=0.3, config=31)
+    w.delete(list(range(0, 3000, 7)))
+    got, want = check_world(oracle, w, broadphase="aabb")
+    assert not np.isin(got["pair_i"], np.arange(0, 3000, 7)).any()
+    w2 = scenes.random_polygons(500, density=3.0, static_frac=1.1, config=32)
+    got2, _ = check_world(oracle, w2, broadphase="aabb")
+    assert len(got2["pair_i"]) == 0 and len(got2["key_i"]) == 0
+
+
+def test_nonfinite_bounds_take_the_exact_path(oracle):
+    """NaN / inf AABBs 'overlap' under boundsOverlap (Aabb.hs:69-72): identical pair set."""
+    w = scenes.random_polygons(1500, density=2.0, static_frac=0.1, config=33)
+    w.pos_x[40] = w.pos_y[40] = np.nan
+    w.pos_x[42] = np.nan
+    w.pos_y[41] = np.inf
+    w.pos_x[1400] = -np.inf
+    got, want = check_world(oracle, w, broadphase="aabb")
+    assert got["_n_big"] >= 4 and (want["pair_i"] == 40).sum() + (want["pair_j"] == 40).sum() > 1000
+
+
+def test_many_vertices_fallback_path(oracle):
+    """Hulls with more than 8 vertices are not staged in shared memory."""
+    rng = np.random.default_rng(5)
+    objs = []
+    for k in range(400):
+        nv = int(rng.integers(3, 20))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        r = rng.uniform(0.3, 0.6)
+        verts = [(r * np.cos(a), r * np.sin(a)) for a in ang]
+        objs.append((verts, (rng.uniform(0, 12), rng.uniform(0, 12)), rng.uniform(0, 6.28),
+                     (0.0, 0.0) if k % 17 == 0 else (1.0, 1.0)))
+    check_world(oracle, World.from_objects(objs), broadphase="aabb")
+
+
+def test_host_supplied_extents_are_used(oracle):
+    """_hullExtents is frozen at construction (ConvexHull.hs:159,165): the library must use the
+    indices it is given, even 'wrong' ones, exactly like extentAlongSelf trusts the cache."""
+    w = scenes.random_polygons(800, density=3.0, config=34)
+    emin, emax = oracle.hull_extents(w)
+    emin2 = emin.copy()
+    nv = np.diff(w.vert_offset)
+    starts = w.vert_offset[:-1]
+    emin2[starts[::3]] = (emin2[starts[::3]] + 1) % nv[::3]     # perturb every third hull's first edge
+    c, s = oracle.cos_sin(w.rot)
+    want = oracle.frame(w, c, s, broadphase="aabb", ext=(emin2, emax))
+    got = gpu_frame(w, (c, s), ext=(emin2, emax))
+    assert_frames_match(got, want)
+    base = oracle.frame(w, c, s, broadphase="aabb")
+    assert len(base["key_i"]) != len(want["key_i"]) or not np.array_equal(base["depth"], want["depth"])
+
+
+def test_cell_size_does_not_change_results(oracle):
+    w = scenes.random_polygons(4000, density=2.0, config=35)
+    c, s = oracle.cos_sin(w.rot)
+    want = oracle.frame(w, c, s, broadphase="sweep")
+    for cell in (0.25, 1.0, 3.7, 50.0, 1e6):
+        got = gpu_frame(w, (c, s), want=("pairs", "contacts", "constraints"), cell=cell)
+        assert_frames_match(got, want)
+
+
+def test_behaviour_parameters(oracle):
+    w = scenes.box_pile(40, 30)
+    check_world(oracle, w, dt=1.0 / 60.0, baumgarte=0.2, slop=0.005)
+
+
+def test_capacity_error_reports_required_sizes(oracle):
+    from shapes_b200.engine import CapacityError, Engine
+    w = scenes.random_polygons(3000, density=3.0, config=36)
+    c, s = oracle.cos_sin(w.rot)
+    want = oracle.frame(w, c, s, broadphase="sweep")
+    with Engine(w, max_pairs=100, max_contacts=50) as eng:
+        with pytest.raises(CapacityError) as ei:
+            eng.frame(cos_sin=(c, s))
+        assert ei.value.n_pairs == len(want["pair_i"])
+    with Engine(w, max_pairs=len(want["pair_i"]), max_contacts=50) as eng:
+        with pytest.raises(CapacityError) as ei:
+            eng.frame(cos_sin=(c, s))
+        assert ei.value.n_contacts == len(want["key_i"])
+        fr = eng.frame_grow(cos_sin=(c, s))
+        assert_frames_match(fr.cols, want)
+
+
+def test_deterministic_and_reusable(oracle):
+    from shapes_b200.engine import Engine
+    w = scenes.random_polygons(20_000, density=1.5, config=37)
+    c, s = oracle.cos_sin(w.rot)
+    with Engine(w) as eng:
+        a = {k: np.array(v) for k, v in eng.frame_grow(cos_sin=(c, s)).cols.items()}
+        for _ in range(3):
+            b = eng.frame(cos_sin=(c, s)).cols
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+        # move everything and run again on the same ctx
+        w.pos_x += 0.37
+        w.rot += 0.1
+        c2, s2 = oracle.cos_sin(w.rot)
+        got = eng.frame_grow(cos_sin=(c2, s2)).cols
+        assert_frames_match(got, oracle.frame(w, c2, s2, broadphase="sweep"))
+
+
+def test_device_sincos_is_close_not_exact(oracle):
+    """cos/sin NULL => device sincos: documented as not bit-exact; pair set and contacts must
+    still agree to 1e-9 on a world away from knife edges."""
+    w = scenes.random_polygons(3000, density=1.0, config=38)
+    c, s = oracle.cos_sin(w.rot)
+    want = oracle.frame(w, c, s, broadphase="sweep")
+    got = gpu_frame(w, None, want=("pairs", "contacts", "constraints"))
+    assert np.array_equal(got["pair_i"], want["pair_i"]) and np.array_equal(got["pair_j"], want["pair_j"])
+    if len(got["key_i"]) == len(want["key_i"]):
+        assert_frames_match(got, want, exact=False, cols=("normal_x", "normal_y", "depth"))
+
+
+def test_empty_and_single_shape_worlds(oracle):
+    w = World.from_objects([(rectangle_vertices(1, 1), (0.0, 0.0), 0.0, (1.0, 1.0))])
+    got = gpu_frame(w, None, want=("pairs", "contacts"))
+    assert len(got["pair_i"]) == 0 and len(got["key_i"]) == 0
+    w0 = World.from_objects([])
+    got0 = gpu_frame(w0, None, want=("pairs", "contacts"))
+    assert len(got0["pair_i"]) == 0
+
+
+def test_config3_full_size_pile(oracle):
+    """BASELINE config 3 at full size (1M boxes + floor): bit-exact against the oracle, plus the
+    size-independent properties (strictly descending unique pairs, keys subset of pairs)."""
+    w = scenes.box_pile(1000, 1000)
+    c, s = oracle.cos_sin(w.rot)
+    got = gpu_frame(w, (c, s), want=("pairs", "contacts", "constraints"))
+    key = (got["pair_i"].astype(np.int64) << 32) | got["pair_j"]
+    assert np.all(key[:-1] > key[1:]) and np.all(got["pair_i"] > got["pair_j"])
+    ck = (got["key_i"].astype(np.int64) << 32) | got["key_j"]
+    assert np.all(ck[:-1] >= ck[1:]) and np.isin(ck, key).all()
+    assert np.allclose(got["normal_x"] ** 2 + got["normal_y"] ** 2, 1.0, atol=1e-12)
+    want = oracle.frame(w, c, s, broadphase="sweep")
+    assert_frames_match(got, want)
+    assert len(want["pair_i"]) > 3_500_000
