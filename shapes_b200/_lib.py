@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_ROOT, "lib", "libshapes_b200.so")
 
 OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
 NCCL_ID_BYTES = 128
+N_STAGES = 9
 
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)
@@ -80,6 +81,9 @@ SYMBOLS = {
     "shapes_stream": (C.c_void_p, [C.c_void_p]),
     "shapes_launch_count": (C.c_int64, [C.c_void_p]),
     "shapes_version": (C.c_char_p, []),
+    "shapes_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "shapes_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "shapes_stage_name": (C.c_char_p, [C.c_int]),
 }
 
 _lib = None

@@ -930,6 +930,9 @@ struct shapes_ctx {
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profiling = false;
+    cudaEvent_t stage_ev[SHAPES_N_STAGES + 1] = {};
+    float stage_ms[SHAPES_N_STAGES] = {};
     int sm_count = 148;
     int64_t max_shapes = 0, max_verts = 0, max_pairs = 0, max_contacts = 0;
     int64_t n_slots = 0, n_verts = 0;
@@ -1026,6 +1029,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
     TRY_CREATE(cu(cudaEventCreate(&c->ev0), "cudaEventCreate"));
     TRY_CREATE(cu(cudaEventCreate(&c->ev1), "cudaEventCreate"));
+    for (int k = 0; k <= SHAPES_N_STAGES; ++k) TRY_CREATE(cu(cudaEventCreate(&c->stage_ev[k]), "cudaEventCreate"));
     if (world > 1) {
         ncclUniqueId id;
         static_assert(sizeof(ncclUniqueId) <= SHAPES_NCCL_ID_BYTES, "nccl id size");
@@ -1123,34 +1127,57 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     cudaStream_t s = c->stream;
     const int sms = c->sm_count;
 
+    int stage = 0;
+#define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
     CU_TRY(c, cudaEventRecord(c->ev0, s));
+    STAGE_MARK(); // 0: transform
     k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
     if (N > 0) {
         CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
         k_transform_aabb<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
-        if (c->world > 1) {
-            // exchange #1: AABB records of every rank's slot range over NVLink (in place)
-            NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
-                                      sizeof(Box) * c->chunk, ncclChar, c->comm, s));
-        }
+    }
+    STAGE_MARK(); // 1: allgather
+    if (N > 0 && c->world > 1) {
+        // exchange #1: AABB records of every rank's slot range over NVLink (in place)
+        NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
+                                         sizeof(Box) * c->chunk, ncclChar, c->comm, s));
+    }
+    STAGE_MARK(); // 2: grid keys
+    if (N > 0) {
         k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
         k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
         k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
         k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
+    }
+    STAGE_MARK(); // 3: sort
+    if (N > 0) {
         size_t sb = c->sort_tmp_bytes;
         CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, N, 0, 32, s));
-        k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches;
+    }
+    STAGE_MARK(); // 4: gather sorted
+    if (N > 0) { k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches; }
+    STAGE_MARK(); // 5: sweep count
+    if (N > 0) {
         k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
         k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
+    }
+    STAGE_MARK(); // 6: scan
+    if (N > 0) {
         if (n_query > 0) {
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
         }
         k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+    }
+    STAGE_MARK(); // 7: sweep emit
+    if (N > 0) {
         k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
         k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
-        k_contacts<<<sms * 4, CT_THREADS, 0, s>>>(P); ++c->launches;
     }
+    STAGE_MARK(); // 8: contacts
+    if (N > 0) { k_contacts<<<sms * 4, CT_THREADS, 0, s>>>(P); ++c->launches; }
+    STAGE_MARK(); // end
+#undef STAGE_MARK
     CU_TRY(c, cudaGetLastError());
     if (c->world > 1) {
         // exchange #2 (counts): every rank learns every rank's pair / contact counts, so the
@@ -1176,6 +1203,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         out->device_ms = ms;
         out->total_ms = ms;
     }
+    if (c->profiling)
+        for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
     if (st.error) {
         c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs)"
                                            : "capacity: max_contacts too small (required count in n_contacts)";
@@ -1234,6 +1263,7 @@ void shapes_destroy(shapes_ctx *c)
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int k = 0; k <= SHAPES_N_STAGES; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1447,5 +1477,27 @@ void shapes_host_free(void *p) { if (p) cudaFreeHost(p); }
 void *shapes_stream(shapes_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int64_t shapes_launch_count(const shapes_ctx *c) { return c ? c->launches : 0; }
+
+int shapes_set_profiling(shapes_ctx *c, int enabled)
+{
+    if (!c) return SHAPES_E_ARG;
+    c->profiling = enabled != 0;
+    return SHAPES_OK;
+}
+
+int shapes_stage_ms(const shapes_ctx *c, float *out_ms)
+{
+    if (!c || !out_ms) return SHAPES_E_ARG;
+    for (int k = 0; k < SHAPES_N_STAGES; ++k) out_ms[k] = c->stage_ms[k];
+    return SHAPES_OK;
+}
+
+const char *shapes_stage_name(int stage)
+{
+    static const char *names[SHAPES_N_STAGES] = { "transform_aabb", "allgather_aabb", "grid_keys", "radix_sort",
+                                                  "gather_sorted", "sweep_count", "scan_offsets", "sweep_emit",
+                                                  "contacts" };
+    return (stage >= 0 && stage < SHAPES_N_STAGES) ? names[stage] : "";
+}
 
 } // extern "C"

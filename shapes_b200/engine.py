@@ -305,6 +305,15 @@ class Engine:
                 self.grow(e.n_pairs, e.n_contacts)
         return self.frame(**kw)
 
+    def set_profiling(self, on: bool = True):
+        self._check(self.lib.shapes_set_profiling(self.ctx, 1 if on else 0))
+
+    def stage_ms(self) -> dict[str, float]:
+        """Device milliseconds of each stage of the last frame (profiling must be on)."""
+        buf = (C.c_float * _lib.N_STAGES)()
+        self._check(self.lib.shapes_stage_ms(self.ctx, buf))
+        return {self.lib.shapes_stage_name(k).decode(): float(buf[k]) for k in range(_lib.N_STAGES)}
+
     @property
     def stream(self) -> int:
         return int(self.lib.shapes_stream(self.ctx) or 0)
