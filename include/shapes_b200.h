@@ -200,7 +200,7 @@ const char *shapes_version(void);
 /* Per-stage device timing (CUDA events on the ctx stream between the stages of a frame).
  * Off by default; when on, shapes_stage_ms fills SHAPES_N_STAGES milliseconds of the last
  * frame, in the order shapes_stage_name reports. */
-#define SHAPES_N_STAGES 9
+#define SHAPES_N_STAGES 11
 int  shapes_set_profiling(shapes_ctx *, int enabled);
 int  shapes_stage_ms(const shapes_ctx *, float *out_ms /* SHAPES_N_STAGES */);
 const char *shapes_stage_name(int stage);

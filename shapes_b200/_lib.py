@@ -9,11 +9,11 @@ import ctypes as C
 import os
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_ROOT, "lib", "libshapes_b200.so")
+LIB_PATH = os.environ.get("SHAPES_B200_LIB") or os.path.join(_ROOT, "lib", "libshapes_b200.so")
 
 OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
 NCCL_ID_BYTES = 128
-N_STAGES = 9
+N_STAGES = 11
 
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)

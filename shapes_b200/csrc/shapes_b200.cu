@@ -142,10 +142,17 @@ struct FrameState {
     unsigned n_cells;
     unsigned n_big;     // shapes on the big-shape path
     unsigned n_small;   // shapes in the grid
-    unsigned ticket;    // tile ticket of k_contacts
     int error;
     long long n_pairs;
     long long n_contacts;
+};
+
+// Clipped contact manifold of one pair, handed from k_manifolds to k_rows.
+struct __align__(64) ManRec {
+    double nx, ny;        // unit normal of the penetrated edge
+    double ref_d;         // n . (first vertex of the penetrated edge)
+    double c0x, c0y, c1x, c1y; // manifold points, descending feature index
+    unsigned long long bits;   // edge [0,20) | pen0 [20,40) | pen1 [40,60) | flip [60]
 };
 
 // Everything the kernels need, passed by value.
@@ -178,8 +185,8 @@ struct Params {
     int64_t max_pairs, max_contacts;
     int32_t *pair_i, *pair_j;
     // contacts
-    unsigned long long *tile_status;
-    unsigned epoch;
+    ManRec *man;                // per pair: clipped manifold (written only when it has contacts)
+    uint32_t *ccnt, *coff;      // per pair: contact count, exclusive row offset
     int32_t *key_i, *key_j, *feat_a, *feat_b;
     uint8_t *flip;
     double *normal_x, *normal_y, *center_x, *center_y, *depth;
@@ -202,7 +209,6 @@ __global__ void k_reset_state(FrameState *st)
     st->n_cells = 1;
     st->n_big = 0;
     st->n_small = 0;
-    st->ticket = 0;
     st->error = 0;
     st->n_pairs = 0;
     st->n_contacts = 0;
@@ -506,13 +512,7 @@ __global__ void k_finish_pairs(Params P, int n_query)
 // ---------------------------------------------------------------------------------------------
 
 constexpr int CT_THREADS = 128;
-
-// tile status word: [63:62] flag, [61:32] epoch, [31:0] value
-constexpr unsigned long long FLAG_AGG = 1ull, FLAG_INC = 2ull;
-__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, unsigned epoch, unsigned v)
-{
-    return (flag << 62) | ((unsigned long long)(epoch & 0x3fffffffu) << 32) | v;
-}
+constexpr int CT_MIN_BLOCKS = 6;
 
 struct HullAcc {
     int slot, off, n;
@@ -522,10 +522,11 @@ struct HullAcc {
 
 struct SatRes { bool sep; int edge; double depth; int pen; };
 
+template <int MAXV>
 struct ContactKernel {
     const Params &P;
-    double2 (*sv)[MAX_STAGED_VERTS][CT_THREADS]; // [2][8][threads] staged world vertices
-    int tid;
+    double2 (*sv)[MAXV][32]; // [2][MAXV][lane] world vertices staged by (and private to) each lane
+    int tid;                 // lane
 
     __device__ __forceinline__ V2 slow_vertex(const HullAcc &h, int k) const
     {
@@ -536,7 +537,7 @@ struct ContactKernel {
     }
     __device__ __forceinline__ V2 vtx(const HullAcc &h, int k) const
     {
-        if (h.n <= MAX_STAGED_VERTS) { const double2 v = sv[h.which][k][tid]; return V2{ v.x, v.y }; }
+        if (h.n <= MAXV) { const double2 v = sv[h.which][k][tid]; return V2{ v.x, v.y }; }
         return slow_vertex(h, k);
     }
     __device__ __forceinline__ void ext(const HullAcc &h, int e, int &imin, int &imax) const
@@ -548,7 +549,7 @@ struct ContactKernel {
     }
     __device__ __forceinline__ void stage(const HullAcc &h) const
     {
-        if (h.n > MAX_STAGED_VERTS) return;
+        if (h.n > MAXV) return;
         const Xf x = P.xf[h.slot];
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         for (int k = 0; k < h.n; ++k) {
@@ -591,14 +592,6 @@ struct ContactKernel {
     }
 };
 
-struct Manifold {
-    int n;        // 0, 1 or 2 flattened contacts
-    int flip, edge;
-    V2 normal, ref0;
-    int pen[2];
-    V2 center[2];
-};
-
 enum { CLIP_LEFT = 0, CLIP_RIGHT = 1, CLIP_BOTH = 2, CLIP_NONE = 3 };
 
 // clipSegment (Linear.hs:327-343) with intersect2 (Linear.hs:244-251) and invM2x2 (Linear.hs:194-199).
@@ -618,209 +611,208 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
     return CLIP_NONE;
 }
 
-__global__ void __launch_bounds__(CT_THREADS) k_contacts(Params P)
+// K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
+// count and, when it has contacts, its manifold record.  No ordering between pairs.
+template <int MAXV>
+__global__ void __launch_bounds__(CT_THREADS, CT_MIN_BLOCKS) k_manifolds(Params P)
 {
-    __shared__ double2 s_verts[2][MAX_STAGED_VERTS][CT_THREADS];
-    __shared__ unsigned s_warp_sum[CT_THREADS / 32];
-    __shared__ unsigned s_tile;
-    __shared__ unsigned s_excl;
+    __shared__ double2 s_verts[CT_THREADS / 32][2][MAXV][32];
 
-    FrameState *st = P.st;
+    const FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = st->n_pairs;
-    const unsigned n_tiles = (unsigned)((n_pairs + CT_THREADS - 1) / CT_THREADS);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    ContactKernel K{ P, s_verts, tid };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ContactKernel<MAXV> K{ P, s_verts[warp], lane };
 
-    while (true) {
-        if (tid == 0) s_tile = atomicAdd(&st->ticket, 1u);
-        __syncthreads();
-        const unsigned tile = s_tile;
-        if (tile >= n_tiles) break;
-        const long long p = (long long)tile * CT_THREADS + tid;
-
-        Manifold m;
-        m.n = 0;
-        int i = 0, j = 0;
-        if (p < n_pairs) {
-            i = P.pair_i[p];
-            j = P.pair_j[p];
-            HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
-            A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
-            B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
-            A.ext = P.ext_packed[i];
-            B.ext = P.ext_packed[j];
-            K.stage(A);
-            K.stage(B);
-            // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
-            // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
-            const SatRes ab = K.min_overlap(A, B);
-            if (!ab.sep) {
-                const SatRes ba = K.min_overlap(B, A);
-                if (!ba.sep) {
-                    const bool same = ab.depth < ba.depth;
-                    const HullAcc &E = same ? A : B;
-                    const HullAcc &Pn = same ? B : A;
-                    const SatRes ov = same ? ab : ba;
-                    const V2 n = K.normal(E, ov.edge); // overlapNormal (SAT.hs:98-100)
-                    // penetratedEdge (SAT.hs:169-171)
-                    const int e1 = (ov.edge < E.n - 1) ? ov.edge + 1 : 0;
-                    const V2 ra = K.vtx(E, ov.edge), rb = K.vtx(E, e1);
-                    // penetratingEdge (SAT.hs:152-166)
-                    const int ib = ov.pen;
-                    const int ic = (ib < Pn.n - 1) ? ib + 1 : 0;
-                    const int ia = (ib > 0) ? ib - 1 : Pn.n - 1;
-                    const V2 va = K.vtx(Pn, ia), vb = K.vtx(Pn, ib), vc = K.vtx(Pn, ic);
-                    const double abn = fabs(dot2(sub2(vb, va), n));
-                    const double bcn = fabs(dot2(sub2(vc, vb), n));
-                    V2 q0, q1;
-                    int i0, i1;
-                    if (bcn < abn) { q0 = vb; i0 = ib; q1 = vc; i1 = ic; }
-                    else { q0 = va; i0 = ia; q1 = vb; i1 = ib; }
-                    // clipEdge (SAT.hs:190-218)
-                    const V2 inc_n = clockwise2(sub2(q1, q0)); // toLine2 c d, unclipped endpoints
-                    const double inc_b = dot2(q0, inc_n);
-                    V2 x;
-                    bool alive = true;
-                    int r = clip_segment(ra, sub2(rb, ra), inc_n, inc_b, q0, q1, x); // perpLine2 a b
+    for (long long p = (long long)blockIdx.x * CT_THREADS + threadIdx.x; p < n_pairs;
+         p += (long long)gridDim.x * CT_THREADS) {
+        const int i = P.pair_i[p], j = P.pair_j[p];
+        HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
+        A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
+        B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
+        A.ext = P.ext_packed[i];
+        B.ext = P.ext_packed[j];
+        K.stage(A);
+        K.stage(B);
+        unsigned cnt = 0;
+        // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
+        // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
+        const SatRes ab = K.min_overlap(A, B);
+        if (!ab.sep) {
+            const SatRes ba = K.min_overlap(B, A);
+            if (!ba.sep) {
+                const bool same = ab.depth < ba.depth;
+                const HullAcc &E = same ? A : B;
+                const HullAcc &Pn = same ? B : A;
+                const SatRes ov = same ? ab : ba;
+                const V2 n = K.normal(E, ov.edge); // overlapNormal (SAT.hs:98-100)
+                // penetratedEdge (SAT.hs:169-171)
+                const int e1 = (ov.edge < E.n - 1) ? ov.edge + 1 : 0;
+                const V2 ra = K.vtx(E, ov.edge), rb = K.vtx(E, e1);
+                // penetratingEdge (SAT.hs:152-166)
+                const int ib = ov.pen;
+                const int ic = (ib < Pn.n - 1) ? ib + 1 : 0;
+                const int ia = (ib > 0) ? ib - 1 : Pn.n - 1;
+                const V2 va = K.vtx(Pn, ia), vb = K.vtx(Pn, ib), vc = K.vtx(Pn, ic);
+                const double abn = fabs(dot2(sub2(vb, va), n));
+                const double bcn = fabs(dot2(sub2(vc, vb), n));
+                V2 q0, q1;
+                int i0, i1;
+                if (bcn < abn) { q0 = vb; i0 = ib; q1 = vc; i1 = ic; }
+                else { q0 = va; i0 = ia; q1 = vb; i1 = ib; }
+                // clipEdge (SAT.hs:190-218)
+                const V2 inc_n = clockwise2(sub2(q1, q0)); // toLine2 c d, unclipped endpoints
+                const double inc_b = dot2(q0, inc_n);
+                V2 x;
+                bool alive = true;
+                int r = clip_segment(ra, sub2(rb, ra), inc_n, inc_b, q0, q1, x); // perpLine2 a b
+                if (r == CLIP_BOTH) alive = false;
+                else if (r == CLIP_LEFT) q0 = x;
+                else if (r == CLIP_RIGHT) q1 = x;
+                if (alive) {
+                    r = clip_segment(rb, sub2(ra, rb), inc_n, inc_b, q0, q1, x); // perpLine2 b a
                     if (r == CLIP_BOTH) alive = false;
                     else if (r == CLIP_LEFT) q0 = x;
                     else if (r == CLIP_RIGHT) q1 = x;
-                    if (alive) {
-                        r = clip_segment(rb, sub2(ra, rb), inc_n, inc_b, q0, q1, x); // perpLine2 b a
-                        if (r == CLIP_BOTH) alive = false;
-                        else if (r == CLIP_LEFT) q0 = x;
-                        else if (r == CLIP_RIGHT) q1 = x;
+                }
+                if (alive) {
+                    r = clip_segment(ra, neg2(n), inc_n, inc_b, q0, q1, x); // Line2 a (negateV2 n)
+                    // applyClip'' (Linear.hs:285-292) removes the clipped endpoint;
+                    // flattenContactPoints (SAT.hs:181-187): descending feature index
+                    V2 c0 = q0, c1 = q1;
+                    int p0 = i0, p1 = i1;
+                    if (r == CLIP_LEFT) { cnt = 1; c0 = q1; p0 = i1; }
+                    else if (r == CLIP_RIGHT) { cnt = 1; }
+                    else if (r == CLIP_NONE) {
+                        cnt = 2;
+                        if (!(i0 > i1)) { c0 = q1; p0 = i1; c1 = q0; p1 = i0; }
                     }
-                    if (alive) {
-                        r = clip_segment(ra, neg2(n), inc_n, inc_b, q0, q1, x); // Line2 a (negateV2 n)
-                        // applyClip'' (Linear.hs:285-292) removes the clipped endpoint
-                        if (r == CLIP_LEFT) { m.n = 1; m.pen[0] = i1; m.center[0] = q1; }
-                        else if (r == CLIP_RIGHT) { m.n = 1; m.pen[0] = i0; m.center[0] = q0; }
-                        else if (r == CLIP_NONE) {
-                            m.n = 2;
-                            // flattenContactPoints (SAT.hs:181-187): descending feature index
-                            if (i0 > i1) { m.pen[0] = i0; m.center[0] = q0; m.pen[1] = i1; m.center[1] = q1; }
-                            else { m.pen[0] = i1; m.center[0] = q1; m.pen[1] = i0; m.center[1] = q0; }
-                        }
+                    if (cnt) {
+                        ManRec rec;
+                        rec.nx = n.x; rec.ny = n.y;
+                        rec.ref_d = dot2(ra, n); // contactDepth_ (HullVsHull.hs:30-37): f v, f = afdot' n
+                        rec.c0x = c0.x; rec.c0y = c0.y; rec.c1x = c1.x; rec.c1y = c1.y;
+                        rec.bits = (unsigned long long)(unsigned)ov.edge | ((unsigned long long)(unsigned)p0 << 20) |
+                                   ((unsigned long long)(unsigned)p1 << 40) | ((unsigned long long)(same ? 0 : 1) << 60);
+                        P.man[p] = rec;
                     }
-                    m.flip = same ? 0 : 1;
-                    m.edge = ov.edge;
-                    m.normal = n;
-                    m.ref0 = ra;
                 }
             }
         }
+        P.ccnt[p] = cnt;
+    }
+}
 
-        // ordered compaction: block exclusive scan + decoupled look-back across tiles
-        const unsigned cnt = (unsigned)m.n;
-        unsigned incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp_sum[warp] = incl;
-        __syncthreads();
-        unsigned warp_base = 0, tile_total = 0;
-        for (int w = 0; w < CT_THREADS / 32; ++w) {
-            if (w < warp) warp_base += s_warp_sum[w];
-            tile_total += s_warp_sum[w];
-        }
-        if (warp == 0) {
-            volatile unsigned long long *status = P.tile_status;
-            unsigned excl = 0;
-            if (tile > 0) {
-                if (lane == 0) status[tile] = pack_status(FLAG_AGG, P.epoch, tile_total);
-                long long look = (long long)tile - 1 - lane;
-                while (true) {
-                    unsigned long long w = 0;
-                    bool ready;
-                    do {
-                        if (look >= 0) {
-                            w = status[look];
-                            ready = (((unsigned)(w >> 32)) & 0x3fffffffu) == (P.epoch & 0x3fffffffu) && (w >> 62) != 0;
-                        } else { w = pack_status(FLAG_INC, P.epoch, 0u); ready = true; }
-                    } while (__any_sync(0xffffffffu, !ready));
-                    const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == FLAG_INC);
-                    const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
-                    unsigned v = (lane <= stop) ? (unsigned)(w & 0xffffffffu) : 0u;
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    excl += v;
-                    if (inc_mask) break;
-                    look -= 32;
-                }
-            }
-            if (lane == 0) {
-                status[tile] = pack_status(FLAG_INC, P.epoch, excl + tile_total);
-                s_excl = excl;
-                if (tile == n_tiles - 1) {
-                    const long long total = (long long)excl + tile_total;
-                    st->n_contacts = total;
-                    if (total > P.max_contacts) atomicOr(&st->error, ERR_CONTACT_CAP);
-                }
-            }
-        }
-        __syncthreads();
-        const long long row0 = (long long)s_excl + warp_base + (incl - cnt);
+__global__ void k_finish_contacts(Params P)
+{
+    FrameState *st = P.st;
+    if (st->error) return;
+    const long long np = st->n_pairs;
+    long long total = 0;
+    if (np > 0) total = (long long)P.coff[np - 1] + (long long)P.ccnt[np - 1];
+    st->n_contacts = total;
+    if (total > P.max_contacts) st->error |= ERR_CONTACT_CAP;
+}
 
-        // flattenContactResult (HullVsHull.hs:54-76) + constraintGen (Constraints/Contact.hs:60-72)
-        if (m.n > 0) {
-            const Xf xi = P.xf[i], xj = P.xf[j];
-            const double2 mi = P.mass[i], mj = P.mass[j];
-            const V2 pos_i{ xi.px, xi.py }, pos_j{ xj.px, xj.py };
-            const V2 n = m.normal;
-            const double ref_d = dot2(m.ref0, n);
-            for (int k = 0; k < m.n; ++k) {
-                const long long row = row0 + k;
-                if (row >= P.max_contacts) break;
-                const V2 c = m.center[k];
-                // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
-                const double d = fsub(ref_d, dot2(c, n));
-                P.key_i[row] = i; P.key_j[row] = j;
-                // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
-                P.feat_a[row] = m.flip ? m.pen[k] : m.edge;
-                P.feat_b[row] = m.flip ? m.edge : m.pen[k];
-                P.flip[row] = (uint8_t)m.flip;
-                P.normal_x[row] = n.x; P.normal_y[row] = n.y;
-                P.center_x[row] = c.x; P.center_y[row] = c.y;
-                P.depth[row] = d;
-                // generators run on (penetrated, penetrator) = (a,b) for Same, (b,a) for Flip, and
-                // flipExtract swaps the Jacobian halves back (Utils.hs:175-177,212-215; Constraint.hs:96-98)
-                const V2 xa = m.flip ? pos_j : pos_i;
-                const V2 xb = m.flip ? pos_i : pos_j;
-                double jn[6], jf[6];
-                // NonPenetration.jacobian (NonPenetration.hs:34-43)
-                const double np_a = cross2(sub2(xa, c), n), np_b = cross2(sub2(c, xb), n);
-                // Friction.jacobian (Friction.hs:31-44)
-                const V2 tb = clockwise2(n), ta = neg2(tb);
-                const double f_a = cross2(sub2(c, xa), ta), f_b = cross2(sub2(c, xb), tb);
-                if (!m.flip) {
-                    jn[0] = -n.x; jn[1] = -n.y; jn[2] = np_a; jn[3] = n.x; jn[4] = n.y; jn[5] = np_b;
-                    jf[0] = ta.x; jf[1] = ta.y; jf[2] = f_a; jf[3] = tb.x; jf[4] = tb.y; jf[5] = f_b;
-                } else {
-                    jn[3] = -n.x; jn[4] = -n.y; jn[5] = np_a; jn[0] = n.x; jn[1] = n.y; jn[2] = np_b;
-                    jf[3] = ta.x; jf[4] = ta.y; jf[5] = f_a; jf[0] = tb.x; jf[1] = tb.y; jf[2] = f_b;
-                }
-#pragma unroll
-                for (int q = 0; q < 6; ++q) { P.j_np[q][row] = jn[q]; P.j_f[q][row] = jf[q]; }
-                // baumgarte (NonPenetration.hs:48-55)
-                P.b_np[row] = (d > P.slop) ? fmul(fdiv(P.baumgarte, P.dt), fsub(P.slop, d)) : 0.0;
-                // Restitution.constraintGen (Restitution.hs:21-31): radii from the unflipped pair
-                P.ra_x[row] = fsub(c.x, pos_i.x); P.ra_y[row] = fsub(c.y, pos_i.y);
-                P.rb_x[row] = fsub(c.x, pos_j.x); P.rb_y[row] = fsub(c.y, pos_j.y);
-                P.rn_x[row] = m.flip ? -n.x : n.x; P.rn_y[row] = m.flip ? -n.y : n.y;
-                // effMassM2 (Constraint.hs:173-179): left fold of (j_k * im_k) * j_k over the unflipped pair
-                const double im[6] = { mi.x, mi.x, mi.y, mj.x, mj.x, mj.y };
-                double en = fmul(fmul(jn[0], im[0]), jn[0]), ef = fmul(fmul(jf[0], im[0]), jf[0]);
-#pragma unroll
-                for (int q = 1; q < 6; ++q) {
-                    en = fadd(en, fmul(fmul(jn[q], im[q]), jn[q]));
-                    ef = fadd(ef, fmul(fmul(jf[q], im[q]), jf[q]));
-                }
-                P.inv_eff_np[row] = en; P.inv_eff_f[row] = ef;
-            }
+// K3b: one lane per contact ROW.  A warp owns 32 consecutive pairs, i.e. up to 64 consecutive
+// rows; lanes look up which pair / manifold point their row belongs to, evaluate
+// flattenContactResult (HullVsHull.hs:54-76) and constraintGen (Constraints/Contact.hs:60-72) for
+// it and store every column fully coalesced.
+__global__ void __launch_bounds__(256) k_rows(Params P)
+{
+    __shared__ uint8_t s_owner[8][64];
+    const FrameState *st = P.st;
+    if (st->error) return;
+    const long long n_pairs = st->n_pairs;
+    const long long n_tiles = (n_pairs + 31) / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *owner = s_owner[warp];
+    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < n_tiles; tile += (long long)gridDim.x * 8) {
+        // level 0: every lane loads ITS pair's data, coalesced and independent of each other
+        const long long p = tile * 32 + lane;
+        unsigned cnt = 0, off = 0;
+        int pi = 0, pj = 0;
+        ManRec rec = {};
+        if (p < n_pairs) { cnt = P.ccnt[p]; off = P.coff[p]; pi = P.pair_i[p]; pj = P.pair_j[p]; }
+        // level 1: the one dependent gather (positions and inverse masses of both bodies)
+        double2 xi = make_double2(0.0, 0.0), xj = xi, mi = xi, mj = xi;
+        if (cnt) {
+            rec = P.man[p];
+            xi = *reinterpret_cast<const double2 *>(&P.xf[pi]);
+            xj = *reinterpret_cast<const double2 *>(&P.xf[pj]);
+            mi = P.mass[pi];
+            mj = P.mass[pj];
         }
-        __syncthreads(); // s_tile / s_warp_sum / staged vertices are reused by the next tile
+        const int n_valid = (n_pairs - tile * 32) < 32 ? (int)(n_pairs - tile * 32) : 32;
+        const unsigned base = __shfl_sync(0xffffffffu, off, 0);
+        const unsigned total = __shfl_sync(0xffffffffu, off + cnt, n_valid - 1) - base;
+        __syncwarp();
+        for (unsigned k = 0; k < cnt; ++k) owner[off - base + k] = (uint8_t)(lane | (k << 5));
+        __syncwarp();
+        for (unsigned r0 = 0; r0 < total; r0 += 32) {
+            const unsigned r = r0 + lane;
+            const bool act = r < total;
+            const unsigned o = act ? owner[r] : 0u;
+            const int src = o & 31, k = o >> 5;
+            // pull the owner pair's data out of the owner lane's registers
+            const int i = __shfl_sync(0xffffffffu, pi, src), j = __shfl_sync(0xffffffffu, pj, src);
+            const unsigned long long bits = __shfl_sync(0xffffffffu, rec.bits, src);
+            const V2 n{ __shfl_sync(0xffffffffu, rec.nx, src), __shfl_sync(0xffffffffu, rec.ny, src) };
+            const double ref_d = __shfl_sync(0xffffffffu, rec.ref_d, src);
+            const double c0x = __shfl_sync(0xffffffffu, rec.c0x, src), c0y = __shfl_sync(0xffffffffu, rec.c0y, src);
+            const double c1x = __shfl_sync(0xffffffffu, rec.c1x, src), c1y = __shfl_sync(0xffffffffu, rec.c1y, src);
+            const V2 pos_i{ __shfl_sync(0xffffffffu, xi.x, src), __shfl_sync(0xffffffffu, xi.y, src) };
+            const V2 pos_j{ __shfl_sync(0xffffffffu, xj.x, src), __shfl_sync(0xffffffffu, xj.y, src) };
+            const double il_i = __shfl_sync(0xffffffffu, mi.x, src), ir_i = __shfl_sync(0xffffffffu, mi.y, src);
+            const double il_j = __shfl_sync(0xffffffffu, mj.x, src), ir_j = __shfl_sync(0xffffffffu, mj.y, src);
+            const long long row = (long long)base + r;
+            if (!act || row >= P.max_contacts) continue;
+            const int flip = (int)((bits >> 60) & 1u);
+            const int edge = (int)(bits & 0xfffffu);
+            const int pen = (int)((bits >> (k ? 40 : 20)) & 0xfffffu);
+            const V2 c = k ? V2{ c1x, c1y } : V2{ c0x, c0y };
+            // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
+            const double d = fsub(ref_d, dot2(c, n));
+            P.key_i[row] = i; P.key_j[row] = j;
+            // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
+            P.feat_a[row] = flip ? pen : edge;
+            P.feat_b[row] = flip ? edge : pen;
+            P.flip[row] = (uint8_t)flip;
+            P.normal_x[row] = n.x; P.normal_y[row] = n.y;
+            P.center_x[row] = c.x; P.center_y[row] = c.y;
+            P.depth[row] = d;
+            // generators run on (penetrated, penetrator) = (a,b) for Same, (b,a) for Flip, and
+            // flipExtract swaps the Jacobian halves back (Utils.hs:175-177,212-215; Constraint.hs:96-98)
+            const V2 xa = flip ? pos_j : pos_i;
+            const V2 xb = flip ? pos_i : pos_j;
+            // NonPenetration.jacobian (NonPenetration.hs:34-43)
+            const double np_a = cross2(sub2(xa, c), n), np_b = cross2(sub2(c, xb), n);
+            // Friction.jacobian (Friction.hs:31-44)
+            const V2 tb = clockwise2(n), ta = neg2(tb);
+            const double f_a = cross2(sub2(c, xa), ta), f_b = cross2(sub2(c, xb), tb);
+            double jn[6], jf[6];
+            jn[0] = flip ? n.x : -n.x; jn[1] = flip ? n.y : -n.y; jn[2] = flip ? np_b : np_a;
+            jn[3] = flip ? -n.x : n.x; jn[4] = flip ? -n.y : n.y; jn[5] = flip ? np_a : np_b;
+            jf[0] = flip ? tb.x : ta.x; jf[1] = flip ? tb.y : ta.y; jf[2] = flip ? f_b : f_a;
+            jf[3] = flip ? ta.x : tb.x; jf[4] = flip ? ta.y : tb.y; jf[5] = flip ? f_a : f_b;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) { P.j_np[t][row] = jn[t]; P.j_f[t][row] = jf[t]; }
+            // baumgarte (NonPenetration.hs:48-55)
+            P.b_np[row] = (d > P.slop) ? fmul(fdiv(P.baumgarte, P.dt), fsub(P.slop, d)) : 0.0;
+            // Restitution.constraintGen (Restitution.hs:21-31): radii from the unflipped pair
+            P.ra_x[row] = fsub(c.x, pos_i.x); P.ra_y[row] = fsub(c.y, pos_i.y);
+            P.rb_x[row] = fsub(c.x, pos_j.x); P.rb_y[row] = fsub(c.y, pos_j.y);
+            P.rn_x[row] = flip ? -n.x : n.x; P.rn_y[row] = flip ? -n.y : n.y;
+            // effMassM2 (Constraint.hs:173-179): left fold of (j_k * im_k) * j_k over the unflipped pair
+            const double im[6] = { il_i, il_i, ir_i, il_j, il_j, ir_j };
+            double en = fmul(fmul(jn[0], im[0]), jn[0]), ef = fmul(fmul(jf[0], im[0]), jf[0]);
+#pragma unroll
+            for (int t = 1; t < 6; ++t) {
+                en = fadd(en, fmul(fmul(jn[t], im[t]), jn[t]));
+                ef = fadd(ef, fmul(fmul(jf[t], im[t]), jf[t]));
+            }
+            P.inv_eff_np[row] = en; P.inv_eff_f[row] = ef;
+        }
     }
 }
 
@@ -938,8 +930,9 @@ struct shapes_ctx {
     int64_t n_slots = 0, n_verts = 0;
     int64_t chunk = 0;          // slots per rank (all-gather granule)
     bool hulls_set = false;
+    int max_hull_verts = 0;
+    int ct_blocks[2] = { 4, 4 }; // resident k_contacts blocks per SM (boxes / general)
     double auto_cell = 1.0, user_cell = 0.0;
-    unsigned epoch = 0;
     int64_t launches = 0;
     std::string err;
     std::vector<void *> allocs;
@@ -1067,9 +1060,10 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.off, N));
     TRY_CREATE(dev_alloc(c, &P.pair_i, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.pair_j, max_pairs));
-    const int64_t n_tiles = (max_pairs + CT_THREADS - 1) / CT_THREADS + 1;
-    TRY_CREATE(dev_alloc(c, &P.tile_status, n_tiles));
-    TRY_CREATE(cu(cudaMemset(P.tile_status, 0, n_tiles * sizeof(unsigned long long)), "cudaMemset"));
+    TRY_CREATE(dev_alloc(c, &P.man, max_pairs));
+    TRY_CREATE(dev_alloc(c, &P.ccnt, max_pairs));
+    TRY_CREATE(dev_alloc(c, &P.coff, max_pairs));
+    TRY_CREATE(cu(cudaMemset(P.ccnt, 0, std::max<int64_t>(max_pairs, 1) * sizeof(uint32_t)), "cudaMemset"));
     const int64_t C = max_contacts;
     TRY_CREATE(dev_alloc(c, &P.key_i, C)); TRY_CREATE(dev_alloc(c, &P.key_j, C));
     TRY_CREATE(dev_alloc(c, &P.feat_a, C)); TRY_CREATE(dev_alloc(c, &P.feat_b, C));
@@ -1088,7 +1082,17 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
                                                   (int)std::max<int64_t>(N, 1), 0, 32, c->stream), "cub sort size"));
     TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb, P.cnt, P.off, (int)std::max<int64_t>(N, 1), c->stream),
                   "cub scan size"));
+    size_t cb2 = 0;
+    TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb2, P.ccnt, P.coff, (int)std::max<int64_t>(max_pairs, 1), c->stream),
+                  "cub scan size"));
+    cb = std::max(cb, cb2);
     c->sort_tmp_bytes = sb; c->scan_tmp_bytes = cb;
+    {   // grid-stride k_manifolds grid: the number of co-resident blocks
+        int b4 = 0, b8 = 0;
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_manifolds<4>, CT_THREADS, 0), "occupancy"));
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b8, k_manifolds<MAX_STAGED_VERTS>, CT_THREADS, 0), "occupancy"));
+        c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1);
+    }
     TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_sort_tmp), sb));
     TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_scan_tmp), cb));
     P.max_pairs = max_pairs; P.max_contacts = max_contacts;
@@ -1122,8 +1126,6 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.cell_size = c->user_cell > 0.0 ? c->user_cell : c->auto_cell;
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
-    P.epoch = ++c->epoch;
-    if ((P.epoch & 0x3fffffffu) == 0) P.epoch = ++c->epoch; // epoch 0 means "never written"
     cudaStream_t s = c->stream;
     const int sms = c->sm_count;
 
@@ -1174,8 +1176,20 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
         k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
     }
-    STAGE_MARK(); // 8: contacts
-    if (N > 0) { k_contacts<<<sms * 4, CT_THREADS, 0, s>>>(P); ++c->launches; }
+    STAGE_MARK(); // 8: manifolds (SAT + clipping)
+    if (N > 0) {
+        if (c->max_hull_verts <= 4) k_manifolds<4><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
+        else k_manifolds<MAX_STAGED_VERTS><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
+        ++c->launches;
+    }
+    STAGE_MARK(); // 9: contact row offsets
+    if (N > 0 && c->max_pairs > 0) {
+        size_t cb = c->scan_tmp_bytes;
+        CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
+        k_finish_contacts<<<1, 1, 0, s>>>(P); ++c->launches;
+    }
+    STAGE_MARK(); // 10: contact rows (flatten + constraint generators)
+    if (N > 0) { k_rows<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
     STAGE_MARK(); // end
 #undef STAGE_MARK
     CU_TRY(c, cudaGetLastError());
@@ -1291,9 +1305,11 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
     std::vector<double2> inter((size_t)n_verts);
     std::vector<double> diam;
     diam.reserve((size_t)n_slots);
+    int max_verts_seen = 0;
     for (int64_t s = 0; s < n_slots; ++s) {
         const int32_t o = vert_offset[s], n = vert_offset[s + 1] - o;
         if (n < 0 || (live[s] && n < 1)) { c->err = "shapes_set_hulls: a filled slot has no vertices"; return SHAPES_E_ARG; }
+        if (live[s] && n > max_verts_seen) max_verts_seen = n;
         double r2 = 0.0;
         for (int32_t k = 0; k < n; ++k) {
             inter[o + k] = make_double2(local_x[o + k], local_y[o + k]);
@@ -1337,6 +1353,7 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
     }
     CU_TRY(c, cudaStreamSynchronize(s));
     c->n_slots = n_slots; c->n_verts = n_verts;
+    c->max_hull_verts = max_verts_seen;
     c->hulls_set = true;
     c->have_frame = false;
     return SHAPES_OK;
@@ -1496,7 +1513,7 @@ const char *shapes_stage_name(int stage)
 {
     static const char *names[SHAPES_N_STAGES] = { "transform_aabb", "allgather_aabb", "grid_keys", "radix_sort",
                                                   "gather_sorted", "sweep_count", "scan_offsets", "sweep_emit",
-                                                  "contacts" };
+                                                  "manifolds", "scan_rows", "contact_rows" };
     return (stage >= 0 && stage < SHAPES_N_STAGES) ? names[stage] : "";
 }
 
