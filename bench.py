@@ -217,6 +217,13 @@ def main():
         run_reference(args)
         return
 
+    # Only the JSON line may reach stdout: libraries (e.g. NCCL's version banner) write to fd 1.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     import torch
     from shapes_b200 import build
     from shapes_b200.engine import Engine, nccl_unique_id
@@ -379,7 +386,7 @@ def main():
         "contacts_per_s": tot_contacts / per_step,
         "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

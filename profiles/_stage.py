@@ -1,5 +1,5 @@
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')][-1])
 print(sys.argv[1], "ms/step %.3f dev %.3f" % (d["ms_per_step"], d["device_ms_per_step"]))
 print("  " + "  ".join("%s %.3f" % (k, v) for k, v in d["stage_ms"].items()))
 r = d["roofline"]
