@@ -53,5 +53,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_TEST_SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp")
+HOST_TEST_EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
+
+
+def build_host_test(force: bool = False) -> str:
+    """g++ build of the C++ host-mirror test program against include/shapes_b200.hpp."""
+    build_library()
+    deps = [HOST_TEST_SRC, os.path.join(INC, "shapes_b200.hpp"), os.path.join(INC, "shapes_b200.h"), LIB]
+    if force or not os.path.exists(HOST_TEST_EXE) or \
+            any(os.path.getmtime(d) > os.path.getmtime(HOST_TEST_EXE) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", INC, HOST_TEST_SRC, "-o", HOST_TEST_EXE,
+                        "-L", LIB_DIR, "-lshapes_b200", "-Wl,-rpath," + LIB_DIR,
+                        "-Wl,-rpath,$ORIGIN/../../shapes_b200/lib"], check=True)
+    return HOST_TEST_EXE
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))

@@ -174,6 +174,7 @@ struct Params {
     uint8_t *is_static;
     Box *box;                   // per slot
     double *world_x, *world_y;  // optional debug output
+    double2 *wv, *wn;           // world vertices / unit edge normals of the OWNED slots (moveShapes result)
     uint32_t *keys, *keys_sorted, *idx, *idx_sorted;
     Box *sbox;                  // AABB records in sorted order
     uint32_t *smeta;            // slot | static << 31, sorted order
@@ -187,6 +188,7 @@ struct Params {
     // contacts
     ManRec *man;                // per pair: clipped manifold (written only when it has contacts)
     uint32_t *ccnt, *coff;      // per pair: contact count, exclusive row offset
+    uint32_t *row_map;          // per contact row: pair << 1 | manifold point
     int32_t *key_i, *key_j, *feat_a, *feat_b;
     uint8_t *flip;
     double *normal_x, *normal_y, *center_x, *center_y, *depth;
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
         for (int k = 0; k < n; ++k) {
             double2 l = __ldg(&P.local[o + k]);
             V2 w = afmul(m, V2{ l.x, l.y });
+            P.wv[o + k] = make_double2(w.x, w.y);
             if (P.world_x) { P.world_x[o + k] = w.x; P.world_y[o + k] = w.y; }
             if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
             else {
@@ -246,6 +249,14 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
                 b.min_y = (b.min_y < w.y) ? b.min_y : w.y;
                 b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
             }
+        }
+        // setHullTransform (ConvexHull.hs:193-194): unit edge normals recomputed from the NEW vertices
+        double2 v0 = P.wv[o], va = v0;
+        for (int k = 0; k < n; ++k) {
+            const double2 vb = (k + 1 < n) ? P.wv[o + k + 1] : v0;
+            const V2 nn = unit_edge_normal(V2{ va.x, va.y }, V2{ vb.x, vb.y });
+            P.wn[o + k] = make_double2(nn.x, nn.y);
+            va = vb;
         }
         P.box[s] = b;
     }
@@ -517,7 +528,9 @@ constexpr int CT_MIN_BLOCKS = 6;
 struct HullAcc {
     int slot, off, n;
     int which;                 // 0 = a, 1 = b (selects the shared-memory plane)
+    bool owned;                // world vertices / normals of this slot were materialised by K0 on this rank
     unsigned long long ext;    // packed extents (n <= 8)
+    V2 n0;                     // unit normal of edge 0, fetched while staging
 };
 
 struct SatRes { bool sep; int edge; double depth; int pen; };
@@ -530,6 +543,7 @@ struct ContactKernel {
 
     __device__ __forceinline__ V2 slow_vertex(const HullAcc &h, int k) const
     {
+        if (h.owned) { const double2 v = P.wv[h.off + k]; return V2{ v.x, v.y }; }
         const Xf x = P.xf[h.slot];
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         const double2 l = __ldg(&P.local[h.off + k]);
@@ -547,19 +561,28 @@ struct ContactKernel {
             imin = bits & 7; imax = (bits >> 3) & 7;
         } else { imin = P.ext_min[h.off + e]; imax = P.ext_max[h.off + e]; }
     }
-    __device__ __forceinline__ void stage(const HullAcc &h) const
+    __device__ __forceinline__ void stage(HullAcc &h) const
     {
-        if (h.n > MAXV) return;
-        const Xf x = P.xf[h.slot];
-        const Aff m = to_transform(x.px, x.py, x.c, x.s);
-        for (int k = 0; k < h.n; ++k) {
-            const double2 l = __ldg(&P.local[h.off + k]);
-            const V2 w = afmul(m, V2{ l.x, l.y });
-            sv[h.which][k][tid] = make_double2(w.x, w.y);
+        h.owned = h.slot >= P.own_lo && h.slot < P.own_hi;
+        if (h.n <= MAXV) {
+            if (h.owned) {
+                for (int k = 0; k < h.n; ++k) sv[h.which][k][tid] = P.wv[h.off + k];
+            } else {
+                const Xf x = P.xf[h.slot];
+                const Aff m = to_transform(x.px, x.py, x.c, x.s);
+                for (int k = 0; k < h.n; ++k) {
+                    const double2 l = __ldg(&P.local[h.off + k]);
+                    const V2 w = afmul(m, V2{ l.x, l.y });
+                    sv[h.which][k][tid] = make_double2(w.x, w.y);
+                }
+            }
         }
+        h.n0 = normal(h, 0);
     }
+    // unit normal of edge e: K0's value for owned slots, else recomputed from the (identical) vertices
     __device__ __forceinline__ V2 normal(const HullAcc &h, int e) const
     {
+        if (h.owned) { const double2 v = P.wn[h.off + e]; return V2{ v.x, v.y }; }
         const int e1 = (e < h.n - 1) ? e + 1 : 0; // nextIndex (ConvexHull.hs:228-230)
         return unit_edge_normal(vtx(h, e), vtx(h, e1));
     }
@@ -569,8 +592,10 @@ struct ContactKernel {
     __device__ SatRes min_overlap(const HullAcc &E, const HullAcc &Pn) const
     {
         SatRes best{ false, 0, 0.0, 0 };
+        V2 dir_next = E.n0;
         for (int e = 0; e < E.n; ++e) {
-            const V2 dir = normal(E, e);
+            const V2 dir = dir_next;
+            if (e + 1 < E.n) dir_next = normal(E, e + 1); // issued one edge ahead of its use
             int imin, imax;
             ext(E, e, imin, imax);
             // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
@@ -703,116 +728,92 @@ __global__ void __launch_bounds__(CT_THREADS, CT_MIN_BLOCKS) k_manifolds(Params 
     }
 }
 
-__global__ void k_finish_contacts(Params P)
+// Row map: row r of the output belongs to manifold point k of pair p, stored as p << 1 | k.
+// Also finishes the contact count.  (Runs after the exclusive scan of the per-pair counts.)
+__global__ void __launch_bounds__(256) k_row_map(Params P)
 {
     FrameState *st = P.st;
     if (st->error) return;
-    const long long np = st->n_pairs;
-    long long total = 0;
-    if (np > 0) total = (long long)P.coff[np - 1] + (long long)P.ccnt[np - 1];
-    st->n_contacts = total;
-    if (total > P.max_contacts) st->error |= ERR_CONTACT_CAP;
+    const long long n_pairs = st->n_pairs;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const unsigned cnt = P.ccnt[p], off = P.coff[p];
+        for (unsigned k = 0; k < cnt; ++k)
+            if ((long long)off + k < P.max_contacts) P.row_map[off + k] = (uint32_t)((p << 1) | k);
+        if (p == n_pairs - 1) {
+            const long long total = (long long)off + cnt;
+            st->n_contacts = total;
+            if (total > P.max_contacts) atomicOr(&st->error, ERR_CONTACT_CAP);
+        }
+    }
 }
 
-// K3b: one lane per contact ROW.  A warp owns 32 consecutive pairs, i.e. up to 64 consecutive
-// rows; lanes look up which pair / manifold point their row belongs to, evaluate
-// flattenContactResult (HullVsHull.hs:54-76) and constraintGen (Constraints/Contact.hs:60-72) for
-// it and store every column fully coalesced.
+// K3b: one lane per contact ROW, warps own 32 ALIGNED rows.  Every column store of a warp is a
+// whole number of 32 B sectors (f64: 256 B, i32: 128 B, u8: 32 B): on B200 a warp store that
+// straddles sector boundaries costs ~2.3x (profiles/micro/write_align.cu), so the kernel is
+// organised around the output layout and gathers its inputs through the row map.
+// flattenContactResult (HullVsHull.hs:54-76) + constraintGen (Constraints/Contact.hs:60-72).
 __global__ void __launch_bounds__(256) k_rows(Params P)
 {
-    __shared__ uint8_t s_owner[8][64];
     const FrameState *st = P.st;
     if (st->error) return;
-    const long long n_pairs = st->n_pairs;
-    const long long n_tiles = (n_pairs + 31) / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *owner = s_owner[warp];
-    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < n_tiles; tile += (long long)gridDim.x * 8) {
-        // level 0: every lane loads ITS pair's data, coalesced and independent of each other
-        const long long p = tile * 32 + lane;
-        unsigned cnt = 0, off = 0;
-        int pi = 0, pj = 0;
-        ManRec rec = {};
-        if (p < n_pairs) { cnt = P.ccnt[p]; off = P.coff[p]; pi = P.pair_i[p]; pj = P.pair_j[p]; }
-        // level 1: the one dependent gather (positions and inverse masses of both bodies)
-        double2 xi = make_double2(0.0, 0.0), xj = xi, mi = xi, mj = xi;
-        if (cnt) {
-            rec = P.man[p];
-            xi = *reinterpret_cast<const double2 *>(&P.xf[pi]);
-            xj = *reinterpret_cast<const double2 *>(&P.xf[pj]);
-            mi = P.mass[pi];
-            mj = P.mass[pj];
-        }
-        const int n_valid = (n_pairs - tile * 32) < 32 ? (int)(n_pairs - tile * 32) : 32;
-        const unsigned base = __shfl_sync(0xffffffffu, off, 0);
-        const unsigned total = __shfl_sync(0xffffffffu, off + cnt, n_valid - 1) - base;
-        __syncwarp();
-        for (unsigned k = 0; k < cnt; ++k) owner[off - base + k] = (uint8_t)(lane | (k << 5));
-        __syncwarp();
-        for (unsigned r0 = 0; r0 < total; r0 += 32) {
-            const unsigned r = r0 + lane;
-            const bool act = r < total;
-            const unsigned o = act ? owner[r] : 0u;
-            const int src = o & 31, k = o >> 5;
-            // pull the owner pair's data out of the owner lane's registers
-            const int i = __shfl_sync(0xffffffffu, pi, src), j = __shfl_sync(0xffffffffu, pj, src);
-            const unsigned long long bits = __shfl_sync(0xffffffffu, rec.bits, src);
-            const V2 n{ __shfl_sync(0xffffffffu, rec.nx, src), __shfl_sync(0xffffffffu, rec.ny, src) };
-            const double ref_d = __shfl_sync(0xffffffffu, rec.ref_d, src);
-            const double c0x = __shfl_sync(0xffffffffu, rec.c0x, src), c0y = __shfl_sync(0xffffffffu, rec.c0y, src);
-            const double c1x = __shfl_sync(0xffffffffu, rec.c1x, src), c1y = __shfl_sync(0xffffffffu, rec.c1y, src);
-            const V2 pos_i{ __shfl_sync(0xffffffffu, xi.x, src), __shfl_sync(0xffffffffu, xi.y, src) };
-            const V2 pos_j{ __shfl_sync(0xffffffffu, xj.x, src), __shfl_sync(0xffffffffu, xj.y, src) };
-            const double il_i = __shfl_sync(0xffffffffu, mi.x, src), ir_i = __shfl_sync(0xffffffffu, mi.y, src);
-            const double il_j = __shfl_sync(0xffffffffu, mj.x, src), ir_j = __shfl_sync(0xffffffffu, mj.y, src);
-            const long long row = (long long)base + r;
-            if (!act || row >= P.max_contacts) continue;
-            const int flip = (int)((bits >> 60) & 1u);
-            const int edge = (int)(bits & 0xfffffu);
-            const int pen = (int)((bits >> (k ? 40 : 20)) & 0xfffffu);
-            const V2 c = k ? V2{ c1x, c1y } : V2{ c0x, c0y };
-            // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
-            const double d = fsub(ref_d, dot2(c, n));
-            P.key_i[row] = i; P.key_j[row] = j;
-            // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
-            P.feat_a[row] = flip ? pen : edge;
-            P.feat_b[row] = flip ? edge : pen;
-            P.flip[row] = (uint8_t)flip;
-            P.normal_x[row] = n.x; P.normal_y[row] = n.y;
-            P.center_x[row] = c.x; P.center_y[row] = c.y;
-            P.depth[row] = d;
-            // generators run on (penetrated, penetrator) = (a,b) for Same, (b,a) for Flip, and
-            // flipExtract swaps the Jacobian halves back (Utils.hs:175-177,212-215; Constraint.hs:96-98)
-            const V2 xa = flip ? pos_j : pos_i;
-            const V2 xb = flip ? pos_i : pos_j;
-            // NonPenetration.jacobian (NonPenetration.hs:34-43)
-            const double np_a = cross2(sub2(xa, c), n), np_b = cross2(sub2(c, xb), n);
-            // Friction.jacobian (Friction.hs:31-44)
-            const V2 tb = clockwise2(n), ta = neg2(tb);
-            const double f_a = cross2(sub2(c, xa), ta), f_b = cross2(sub2(c, xb), tb);
-            double jn[6], jf[6];
-            jn[0] = flip ? n.x : -n.x; jn[1] = flip ? n.y : -n.y; jn[2] = flip ? np_b : np_a;
-            jn[3] = flip ? -n.x : n.x; jn[4] = flip ? -n.y : n.y; jn[5] = flip ? np_a : np_b;
-            jf[0] = flip ? tb.x : ta.x; jf[1] = flip ? tb.y : ta.y; jf[2] = flip ? f_b : f_a;
-            jf[3] = flip ? ta.x : tb.x; jf[4] = flip ? ta.y : tb.y; jf[5] = flip ? f_a : f_b;
+    const long long n_rows = st->n_contacts < P.max_contacts ? st->n_contacts : P.max_contacts;
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+         row += (long long)gridDim.x * blockDim.x) {
+        const uint32_t m = P.row_map[row];
+        const long long q = m >> 1;
+        const int k = m & 1;
+        const int i = P.pair_i[q], j = P.pair_j[q];
+        const ManRec rec = P.man[q];
+        const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
+        const double2 xj = *reinterpret_cast<const double2 *>(&P.xf[j]);
+        const double2 mi = P.mass[i], mj = P.mass[j];
+        const int flip = (int)((rec.bits >> 60) & 1u);
+        const int edge = (int)(rec.bits & 0xfffffu);
+        const int pen = (int)((rec.bits >> (k ? 40 : 20)) & 0xfffffu);
+        const V2 n{ rec.nx, rec.ny };
+        const V2 c = k ? V2{ rec.c1x, rec.c1y } : V2{ rec.c0x, rec.c0y };
+        const V2 pos_i{ xi.x, xi.y }, pos_j{ xj.x, xj.y };
+        // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
+        const double d = fsub(rec.ref_d, dot2(c, n));
+        P.key_i[row] = i; P.key_j[row] = j;
+        // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
+        P.feat_a[row] = flip ? pen : edge;
+        P.feat_b[row] = flip ? edge : pen;
+        P.flip[row] = (uint8_t)flip;
+        P.normal_x[row] = n.x; P.normal_y[row] = n.y;
+        P.center_x[row] = c.x; P.center_y[row] = c.y;
+        P.depth[row] = d;
+        // generators run on (penetrated, penetrator) = (a,b) for Same, (b,a) for Flip, and
+        // flipExtract swaps the Jacobian halves back (Utils.hs:175-177,212-215; Constraint.hs:96-98)
+        const V2 xa = flip ? pos_j : pos_i;
+        const V2 xb = flip ? pos_i : pos_j;
+        // NonPenetration.jacobian (NonPenetration.hs:34-43)
+        const double np_a = cross2(sub2(xa, c), n), np_b = cross2(sub2(c, xb), n);
+        // Friction.jacobian (Friction.hs:31-44)
+        const V2 tb = clockwise2(n), ta = neg2(tb);
+        const double f_a = cross2(sub2(c, xa), ta), f_b = cross2(sub2(c, xb), tb);
+        double jn[6], jf[6];
+        jn[0] = flip ? n.x : -n.x; jn[1] = flip ? n.y : -n.y; jn[2] = flip ? np_b : np_a;
+        jn[3] = flip ? -n.x : n.x; jn[4] = flip ? -n.y : n.y; jn[5] = flip ? np_a : np_b;
+        jf[0] = flip ? tb.x : ta.x; jf[1] = flip ? tb.y : ta.y; jf[2] = flip ? f_b : f_a;
+        jf[3] = flip ? ta.x : tb.x; jf[4] = flip ? ta.y : tb.y; jf[5] = flip ? f_a : f_b;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) { P.j_np[t][row] = jn[t]; P.j_f[t][row] = jf[t]; }
-            // baumgarte (NonPenetration.hs:48-55)
-            P.b_np[row] = (d > P.slop) ? fmul(fdiv(P.baumgarte, P.dt), fsub(P.slop, d)) : 0.0;
-            // Restitution.constraintGen (Restitution.hs:21-31): radii from the unflipped pair
-            P.ra_x[row] = fsub(c.x, pos_i.x); P.ra_y[row] = fsub(c.y, pos_i.y);
-            P.rb_x[row] = fsub(c.x, pos_j.x); P.rb_y[row] = fsub(c.y, pos_j.y);
-            P.rn_x[row] = flip ? -n.x : n.x; P.rn_y[row] = flip ? -n.y : n.y;
-            // effMassM2 (Constraint.hs:173-179): left fold of (j_k * im_k) * j_k over the unflipped pair
-            const double im[6] = { il_i, il_i, ir_i, il_j, il_j, ir_j };
-            double en = fmul(fmul(jn[0], im[0]), jn[0]), ef = fmul(fmul(jf[0], im[0]), jf[0]);
+        for (int t = 0; t < 6; ++t) { P.j_np[t][row] = jn[t]; P.j_f[t][row] = jf[t]; }
+        // baumgarte (NonPenetration.hs:48-55)
+        P.b_np[row] = (d > P.slop) ? fmul(fdiv(P.baumgarte, P.dt), fsub(P.slop, d)) : 0.0;
+        // Restitution.constraintGen (Restitution.hs:21-31): radii from the unflipped pair
+        P.ra_x[row] = fsub(c.x, pos_i.x); P.ra_y[row] = fsub(c.y, pos_i.y);
+        P.rb_x[row] = fsub(c.x, pos_j.x); P.rb_y[row] = fsub(c.y, pos_j.y);
+        P.rn_x[row] = flip ? -n.x : n.x; P.rn_y[row] = flip ? -n.y : n.y;
+        // effMassM2 (Constraint.hs:173-179): left fold of (j_k * im_k) * j_k over the unflipped pair
+        const double im[6] = { mi.x, mi.x, mi.y, mj.x, mj.x, mj.y };
+        double en = fmul(fmul(jn[0], im[0]), jn[0]), ef = fmul(fmul(jf[0], im[0]), jf[0]);
 #pragma unroll
-            for (int t = 1; t < 6; ++t) {
-                en = fadd(en, fmul(fmul(jn[t], im[t]), jn[t]));
-                ef = fadd(ef, fmul(fmul(jf[t], im[t]), jf[t]));
-            }
-            P.inv_eff_np[row] = en; P.inv_eff_f[row] = ef;
+        for (int t = 1; t < 6; ++t) {
+            en = fadd(en, fmul(fmul(jn[t], im[t]), jn[t]));
+            ef = fadd(ef, fmul(fmul(jf[t], im[t]), jf[t]));
         }
+        P.inv_eff_np[row] = en; P.inv_eff_f[row] = ef;
     }
 }
 
@@ -931,7 +932,8 @@ struct shapes_ctx {
     int64_t chunk = 0;          // slots per rank (all-gather granule)
     bool hulls_set = false;
     int max_hull_verts = 0;
-    int ct_blocks[2] = { 4, 4 }; // resident k_contacts blocks per SM (boxes / general)
+    int ct_blocks[2] = { 4, 4 }; // resident k_manifolds blocks per SM (boxes / general)
+    int rows_blocks = 4;         // resident k_rows blocks per SM
     double auto_cell = 1.0, user_cell = 0.0;
     int64_t launches = 0;
     std::string err;
@@ -1047,6 +1049,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.mass, N));
     TRY_CREATE(dev_alloc(c, &P.is_static, N));
     TRY_CREATE(dev_alloc(c, &P.box, Npad));
+    TRY_CREATE(dev_alloc(c, &P.wv, V));
+    TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
     TRY_CREATE(dev_alloc(c, &P.idx, N));
@@ -1063,6 +1067,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.man, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.ccnt, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.coff, max_pairs));
+    TRY_CREATE(dev_alloc(c, &P.row_map, max_contacts));
     TRY_CREATE(cu(cudaMemset(P.ccnt, 0, std::max<int64_t>(max_pairs, 1) * sizeof(uint32_t)), "cudaMemset"));
     const int64_t C = max_contacts;
     TRY_CREATE(dev_alloc(c, &P.key_i, C)); TRY_CREATE(dev_alloc(c, &P.key_j, C));
@@ -1092,6 +1097,9 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_manifolds<4>, CT_THREADS, 0), "occupancy"));
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b8, k_manifolds<MAX_STAGED_VERTS>, CT_THREADS, 0), "occupancy"));
         c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1);
+        int br = 0;
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_rows, 256, 0), "occupancy"));
+        c->rows_blocks = std::max(br, 1);
     }
     TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_sort_tmp), sb));
     TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_scan_tmp), cb));
@@ -1186,10 +1194,10 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     if (N > 0 && c->max_pairs > 0) {
         size_t cb = c->scan_tmp_bytes;
         CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
-        k_finish_contacts<<<1, 1, 0, s>>>(P); ++c->launches;
+        k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
     }
     STAGE_MARK(); // 10: contact rows (flatten + constraint generators)
-    if (N > 0) { k_rows<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
+    if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
     STAGE_MARK(); // end
 #undef STAGE_MARK
     CU_TRY(c, cudaGetLastError());

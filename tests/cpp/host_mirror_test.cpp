@@ -1,0 +1,90 @@
+// Exercises include/shapes_b200.hpp the way the reference's own bench fixtures would:
+//   * testOptBoxes   (shapes/bench/Physics/Contact/Benchmark.hs:16-27)  -> KAT-1
+//   * testWorld      (shapes/bench/Physics/Broadphase/Benchmark.hs:50-52) -> KAT-3
+//   * Stacks.makeScene (30,30) 0 (shapes/src/Physics/Scenes/Stacks.hs:110-113) -> config 1 counts
+// Exit code 0 = all checks passed; 3 = no usable GPU (the library refuses, it never falls back).
+#include "shapes_b200.hpp"
+
+#include <cstdio>
+
+using namespace shapes;
+
+static int fails = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #cond); ++fails; } } while (0)
+
+// stacks / boxStack with the reference's repeated additions (Stacks.hs:34-56)
+static void stacks(World &w, double bw, double bh, double center, double bottom, double spacing, int n_w, int n_h)
+{
+    double left = center - (bw * double(n_w - 1) / 2.0);
+    for (int c = 0; c < n_w; ++c) {
+        double y = bottom;
+        for (int r = 0; r < n_h; ++r) {
+            w.append(makePhysicalObj({ left, y }, 0.0, { 2.0, 1.0 }), makeRectangleHull(bw, bh));
+            y = y + (bh + spacing);
+        }
+        left = left + bw;
+    }
+}
+
+int main()
+{
+    try {
+        Engine eng(0);
+        {   // KAT-1
+            World w;
+            w.append(makePhysicalObj({ 1.0, 3.0 }, 0.0, { 1.0, 1.0 }), makeRectangleHull(2.0, 2.0));
+            w.append(makePhysicalObj({ 0.0, 0.0 }, 0.0, { 1.0, 1.0 }), makeRectangleHull(4.0, 4.0));
+            auto keys = culledKeys(eng, w);
+            CHECK(keys.size() == 1 && keys[0] == std::make_pair(1, 0));
+            auto cs = prepareFrame(eng, w);
+            CHECK(cs.size() == 2);
+            if (cs.size() == 2) {
+                CHECK(cs[0].featA == 1 && cs[0].featB == 2 && cs[0].flip);
+                CHECK(cs[1].featA == 0 && cs[1].featB == 2 && cs[1].flip);
+                CHECK(cs[0].normal.x == 0.0 && cs[0].normal.y == -1.0);
+                CHECK(cs[0].center.x == 0.0 && cs[0].center.y == 2.0 && cs[0].depth == 0.0);
+                CHECK(cs[1].center.x == 2.0 && cs[1].center.y == 2.0 && cs[1].depth == 0.0);
+            }
+            Frame f = constraintGen(eng, ContactBehavior{ 0.01, 0.02 }, 0.01, w);
+            CHECK(f.constraints.size() == 2);
+            if (f.constraints.size() == 2) {
+                // Flip: penetrated body is b (key 0, at (1,3)); J halves swapped back (Constraint.hs:96-98)
+                const ContactConstraint &c0 = f.constraints[0];
+                CHECK(c0.nonPen.j[0] == 0.0 && c0.nonPen.j[1] == -1.0);   // +n for the penetrator (a), n = (0,-1)
+                CHECK(c0.nonPen.j[3] == -0.0 && c0.nonPen.j[4] == 1.0);   // -n for the penetrated body (b)
+                CHECK(c0.nonPen.b == 0.0 && c0.friction.b == 0.0);
+                CHECK(c0.normal.x == -0.0 && c0.normal.y == 1.0);         // Restitution: -n for Flip
+            }
+        }
+        {   // KAT-3
+            World w;
+            stacks(w, 0.2, 0.2, 0.0, -4.5, 0.0, 30, 30);
+            auto keys = culledKeys(eng, w);
+            CHECK(keys.size() == 3076);
+            CHECK(!keys.empty() && keys[0] == std::make_pair(899, 898));
+            World w1;
+            stacks(w1, 0.2, 0.2, 0.0, -4.5, 1.0, 30, 30);
+            auto keys1 = culledKeys(eng, w1);
+            CHECK(keys1.size() == 840);
+            CHECK(!keys1.empty() && keys1[0] == std::make_pair(899, 869));
+        }
+        {   // config 1: floor + 900 boxes; keys strictly descending, delete keeps keys sparse
+            World w;
+            w.append(makePhysicalObj({ 0.0, -6.0 }, 0.0, { 0.0, 0.0 }), makeRectangleHull(18.0, 1.0));
+            stacks(w, 0.2, 0.2, 0.0, -4.5, 0.0, 30, 30);
+            Frame f = constraintGen(eng, ContactBehavior{ 0.01, 0.02 }, 0.01, w);
+            CHECK(f.keys.size() == 3076);   // the floor is 0.9 below the bottom row at frame 0
+            for (size_t k = 1; k < f.keys.size(); ++k) CHECK(f.keys[k - 1] > f.keys[k]);
+            CHECK(f.contacts.size() == f.constraints.size() && !f.contacts.empty());
+            w.remove(900);
+            auto keys = culledKeys(eng, w);
+            for (auto &p : keys) CHECK(p.first != 900 && p.second != 900);
+            CHECK(keys.size() < 3076);
+        }
+    } catch (const Error &e) {
+        std::printf("shapes::Error: %s\n", e.what());
+        return e.code == SHAPES_E_CUDA ? 3 : 2;
+    }
+    std::printf(fails ? "host mirror: %d check(s) failed\n" : "host mirror: all checks passed\n", fails);
+    return fails ? 1 : 0;
+}
