@@ -35,6 +35,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -129,7 +130,6 @@ __device__ __forceinline__ double dec_ordered(unsigned long long u)
     return __longlong_as_double((long long)u);
 }
 
-constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr int ERR_PAIR_CAP = 1;
 constexpr int ERR_CONTACT_CAP = 2;
 constexpr int MAX_STAGED_VERTS = 8; // hulls up to this many vertices are staged in shared memory
@@ -180,6 +180,7 @@ struct Params {
     uint32_t *smeta;            // slot | static << 31, sorted order
     uint2 *cells;               // [begin, end) sorted positions per cell
     unsigned cell_cap;
+    uint32_t key_none;          // sort key of slots outside the grid (dead / big): first value past the cell table
     double cell_size;
     uint32_t *big_idx;
     unsigned long long *cnt, *off; // per query slot, indexed own_hi-1-i
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(256) k_cell_keys(Params P)
     const int W = st->W;
     unsigned small = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        uint32_t key = KEY_NONE;
+        uint32_t key = P.key_none;
         if (P.alive[s]) {
             Box b = P.box[s];
             bool big = true;
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(Params P)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_slots) return;
     const uint32_t key = P.keys_sorted[p];
-    if (key == KEY_NONE) return;
+    if (key >= P.key_none) return;
     const uint32_t s = P.idx_sorted[p];
     P.sbox[p] = P.box[s];
     P.smeta[p] = s | ((uint32_t)P.is_static[s] << 31);
@@ -917,6 +918,10 @@ static NcclApi &nccl_api()
     return api;
 }
 
+struct FrameKey {   // everything a captured frame graph bakes in
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling; int64_t geometry;
+};
+
 struct shapes_ctx {
     int device = 0;
     int rank = 0, world = 1;
@@ -931,7 +936,13 @@ struct shapes_ctx {
     int64_t n_slots = 0, n_verts = 0;
     int64_t chunk = 0;          // slots per rank (all-gather granule)
     bool hulls_set = false;
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    FrameKey graph_key{};
+    int64_t graph_launches = 0;
+    int64_t geometry_version = 0;
     int max_hull_verts = 0;
+    int sort_bits = 32;
     int ct_blocks[2] = { 4, 4 }; // resident k_manifolds blocks per SM (boxes / general)
     int rows_blocks = 4;         // resident k_rows blocks per SM
     double auto_cell = 1.0, user_cell = 0.0;
@@ -1010,6 +1021,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     c->device = device_id; c->rank = rank; c->world = world;
     c->max_shapes = max_shapes; c->max_verts = max_verts;
     c->max_pairs = max_pairs; c->max_contacts = max_contacts;
+    c->use_graph = std::getenv("SHAPES_B200_NO_GRAPH") == nullptr;
     auto fail = [&](int code) { g_create_error = c->err; shapes_destroy(c); return code; };
 #define TRY_CREATE(expr) do { int rc__ = (expr); if (rc__ != SHAPES_OK) return fail(rc__); } while (0)
     auto cu = [&](cudaError_t e, const char *what) {
@@ -1059,6 +1071,9 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.smeta, N));
     P.cell_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(4 * N, 1 << 16), 1ll << 28);
     TRY_CREATE(dev_alloc(c, &P.cells, P.cell_cap));
+    P.key_none = P.cell_cap;
+    c->sort_bits = 1;
+    while ((1ull << c->sort_bits) <= (unsigned long long)P.key_none) ++c->sort_bits;
     TRY_CREATE(dev_alloc(c, &P.big_idx, N));
     TRY_CREATE(dev_alloc(c, &P.cnt, N));
     TRY_CREATE(dev_alloc(c, &P.off, N));
@@ -1137,78 +1152,109 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     cudaStream_t s = c->stream;
     const int sms = c->sm_count;
 
-    int stage = 0;
-#define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
-    CU_TRY(c, cudaEventRecord(c->ev0, s));
-    STAGE_MARK(); // 0: transform
-    k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
-    if (N > 0) {
-        CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
-        k_transform_aabb<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
-    }
-    STAGE_MARK(); // 1: allgather
-    if (N > 0 && c->world > 1) {
-        // exchange #1: AABB records of every rank's slot range over NVLink (in place)
-        NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
-                                         sizeof(Box) * c->chunk, ncclChar, c->comm, s));
-    }
-    STAGE_MARK(); // 2: grid keys
-    if (N > 0) {
-        k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
-        k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
-        k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
-        k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
-    }
-    STAGE_MARK(); // 3: sort
-    if (N > 0) {
-        size_t sb = c->sort_tmp_bytes;
-        CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, N, 0, 32, s));
-    }
-    STAGE_MARK(); // 4: gather sorted
-    if (N > 0) { k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches; }
-    STAGE_MARK(); // 5: sweep count
-    if (N > 0) {
-        k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
-        k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
-    }
-    STAGE_MARK(); // 6: scan
-    if (N > 0) {
-        if (n_query > 0) {
-            size_t cb = c->scan_tmp_bytes;
-            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+    // The launch sequence of a frame is fixed for given buffers and scalars (all counts live in
+    // device memory), so it is captured once into a CUDA graph and replayed: one cudaGraphLaunch
+    // instead of ~25 launches per frame.
+    auto issue = [&]() -> int {
+        int stage = 0;
+    #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
+        STAGE_MARK(); // 0: transform
+        k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
+        if (N > 0) {
+            CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
+            k_transform_aabb<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
         }
-        k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
-    }
-    STAGE_MARK(); // 7: sweep emit
-    if (N > 0) {
-        k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
-        k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
-    }
-    STAGE_MARK(); // 8: manifolds (SAT + clipping)
-    if (N > 0) {
-        if (c->max_hull_verts <= 4) k_manifolds<4><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
-        else k_manifolds<MAX_STAGED_VERTS><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
-        ++c->launches;
-    }
-    STAGE_MARK(); // 9: contact row offsets
-    if (N > 0 && c->max_pairs > 0) {
-        size_t cb = c->scan_tmp_bytes;
-        CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
-        k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
-    }
-    STAGE_MARK(); // 10: contact rows (flatten + constraint generators)
-    if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
-    STAGE_MARK(); // end
-#undef STAGE_MARK
-    CU_TRY(c, cudaGetLastError());
-    if (c->world > 1) {
-        // exchange #2 (counts): every rank learns every rank's pair / contact counts, so the
-        // global row offset of each rank's slice is known everywhere.
-        NCCL_TRY(c, nccl_api().AllGather(&P.st->n_pairs, c->d_counts, 2, ncclInt64, c->comm, s));
-        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int64_t) * 2 * c->world, cudaMemcpyDeviceToHost, s));
+        STAGE_MARK(); // 1: allgather
+        if (N > 0 && c->world > 1) {
+            // exchange #1: AABB records of every rank's slot range over NVLink (in place)
+            NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
+                                             sizeof(Box) * c->chunk, ncclChar, c->comm, s));
+        }
+        STAGE_MARK(); // 2: grid keys
+        if (N > 0) {
+            k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
+            k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
+            k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+            k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 3: sort
+        if (N > 0) {
+            size_t sb = c->sort_tmp_bytes;
+            CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, N, 0, c->sort_bits, s));
+        }
+        STAGE_MARK(); // 4: gather sorted
+        if (N > 0) { k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 5: sweep count
+        if (N > 0) {
+            k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 6: scan
+        if (N > 0) {
+            if (n_query > 0) {
+                size_t cb = c->scan_tmp_bytes;
+                CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+            }
+            k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+        }
+        STAGE_MARK(); // 7: sweep emit
+        if (N > 0) {
+            k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 8: manifolds (SAT + clipping)
+        if (N > 0) {
+            if (c->max_hull_verts <= 4) k_manifolds<4><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
+            else k_manifolds<MAX_STAGED_VERTS><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
+            ++c->launches;
+        }
+        STAGE_MARK(); // 9: contact row offsets
+        if (N > 0 && c->max_pairs > 0) {
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
+            k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 10: contact rows (flatten + constraint generators)
+        if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // end
+    #undef STAGE_MARK
+        CU_TRY(c, cudaGetLastError());
+        if (c->world > 1) {
+            // exchange #2 (counts): every rank learns every rank's pair / contact counts, so the
+            // global row offset of each rank's slice is known everywhere.
+            NCCL_TRY(c, nccl_api().AllGather(&P.st->n_pairs, c->d_counts, 2, ncclInt64, c->comm, s));
+            CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(int64_t) * 2 * c->world, cudaMemcpyDeviceToHost, s));
+        }
+        CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+        return SHAPES_OK;
+    };
+    FrameKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
+    key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
+    key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
+    const int64_t launches_before = c->launches;
+    CU_TRY(c, cudaEventRecord(c->ev0, s));
+    if (!c->use_graph || c->profiling) { // per-stage events cannot be timed from inside a graph
+        const int rc = issue();
+        if (rc != SHAPES_OK) return rc;
+    } else {
+        if (!c->graph_exec || std::memcmp(&key, &c->graph_key, sizeof(key)) != 0) {
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = issue();
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != SHAPES_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            CU_TRY(c, ce);
+            CU_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            c->graph_key = key;
+            c->graph_launches = c->launches - launches_before;
+        } else c->launches += c->graph_launches;
+        CU_TRY(c, cudaGraphLaunch(c->graph_exec, s));
     }
     CU_TRY(c, cudaEventRecord(c->ev1, s));
-    CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaStreamSynchronize(s));
     const FrameState &st = *c->h_state;
     c->last_pairs = st.n_pairs;
@@ -1279,6 +1325,7 @@ void shapes_destroy(shapes_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -1364,6 +1411,7 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
     c->max_hull_verts = max_verts_seen;
     c->hulls_set = true;
     c->have_frame = false;
+    ++c->geometry_version;
     return SHAPES_OK;
 }
 
