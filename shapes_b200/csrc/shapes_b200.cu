@@ -524,7 +524,10 @@ __global__ void k_finish_pairs(Params P, int n_query)
 // ---------------------------------------------------------------------------------------------
 
 constexpr int CT_THREADS = 128;
-constexpr int CT_MIN_BLOCKS = 6;
+#ifndef CT_MIN_BLOCKS_OVERRIDE
+#define CT_MIN_BLOCKS_OVERRIDE 6
+#endif
+constexpr int CT_MIN_BLOCKS = CT_MIN_BLOCKS_OVERRIDE;
 
 struct HullAcc {
     int slot, off, n;
@@ -590,13 +593,18 @@ struct ContactKernel {
 
     // minOverlap' sEdge sPen (SAT.hs:121-143) with overlap (SAT.hs:103-117): the first
     // separating edge wins (later edges cannot change the fold), else strictly smaller depth.
-    __device__ SatRes min_overlap(const HullAcc &E, const HullAcc &Pn) const
+    // NE / NP: compile-time vertex counts (0 = read them from the hull) so the common box-box
+    // case is fully unrolled.
+    template <int NE, int NP>
+    __device__ __forceinline__ SatRes min_overlap(const HullAcc &E, const HullAcc &Pn) const
     {
+        const int ne = NE ? NE : E.n, np = NP ? NP : Pn.n;
         SatRes best{ false, 0, 0.0, 0 };
         V2 dir_next = E.n0;
-        for (int e = 0; e < E.n; ++e) {
+#pragma unroll
+        for (int e = 0; e < ne; ++e) {
             const V2 dir = dir_next;
-            if (e + 1 < E.n) dir_next = normal(E, e + 1); // issued one edge ahead of its use
+            if (e + 1 < ne) dir_next = normal(E, e + 1); // issued one edge ahead of its use
             int imin, imax;
             ext(E, e, imin, imax);
             // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
@@ -605,7 +613,8 @@ struct ContactKernel {
             // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
             double p_min = dot2(vtx(Pn, 0), dir), p_max = p_min;
             int p_idx = 0;
-            for (int k = 1; k < Pn.n; ++k) {
+#pragma unroll
+            for (int k = 1; k < np; ++k) {
                 const double d = dot2(vtx(Pn, k), dir);
                 if (d < p_min) { p_min = d; p_idx = k; }
                 if (d > p_max) p_max = d;
@@ -663,9 +672,10 @@ __global__ void __launch_bounds__(CT_THREADS, CT_MIN_BLOCKS) k_manifolds(Params 
         unsigned cnt = 0;
         // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
         // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
-        const SatRes ab = K.min_overlap(A, B);
+        const bool boxes = (A.n == 4) & (B.n == 4);
+        const SatRes ab = boxes ? K.template min_overlap<4, 4>(A, B) : K.template min_overlap<0, 0>(A, B);
         if (!ab.sep) {
-            const SatRes ba = K.min_overlap(B, A);
+            const SatRes ba = boxes ? K.template min_overlap<4, 4>(B, A) : K.template min_overlap<0, 0>(B, A);
             if (!ba.sep) {
                 const bool same = ab.depth < ba.depth;
                 const HullAcc &E = same ? A : B;
