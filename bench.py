@@ -358,16 +358,26 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     st_ms = {k: v / prof_steps for k, v in stage_acc.items()}
+    traffic = {}
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("shapes") == n and tj.get("workload") == world_desc:
+            traffic = tj["dram_bytes_per_launch"]
+            traffic["_source"] = tj["source"]
+    except Exception:
+        pass
     kernels = []
     for kname, stage, nbytes in (("k_manifolds", "manifolds", manifolds_algorithmic_bytes(n_pairs, n_contacts, vbar)),
                                  ("k_rows", "contact_rows", rows_algorithmic_bytes(n_pairs, n_contacts))):
         ms = st_ms.get(stage, 0.0)
         ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels.append({"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": nbytes,
+                        "frac": ach / peak, "traffic": traffic.get(kname), "algorithmic_bytes_per_launch": nbytes,
                         "avg_launch_ms": ms, "share_of_device_time": ms / max(dev_ms / args.steps, 1e-9)})
     roofline = dict(max(kernels, key=lambda k: k["avg_launch_ms"]))
     roofline["peak_source"] = peak_src
+    roofline["traffic_source"] = traffic.get("_source")
     roofline["other_kernels"] = [k for k in kernels if k["kernel"] != roofline["kernel"]]
     k3_bytes = sum(k["algorithmic_bytes_per_launch"] for k in kernels)
 

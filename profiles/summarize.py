@@ -57,7 +57,12 @@ def launches_table(path):
     return "\n".join(lines), tot
 
 
-def raw_tables(rep):
+def to_bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return float(value) * scale[unit]
+
+
+def raw_tables(rep, traffic):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
@@ -70,6 +75,8 @@ def raw_tables(rep):
         if name in seen:
             continue
         seen.add(name)
+        traffic[name.split("<")[0]] = (to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) +
+                                       to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"]))
         lines = [f"### `{name}`", "", "| metric | value |", "|---|---|"]
         for key, label in RAW_KEYS:
             if key in d:
@@ -108,7 +115,13 @@ def main():
                table, ""]
     rep = os.path.join(OUT, f"prof_{tag}.ncu-rep")
     if os.path.exists(rep):
-        md += ["## ncu --set full captures", "", raw_tables(rep), ""]
+        traffic = {}
+        md += ["## ncu --set full captures", "", raw_tables(rep, traffic), ""]
+        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            json.dump({"source": f"prof_{tag}.ncu-rep (ncu --set full --clock-control none)",
+                       "workload": d["config"]["workload"] if os.path.exists(bj) else None,
+                       "shapes": d["config"]["shapes"] if os.path.exists(bj) else None,
+                       "dram_bytes_per_launch": traffic}, f, indent=1)
     path = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
     with open(path, "w") as f:
         f.write("\n".join(md))
