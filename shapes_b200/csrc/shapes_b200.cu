@@ -570,7 +570,17 @@ struct ContactKernel {
         h.owned = h.slot >= P.own_lo && h.slot < P.own_hi;
         if (h.n <= MAXV) {
             if (h.owned) {
-                for (int k = 0; k < h.n; ++k) sv[h.which][k][tid] = P.wv[h.off + k];
+                if (MAXV > 4) {
+                    // general worlds: partners are far apart in memory, so every vertex load is
+                    // issued before the first is consumed (one DRAM latency instead of n)
+                    double2 tmp[MAXV];
+#pragma unroll
+                    for (int k = 0; k < MAXV; ++k) if (k < h.n) tmp[k] = P.wv[h.off + k];
+#pragma unroll
+                    for (int k = 0; k < MAXV; ++k) if (k < h.n) sv[h.which][k][tid] = tmp[k];
+                } else {
+                    for (int k = 0; k < h.n; ++k) sv[h.which][k][tid] = P.wv[h.off + k];
+                }
             } else {
                 const Xf x = P.xf[h.slot];
                 const Aff m = to_transform(x.px, x.py, x.c, x.s);
@@ -591,39 +601,78 @@ struct ContactKernel {
         return unit_edge_normal(vtx(h, e), vtx(h, e1));
     }
 
-    // minOverlap' sEdge sPen (SAT.hs:121-143) with overlap (SAT.hs:103-117): the first
-    // separating edge wins (later edges cannot change the fold), else strictly smaller depth.
-    // NE / NP: compile-time vertex counts (0 = read them from the hull) so the common box-box
-    // case is fully unrolled.
+    // minOverlap' sEdge sPen (SAT.hs:121-143): the first separating edge wins (later edges cannot
+    // change the fold), else strictly smaller depth.  NE / NP: compile-time vertex counts (0 = read
+    // them from the hull).  Two schedules for the edge normals:
+    //  * boxes-only kernel (MAXV <= 4): partners are neighbours in memory, normals come from L1/L2
+    //    one edge ahead of their use (keeps registers and shared memory small => more L1);
+    //  * general kernel: partners are scattered, so all normals of E are requested as one batch.
+    //    Loops have compile-time bounds with `break` guards so lanes with different vertex counts
+    //    stay converged (runtime trip counts under `#pragma unroll` made ptxas emit remainder
+    //    jumps that serialised the lanes: 4.7 active threads per instruction).
     template <int NE, int NP>
     __device__ __forceinline__ SatRes min_overlap(const HullAcc &E, const HullAcc &Pn) const
     {
         const int ne = NE ? NE : E.n, np = NP ? NP : Pn.n;
         SatRes best{ false, 0, 0.0, 0 };
-        V2 dir_next = E.n0;
+        if (MAXV <= 4 || NE) {
+            V2 dir_next = E.n0;
 #pragma unroll
-        for (int e = 0; e < ne; ++e) {
-            const V2 dir = dir_next;
-            if (e + 1 < ne) dir_next = normal(E, e + 1); // issued one edge ahead of its use
-            int imin, imax;
-            ext(E, e, imin, imax);
-            // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
-            const double s_min = dot2(vtx(E, imin), dir);
-            const double s_max = dot2(vtx(E, imax), dir);
-            // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
-            double p_min = dot2(vtx(Pn, 0), dir), p_max = p_min;
-            int p_idx = 0;
+            for (int e = 0; e < (NE ? NE : MAXV); ++e) {
+                if (e >= ne) break;
+                const V2 dir = dir_next;
+                if (e + 1 < ne) dir_next = normal(E, e + 1); // issued one edge ahead of its use
+                if (edge_test<NP>(E, Pn, e, dir, np, best)) return best;
+            }
+        } else if (ne <= MAXV) {
+            V2 nrm[MAXV];
+            nrm[0] = E.n0;
 #pragma unroll
+            for (int e = 1; e < MAXV; ++e) if (e < ne) nrm[e] = normal(E, e);
+#pragma unroll
+            for (int e = 0; e < MAXV; ++e) {
+                if (e >= ne) break;
+                if (edge_test<NP>(E, Pn, e, nrm[e], np, best)) return best;
+            }
+        } else {
+#pragma unroll 1
+            for (int e = 0; e < ne; ++e)
+                if (edge_test<NP>(E, Pn, e, normal(E, e), np, best)) return best;
+        }
+        return best;
+    }
+
+    // overlap sEdge edge sPen (SAT.hs:103-117) folded into minOverlap's accumulator; true = separated
+    template <int NP>
+    __device__ __forceinline__ bool edge_test(const HullAcc &E, const HullAcc &Pn, int e, V2 dir, int np, SatRes &best) const
+    {
+        int imin, imax;
+        ext(E, e, imin, imax);
+        // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
+        const double s_min = dot2(vtx(E, imin), dir);
+        const double s_max = dot2(vtx(E, imax), dir);
+        // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
+        double p_min = dot2(vtx(Pn, 0), dir), p_max = p_min;
+        int p_idx = 0;
+        if (NP) {
+#pragma unroll
+            for (int k = 1; k < NP; ++k) {
+                const double d = dot2(vtx(Pn, k), dir);
+                if (d < p_min) { p_min = d; p_idx = k; }
+                if (d > p_max) p_max = d;
+            }
+        } else {
+#pragma unroll 1
             for (int k = 1; k < np; ++k) {
                 const double d = dot2(vtx(Pn, k), dir);
                 if (d < p_min) { p_min = d; p_idx = k; }
                 if (d > p_max) p_max = d;
             }
-            if ((p_min > s_max) || (p_max < s_min)) { best.sep = true; best.edge = e; return best; } // overlapTest (SAT.hs:74-83)
-            const double depth = fsub(s_max, p_min); // overlapAmount (SAT.hs:86-96)
-            if (e == 0 || depth < best.depth) { best.edge = e; best.depth = depth; best.pen = p_idx; }
         }
-        return best;
+        if ((p_min > s_max) || (p_max < s_min)) { best.sep = true; best.edge = e; return true; } // overlapTest (SAT.hs:74-83)
+        const double depth = fsub(s_max, p_min); // overlapAmount (SAT.hs:86-96)
+        if (e == 0 || depth < best.depth) { best.edge = e; best.depth = depth; best.pen = p_idx; }
+        return false;
     }
 };
 
@@ -649,7 +698,7 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
 // K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
 // count and, when it has contacts, its manifold record.  No ordering between pairs.
 template <int MAXV>
-__global__ void __launch_bounds__(CT_THREADS, CT_MIN_BLOCKS) k_manifolds(Params P)
+__global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : 4) k_manifolds(Params P)
 {
     __shared__ double2 s_verts[CT_THREADS / 32][2][MAXV][32];
 
