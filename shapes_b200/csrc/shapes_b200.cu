@@ -27,7 +27,6 @@
 #include "shapes_b200.h"
 
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <nccl.h>   // types only: NCCL is bound at run time (see NcclApi), never at link time
 #include <dlfcn.h>
@@ -175,10 +174,14 @@ struct Params {
     Box *box;                   // per slot
     double *world_x, *world_y;  // optional debug output
     double2 *wv, *wn;           // world vertices / unit edge normals of the OWNED slots (moveShapes result)
-    uint32_t *keys, *keys_sorted, *idx, *idx_sorted;
+    uint32_t *keys, *keys_sorted; // cell key per slot / per sorted position
+    uint32_t *rank;             // per slot: arrival order within its cell (counting sort)
     Box *sbox;                  // AABB records in sorted order
     uint32_t *smeta;            // slot | static << 31, sorted order
-    uint2 *cells;               // [begin, end) sorted positions per cell
+    uint32_t *cell_count;       // per cell: shapes binned this frame
+    uint32_t *cell_begin;       // exclusive scan of cell_count: cell c = sorted positions [begin[c], begin[c+1])
+    uint8_t *cell_mark;         // multi-rank: cells inside the 3x3 neighbourhood of an owned shape
+    int multi_rank;
     unsigned cell_cap;
     uint32_t key_none;          // sort key of slots outside the grid (dead / big): first value past the cell table
     double cell_size;
@@ -324,62 +327,87 @@ __global__ void k_plan_grid(Params P)
     st->n_cells = (unsigned)(st->W * st->H);
 }
 
-// Cell of the AABB's min corner if the box spans at most 2 cells per axis ("small"); otherwise
-// (or with any non-finite bound) the shape goes to the big list and is tested against everything.
+// Cell of an AABB's min corner if the box spans at most 2 cells per axis ("small"), else -1.
 // Monotonicity of x -> floor((x - ox) / h) alone guarantees that two overlapping small boxes have
 // min-corner cells at most 1 apart per axis, so the 3x3 neighbourhood search is exhaustive.
-__global__ void __launch_bounds__(256) k_cell_keys(Params P)
+__device__ __forceinline__ bool small_cell(const Box &b, const FrameState *st, int &cx, int &cy)
 {
-    const FrameState *st = P.st;
+    if (!finite4(b)) return false;
     const double ox = st->ox, oy = st->oy, h = st->h;
-    const int W = st->W;
-    unsigned small = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        uint32_t key = P.key_none;
-        if (P.alive[s]) {
-            Box b = P.box[s];
-            bool big = true;
-            if (finite4(b)) {
-                double x0 = floor((b.min_x - ox) / h), x1 = floor((b.max_x - ox) / h);
-                double y0 = floor((b.min_y - oy) / h), y1 = floor((b.max_y - oy) / h);
-                if (isfinite(x0) && isfinite(x1) && isfinite(y0) && isfinite(y1) &&
-                    x1 - x0 <= 1.0 && y1 - y0 <= 1.0 && x0 >= 0.0 && y0 >= 0.0 &&
-                    x0 < (double)W && y0 < (double)st->H) {
-                    key = (uint32_t)y0 * (uint32_t)W + (uint32_t)x0;
-                    big = false;
-                }
-            }
-            if (big) {
-                unsigned pos = atomicAdd(&P.st->n_big, 1u);
-                P.big_idx[pos] = (uint32_t)s;
-            } else ++small;
-        }
-        P.keys[s] = key;
-        P.idx[s] = (uint32_t)s;
-    }
-    for (int o = 16; o > 0; o >>= 1) small += __shfl_xor_sync(0xffffffffu, small, o);
-    if ((threadIdx.x & 31) == 0 && small) atomicAdd(&P.st->n_small, small);
+    const double x0 = floor((b.min_x - ox) / h), x1 = floor((b.max_x - ox) / h);
+    const double y0 = floor((b.min_y - oy) / h), y1 = floor((b.max_y - oy) / h);
+    if (!(isfinite(x0) && isfinite(x1) && isfinite(y0) && isfinite(y1))) return false;
+    if (!(x1 - x0 <= 1.0 && y1 - y0 <= 1.0 && x0 >= 0.0 && y0 >= 0.0 && x0 < (double)st->W && y0 < (double)st->H)) return false;
+    cx = (int)x0; cy = (int)y0;
+    return true;
 }
 
 __global__ void __launch_bounds__(256) k_clear_cells(Params P)
 {
     const unsigned n = P.st->n_cells;
-    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
-        P.cells[c] = make_uint2(0u, 0u);
+    for (unsigned c = blockIdx.x * blockDim.x + threadIdx.x; c <= n; c += gridDim.x * blockDim.x) {
+        P.cell_count[c] = 0u;
+        if (P.multi_rank && c < n) P.cell_mark[c] = 0;
+    }
 }
 
-// After the sort: AABB records in sorted order (coalesced for the sweep) and per-cell ranges.
-__global__ void __launch_bounds__(256) k_gather_sorted(Params P)
+// Multi-rank only: mark the cells an owned shape's partners can live in.  Shapes of other ranks
+// outside these cells can never pair with an owned query and are left out of this rank's grid.
+__global__ void __launch_bounds__(256) k_mark_cells(Params P)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.n_slots) return;
-    const uint32_t key = P.keys_sorted[p];
-    if (key >= P.key_none) return;
-    const uint32_t s = P.idx_sorted[p];
-    P.sbox[p] = P.box[s];
-    P.smeta[p] = s | ((uint32_t)P.is_static[s] << 31);
-    if (p == 0 || P.keys_sorted[p - 1] != key) P.cells[key].x = (unsigned)p;
-    if (p + 1 == P.n_slots || P.keys_sorted[p + 1] != key) P.cells[key].y = (unsigned)(p + 1);
+    const FrameState *st = P.st;
+    const int W = st->W, H = st->H;
+    for (int s = P.own_lo + blockIdx.x * blockDim.x + threadIdx.x; s < P.own_hi; s += gridDim.x * blockDim.x) {
+        if (!P.alive[s]) continue;
+        int cx, cy;
+        if (!small_cell(P.box[s], st, cx, cy)) continue;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int nx = cx + dx, ny = cy + dy;
+                if (nx >= 0 && nx < W && ny >= 0 && ny < H) P.cell_mark[(size_t)ny * W + nx] = 1;
+            }
+    }
+}
+
+// K1a: key of every live shape + histogram of the cells (the shape's arrival rank in its cell is
+// the counting sort's scatter slot).  Shapes spanning more than 2 cells per axis or with
+// non-finite bounds go to the big list and are tested against everything.
+__global__ void __launch_bounds__(256) k_cell_keys(Params P)
+{
+    const FrameState *st = P.st;
+    const int W = st->W;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        uint32_t key = P.key_none;
+        if (P.alive[s]) {
+            int cx, cy;
+            if (small_cell(P.box[s], st, cx, cy)) {
+                const uint32_t k = (uint32_t)cy * (uint32_t)W + (uint32_t)cx;
+                const bool own = s >= P.own_lo && s < P.own_hi;
+                if (!P.multi_rank || own || P.cell_mark[k]) {
+                    key = k;
+                    P.rank[s] = atomicAdd(&P.cell_count[k], 1u);
+                }
+            } else {
+                const unsigned pos = atomicAdd(&P.st->n_big, 1u);
+                P.big_idx[pos] = (uint32_t)s;
+            }
+        }
+        P.keys[s] = key;
+    }
+}
+
+// K1b: scatter into cell order (after the exclusive scan of the histogram): AABB records, slot ids
+// and keys in sorted order, contiguous per cell and per grid row.
+__global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        const uint32_t key = P.keys[s];
+        if (key >= P.key_none) continue;
+        const uint32_t p = P.cell_begin[key] + P.rank[s];
+        P.sbox[p] = P.box[s];
+        P.smeta[p] = (uint32_t)s | ((uint32_t)P.is_static[s] << 31);
+        P.keys_sorted[p] = key;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -396,7 +424,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
     const FrameState *st = P.st;
     if (EMIT && st->error) return;
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= st->n_small) return;
+    if (p >= P.cell_begin[st->n_cells]) return; // shapes in this rank's grid
     const uint32_t meta = P.smeta[p];
     const int i = (int)(meta & 0x7fffffffu);
     const bool si = (meta >> 31) != 0;
@@ -423,17 +451,17 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
     for (int dy = -1; dy <= 1; ++dy) {
         const int ny = cy + dy;
         if (ny < 0 || ny >= H) continue;
+        // the three cells of a grid row are consecutive keys => one contiguous run of candidates
         const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
-        for (int nx = x_lo; nx <= x_hi; ++nx) {
-            const uint2 rng = __ldg(&P.cells[(size_t)ny * W + nx]);
-            for (unsigned q = rng.x; q < rng.y; ++q) {
-                const uint32_t m = __ldg(&P.smeta[q]);
-                const int j = (int)(m & 0x7fffffffu);
-                if (j >= i) continue;
-                if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
-                const Box bj = P.sbox[q];
-                if (aabb_check(bi, bj)) hit(j);
-            }
+        const unsigned q_lo = __ldg(&P.cell_begin[(size_t)ny * W + x_lo]);
+        const unsigned q_hi = __ldg(&P.cell_begin[(size_t)ny * W + x_hi + 1]);
+        for (unsigned q = q_lo; q < q_hi; ++q) {
+            const uint32_t m = __ldg(&P.smeta[q]);
+            const int j = (int)(m & 0x7fffffffu);
+            if (j >= i) continue;
+            if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
+            const Box bj = P.sbox[q];
+            if (aabb_check(bi, bj)) hit(j);
         }
     }
     const unsigned n_big = st->n_big;
@@ -1001,7 +1029,6 @@ struct shapes_ctx {
     int64_t graph_launches = 0;
     int64_t geometry_version = 0;
     int max_hull_verts = 0;
-    int sort_bits = 32;
     int ct_blocks[2] = { 4, 4 }; // resident k_manifolds blocks per SM (boxes / general)
     int rows_blocks = 4;         // resident k_rows blocks per SM
     double auto_cell = 1.0, user_cell = 0.0;
@@ -1015,8 +1042,8 @@ struct shapes_ctx {
     unsigned long long *d_ext_packed = nullptr;
     double *d_in[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     double *d_world_x = nullptr, *d_world_y = nullptr, *d_split = nullptr;
-    void *d_sort_tmp = nullptr, *d_scan_tmp = nullptr;
-    size_t sort_tmp_bytes = 0, scan_tmp_bytes = 0;
+    void *d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
     FrameState *h_state = nullptr; // pinned
     int64_t *d_counts = nullptr;   // world x 2 (pairs, contacts), all-gathered
     int64_t *h_counts = nullptr;   // pinned
@@ -1124,15 +1151,16 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
-    TRY_CREATE(dev_alloc(c, &P.idx, N));
-    TRY_CREATE(dev_alloc(c, &P.idx_sorted, N));
+    TRY_CREATE(dev_alloc(c, &P.rank, N));
     TRY_CREATE(dev_alloc(c, &P.sbox, N));
     TRY_CREATE(dev_alloc(c, &P.smeta, N));
     P.cell_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(4 * N, 1 << 16), 1ll << 28);
-    TRY_CREATE(dev_alloc(c, &P.cells, P.cell_cap));
+    TRY_CREATE(dev_alloc(c, &P.cell_count, (size_t)P.cell_cap + 2));
+    TRY_CREATE(dev_alloc(c, &P.cell_begin, (size_t)P.cell_cap + 2));
+    TRY_CREATE(dev_alloc(c, &P.cell_mark, (size_t)P.cell_cap + 2));
+    TRY_CREATE(cu(cudaMemset(P.cell_count, 0, ((size_t)P.cell_cap + 2) * sizeof(uint32_t)), "cudaMemset"));
     P.key_none = P.cell_cap;
-    c->sort_bits = 1;
-    while ((1ull << c->sort_bits) <= (unsigned long long)P.key_none) ++c->sort_bits;
+    P.multi_rank = world > 1 ? 1 : 0;
     TRY_CREATE(dev_alloc(c, &P.big_idx, N));
     TRY_CREATE(dev_alloc(c, &P.cnt, N));
     TRY_CREATE(dev_alloc(c, &P.off, N));
@@ -1156,16 +1184,18 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
     TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 2 * world), "cudaMallocHost"));
     // library scratch: radix sort of (cell key, slot) and the offset scan
-    size_t sb = 0, cb = 0;
-    TRY_CREATE(cu(cub::DeviceRadixSort::SortPairs(nullptr, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted,
-                                                  (int)std::max<int64_t>(N, 1), 0, 32, c->stream), "cub sort size"));
+    size_t cb = 0;
     TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb, P.cnt, P.off, (int)std::max<int64_t>(N, 1), c->stream),
                   "cub scan size"));
+    size_t cb3 = 0;
+    TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb3, P.cell_count, P.cell_begin, (int)P.cell_cap + 1, c->stream),
+                  "cub scan size"));
+    cb = std::max(cb, cb3);
     size_t cb2 = 0;
     TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb2, P.ccnt, P.coff, (int)std::max<int64_t>(max_pairs, 1), c->stream),
                   "cub scan size"));
     cb = std::max(cb, cb2);
-    c->sort_tmp_bytes = sb; c->scan_tmp_bytes = cb;
+    c->scan_tmp_bytes = cb;
     {   // grid-stride k_manifolds grid: the number of co-resident blocks
         int b4 = 0, b8 = 0;
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_manifolds<4>, CT_THREADS, 0), "occupancy"));
@@ -1175,7 +1205,6 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_rows, 256, 0), "occupancy"));
         c->rows_blocks = std::max(br, 1);
     }
-    TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_sort_tmp), sb));
     TRY_CREATE(dev_alloc(c, reinterpret_cast<uint8_t **>(&c->d_scan_tmp), cb));
     P.max_pairs = max_pairs; P.max_contacts = max_contacts;
     P.alive = c->d_alive; P.vert_offset = c->d_vert_offset; P.local = c->d_local;
@@ -1233,16 +1262,17 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         if (N > 0) {
             k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
             k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
-            k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
             k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
+            if (c->world > 1) { k_mark_cells<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
+            k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
         }
-        STAGE_MARK(); // 3: sort
+        STAGE_MARK(); // 3: cell offsets (exclusive scan of the histogram)
         if (N > 0) {
-            size_t sb = c->sort_tmp_bytes;
-            CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, sb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, N, 0, c->sort_bits, s));
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cell_count, P.cell_begin, (int)P.cell_cap + 1, s));
         }
-        STAGE_MARK(); // 4: gather sorted
-        if (N > 0) { k_gather_sorted<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 4: scatter into cell order
+        if (N > 0) { k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
         STAGE_MARK(); // 5: sweep count
         if (N > 0) {
             k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
@@ -1626,8 +1656,8 @@ int shapes_stage_ms(const shapes_ctx *c, float *out_ms)
 
 const char *shapes_stage_name(int stage)
 {
-    static const char *names[SHAPES_N_STAGES] = { "transform_aabb", "allgather_aabb", "grid_keys", "radix_sort",
-                                                  "gather_sorted", "sweep_count", "scan_offsets", "sweep_emit",
+    static const char *names[SHAPES_N_STAGES] = { "transform_aabb", "allgather_aabb", "grid_keys", "cell_scan",
+                                                  "scatter_sorted", "sweep_count", "scan_offsets", "sweep_emit",
                                                   "manifolds", "scan_rows", "contact_rows" };
     return (stage >= 0 && stage < SHAPES_N_STAGES) ? names[stage] : "";
 }
