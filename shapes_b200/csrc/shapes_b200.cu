@@ -9,8 +9,8 @@
 // Pipeline (one stream, no host round trip between kernels):
 //   K0  k_transform_aabb  moveShapes + toAabb per slot                 (World.hs:132-140, Aabb.hs:81-110)
 //   [N>1: ncclAllGather of the AABB records over NVLink]
-//   K0b k_bounds / k_plan_grid / k_cell_keys   uniform-grid cell key of each AABB's min corner
-//   K1  radix sort (key, slot)  + k_gather_sorted (sorted AABB records, per-cell ranges)
+//   K0b k_plan_grid / k_cell_keys   uniform-grid cell key of each AABB's min corner + cell histogram
+//   K1  counting sort on the cell table: exclusive scan of the histogram + k_scatter_sorted
 //   K2  k_sweep<count> -> exclusive scan over slots in DESCENDING key order -> k_sweep<emit>
 //       (+ k_big<count/emit> for shapes spanning more than 2 cells or with non-finite bounds)
 //       => pairs come out in the reference's descending (i, j) order by construction.
@@ -146,6 +146,11 @@ struct FrameState {
     long long n_contacts;
 };
 
+struct Params;
+__device__ __forceinline__ bool slot_static(const Params &P, int s);
+__device__ __forceinline__ Xf slot_xf(const Params &P, int s);
+__device__ __forceinline__ double2 slot_mass(const Params &P, int s);
+
 // Clipped contact manifold of one pair, handed from k_manifolds to k_rows.
 struct __align__(64) ManRec {
     double nx, ny;        // unit normal of the penetrated edge
@@ -170,7 +175,6 @@ struct Params {
     // per-frame derived
     Xf *xf;                     // (px, py, cos, sin)
     double2 *mass;              // (inv_lin, inv_rot)
-    uint8_t *is_static;
     Box *box;                   // per slot
     double *world_x, *world_y;  // optional debug output
     double2 *wv, *wn;           // world vertices / unit edge normals of the OWNED slots (moveShapes result)
@@ -186,6 +190,7 @@ struct Params {
     uint32_t key_none;          // sort key of slots outside the grid (dead / big): first value past the cell table
     double cell_size;
     uint32_t *big_idx;
+    unsigned long long *rank_bounds; // world x 4 ordered-uint bounds (multi-rank)
     unsigned long long *cnt, *off; // per query slot, indexed own_hi-1-i
     int64_t max_pairs, max_contacts;
     int32_t *pair_i, *pair_j;
@@ -200,6 +205,23 @@ struct Params {
     double *inv_eff_np, *inv_eff_f;
     FrameState *st;
 };
+
+// isStatic (Constraint.hs:123-125), straight from the host's inverse-mass columns
+__device__ __forceinline__ bool slot_static(const Params &P, int s) { return P.inv_lin[s] == 0.0 && P.inv_rot[s] == 0.0; }
+// (px, py, cos, sin): K0 packs it for the rank's own slots; other slots are read from the raw columns
+__device__ __forceinline__ Xf slot_xf(const Params &P, int s)
+{
+    if (s >= P.own_lo && s < P.own_hi) return P.xf[s];
+    double c, sn;
+    if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
+    else sincos(P.rot[s], &sn, &c);
+    return Xf{ P.pos_x[s], P.pos_y[s], c, sn };
+}
+__device__ __forceinline__ double2 slot_mass(const Params &P, int s)
+{
+    if (s >= P.own_lo && s < P.own_hi) return P.mass[s];
+    return make_double2(P.inv_lin[s], P.inv_rot[s]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // K0: moveShapes + toAabb
@@ -220,23 +242,34 @@ __global__ void k_reset_state(FrameState *st)
     st->n_contacts = 0;
 }
 
-// One thread per slot.  Packs the per-frame body state every later kernel gathers (xf, mass,
-// static flag) for ALL slots, and transforms + bounds the hulls of the slots in [lo, hi).
+__device__ __forceinline__ double warp_min(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// One thread per OWNED slot: packs the body state later kernels gather (xf, mass), transforms the
+// hull, stores world vertices + recomputed unit edge normals, folds the AABB and reduces the
+// finite world bounds of the rank's shapes.
 // moveShape (World.hs:132-134) -> setHullTransform (ConvexHull.hs:184-195): world vertex =
 // afmul (toTransform pos rot) local; hullToAabb (Aabb.hs:81-84) = foldl1 mergeAabb with
 // mergeRange's `if a < c then a else c` / `if b > d then b else d` (Aabb.hs:104-110).
 __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi)
 {
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
         double px = P.pos_x[s], py = P.pos_y[s];
         double c, sn;
         if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
         else sincos(P.rot[s], &sn, &c); // not bit-exact against libm (documented at the ABI)
-        double il = P.inv_lin[s], ir = P.inv_rot[s];
         P.xf[s] = Xf{ px, py, c, sn };
-        P.mass[s] = make_double2(il, ir);
-        P.is_static[s] = (il == 0.0 && ir == 0.0) ? 1 : 0; // isStatic (Constraint.hs:123-125)
-        if (s < lo || s >= hi || !P.alive[s]) continue;
+        P.mass[s] = make_double2(P.inv_lin[s], P.inv_rot[s]);
+        if (!P.alive[s]) continue;
         const int o = P.vert_offset[s];
         const int n = P.vert_offset[s + 1] - o;
         const Aff m = to_transform(px, py, c, sn);
@@ -263,48 +296,54 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             va = vb;
         }
         P.box[s] = b;
+        if (finite4(b)) {
+            mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
+            mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+        }
     }
+    // block-level reduction, then one set of atomics per block
+    __shared__ double s_red[4][8];
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
+    __syncthreads();
+    if (warp == 0) {
+        mnx = lane < 8 ? s_red[0][lane] : INFINITY; mny = lane < 8 ? s_red[1][lane] : INFINITY;
+        mxx = lane < 8 ? s_red[2][lane] : -INFINITY; mxy = lane < 8 ? s_red[3][lane] : -INFINITY;
+        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+        if (lane == 0 && mnx <= mxx) {
+            atomicMin(&P.st->bmin_x, enc_ordered(mnx));
+            atomicMin(&P.st->bmin_y, enc_ordered(mny));
+            atomicMax(&P.st->bmax_x, enc_ordered(mxx));
+            atomicMax(&P.st->bmax_y, enc_ordered(mxy));
+        }
+    }
+}
+
+// Multi-rank: publish this rank's bounds (still in ordered-uint form) for the bounds all-gather.
+__global__ void k_publish_bounds(Params P, int rank)
+{
+    const FrameState *st = P.st;
+    unsigned long long *dst = P.rank_bounds + 4 * rank;
+    dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K0b: world bounds, grid plan, cell keys
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ double warp_min(double v)
-{
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-__global__ void __launch_bounds__(256) k_bounds(Params P)
-{
-    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        if (!P.alive[s]) continue;
-        Box b = P.box[s];
-        if (!finite4(b)) continue;
-        mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
-        mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
-    }
-    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
-    if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
-        atomicMin(&P.st->bmin_x, enc_ordered(mnx));
-        atomicMin(&P.st->bmin_y, enc_ordered(mny));
-        atomicMax(&P.st->bmax_x, enc_ordered(mxx));
-        atomicMax(&P.st->bmax_y, enc_ordered(mxy));
-    }
-}
-
 // Single thread: choose origin, cell edge and grid extent.  The cell edge starts at the static
 // estimate (largest hull diameter outside the big set) and doubles until the table fits.
-__global__ void k_plan_grid(Params P)
+__global__ void k_plan_grid(Params P, int world)
 {
     FrameState *st = P.st;
+    for (int r = 0; r < world && world > 1; ++r) { // merge every rank's bounds (all-gathered)
+        const unsigned long long *b = P.rank_bounds + 4 * r;
+        if (b[0] < st->bmin_x) st->bmin_x = b[0];
+        if (b[1] < st->bmin_y) st->bmin_y = b[1];
+        if (b[2] > st->bmax_x) st->bmax_x = b[2];
+        if (b[3] > st->bmax_y) st->bmax_y = b[3];
+    }
     if (st->bmax_x == 0ull) { // no finite shape
         st->ox = st->oy = 0.0; st->h = P.cell_size; st->W = st->H = 1; st->n_cells = 1;
         return;
@@ -405,7 +444,7 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
         if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
         P.sbox[p] = P.box[s];
-        P.smeta[p] = (uint32_t)s | ((uint32_t)P.is_static[s] << 31);
+        P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
         P.keys_sorted[p] = key;
     }
 }
@@ -468,7 +507,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
     for (unsigned b = 0; b < n_big; ++b) {
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
-        if (si && P.is_static[j]) continue;
+        if (si && slot_static(P, j)) continue;
         const Box bj = P.box[j];
         if (aabb_check(bi, bj)) hit(j);
     }
@@ -510,7 +549,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
         const int i = (int)P.big_idx[b];
         if (i < P.own_lo || i >= P.own_hi) continue;
         const Box bi = P.box[i];
-        const bool si = P.is_static[i] != 0;
+        const bool si = slot_static(P, i);
         const int r = P.own_hi - 1 - i;
         const unsigned long long base = EMIT ? P.off[r] : 0ull;
         if (threadIdx.x == 0) s_run = 0;
@@ -518,7 +557,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
-            if (j >= 0 && P.alive[j] && !(si && P.is_static[j])) pred = aabb_check(bi, P.box[j]);
+            if (j >= 0 && P.alive[j] && !(si && slot_static(P, j))) pred = aabb_check(bi, P.box[j]);
             const unsigned bal = __ballot_sync(0xffffffffu, pred);
             if (lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
@@ -576,7 +615,7 @@ struct ContactKernel {
     __device__ __forceinline__ V2 slow_vertex(const HullAcc &h, int k) const
     {
         if (h.owned) { const double2 v = P.wv[h.off + k]; return V2{ v.x, v.y }; }
-        const Xf x = P.xf[h.slot];
+        const Xf x = slot_xf(P, h.slot);
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         const double2 l = __ldg(&P.local[h.off + k]);
         return afmul(m, V2{ l.x, l.y });
@@ -610,7 +649,7 @@ struct ContactKernel {
                     for (int k = 0; k < h.n; ++k) sv[h.which][k][tid] = P.wv[h.off + k];
                 }
             } else {
-                const Xf x = P.xf[h.slot];
+                const Xf x = slot_xf(P, h.slot);
                 const Aff m = to_transform(x.px, x.py, x.c, x.s);
                 for (int k = 0; k < h.n; ++k) {
                     const double2 l = __ldg(&P.local[h.off + k]);
@@ -852,9 +891,11 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const int k = m & 1;
         const int i = P.pair_i[q], j = P.pair_j[q];
         const ManRec rec = P.man[q];
+        // i is always an owned slot; j may belong to another rank (raw input columns)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
-        const double2 xj = *reinterpret_cast<const double2 *>(&P.xf[j]);
-        const double2 mi = P.mass[i], mj = P.mass[j];
+        const bool j_own = j >= P.own_lo && j < P.own_hi;
+        const double2 xj = j_own ? *reinterpret_cast<const double2 *>(&P.xf[j]) : make_double2(P.pos_x[j], P.pos_y[j]);
+        const double2 mi = P.mass[i], mj = slot_mass(P, j);
         const int flip = (int)((rec.bits >> 60) & 1u);
         const int edge = (int)(rec.bits & 0xfffffu);
         const int pen = (int)((rec.bits >> (k ? 40 : 20)) & 0xfffffu);
@@ -1145,7 +1186,6 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     for (int k = 0; k < 7; ++k) TRY_CREATE(dev_alloc(c, &c->d_in[k], N));
     TRY_CREATE(dev_alloc(c, &P.xf, N));
     TRY_CREATE(dev_alloc(c, &P.mass, N));
-    TRY_CREATE(dev_alloc(c, &P.is_static, N));
     TRY_CREATE(dev_alloc(c, &P.box, Npad));
     TRY_CREATE(dev_alloc(c, &P.wv, V));
     TRY_CREATE(dev_alloc(c, &P.wn, V));
@@ -1162,6 +1202,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     P.key_none = P.cell_cap;
     P.multi_rank = world > 1 ? 1 : 0;
     TRY_CREATE(dev_alloc(c, &P.big_idx, N));
+    TRY_CREATE(dev_alloc(c, &P.rank_bounds, (size_t)4 * world));
     TRY_CREATE(dev_alloc(c, &P.cnt, N));
     TRY_CREATE(dev_alloc(c, &P.off, N));
     TRY_CREATE(dev_alloc(c, &P.pair_i, max_pairs));
@@ -1250,18 +1291,22 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
         if (N > 0) {
             CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
-            k_transform_aabb<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
+            k_transform_aabb<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
         }
         STAGE_MARK(); // 1: allgather
         if (N > 0 && c->world > 1) {
-            // exchange #1: AABB records of every rank's slot range over NVLink (in place)
+            // exchange #1: AABB records of every rank's slot range over NVLink (in place), plus each
+            // rank's finite bounds (32 B per rank) so that nobody re-reduces all N boxes
+            k_publish_bounds<<<1, 1, 0, s>>>(P, c->rank); ++c->launches;
+            NCCL_TRY(c, nccl_api().GroupStart());
             NCCL_TRY(c, nccl_api().AllGather(reinterpret_cast<const char *>(P.box) + sizeof(Box) * c->chunk * c->rank, P.box,
                                              sizeof(Box) * c->chunk, ncclChar, c->comm, s));
+            NCCL_TRY(c, nccl_api().AllGather(P.rank_bounds + 4 * c->rank, P.rank_bounds, 4, ncclUint64, c->comm, s));
+            NCCL_TRY(c, nccl_api().GroupEnd());
         }
         STAGE_MARK(); // 2: grid keys
         if (N > 0) {
-            k_bounds<<<grid_for(N, 256, sms * 4), 256, 0, s>>>(P); ++c->launches;
-            k_plan_grid<<<1, 1, 0, s>>>(P); ++c->launches;
+            k_plan_grid<<<1, 1, 0, s>>>(P, c->world); ++c->launches;
             k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
             if (c->world > 1) { k_mark_cells<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
             k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
