@@ -80,6 +80,14 @@ typedef struct shapes_frame_out {
      * the reference recomputes it in every lagrangian2 call. Optional. */
     double  *inv_eff_np, *inv_eff_f;
 
+    /* Warm start, the cache join of applyCachedSlns (Solvers/Contact.hs:84-121) = descZipVector
+     * (Utils/Descending.hs:47-71): per contact, the ContactLagrangian (non-penetration, friction)
+     * cached for the same ObjectFeatureKey in the previous frame, else 0 (newCache); warm_hit = 1
+     * where useCache applies (the host then calls applySln for those rows).  Filled from the cache
+     * given to shapes_set_lagrangian_cache; all zeros when none was given. Optional. */
+    double  *warm_np, *warm_f;
+    uint8_t *warm_hit;
+
     /* optional debug outputs, n_slots / n_verts elements */
     double  *aabb_min_x, *aabb_max_x, *aabb_min_y, *aabb_max_y; /* toAabb (Aabb.hs:81-110) */
     double  *world_x, *world_y;            /* _hullVertices after moveShapes (World.hs:136-140) */
@@ -104,6 +112,8 @@ typedef struct shapes_device_view {
     const double  *ra_x, *ra_y, *rb_x, *rb_y, *rn_x, *rn_y;
     const double  *j_f[6];
     const double  *inv_eff_np, *inv_eff_f;
+    const double  *warm_np, *warm_f;     /* NULL unless the frame ran the cache join */
+    const uint8_t *warm_hit;
     const double  *aabb;   /* n_slots x (min_x, max_x, min_y, max_y) */
 } shapes_device_view;
 
@@ -174,6 +184,14 @@ int  shapes_frame_device(shapes_ctx *, int64_t n_slots,
 
 int  shapes_device_view_get(shapes_ctx *, shapes_device_view *view);
 
+/* Warm start.  The ctx keeps the ObjectFeatureKeys of the last
+ * completed frame on the device.  Hand it the (key, ContactLagrangian) cache the host solver left
+ * for that frame (EngineCache, Engine/Main.hs:32; row k <-> that frame's contact k; n_prev must
+ * equal that frame's n_contacts) and the NEXT frame also produces warm_np / warm_f / warm_hit.
+ * A cache is consumed by exactly one frame.  Host pointers / device pointers. */
+int  shapes_set_lagrangian_cache(shapes_ctx *, int64_t n_prev, const double *lambda_np, const double *lambda_f);
+int  shapes_set_lagrangian_cache_device(shapes_ctx *, int64_t n_prev, const double *lambda_np, const double *lambda_f);
+
 /* Copy the last frame's results from HBM into the non-NULL arrays of `out`
  * (what shapes_frame does after the kernels). */
 int  shapes_fetch(shapes_ctx *, shapes_frame_out *out);
@@ -200,7 +218,7 @@ const char *shapes_version(void);
 /* Per-stage device timing (CUDA events on the ctx stream between the stages of a frame).
  * Off by default; when on, shapes_stage_ms fills SHAPES_N_STAGES milliseconds of the last
  * frame, in the order shapes_stage_name reports. */
-#define SHAPES_N_STAGES 11
+#define SHAPES_N_STAGES 12
 int  shapes_set_profiling(shapes_ctx *, int enabled);
 int  shapes_stage_ms(const shapes_ctx *, float *out_ms /* SHAPES_N_STAGES */);
 const char *shapes_stage_name(int stage);

@@ -189,3 +189,15 @@ def frame(world, cos_rot=None, sin_rot=None, dt=0.01, baumgarte=0.01, slop=0.02,
                aabb_max_y=boxes[3], world_x=wx, world_y=wy, normal_wx=nx, normal_wy=ny,
                ext_min=emin, ext_max=emax, is_static=static)
     return res
+
+
+def warm_join(this, that, that_np, that_f):
+    """descZipVector join: `this`/`that` are dicts with key_i, key_j, feat_a, feat_b (descending)."""
+    n = int(this["key_i"].shape[0]); m = int(that["key_i"].shape[0])
+    out_np = np.zeros(n); out_f = np.zeros(n); hit = np.zeros(n, np.uint8)
+    a = [np.ascontiguousarray(this[k], np.int32) for k in ("key_i", "key_j", "feat_a", "feat_b")]
+    b = [np.ascontiguousarray(that[k], np.int32) for k in ("key_i", "key_j", "feat_a", "feat_b")]
+    tn = np.ascontiguousarray(that_np, np.float64); tf = np.ascontiguousarray(that_f, np.float64)
+    lib().orc_warm_join(C.c_int64(n), *[_p(x, _i32p) for x in a], C.c_int64(m), *[_p(x, _i32p) for x in b],
+                        _f(tn), _f(tf), _f(out_np), _f(out_f), _p(hit, _u8p))
+    return out_np, out_f, hit

@@ -733,3 +733,43 @@ void orc_solve_constraint(const double *j6, double b, const double *inv_mass6, d
         vel6[k] = vel6[k] + (pc * inv_mass6[k]); /* updateVelocity2_: v + (im vmulDiag6' pc) */
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* Warm start: descZipVector (Utils/Descending.hs:47-71)               */
+/* ------------------------------------------------------------------ */
+
+static int key_cmp(int32_t ai, int32_t aj, int32_t afa, int32_t afb,
+                   int32_t bi, int32_t bj, int32_t bfa, int32_t bfb)
+{
+    /* derived Ord on ObjectFeatureKey: (_ofkObjKeys, _ofkFeatKeys) lexicographic */
+    if (ai != bi) return ai < bi ? -1 : 1;
+    if (aj != bj) return aj < bj ? -1 : 1;
+    if (afa != bfa) return afa < bfa ? -1 : 1;
+    if (afb != bfb) return afb < bfb ? -1 : 1;
+    return 0;
+}
+
+void orc_warm_join(int64_t n_this, const int32_t *ti, const int32_t *tj, const int32_t *tfa, const int32_t *tfb,
+                   int64_t n_that, const int32_t *pi, const int32_t *pj, const int32_t *pfa, const int32_t *pfb,
+                   const double *that_np, const double *that_f,
+                   double *out_np, double *out_f, uint8_t *out_hit)
+{
+    /* foldM f (0, accum0) these: that_i only ever moves forward */
+    int64_t that_i = 0;
+    for (int64_t k = 0; k < n_this; ++k) {
+        int done = 0;
+        while (!done) {
+            if (that_i < n_that) {
+                int c = key_cmp(ti[k], tj[k], tfa[k], tfb[k], pi[that_i], pj[that_i], pfa[that_i], pfb[that_i]);
+                if (c < 0) { ++that_i; continue; }             /* thisKey < thatKey: keep looking */
+                if (c == 0) {                                  /* accumBoth = useCache */
+                    out_np[k] = that_np[that_i]; out_f[k] = that_f[that_i]; out_hit[k] = 1;
+                    ++that_i;
+                } else {                                       /* accumThis = newCache: ContactLagrangian 0 0 */
+                    out_np[k] = 0.0; out_f[k] = 0.0; out_hit[k] = 0;
+                }
+            } else { out_np[k] = 0.0; out_f[k] = 0.0; out_hit[k] = 0; }
+            done = 1;
+        }
+    }
+}

@@ -121,6 +121,17 @@ int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair
                      double dt, double baumgarte, double slop,
                      orc_contacts_out *out);
 
+/* The cache join of applyCachedSlns (shapes/src/Physics/Solvers/Contact.hs:84-121): descZipVector
+ * (shapes/src/Utils/Descending.hs:47-71) walks this frame's contacts (descending ObjectFeatureKey)
+ * against the previous frame's (key, ContactLagrangian) cache (descending): keys equal => useCache
+ * (the cached Lagrangians are propagated, hit = 1), otherwise newCache (ContactLagrangian 0 0).
+ * Keys are (i, j, featA, featB) compared lexicographically (derived Ord, Constraints/Contact.hs:36-39).
+ * The velocity update of useCache (applySln) is host-side and not restated. */
+void orc_warm_join(int64_t n_this, const int32_t *ti, const int32_t *tj, const int32_t *tfa, const int32_t *tfb,
+                   int64_t n_that, const int32_t *pi, const int32_t *pj, const int32_t *pfa, const int32_t *pfb,
+                   const double *that_np, const double *that_f,
+                   double *out_np, double *out_f, uint8_t *out_hit);
+
 /* dotV2 / mul2x2x2 as the TH templates generate them
  * (shapes-math/src/Shapes/Linear/Template.hs:108-110, MatrixTemplate.hs:47-67);
  * exported so the TemplateSpec property can be restated. */

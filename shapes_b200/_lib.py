@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SHAPES_B200_LIB") or os.path.join(_ROOT, "lib", "libs
 
 OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
 NCCL_ID_BYTES = 128
-N_STAGES = 11
+N_STAGES = 12
 
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)
@@ -34,6 +34,7 @@ class FrameOut(C.Structure):
         ("rn_x", _f64p), ("rn_y", _f64p),
         ("j_f", _f64p * 6), ("b_f", _f64p),
         ("inv_eff_np", _f64p), ("inv_eff_f", _f64p),
+        ("warm_np", _f64p), ("warm_f", _f64p), ("warm_hit", _u8p),
         ("aabb_min_x", _f64p), ("aabb_max_x", _f64p), ("aabb_min_y", _f64p), ("aabb_max_y", _f64p),
         ("world_x", _f64p), ("world_y", _f64p),
         ("n_big", C.c_int64), ("grid_w", C.c_int32), ("grid_h", C.c_int32),
@@ -55,6 +56,7 @@ class DeviceView(C.Structure):
         ("rn_x", C.c_void_p), ("rn_y", C.c_void_p),
         ("j_f", C.c_void_p * 6),
         ("inv_eff_np", C.c_void_p), ("inv_eff_f", C.c_void_p),
+        ("warm_np", C.c_void_p), ("warm_f", C.c_void_p), ("warm_hit", C.c_void_p),
         ("aabb", C.c_void_p),
     ]
 
@@ -74,6 +76,8 @@ SYMBOLS = {
     "shapes_frame_device": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
     "shapes_device_view_get": (C.c_int, [C.c_void_p, C.POINTER(DeviceView)]),
     "shapes_fetch": (C.c_int, [C.c_void_p, C.POINTER(FrameOut)]),
+    "shapes_set_lagrangian_cache": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "shapes_set_lagrangian_cache_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "shapes_rank_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "shapes_host_alloc": (C.c_void_p, [C.c_size_t]),

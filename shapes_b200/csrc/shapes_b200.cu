@@ -203,6 +203,12 @@ struct Params {
     double *normal_x, *normal_y, *center_x, *center_y, *depth;
     double *j_np[6], *b_np, *ra_x, *ra_y, *rb_x, *rb_y, *rn_x, *rn_y, *j_f[6];
     double *inv_eff_np, *inv_eff_f;
+    // warm start (descZipVector): previous frame's keys + the host solver's Lagrangian cache for them
+    const int32_t *pk_i, *pk_j, *pk_fa, *pk_fb;
+    const double *cache_np, *cache_f;
+    long long n_prev;
+    double *warm_np, *warm_f;
+    uint8_t *warm_hit;
     FrameState *st;
 };
 
@@ -947,6 +953,45 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warm start: the cache join of applyCachedSlns
+// ---------------------------------------------------------------------------------------------
+
+// descZipVector (Utils/Descending.hs:47-71) over this frame's contacts and the previous frame's
+// (ObjectFeatureKey, ContactLagrangian) cache, both descending with unique keys: a contact whose key
+// existed last frame gets the cached Lagrangians (useCache, Solvers/Contact.hs:99-112), any other
+// contact gets ContactLagrangian 0 0 (newCache, :85-97).  With unique descending keys the sequential
+// two-pointer walk equals an independent lookup per contact: a binary search on the (i, j) columns,
+// then the (at most two) rows of that pair are compared on the feature keys.
+// Rows are aligned to the output (32 consecutive rows per warp) like k_rows.
+__global__ void __launch_bounds__(256) k_warm_join(Params P)
+{
+    const FrameState *st = P.st;
+    if (st->error) return;
+    const long long n_rows = st->n_contacts < P.max_contacts ? st->n_contacts : P.max_contacts;
+    const long long n_prev = P.n_prev;
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
+         row += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = ((unsigned long long)(unsigned)P.key_i[row] << 32) | (unsigned)P.key_j[row];
+        const int fa = P.feat_a[row], fb = P.feat_b[row];
+        // first previous row whose (i, j) is <= key in the descending order, i.e. packed value <= key
+        long long lo = 0, hi = n_prev;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            const unsigned long long k = ((unsigned long long)(unsigned)__ldg(&P.pk_i[mid]) << 32) | (unsigned)__ldg(&P.pk_j[mid]);
+            if (k > key) lo = mid + 1; else hi = mid;
+        }
+        double np = 0.0, f = 0.0;
+        uint8_t hit = 0;
+        for (long long t = lo; t < n_prev; ++t) {
+            const unsigned long long k = ((unsigned long long)(unsigned)P.pk_i[t] << 32) | (unsigned)P.pk_j[t];
+            if (k != key) break;
+            if (P.pk_fa[t] == fa && P.pk_fb[t] == fb) { np = P.cache_np[t]; f = P.cache_f[t]; hit = 1; break; }
+        }
+        P.warm_np[row] = np; P.warm_f[row] = f; P.warm_hit[row] = hit;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // static geometry kernels
 // ---------------------------------------------------------------------------------------------
 
@@ -1047,7 +1092,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling; int64_t geometry;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm; int64_t geometry, n_prev;
 };
 
 struct shapes_ctx {
@@ -1065,8 +1110,8 @@ struct shapes_ctx {
     int64_t chunk = 0;          // slots per rank (all-gather granule)
     bool hulls_set = false;
     bool use_graph = true;
-    cudaGraphExec_t graph_exec = nullptr;
-    FrameKey graph_key{};
+    cudaGraphExec_t graph_exec[2] = { nullptr, nullptr }; // one per key-buffer parity
+    FrameKey graph_key[2] = {};
     int64_t graph_launches = 0;
     int64_t geometry_version = 0;
     int max_hull_verts = 0;
@@ -1089,6 +1134,13 @@ struct shapes_ctx {
     int64_t *d_counts = nullptr;   // world x 2 (pairs, contacts), all-gathered
     int64_t *h_counts = nullptr;   // pinned
     Params P{};
+    // warm start: the other half of the double-buffered key columns, and the cache
+    int32_t *alt_key[4] = { nullptr, nullptr, nullptr, nullptr };
+    double *d_cache_np = nullptr, *d_cache_f = nullptr;
+    int64_t n_prev_keys = 0;      // rows of the previous completed frame (keys live in alt_key after the swap)
+    bool cache_valid = false;     // a Lagrangian cache for those rows has been supplied
+    bool warm_done = false;       // the last frame ran the join
+    int parity = 0;
     // last frame
     int64_t last_pairs = 0, last_contacts = 0;
     bool have_frame = false;
@@ -1216,6 +1268,9 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.key_i, C)); TRY_CREATE(dev_alloc(c, &P.key_j, C));
     TRY_CREATE(dev_alloc(c, &P.feat_a, C)); TRY_CREATE(dev_alloc(c, &P.feat_b, C));
     TRY_CREATE(dev_alloc(c, &P.flip, C));
+    for (int q = 0; q < 4; ++q) TRY_CREATE(dev_alloc(c, &c->alt_key[q], C));
+    TRY_CREATE(dev_alloc(c, &c->d_cache_np, C)); TRY_CREATE(dev_alloc(c, &c->d_cache_f, C));
+    TRY_CREATE(dev_alloc(c, &P.warm_np, C)); TRY_CREATE(dev_alloc(c, &P.warm_f, C)); TRY_CREATE(dev_alloc(c, &P.warm_hit, C));
     double **cols[] = { &P.normal_x, &P.normal_y, &P.center_x, &P.center_y, &P.depth, &P.b_np,
                         &P.ra_x, &P.ra_y, &P.rb_x, &P.rb_y, &P.rn_x, &P.rn_y, &P.inv_eff_np, &P.inv_eff_f };
     for (double **col : cols) TRY_CREATE(dev_alloc(c, col, C));
@@ -1276,6 +1331,17 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.inv_lin = in[5]; P.inv_rot = in[6];
     P.dt = dt; P.baumgarte = baumgarte; P.slop = slop;
     P.cell_size = c->user_cell > 0.0 ? c->user_cell : c->auto_cell;
+    // the previous frame's key columns become the join's "that" side; this frame writes the other set
+    if (c->have_frame) {
+        std::swap(P.key_i, c->alt_key[0]); std::swap(P.key_j, c->alt_key[1]);
+        std::swap(P.feat_a, c->alt_key[2]); std::swap(P.feat_b, c->alt_key[3]);
+        c->parity ^= 1;
+        c->n_prev_keys = c->last_contacts;
+    } else { c->n_prev_keys = 0; c->cache_valid = false; }
+    const bool warm = c->cache_valid && c->n_prev_keys >= 0;
+    P.pk_i = c->alt_key[0]; P.pk_j = c->alt_key[1]; P.pk_fa = c->alt_key[2]; P.pk_fb = c->alt_key[3];
+    P.cache_np = c->d_cache_np; P.cache_f = c->d_cache_f;
+    P.n_prev = warm ? c->n_prev_keys : 0;
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
     cudaStream_t s = c->stream;
@@ -1350,6 +1416,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         }
         STAGE_MARK(); // 10: contact rows (flatten + constraint generators)
         if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 11: warm-start cache join
+        if (N > 0 && warm) { k_warm_join<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
         STAGE_MARK(); // end
     #undef STAGE_MARK
         CU_TRY(c, cudaGetLastError());
@@ -1367,26 +1435,28 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
+    key.warm = warm; key.n_prev = P.n_prev;
     const int64_t launches_before = c->launches;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
     if (!c->use_graph || c->profiling) { // per-stage events cannot be timed from inside a graph
         const int rc = issue();
         if (rc != SHAPES_OK) return rc;
     } else {
-        if (!c->graph_exec || std::memcmp(&key, &c->graph_key, sizeof(key)) != 0) {
-            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        cudaGraphExec_t &gexec = c->graph_exec[c->parity];
+        if (!gexec || std::memcmp(&key, &c->graph_key[c->parity], sizeof(key)) != 0) {
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t g = nullptr;
             CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             const int rc = issue();
             cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc != SHAPES_OK) { if (g) cudaGraphDestroy(g); return rc; }
             CU_TRY(c, ce);
-            CU_TRY(c, cudaGraphInstantiate(&c->graph_exec, g, 0));
+            CU_TRY(c, cudaGraphInstantiate(&gexec, g, 0));
             cudaGraphDestroy(g);
-            c->graph_key = key;
+            c->graph_key[c->parity] = key;
             c->graph_launches = c->launches - launches_before;
         } else c->launches += c->graph_launches;
-        CU_TRY(c, cudaGraphLaunch(c->graph_exec, s));
+        CU_TRY(c, cudaGraphLaunch(gexec, s));
     }
     CU_TRY(c, cudaEventRecord(c->ev1, s));
     CU_TRY(c, cudaStreamSynchronize(s));
@@ -1394,6 +1464,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     c->last_pairs = st.n_pairs;
     c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
     c->have_frame = (st.error == 0);
+    c->warm_done = warm && c->have_frame;
+    c->cache_valid = false; // a cache describes exactly one previous frame
     if (c->world == 1) { c->h_counts[0] = c->last_pairs; c->h_counts[1] = c->last_contacts; }
     if (out) {
         out->n_pairs = c->last_pairs;
@@ -1459,7 +1531,7 @@ void shapes_destroy(shapes_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (int q = 0; q < 2; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -1588,6 +1660,7 @@ int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
     FETCH(out->rb_x, P.rb_x, nc); FETCH(out->rb_y, P.rb_y, nc);
     FETCH(out->rn_x, P.rn_x, nc); FETCH(out->rn_y, P.rn_y, nc);
     FETCH(out->inv_eff_np, P.inv_eff_np, nc); FETCH(out->inv_eff_f, P.inv_eff_f, nc);
+    if (c->warm_done) { FETCH(out->warm_np, P.warm_np, nc); FETCH(out->warm_f, P.warm_f, nc); FETCH(out->warm_hit, P.warm_hit, nc); }
     if (out->aabb_min_x || out->aabb_max_x || out->aabb_min_y || out->aabb_max_y) {
         const int64_t N = c->n_slots;
         if (!c->d_split) { rc = dev_alloc(c, &c->d_split, 4 * (size_t)std::max<int64_t>(c->max_shapes, 1)); if (rc) return rc; }
@@ -1600,6 +1673,11 @@ int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
 #undef FETCH
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (out->b_f && nc > 0) std::memset(out->b_f, 0, sizeof(double) * (size_t)nc); // Friction.toConstraint: b = 0 (Friction.hs:26-29)
+    if (!c->warm_done && nc > 0) { // no cache was supplied: every contact is a newCache (ContactLagrangian 0 0)
+        if (out->warm_np) std::memset(out->warm_np, 0, sizeof(double) * (size_t)nc);
+        if (out->warm_f) std::memset(out->warm_f, 0, sizeof(double) * (size_t)nc);
+        if (out->warm_hit) std::memset(out->warm_hit, 0, (size_t)nc);
+    }
     return SHAPES_OK;
 }
 
@@ -1641,6 +1719,33 @@ int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const doub
     return rc;
 }
 
+static int set_cache(shapes_ctx *c, int64_t n_prev, const double *np, const double *f, cudaMemcpyKind kind)
+{
+    if (!c) return SHAPES_E_ARG;
+    if (!c->have_frame || n_prev != c->last_contacts || (n_prev > 0 && (!np || !f))) {
+        c->err = "shapes_set_lagrangian_cache: n_prev must equal the last completed frame's n_contacts";
+        return SHAPES_E_ARG;
+    }
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (n_prev > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->d_cache_np, np, sizeof(double) * (size_t)n_prev, kind, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->d_cache_f, f, sizeof(double) * (size_t)n_prev, kind, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->cache_valid = true;
+    return SHAPES_OK;
+}
+
+int shapes_set_lagrangian_cache(shapes_ctx *c, int64_t n_prev, const double *lambda_np, const double *lambda_f)
+{
+    return set_cache(c, n_prev, lambda_np, lambda_f, cudaMemcpyHostToDevice);
+}
+
+int shapes_set_lagrangian_cache_device(shapes_ctx *c, int64_t n_prev, const double *lambda_np, const double *lambda_f)
+{
+    return set_cache(c, n_prev, lambda_np, lambda_f, cudaMemcpyDeviceToDevice);
+}
+
 int shapes_device_view_get(shapes_ctx *c, shapes_device_view *v)
 {
     if (!c || !v) return SHAPES_E_ARG;
@@ -1656,6 +1761,8 @@ int shapes_device_view_get(shapes_ctx *c, shapes_device_view *v)
     v->b_np = P.b_np;
     v->ra_x = P.ra_x; v->ra_y = P.ra_y; v->rb_x = P.rb_x; v->rb_y = P.rb_y; v->rn_x = P.rn_x; v->rn_y = P.rn_y;
     v->inv_eff_np = P.inv_eff_np; v->inv_eff_f = P.inv_eff_f;
+    v->warm_np = c->warm_done ? P.warm_np : nullptr; v->warm_f = c->warm_done ? P.warm_f : nullptr;
+    v->warm_hit = c->warm_done ? P.warm_hit : nullptr;
     v->aabb = reinterpret_cast<const double *>(P.box);
     return SHAPES_OK;
 }
@@ -1703,7 +1810,7 @@ const char *shapes_stage_name(int stage)
 {
     static const char *names[SHAPES_N_STAGES] = { "transform_aabb", "allgather_aabb", "grid_keys", "cell_scan",
                                                   "scatter_sorted", "sweep_count", "scan_offsets", "sweep_emit",
-                                                  "manifolds", "scan_rows", "contact_rows" };
+                                                  "manifolds", "scan_rows", "contact_rows", "warm_join" };
     return (stage >= 0 && stage < SHAPES_N_STAGES) ? names[stage] : "";
 }
 

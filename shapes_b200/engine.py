@@ -28,6 +28,7 @@ CONTACT_I32 = ("key_i", "key_j", "feat_a", "feat_b")
 CONTACT_F64 = ("normal_x", "normal_y", "center_x", "center_y", "depth")
 CONSTRAINT_F64 = (tuple(f"j_np{q}" for q in range(6)) + ("b_np", "ra_x", "ra_y", "rb_x", "rb_y", "rn_x", "rn_y")
                   + tuple(f"j_f{q}" for q in range(6)) + ("b_f", "inv_eff_np", "inv_eff_f"))
+WARM_F64 = ("warm_np", "warm_f")
 AABB_COLS = ("aabb_min_x", "aabb_max_x", "aabb_min_y", "aabb_max_y")
 WORLD_COLS = ("world_x", "world_y")
 
@@ -88,6 +89,10 @@ class _HostBuffers:
         if "constraints" in want:
             for k in CONSTRAINT_F64:
                 self.cols[k] = alloc(max_contacts, np.float64)
+        if "warm" in want:
+            for k in WARM_F64:
+                self.cols[k] = alloc(max_contacts, np.float64)
+            self.cols["warm_hit"] = alloc(max_contacts, np.uint8)
         if "aabb" in want:
             for k in AABB_COLS:
                 self.cols[k] = alloc(n_slots, np.float64)
@@ -222,6 +227,17 @@ class Engine:
         self._check(self.lib.shapes_set_hulls(self.ctx, world.n_slots, _ptr(world.alive), _ptr(world.vert_offset),
                                               _ptr(world.local_x), _ptr(world.local_y), _ptr(emin), _ptr(emax)))
         self.world = world
+
+    def set_lagrangian_cache(self, lambda_np: np.ndarray, lambda_f: np.ndarray):
+        """The (key, ContactLagrangian) cache of the LAST frame (row k <-> that frame's contact k):
+        the next frame(want=(..., "warm")) returns the descZipVector join against it."""
+        a = np.ascontiguousarray(lambda_np, np.float64); b = np.ascontiguousarray(lambda_f, np.float64)
+        assert a.shape == b.shape
+        self._check(self.lib.shapes_set_lagrangian_cache(self.ctx, a.shape[0], _ptr(a), _ptr(b)))
+
+    def set_lagrangian_cache_device(self, n_prev: int, lambda_np_ptr: int, lambda_f_ptr: int):
+        """Same, with DEVICE addresses (a solver that keeps its cache in HBM)."""
+        self._check(self.lib.shapes_set_lagrangian_cache_device(self.ctx, int(n_prev), lambda_np_ptr, lambda_f_ptr))
 
     def set_cell_size(self, cell: float):
         self._check(self.lib.shapes_set_cell_size(self.ctx, float(cell)))

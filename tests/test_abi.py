@@ -28,7 +28,9 @@ def test_header_symbols_are_bound_and_exported(product_lib):
 def test_struct_layout_matches_header(product_lib):
     from shapes_b200 import _lib
     # pointers and int64 only before the stats block: 2 + 1 + 5 + 5 + 7 + 6 + 7 + 2 + 6 = 41 words, then stats
-    assert C.sizeof(_lib.FrameOut) == 8 * (3 + 1 + 4 + 1 + 5 + 6 + 1 + 6 + 6 + 1 + 2 + 4 + 2) + 8 + 4 + 4 + 8 + 4 + 4
+    # pairs 3, n_contacts 1, keys 4, flip 1, contact 5, j_np 6, b_np 1, radii/normal 6, j_f 6, b_f 1,
+    # inverse effective masses 2, warm start 3, aabb 4, world 2 words; then the stats block
+    assert C.sizeof(_lib.FrameOut) == 8 * (3 + 1 + 4 + 1 + 5 + 6 + 1 + 6 + 6 + 1 + 2 + 3 + 4 + 2) + 8 + 4 + 4 + 8 + 4 + 4
     assert _lib.FrameOut.n_contacts.offset == 24
     assert product_lib.shapes_version().startswith(b"shapes_b200")
 

@@ -165,3 +165,19 @@ def test_golden_regression(oracle):
         if k in ("cos", "sin"):
             continue
         assert np.array_equal(r[k], z[k], equal_nan=True), k
+
+
+def test_warm_join_desc_zip_vector_semantics(oracle):
+    """descZipVector (Utils/Descending.hs:47-71) on a hand example: descending keys on both
+    sides; equal key => cached Lagrangians (useCache), otherwise ContactLagrangian 0 0 (newCache)."""
+    this = {"key_i": np.array([9, 9, 7, 5, 5, 2]), "key_j": np.array([3, 3, 1, 4, 4, 0]),
+            "feat_a": np.array([2, 1, 0, 3, 3, 1]), "feat_b": np.array([0, 0, 2, 1, 0, 1])}
+    that = {"key_i": np.array([9, 8, 7, 5, 1]), "key_j": np.array([3, 2, 1, 4, 0]),
+            "feat_a": np.array([1, 0, 0, 3, 0]), "feat_b": np.array([0, 0, 2, 0, 0])}
+    np_, f_, hit = oracle.warm_join(this, that, np.array([1., 2, 3, 4, 5]), np.array([10., 20, 30, 40, 50]))
+    assert hit.tolist() == [0, 1, 1, 0, 1, 0]
+    assert np_.tolist() == [0, 1, 3, 0, 4, 0] and f_.tolist() == [0, 10, 30, 0, 40, 0]
+    # empty cache / empty frame
+    empty = {k: np.zeros(0, np.int32) for k in this}
+    assert oracle.warm_join(this, empty, np.zeros(0), np.zeros(0))[2].tolist() == [0] * 6
+    assert len(oracle.warm_join(empty, that, np.ones(5), np.ones(5))[2]) == 0
