@@ -770,8 +770,11 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
 
 // K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
 // count and, when it has contacts, its manifold record.  No ordering between pairs.
+#ifndef CT_MIN_BLOCKS_GENERAL
+#define CT_MIN_BLOCKS_GENERAL 4
+#endif
 template <int MAXV>
-__global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : 4) k_manifolds(Params P)
+__global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN_BLOCKS_GENERAL) k_manifolds(Params P)
 {
     __shared__ double2 s_verts[CT_THREADS / 32][2][MAXV][32];
 
@@ -963,6 +966,21 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
 // two-pointer walk equals an independent lookup per contact: a binary search on the (i, j) columns,
 // then the (at most two) rows of that pair are compared on the feature keys.
 // Rows are aligned to the output (32 consecutive rows per warp) like k_rows.
+__device__ __forceinline__ unsigned long long prev_pair_key(const Params &P, long long t)
+{
+    return ((unsigned long long)(unsigned)__ldg(&P.pk_i[t]) << 32) | (unsigned)__ldg(&P.pk_j[t]);
+}
+
+// first previous row in [lo, hi) whose packed (i, j) is <= key (rows are descending)
+__device__ __forceinline__ long long prev_lower_bound(const Params &P, unsigned long long key, long long lo, long long hi)
+{
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (prev_pair_key(P, mid) > key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256) k_warm_join(Params P)
 {
     const FrameState *st = P.st;
@@ -973,18 +991,36 @@ __global__ void __launch_bounds__(256) k_warm_join(Params P)
          row += (long long)gridDim.x * blockDim.x) {
         const unsigned long long key = ((unsigned long long)(unsigned)P.key_i[row] << 32) | (unsigned)P.key_j[row];
         const int fa = P.feat_a[row], fb = P.feat_b[row];
-        // first previous row whose (i, j) is <= key in the descending order, i.e. packed value <= key
+        // Contact sets change little from frame to frame, so the match sits near the same relative
+        // position: gallop outwards from there (O(log distance) probes) instead of bisecting all
+        // n_prev rows.  lo/hi bracket the first previous row whose (i, j) is <= key.
         long long lo = 0, hi = n_prev;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            const unsigned long long k = ((unsigned long long)(unsigned)__ldg(&P.pk_i[mid]) << 32) | (unsigned)__ldg(&P.pk_j[mid]);
-            if (k > key) lo = mid + 1; else hi = mid;
+        if (n_prev > 0) {
+            long long t = (long long)((double)row * (double)n_prev / (double)n_rows);
+            if (t >= n_prev) t = n_prev - 1;
+            if (prev_pair_key(P, t) > key) {            // answer is after t
+                long long step = 1;
+                lo = t + 1;
+                while (lo < n_prev) {
+                    const long long probe = (lo + step - 1 < n_prev) ? lo + step - 1 : n_prev - 1;
+                    if (prev_pair_key(P, probe) > key) { lo = probe + 1; step <<= 1; }
+                    else { hi = probe; break; }
+                }
+            } else {                                     // answer is at or before t
+                long long step = 1;
+                hi = t;
+                while (hi > 0) {
+                    const long long probe = (hi - step > 0) ? hi - step : 0;
+                    if (prev_pair_key(P, probe) > key) { lo = probe + 1; break; }
+                    hi = probe; step <<= 1;
+                }
+            }
         }
+        lo = prev_lower_bound(P, key, lo, hi);
         double np = 0.0, f = 0.0;
         uint8_t hit = 0;
         for (long long t = lo; t < n_prev; ++t) {
-            const unsigned long long k = ((unsigned long long)(unsigned)P.pk_i[t] << 32) | (unsigned)P.pk_j[t];
-            if (k != key) break;
+            if (prev_pair_key(P, t) != key) break;
             if (P.pk_fa[t] == fa && P.pk_fb[t] == fb) { np = P.cache_np[t]; f = P.cache_f[t]; hit = 1; break; }
         }
         P.warm_np[row] = np; P.warm_f[row] = f; P.warm_hit[row] = hit;
