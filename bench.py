@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -175,7 +175,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
-    frames = max(1, min(steps, 6))
+    frames = max(1, min(steps, 6))   # each frame of the 200k-shape sample is ~0.5 s of single-thread CPU work
     s = cpu_sample(args.workload, budget_frames=frames + min(warm, 1))
     secs = s["seconds"][min(warm, 1):]
     per = float(np.mean(secs))
@@ -203,8 +203,8 @@ def make_world_desc(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pile", choices=["pile", "polygons", "mixed", "blob", "stacks"])
     ap.add_argument("--shapes-per-gpu", type=int, default=1_000_000)
@@ -260,6 +260,14 @@ def main():
     eng = Engine(world, max_pairs=max_pairs, max_contacts=2 * max_pairs, device=local_rank, rank=rank,
                  world_size=world_size, nccl_id=nccl_id)
     dev = torch.device("cuda", local_rank)
+    exchange = "none"
+    if dist is not None:
+        exchange = "NCCL all-gather"
+        if os.environ.get("SHAPES_B200_NO_P2P") is None:
+            blobs = [None] * world_size
+            dist.all_gather_object(blobs, eng.ipc_export())
+            eng.ipc_import(blobs)
+            exchange = "peer-to-peer stores from K0 (CUDA IPC over NVLink), flag barrier"
     cols = [world.pos_x, world.pos_y, world.rot, cos_rot, sin_rot, world.inv_lin, world.inv_rot]
     d_in = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cols]
     ptrs = [t.data_ptr() for t in d_in]
@@ -416,7 +424,7 @@ def main():
                    "big_shapes": int(out.n_big),
                    "l2": "per-frame working set (~%.0f MB written + read) exceeds the 126 MB L2; no explicit flush" %
                          ((k3_bytes + n * 300.0) / 1e6),
-                   "parallelism": "1 GPU" if world_size == 1 else f"slot-range ownership over {world_size} ranks, NCCL all-gather of AABB records"},
+                   "parallelism": "1 GPU" if world_size == 1 else f"slot-range ownership over {world_size} ranks; AABB exchange: {exchange}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "gpu_launches_note": "own kernels only; CUB radix sort / scan launch ~9 more per step",
         "device_ms_per_step": dev_ms / args.steps, "stage_ms": st_ms,

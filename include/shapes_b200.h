@@ -205,6 +205,16 @@ int  shapes_fetch(shapes_ctx *, shapes_frame_out *out);
 int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
                       int64_t *all_pairs, int64_t *all_contacts);
 
+/* Peer-to-peer AABB exchange (optional, replaces the NCCL all-gather): K0 stores every AABB record
+ * straight into all ranks' arrays over NVLink (fused compute + collective), with per-frame flags as
+ * the cross-GPU barrier.  Each rank exports SHAPES_IPC_BYTES (CUDA IPC handles of its exchange
+ * buffers); the host gathers the blobs of all ranks (rank order) and hands them to every rank.
+ * Ranks live in different processes (CUDA IPC does not map a process's own handles).  Without an
+ * import the exchange goes through NCCL.  SHAPES_B200_NO_P2P=1 forces the NCCL path. */
+#define SHAPES_IPC_BYTES 512
+int  shapes_ipc_export(shapes_ctx *, void *out_blob /* SHAPES_IPC_BYTES */);
+int  shapes_ipc_import(shapes_ctx *, const void *all_blobs /* world_size x SHAPES_IPC_BYTES */);
+
 /* ---- helpers ----------------------------------------------------------- */
 
 void *shapes_host_alloc(size_t bytes);     /* pinned host memory, NULL on failure */

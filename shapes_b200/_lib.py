@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("SHAPES_B200_LIB") or os.path.join(_ROOT, "lib", "libs
 
 OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
 NCCL_ID_BYTES = 128
+IPC_BYTES = 512
 N_STAGES = 12
 
 _i32p = C.POINTER(C.c_int32)
@@ -78,6 +79,8 @@ SYMBOLS = {
     "shapes_fetch": (C.c_int, [C.c_void_p, C.POINTER(FrameOut)]),
     "shapes_set_lagrangian_cache": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "shapes_set_lagrangian_cache_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "shapes_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "shapes_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "shapes_rank_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "shapes_host_alloc": (C.c_void_p, [C.c_size_t]),

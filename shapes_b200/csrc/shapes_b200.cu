@@ -26,6 +26,7 @@
 
 #include "shapes_b200.h"
 
+
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <nccl.h>   // types only: NCCL is bound at run time (see NcclApi), never at link time
@@ -129,7 +130,9 @@ __device__ __forceinline__ double dec_ordered(unsigned long long u)
     return __longlong_as_double((long long)u);
 }
 
+constexpr int SHAPES_MAX_RANKS = 16;
 constexpr int ERR_PAIR_CAP = 1;
+constexpr int ERR_PEER_TIMEOUT = 4;
 constexpr int ERR_CONTACT_CAP = 2;
 constexpr int MAX_STAGED_VERTS = 8; // hulls up to this many vertices are staged in shared memory
 
@@ -191,6 +194,14 @@ struct Params {
     double cell_size;
     uint32_t *big_idx;
     unsigned long long *rank_bounds; // world x 4 ordered-uint bounds (multi-rank)
+    // peer-to-peer exchange (multi-rank, CUDA IPC): every rank's buffers, indexed by rank (own included)
+    Box *peer_box[SHAPES_MAX_RANKS];
+    unsigned long long *peer_bounds[SHAPES_MAX_RANKS];
+    unsigned long long *peer_flags[SHAPES_MAX_RANKS];
+    unsigned long long *flags;  // this rank's flag words, written by the peers (one per rank)
+    int n_peers;                // 0 = exchange through NCCL
+    int my_rank;
+    unsigned long long frame_no;
     unsigned long long *cnt, *off; // per query slot, indexed own_hi-1-i
     int64_t max_pairs, max_contacts;
     int32_t *pair_i, *pair_j;
@@ -301,7 +312,10 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             P.wn[o + k] = make_double2(nn.x, nn.y);
             va = vb;
         }
-        P.box[s] = b;
+        // fused compute + collective: with peer pointers mapped, the record goes straight into
+        // every rank's box array over NVLink while the rest of the grid is still transforming
+        if (P.n_peers > 0) { for (int r = 0; r < P.n_peers; ++r) P.peer_box[r][s] = b; }
+        else P.box[s] = b;
         if (finite4(b)) {
             mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
             mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
@@ -324,6 +338,35 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             atomicMax(&P.st->bmax_y, enc_ordered(mxy));
         }
     }
+}
+
+// Peer exchange, step 2 (after K0 has finished on this rank): write this rank's bounds into every
+// peer's table and raise this frame's flag there.  K0's peer stores were issued by an earlier
+// kernel of the same stream; the system-scope fence orders them before the flag.
+__global__ void k_publish_peers(Params P)
+{
+    const FrameState *st = P.st;
+    const int r = threadIdx.x;
+    if (r >= P.n_peers) return;
+    unsigned long long *dst = P.peer_bounds[r] + 4 * P.my_rank;
+    dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(P.peer_flags[r] + P.my_rank) = P.frame_no;
+}
+
+// Peer exchange, step 3: wait until every rank has raised this frame's flag here (their records
+// and bounds are then visible).  Bounded spin: a missing peer turns into an error, not a hang.
+__global__ void k_wait_peers(Params P)
+{
+    const int r = threadIdx.x;
+    if (r >= P.n_peers) return;
+    const volatile unsigned long long *flag = P.flags + r;
+    const long long t0 = clock64();
+    while (*flag < P.frame_no) {
+        if (clock64() - t0 > 8000000000ll) { atomicOr(&P.st->error, ERR_PEER_TIMEOUT); break; } // ~4 s
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // Multi-rank: publish this rank's bounds (still in ordered-uint form) for the bounds all-gather.
@@ -1128,7 +1171,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm; int64_t geometry, n_prev;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p; int64_t geometry, n_prev;
 };
 
 struct shapes_ctx {
@@ -1170,6 +1213,18 @@ struct shapes_ctx {
     int64_t *d_counts = nullptr;   // world x 2 (pairs, contacts), all-gathered
     int64_t *h_counts = nullptr;   // pinned
     Params P{};
+    // peer-to-peer exchange: boxes are double buffered by frame parity so that a rank running one
+    // frame ahead never overwrites records a slower rank is still reading
+    Box *d_box2[2] = { nullptr, nullptr };
+    unsigned long long *d_bounds2[2] = { nullptr, nullptr };
+    unsigned long long *d_flags = nullptr;
+    bool peers_ready = false;
+    bool use_p2p = true;
+    Box *peer_box2[2][SHAPES_MAX_RANKS] = {};
+    unsigned long long *peer_bounds2[2][SHAPES_MAX_RANKS] = {};
+    unsigned long long *peer_flags[SHAPES_MAX_RANKS] = {};
+    std::vector<void *> ipc_opened;
+    unsigned long long frame_no = 0;
     // warm start: the other half of the double-buffered key columns, and the cache
     int32_t *alt_key[4] = { nullptr, nullptr, nullptr, nullptr };
     double *d_cache_np = nullptr, *d_cache_f = nullptr;
@@ -1227,7 +1282,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
 {
     if (!out || max_shapes < 0 || max_verts < 0 || max_pairs < 0 || max_contacts < 0 ||
         max_shapes > 0x7ffffff0ll || max_verts > 0x7ffffff0ll || max_pairs > 0x7ffffff0ll ||
-        max_contacts > 0xfffffff0ll || world < 1 || rank < 0 || rank >= world ||
+        max_contacts > 0xfffffff0ll || world < 1 || world > SHAPES_MAX_RANKS || rank < 0 || rank >= world ||
         (world > 1 && !nccl_id)) {
         g_create_error = "shapes_create: bad argument";
         return SHAPES_E_ARG;
@@ -1274,7 +1329,9 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     for (int k = 0; k < 7; ++k) TRY_CREATE(dev_alloc(c, &c->d_in[k], N));
     TRY_CREATE(dev_alloc(c, &P.xf, N));
     TRY_CREATE(dev_alloc(c, &P.mass, N));
-    TRY_CREATE(dev_alloc(c, &P.box, Npad));
+    TRY_CREATE(dev_alloc(c, &c->d_box2[0], Npad));
+    TRY_CREATE(dev_alloc(c, &c->d_box2[1], world > 1 ? Npad : 1));
+    P.box = c->d_box2[0];
     TRY_CREATE(dev_alloc(c, &P.wv, V));
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
@@ -1290,7 +1347,13 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     P.key_none = P.cell_cap;
     P.multi_rank = world > 1 ? 1 : 0;
     TRY_CREATE(dev_alloc(c, &P.big_idx, N));
-    TRY_CREATE(dev_alloc(c, &P.rank_bounds, (size_t)4 * world));
+    TRY_CREATE(dev_alloc(c, &c->d_bounds2[0], (size_t)4 * world));
+    TRY_CREATE(dev_alloc(c, &c->d_bounds2[1], (size_t)4 * world));
+    TRY_CREATE(dev_alloc(c, &c->d_flags, (size_t)SHAPES_MAX_RANKS));
+    TRY_CREATE(cu(cudaMemset(c->d_flags, 0, sizeof(unsigned long long) * SHAPES_MAX_RANKS), "cudaMemset"));
+    P.rank_bounds = c->d_bounds2[0];
+    P.flags = c->d_flags; P.n_peers = 0; P.my_rank = rank;
+    c->use_p2p = std::getenv("SHAPES_B200_NO_P2P") == nullptr;
     TRY_CREATE(dev_alloc(c, &P.cnt, N));
     TRY_CREATE(dev_alloc(c, &P.off, N));
     TRY_CREATE(dev_alloc(c, &P.pair_i, max_pairs));
@@ -1378,6 +1441,15 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.pk_i = c->alt_key[0]; P.pk_j = c->alt_key[1]; P.pk_fa = c->alt_key[2]; P.pk_fb = c->alt_key[3];
     P.cache_np = c->d_cache_np; P.cache_f = c->d_cache_f;
     P.n_prev = warm ? c->n_prev_keys : 0;
+    ++c->frame_no;
+    P.frame_no = c->frame_no;
+    const int fpar = (int)(c->frame_no & 1);
+    const bool p2p = c->world > 1 && c->peers_ready && c->use_p2p;
+    if (c->world > 1) { P.box = c->d_box2[fpar]; P.rank_bounds = c->d_bounds2[fpar]; }
+    P.n_peers = p2p ? c->world : 0;
+    for (int r = 0; r < c->world && p2p; ++r) {
+        P.peer_box[r] = c->peer_box2[fpar][r]; P.peer_bounds[r] = c->peer_bounds2[fpar][r]; P.peer_flags[r] = c->peer_flags[r];
+    }
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
     cudaStream_t s = c->stream;
@@ -1396,8 +1468,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             k_transform_aabb<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
         }
         STAGE_MARK(); // 1: allgather
-        if (N > 0 && c->world > 1) {
-            // exchange #1: AABB records of every rank's slot range over NVLink (in place), plus each
+        if (N > 0 && c->world > 1 && p2p) {
+            // exchange #1, peer-to-peer: K0 already stored this rank's records into every rank's
+            // array; publish bounds + flag, then wait for everybody else's flag
+            k_publish_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P); ++c->launches;
+            k_wait_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P); ++c->launches;
+        } else if (N > 0 && c->world > 1) {
+            // exchange #1 through NCCL: AABB records of every rank's slot range (in place), plus each
             // rank's finite bounds (32 B per rank) so that nobody re-reduces all N boxes
             k_publish_bounds<<<1, 1, 0, s>>>(P, c->rank); ++c->launches;
             NCCL_TRY(c, nccl_api().GroupStart());
@@ -1471,10 +1548,11 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
-    key.warm = warm; key.n_prev = P.n_prev;
+    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p;
     const int64_t launches_before = c->launches;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
-    if (!c->use_graph || c->profiling) { // per-stage events cannot be timed from inside a graph
+    // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
+    if (!c->use_graph || c->profiling || c->world > 1) { // per-stage events cannot be timed from inside a graph
         const int rc = issue();
         if (rc != SHAPES_OK) return rc;
     } else {
@@ -1515,6 +1593,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     }
     if (c->profiling)
         for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
+    if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its AABB records"; c->have_frame = false; return SHAPES_E_NCCL; }
     if (st.error) {
         c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs)"
                                            : "capacity: max_contacts too small (required count in n_contacts)";
@@ -1568,6 +1647,7 @@ void shapes_destroy(shapes_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int q = 0; q < 2; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -1800,6 +1880,49 @@ int shapes_device_view_get(shapes_ctx *c, shapes_device_view *v)
     v->warm_np = c->warm_done ? P.warm_np : nullptr; v->warm_f = c->warm_done ? P.warm_f : nullptr;
     v->warm_hit = c->warm_done ? P.warm_hit : nullptr;
     v->aabb = reinterpret_cast<const double *>(P.box);
+    return SHAPES_OK;
+}
+
+int shapes_ipc_export(shapes_ctx *c, void *out)
+{
+    if (!c || !out) return SHAPES_E_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h[5];
+    CU_TRY(c, cudaIpcGetMemHandle(&h[0], c->d_box2[0]));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[1], c->d_box2[1]));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[2], c->d_bounds2[0]));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[3], c->d_bounds2[1]));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[4], c->d_flags));
+    static_assert(sizeof(h) <= SHAPES_IPC_BYTES, "ipc blob size");
+    std::memset(out, 0, SHAPES_IPC_BYTES);
+    std::memcpy(out, h, sizeof(h));
+    return SHAPES_OK;
+}
+
+int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
+{
+    if (!c || !all_blobs || c->world < 2) return SHAPES_E_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) {
+            c->peer_box2[0][r] = c->d_box2[0]; c->peer_box2[1][r] = c->d_box2[1];
+            c->peer_bounds2[0][r] = c->d_bounds2[0]; c->peer_bounds2[1][r] = c->d_bounds2[1];
+            c->peer_flags[r] = c->d_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h[5];
+        std::memcpy(h, static_cast<const char *>(all_blobs) + (size_t)r * SHAPES_IPC_BYTES, sizeof(h));
+        void *p[5];
+        for (int q = 0; q < 5; ++q) {
+            CU_TRY(c, cudaIpcOpenMemHandle(&p[q], h[q], cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p[q]);
+        }
+        c->peer_box2[0][r] = static_cast<Box *>(p[0]); c->peer_box2[1][r] = static_cast<Box *>(p[1]);
+        c->peer_bounds2[0][r] = static_cast<unsigned long long *>(p[2]);
+        c->peer_bounds2[1][r] = static_cast<unsigned long long *>(p[3]);
+        c->peer_flags[r] = static_cast<unsigned long long *>(p[4]);
+    }
+    c->peers_ready = true;
     return SHAPES_OK;
 }
 

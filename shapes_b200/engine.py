@@ -296,6 +296,18 @@ class Engine:
         self._check(self.lib.shapes_device_view_get(self.ctx, C.byref(v)))
         return v
 
+    def ipc_export(self) -> bytes:
+        """CUDA IPC handles of this rank's exchange buffers (shapes_ipc_export)."""
+        buf = C.create_string_buffer(_lib.IPC_BYTES)
+        self._check(self.lib.shapes_ipc_export(self.ctx, buf))
+        return buf.raw
+
+    def ipc_import(self, blobs: list[bytes]):
+        """Blobs of ALL ranks in rank order: switches the AABB exchange to peer-to-peer stores."""
+        assert len(blobs) == self.world_size
+        buf = C.create_string_buffer(b"".join(blobs), _lib.IPC_BYTES * self.world_size)
+        self._check(self.lib.shapes_ipc_import(self.ctx, buf))
+
     def rank_info(self):
         lo, hi = C.c_int64(), C.c_int64()
         pairs = (C.c_int64 * self.world_size)()

@@ -16,25 +16,39 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world_size, nccl_id, q, kind):
+def _worker(rank, world_size, nccl_id, q, kind, p2p, port):
     import torch
+    import torch.distributed as dist
     torch.cuda.set_device(rank)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
     from oracle import binding as orc
     from shapes_b200 import scenes
     from shapes_b200.engine import Engine
     w = scenes.box_pile(150, 120) if kind == "pile" else scenes.random_polygons(40_000, density=1.5, config=71)
     c, s = orc.cos_sin(w.rot)
     with Engine(w, device=rank, rank=rank, world_size=world_size, nccl_id=nccl_id) as eng:
+        if p2p:   # AABB records stored straight into the peers' arrays instead of the NCCL all-gather
+            blobs = [None] * world_size
+            dist.all_gather_object(blobs, eng.ipc_export())
+            eng.ipc_import(blobs)
         fr = eng.frame(cos_sin=(c, s))
         fr2 = eng.frame(cos_sin=(c, s))
         assert fr.n_pairs == fr2.n_pairs and fr.n_contacts == fr2.n_contacts
         lo, hi, pairs, contacts = eng.rank_info()
         assert pairs[rank] == fr.n_pairs and contacts[rank] == fr.n_contacts
-        q.put((rank, {k: np.array(v) for k, v in fr.cols.items()}, (lo, hi), pairs, contacts))
+        for _ in range(3):   # frames alternate exchange buffers: results must not change
+            fr3 = eng.frame(cos_sin=(c, s))
+            assert fr3.n_pairs == fr.n_pairs and fr3.n_contacts == fr.n_contacts
+        q.put((rank, {k: np.array(v) for k, v in fr3.cols.items()}, (lo, hi), pairs, contacts))
+        dist.barrier()
+    dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("kind", ["pile", "polygons"])
-def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind):
+def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind, p2p):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -46,7 +60,8 @@ def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind):
     nccl_id = nccl_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world_size, nccl_id, q, kind)) for r in range(world_size)]
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world_size, nccl_id, q, kind, p2p, port)) for r in range(world_size)]
     for p in procs:
         p.start()
     got = {}
