@@ -9,7 +9,7 @@
 // Pipeline (one stream, no host round trip between kernels):
 //   K0  k_transform_aabb  moveShapes + toAabb per slot                 (World.hs:132-140, Aabb.hs:81-110)
 //   [N>1: ncclAllGather of the AABB records over NVLink]
-//   K0b k_plan_grid / k_cell_keys   uniform-grid cell key of each AABB's min corner + cell histogram
+//   K0b k_plan_grid / k_keys / k_bin   uniform-grid cell key of each AABB's min corner + cell histogram
 //   K1  counting sort on the cell table: exclusive scan of the histogram + k_scatter_sorted
 //   K2  k_sweep<count> -> exclusive scan over slots in DESCENDING key order -> k_sweep<emit>
 //       (+ k_big<count/emit> for shapes spanning more than 2 cells or with non-finite bounds)
@@ -196,6 +196,9 @@ struct Params {
     unsigned long long *rank_bounds; // world x 4 ordered-uint bounds (multi-rank)
     // peer-to-peer exchange (multi-rank, CUDA IPC): every rank's buffers, indexed by rank (own included)
     Box *peer_box[SHAPES_MAX_RANKS];
+    uint32_t *peer_keys[SHAPES_MAX_RANKS];
+    uint32_t *gkeys;            // cell key of EVERY slot (own: computed here; others: pushed by their owner)
+    int chunk;                  // slots per rank
     unsigned long long *peer_bounds[SHAPES_MAX_RANKS];
     unsigned long long *peer_flags[SHAPES_MAX_RANKS];
     unsigned long long *flags;  // this rank's flag words, written by the peers (one per rank)
@@ -238,6 +241,14 @@ __device__ __forceinline__ double2 slot_mass(const Params &P, int s)
 {
     if (s >= P.own_lo && s < P.own_hi) return P.mass[s];
     return make_double2(P.inv_lin[s], P.inv_rot[s]);
+}
+
+// AABB record of any slot: with the peer exchange a rank's box array holds only its own slots and
+// the records of other ranks are PULLED through the peer pointers (NVLink loads) where needed.
+__device__ __forceinline__ Box box_of(const Params &P, int s)
+{
+    if (P.n_peers > 0) return P.peer_box[s / P.chunk][s];
+    return P.box[s];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,10 +323,7 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             P.wn[o + k] = make_double2(nn.x, nn.y);
             va = vb;
         }
-        // fused compute + collective: with peer pointers mapped, the record goes straight into
-        // every rank's box array over NVLink while the rest of the grid is still transforming
-        if (P.n_peers > 0) { for (int r = 0; r < P.n_peers; ++r) P.peer_box[r][s] = b; }
-        else P.box[s] = b;
+        P.box[s] = b;
         if (finite4(b)) {
             mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
             mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
@@ -340,27 +348,29 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
     }
 }
 
-// Peer exchange, step 2 (after K0 has finished on this rank): write this rank's bounds into every
-// peer's table and raise this frame's flag there.  K0's peer stores were issued by an earlier
-// kernel of the same stream; the system-scope fence orders them before the flag.
-__global__ void k_publish_peers(Params P)
+// Peer exchange barrier, arrive side (phase 0: after K0, also carries this rank's bounds; phase 1:
+// after the cell keys were pushed): raise this frame's flag in every peer.  The peer stores of
+// earlier kernels of this stream are ordered before the flag by the system-scope fence.
+__global__ void k_publish_peers(Params P, int phase)
 {
     const FrameState *st = P.st;
     const int r = threadIdx.x;
     if (r >= P.n_peers) return;
-    unsigned long long *dst = P.peer_bounds[r] + 4 * P.my_rank;
-    dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+    if (phase == 0) {
+        unsigned long long *dst = P.peer_bounds[r] + 4 * P.my_rank;
+        dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+    }
     __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long *>(P.peer_flags[r] + P.my_rank) = P.frame_no;
+    *reinterpret_cast<volatile unsigned long long *>(P.peer_flags[r] + phase * SHAPES_MAX_RANKS + P.my_rank) = P.frame_no;
 }
 
 // Peer exchange, step 3: wait until every rank has raised this frame's flag here (their records
 // and bounds are then visible).  Bounded spin: a missing peer turns into an error, not a hang.
-__global__ void k_wait_peers(Params P)
+__global__ void k_wait_peers(Params P, int phase)
 {
     const int r = threadIdx.x;
     if (r >= P.n_peers) return;
-    const volatile unsigned long long *flag = P.flags + r;
+    const volatile unsigned long long *flag = P.flags + phase * SHAPES_MAX_RANKS + r;
     const long long t0 = clock64();
     while (*flag < P.frame_no) {
         if (clock64() - t0 > 8000000000ll) { atomicOr(&P.st->error, ERR_PEER_TIMEOUT); break; } // ~4 s
@@ -439,46 +449,47 @@ __global__ void __launch_bounds__(256) k_clear_cells(Params P)
     }
 }
 
-// Multi-rank only: mark the cells an owned shape's partners can live in.  Shapes of other ranks
-// outside these cells can never pair with an owned query and are left out of this rank's grid.
-__global__ void __launch_bounds__(256) k_mark_cells(Params P)
+// K1a: cell key of the slots in [lo, hi) from their AABB records; with the peer exchange the 4 B key
+// is the only thing PUSHED to the other ranks (key_none = not in any grid, key_none + 1 = big shape).
+// Multi-rank: owned small shapes also mark the cells their partners can live in.
+__global__ void __launch_bounds__(256) k_keys(Params P, int lo, int hi)
 {
     const FrameState *st = P.st;
     const int W = st->W, H = st->H;
-    for (int s = P.own_lo + blockIdx.x * blockDim.x + threadIdx.x; s < P.own_hi; s += gridDim.x * blockDim.x) {
-        if (!P.alive[s]) continue;
-        int cx, cy;
-        if (!small_cell(P.box[s], st, cx, cy)) continue;
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int nx = cx + dx, ny = cy + dy;
-                if (nx >= 0 && nx < W && ny >= 0 && ny < H) P.cell_mark[(size_t)ny * W + nx] = 1;
-            }
-    }
-}
-
-// K1a: key of every live shape + histogram of the cells (the shape's arrival rank in its cell is
-// the counting sort's scatter slot).  Shapes spanning more than 2 cells per axis or with
-// non-finite bounds go to the big list and are tested against everything.
-__global__ void __launch_bounds__(256) k_cell_keys(Params P)
-{
-    const FrameState *st = P.st;
-    const int W = st->W;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+    for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
         uint32_t key = P.key_none;
         if (P.alive[s]) {
             int cx, cy;
             if (small_cell(P.box[s], st, cx, cy)) {
-                const uint32_t k = (uint32_t)cy * (uint32_t)W + (uint32_t)cx;
-                const bool own = s >= P.own_lo && s < P.own_hi;
-                if (!P.multi_rank || own || P.cell_mark[k]) {
-                    key = k;
-                    P.rank[s] = atomicAdd(&P.cell_count[k], 1u);
-                }
-            } else {
-                const unsigned pos = atomicAdd(&P.st->n_big, 1u);
-                P.big_idx[pos] = (uint32_t)s;
-            }
+                key = (uint32_t)cy * (uint32_t)W + (uint32_t)cx;
+                if (P.multi_rank && s >= P.own_lo && s < P.own_hi)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int nx = cx + dx, ny = cy + dy;
+                            if (nx >= 0 && nx < W && ny >= 0 && ny < H) P.cell_mark[(size_t)ny * W + nx] = 1;
+                        }
+            } else key = P.key_none + 1u;
+        }
+        if (P.n_peers > 0) { for (int r = 0; r < P.n_peers; ++r) P.peer_keys[r][s] = key; }
+        else P.gkeys[s] = key;
+    }
+}
+
+// K1a': histogram of the cell table over ALL slots' keys (the shape's arrival rank in its cell is
+// the counting sort's scatter slot); big shapes go to the big list and are tested against
+// everything; multi-rank: shapes of other ranks outside the marked cells are left out.
+__global__ void __launch_bounds__(256) k_bin(Params P)
+{
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        uint32_t key = P.gkeys[s];
+        if (key == P.key_none + 1u) {
+            const unsigned pos = atomicAdd(&P.st->n_big, 1u);
+            P.big_idx[pos] = (uint32_t)s;
+            key = P.key_none;
+        } else if (key < P.key_none) {
+            const bool own = s >= P.own_lo && s < P.own_hi;
+            if (!P.multi_rank || own || P.cell_mark[key]) P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
+            else key = P.key_none;
         }
         P.keys[s] = key;
     }
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
         const uint32_t key = P.keys[s];
         if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
-        P.sbox[p] = P.box[s];
+        P.sbox[p] = box_of(P, s);
         P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
         P.keys_sorted[p] = key;
     }
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
         if (si && slot_static(P, j)) continue;
-        const Box bj = P.box[j];
+        const Box bj = box_of(P, j);
         if (aabb_check(bi, bj)) hit(j);
     }
 
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
-            if (j >= 0 && P.alive[j] && !(si && slot_static(P, j))) pred = aabb_check(bi, P.box[j]);
+            if (j >= 0 && P.alive[j] && !(si && slot_static(P, j))) pred = aabb_check(bi, box_of(P, j));
             const unsigned bal = __ballot_sync(0xffffffffu, pred);
             if (lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
@@ -1216,6 +1227,8 @@ struct shapes_ctx {
     // peer-to-peer exchange: boxes are double buffered by frame parity so that a rank running one
     // frame ahead never overwrites records a slower rank is still reading
     Box *d_box2[2] = { nullptr, nullptr };
+    uint32_t *d_gkeys2[2] = { nullptr, nullptr };
+    uint32_t *peer_keys2[2][SHAPES_MAX_RANKS] = {};
     unsigned long long *d_bounds2[2] = { nullptr, nullptr };
     unsigned long long *d_flags = nullptr;
     bool peers_ready = false;
@@ -1332,6 +1345,10 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &c->d_box2[0], Npad));
     TRY_CREATE(dev_alloc(c, &c->d_box2[1], world > 1 ? Npad : 1));
     P.box = c->d_box2[0];
+    TRY_CREATE(dev_alloc(c, &c->d_gkeys2[0], Npad));
+    TRY_CREATE(dev_alloc(c, &c->d_gkeys2[1], world > 1 ? Npad : 1));
+    P.gkeys = c->d_gkeys2[0];
+    P.chunk = (int)std::max<int64_t>(c->chunk, 1);
     TRY_CREATE(dev_alloc(c, &P.wv, V));
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
@@ -1349,8 +1366,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.big_idx, N));
     TRY_CREATE(dev_alloc(c, &c->d_bounds2[0], (size_t)4 * world));
     TRY_CREATE(dev_alloc(c, &c->d_bounds2[1], (size_t)4 * world));
-    TRY_CREATE(dev_alloc(c, &c->d_flags, (size_t)SHAPES_MAX_RANKS));
-    TRY_CREATE(cu(cudaMemset(c->d_flags, 0, sizeof(unsigned long long) * SHAPES_MAX_RANKS), "cudaMemset"));
+    TRY_CREATE(dev_alloc(c, &c->d_flags, (size_t)2 * SHAPES_MAX_RANKS));
+    TRY_CREATE(cu(cudaMemset(c->d_flags, 0, sizeof(unsigned long long) * 2 * SHAPES_MAX_RANKS), "cudaMemset"));
     P.rank_bounds = c->d_bounds2[0];
     P.flags = c->d_flags; P.n_peers = 0; P.my_rank = rank;
     c->use_p2p = std::getenv("SHAPES_B200_NO_P2P") == nullptr;
@@ -1445,10 +1462,11 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.frame_no = c->frame_no;
     const int fpar = (int)(c->frame_no & 1);
     const bool p2p = c->world > 1 && c->peers_ready && c->use_p2p;
-    if (c->world > 1) { P.box = c->d_box2[fpar]; P.rank_bounds = c->d_bounds2[fpar]; }
+    if (c->world > 1) { P.box = c->d_box2[fpar]; P.rank_bounds = c->d_bounds2[fpar]; P.gkeys = c->d_gkeys2[fpar]; }
     P.n_peers = p2p ? c->world : 0;
     for (int r = 0; r < c->world && p2p; ++r) {
         P.peer_box[r] = c->peer_box2[fpar][r]; P.peer_bounds[r] = c->peer_bounds2[fpar][r]; P.peer_flags[r] = c->peer_flags[r];
+        P.peer_keys[r] = c->peer_keys2[fpar][r];
     }
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
@@ -1469,10 +1487,9 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         }
         STAGE_MARK(); // 1: allgather
         if (N > 0 && c->world > 1 && p2p) {
-            // exchange #1, peer-to-peer: K0 already stored this rank's records into every rank's
-            // array; publish bounds + flag, then wait for everybody else's flag
-            k_publish_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P); ++c->launches;
-            k_wait_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P); ++c->launches;
+            // exchange #1, peer-to-peer, barrier A: every rank's own AABB records and bounds are in place
+            k_publish_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P, 0); ++c->launches;
+            k_wait_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P, 0); ++c->launches;
         } else if (N > 0 && c->world > 1) {
             // exchange #1 through NCCL: AABB records of every rank's slot range (in place), plus each
             // rank's finite bounds (32 B per rank) so that nobody re-reduces all N boxes
@@ -1487,8 +1504,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         if (N > 0) {
             k_plan_grid<<<1, 1, 0, s>>>(P, c->world); ++c->launches;
             k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
-            if (c->world > 1) { k_mark_cells<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
-            k_cell_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+            if (p2p) {
+                // keys of the OWN slots, pushed (4 B each) to every rank; barrier B; then every rank bins all keys
+                k_keys<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
+                k_publish_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P, 1); ++c->launches;
+                k_wait_peers<<<1, SHAPES_MAX_RANKS, 0, s>>>(P, 1); ++c->launches;
+            } else { k_keys<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, 0, N); ++c->launches; }
+            k_bin<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 3: cell offsets (exclusive scan of the histogram)
         if (N > 0) {
@@ -1887,12 +1909,14 @@ int shapes_ipc_export(shapes_ctx *c, void *out)
 {
     if (!c || !out) return SHAPES_E_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h[5];
+    cudaIpcMemHandle_t h[7];
     CU_TRY(c, cudaIpcGetMemHandle(&h[0], c->d_box2[0]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[1], c->d_box2[1]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[2], c->d_bounds2[0]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[3], c->d_bounds2[1]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[4], c->d_flags));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[5], c->d_gkeys2[0]));
+    CU_TRY(c, cudaIpcGetMemHandle(&h[6], c->d_gkeys2[1]));
     static_assert(sizeof(h) <= SHAPES_IPC_BYTES, "ipc blob size");
     std::memset(out, 0, SHAPES_IPC_BYTES);
     std::memcpy(out, h, sizeof(h));
@@ -1908,12 +1932,13 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
             c->peer_box2[0][r] = c->d_box2[0]; c->peer_box2[1][r] = c->d_box2[1];
             c->peer_bounds2[0][r] = c->d_bounds2[0]; c->peer_bounds2[1][r] = c->d_bounds2[1];
             c->peer_flags[r] = c->d_flags;
+            c->peer_keys2[0][r] = c->d_gkeys2[0]; c->peer_keys2[1][r] = c->d_gkeys2[1];
             continue;
         }
-        cudaIpcMemHandle_t h[5];
+        cudaIpcMemHandle_t h[7];
         std::memcpy(h, static_cast<const char *>(all_blobs) + (size_t)r * SHAPES_IPC_BYTES, sizeof(h));
-        void *p[5];
-        for (int q = 0; q < 5; ++q) {
+        void *p[7];
+        for (int q = 0; q < 7; ++q) {
             CU_TRY(c, cudaIpcOpenMemHandle(&p[q], h[q], cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(p[q]);
         }
@@ -1921,6 +1946,7 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
         c->peer_bounds2[0][r] = static_cast<unsigned long long *>(p[2]);
         c->peer_bounds2[1][r] = static_cast<unsigned long long *>(p[3]);
         c->peer_flags[r] = static_cast<unsigned long long *>(p[4]);
+        c->peer_keys2[0][r] = static_cast<uint32_t *>(p[5]); c->peer_keys2[1][r] = static_cast<uint32_t *>(p[6]);
     }
     c->peers_ready = true;
     return SHAPES_OK;
