@@ -190,6 +190,7 @@ struct Params {
     uint8_t *cell_mark;         // multi-rank: cells inside the 3x3 neighbourhood of an owned shape
     int multi_rank;
     unsigned cell_cap;
+    unsigned cell_limit;        // cells the planner may use this frame (<= cell_cap); what the scan covers
     uint32_t key_none;          // sort key of slots outside the grid (dead / big): first value past the cell table
     double cell_size;
     uint32_t *big_idx;
@@ -416,7 +417,7 @@ __global__ void k_plan_grid(Params P, int world)
         wx = floor(ex / h) + 1.0;
         wy = floor(ey / h) + 1.0;
         if (isfinite(wx) && isfinite(wy) && wx < 1073741824.0 && wy < 1073741824.0 &&
-            wx * wy <= (double)P.cell_cap) { ok = true; break; }
+            wx * wy <= (double)P.cell_limit) { ok = true; break; }
         h *= 2.0;
     }
     if (!ok) { wx = wy = 1.0; h = INFINITY; } // every finite shape lands in cell (0,0) or the big set
@@ -522,12 +523,12 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
 {
     const FrameState *st = P.st;
     if (EMIT && st->error) return;
-    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.cell_begin[st->n_cells]) return; // shapes in this rank's grid
+    const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sorted; p += gridDim.x * blockDim.x) {
     const uint32_t meta = P.smeta[p];
     const int i = (int)(meta & 0x7fffffffu);
     const bool si = (meta >> 31) != 0;
-    if (i < P.own_lo || i >= P.own_hi) return;
+    if (i < P.own_lo || i >= P.own_hi) continue;
     const Box bi = P.sbox[p];
     const uint32_t key = P.keys_sorted[p];
     const int W = st->W, H = st->H;
@@ -572,8 +573,8 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         if (aabb_check(bi, bj)) hit(j);
     }
 
-    if (!EMIT) { P.cnt[r] = count; return; }
-    if (count == 0) return;
+    if (!EMIT) { P.cnt[r] = count; continue; }
+    if (count == 0) continue;
     if (count <= EMIT_LOCAL) {
         const int n = (int)count;
         for (int a = 1; a < n; ++a) { // insertion sort, descending
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             seg[b2 + 1] = v;
         }
         for (unsigned long long a = 0; a < count; ++a) P.pair_i[base + a] = i;
+    }
     }
 }
 
@@ -1182,7 +1184,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p; int64_t geometry, n_prev;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p; int64_t geometry, n_prev; unsigned cell_limit;
 };
 
 struct shapes_ctx {
@@ -1205,6 +1207,7 @@ struct shapes_ctx {
     int64_t graph_launches = 0;
     int64_t geometry_version = 0;
     int max_hull_verts = 0;
+    unsigned cell_limit = 0;     // sticky per-frame cell budget (0 = not chosen yet)
     int ct_blocks[2] = { 4, 4 }; // resident k_manifolds blocks per SM (boxes / general)
     int rows_blocks = 4;         // resident k_rows blocks per SM
     double auto_cell = 1.0, user_cell = 0.0;
@@ -1458,6 +1461,16 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.pk_i = c->alt_key[0]; P.pk_j = c->alt_key[1]; P.pk_fa = c->alt_key[2]; P.pk_fb = c->alt_key[3];
     P.cache_np = c->d_cache_np; P.cache_f = c->d_cache_f;
     P.n_prev = warm ? c->n_prev_keys : 0;
+    // Cell budget of this frame: the scan and the clear cover exactly this many cells, so it follows
+    // the grid the last frame needed (x2 head-room) instead of the table capacity; the planner coarsens
+    // the cells if the world outgrows it within one frame (results do not depend on the cell size).
+    if (c->cell_limit == 0) c->cell_limit = P.cell_cap;
+    else if (c->have_frame) {
+        const unsigned used = c->h_state->n_cells;
+        if (used > c->cell_limit / 2 + c->cell_limit / 4 || (unsigned long long)used * 8 < c->cell_limit)
+            c->cell_limit = (unsigned)std::min<unsigned long long>(P.cell_cap, std::max<unsigned long long>(65536ull, 2ull * used));
+    }
+    P.cell_limit = c->cell_limit;
     ++c->frame_no;
     P.frame_no = c->frame_no;
     const int fpar = (int)(c->frame_no & 1);
@@ -1515,13 +1528,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         STAGE_MARK(); // 3: cell offsets (exclusive scan of the histogram)
         if (N > 0) {
             size_t cb = c->scan_tmp_bytes;
-            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cell_count, P.cell_begin, (int)P.cell_cap + 1, s));
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cell_count, P.cell_begin, (int)P.cell_limit + 1, s));
         }
         STAGE_MARK(); // 4: scatter into cell order
         if (N > 0) { k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
         STAGE_MARK(); // 5: sweep count
         if (N > 0) {
-            k_sweep<false><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            k_sweep<false><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
             k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 6: scan
@@ -1534,7 +1547,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         }
         STAGE_MARK(); // 7: sweep emit
         if (N > 0) {
-            k_sweep<true><<<grid_for(N, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            k_sweep<true><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
             k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 8: manifolds (SAT + clipping)
@@ -1570,7 +1583,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
-    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p;
+    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p; key.cell_limit = P.cell_limit;
     const int64_t launches_before = c->launches;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
     // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
