@@ -370,8 +370,9 @@ def main():
             t = torch.tensor([e_elapsed], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_elapsed = float(t.item())
-        h2d = 6 * 8 * n  # pos_x, pos_y, cos, sin, inv_lin, inv_rot (rot is not sent when cos/sin are)
-        h2d += 8 * n     # rot column is still copied by shapes_frame when given
+        # 7 body columns; with the peer exchange each rank uploads only its own slot range
+        n_up = (eng.rank_info()[1] - eng.rank_info()[0]) if exchange.startswith("peer") else n
+        h2d = 7 * 8 * n_up
         d2h = eng._bufs.bytes_for(fr.n_pairs, fr.n_contacts, n, world.n_verts)
         e2e = {"value": tot_pairs / (e_elapsed / e_steps), "unit": UNIT, "ms_per_step": e_elapsed / e_steps * 1e3,
                "steps": e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -210,8 +210,9 @@ int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
  * the cross-GPU barrier.  Each rank exports SHAPES_IPC_BYTES (CUDA IPC handles of its exchange
  * buffers); the host gathers the blobs of all ranks (rank order) and hands them to every rank.
  * Ranks live in different processes (CUDA IPC does not map a process's own handles).  Without an
- * import the exchange goes through NCCL.  SHAPES_B200_NO_P2P=1 forces the NCCL path. */
-#define SHAPES_IPC_BYTES 512
+ * import the exchange goes through NCCL.  With it, shapes_frame also uploads only the rank's own
+ * slots of the body columns; foreign bodies are pulled from their owner's columns.  SHAPES_B200_NO_P2P=1 forces the NCCL path. */
+#define SHAPES_IPC_BYTES 2048
 int  shapes_ipc_export(shapes_ctx *, void *out_blob /* SHAPES_IPC_BYTES */);
 int  shapes_ipc_import(shapes_ctx *, const void *all_blobs /* world_size x SHAPES_IPC_BYTES */);
 

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SHAPES_B200_LIB") or os.path.join(_ROOT, "lib", "libs
 
 OK, E_ARG, E_CUDA, E_NCCL, E_CAPACITY = 0, -1, -2, -3, -4
 NCCL_ID_BYTES = 128
-IPC_BYTES = 512
+IPC_BYTES = 2048
 N_STAGES = 12
 
 _i32p = C.POINTER(C.c_int32)

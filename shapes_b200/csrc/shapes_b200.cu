@@ -198,6 +198,8 @@ struct Params {
     // peer-to-peer exchange (multi-rank, CUDA IPC): every rank's buffers, indexed by rank (own included)
     Box *peer_box[SHAPES_MAX_RANKS];
     uint32_t *peer_keys[SHAPES_MAX_RANKS];
+    const double *peer_in[7][SHAPES_MAX_RANKS]; // every rank's body columns (host API: each rank uploads only its own slots)
+    int remote_inputs;          // 1 = body columns of foreign slots are read through peer_in
     uint32_t *gkeys;            // cell key of EVERY slot (own: computed here; others: pushed by their owner)
     int chunk;                  // slots per rank
     unsigned long long *peer_bounds[SHAPES_MAX_RANKS];
@@ -227,21 +229,32 @@ struct Params {
     FrameState *st;
 };
 
+// Body column k (0 pos_x, 1 pos_y, 2 rot, 3 cos, 4 sin, 5 inv_lin, 6 inv_rot) of ANY slot.  When every
+// rank uploaded only its own slots (shapes_frame with the peer exchange) the value of a foreign slot
+// is pulled from its owner's column over NVLink.
+__device__ __forceinline__ double in_col(const Params &P, int k, const double *local, int s)
+{
+    if (P.remote_inputs) return P.peer_in[k][s / P.chunk][s];
+    return local[s];
+}
 // isStatic (Constraint.hs:123-125), straight from the host's inverse-mass columns
-__device__ __forceinline__ bool slot_static(const Params &P, int s) { return P.inv_lin[s] == 0.0 && P.inv_rot[s] == 0.0; }
+__device__ __forceinline__ bool slot_static(const Params &P, int s)
+{
+    return in_col(P, 5, P.inv_lin, s) == 0.0 && in_col(P, 6, P.inv_rot, s) == 0.0;
+}
 // (px, py, cos, sin): K0 packs it for the rank's own slots; other slots are read from the raw columns
 __device__ __forceinline__ Xf slot_xf(const Params &P, int s)
 {
     if (s >= P.own_lo && s < P.own_hi) return P.xf[s];
     double c, sn;
-    if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
-    else sincos(P.rot[s], &sn, &c);
-    return Xf{ P.pos_x[s], P.pos_y[s], c, sn };
+    if (P.cos_rot) { c = in_col(P, 3, P.cos_rot, s); sn = in_col(P, 4, P.sin_rot, s); }
+    else sincos(in_col(P, 2, P.rot, s), &sn, &c);
+    return Xf{ in_col(P, 0, P.pos_x, s), in_col(P, 1, P.pos_y, s), c, sn };
 }
 __device__ __forceinline__ double2 slot_mass(const Params &P, int s)
 {
     if (s >= P.own_lo && s < P.own_hi) return P.mass[s];
-    return make_double2(P.inv_lin[s], P.inv_rot[s]);
+    return make_double2(in_col(P, 5, P.inv_lin, s), in_col(P, 6, P.inv_rot, s));
 }
 
 // AABB record of any slot: with the peer exchange a rank's box array holds only its own slots and
@@ -959,7 +972,8 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         // i is always an owned slot; j may belong to another rank (raw input columns)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
         const bool j_own = j >= P.own_lo && j < P.own_hi;
-        const double2 xj = j_own ? *reinterpret_cast<const double2 *>(&P.xf[j]) : make_double2(P.pos_x[j], P.pos_y[j]);
+        const double2 xj = j_own ? *reinterpret_cast<const double2 *>(&P.xf[j])
+                                 : make_double2(in_col(P, 0, P.pos_x, j), in_col(P, 1, P.pos_y, j));
         const double2 mi = P.mass[i], mj = slot_mass(P, j);
         const int flip = (int)((rec.bits >> 60) & 1u);
         const int edge = (int)(rec.bits & 0xfffffu);
@@ -1184,7 +1198,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p; int64_t geometry, n_prev; unsigned cell_limit;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote; int64_t geometry, n_prev; unsigned cell_limit;
 };
 
 struct shapes_ctx {
@@ -1231,6 +1245,8 @@ struct shapes_ctx {
     // frame ahead never overwrites records a slower rank is still reading
     Box *d_box2[2] = { nullptr, nullptr };
     uint32_t *d_gkeys2[2] = { nullptr, nullptr };
+    double *d_in2[2][7] = {};   // body columns, double buffered by frame parity (multi-rank)
+    const double *peer_in2[2][7][SHAPES_MAX_RANKS] = {};
     uint32_t *peer_keys2[2][SHAPES_MAX_RANKS] = {};
     unsigned long long *d_bounds2[2] = { nullptr, nullptr };
     unsigned long long *d_flags = nullptr;
@@ -1342,7 +1358,11 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &c->d_ext_max, V));
     TRY_CREATE(dev_alloc(c, &c->d_local, V));
     TRY_CREATE(dev_alloc(c, &c->d_ext_packed, N));
-    for (int k = 0; k < 7; ++k) TRY_CREATE(dev_alloc(c, &c->d_in[k], N));
+    for (int k = 0; k < 7; ++k) {
+        TRY_CREATE(dev_alloc(c, &c->d_in[k], N));
+        c->d_in2[0][k] = c->d_in[k];
+        TRY_CREATE(dev_alloc(c, &c->d_in2[1][k], world > 1 ? N : 1));
+    }
     TRY_CREATE(dev_alloc(c, &P.xf, N));
     TRY_CREATE(dev_alloc(c, &P.mass, N));
     TRY_CREATE(dev_alloc(c, &c->d_box2[0], Npad));
@@ -1431,7 +1451,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
 
 // Issue one frame on the ctx stream.  `in` = device pointers (pos_x, pos_y, rot, cos, sin, inv_lin, inv_rot).
 int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double dt, double baumgarte,
-              double slop, bool want_world, shapes_frame_out *out)
+              double slop, bool want_world, shapes_frame_out *out, bool own_slots_only = false)
 {
     if (!c->hulls_set) { c->err = "shapes_frame: shapes_set_hulls has not been called"; return SHAPES_E_ARG; }
     if (n_slots != c->n_slots) { c->err = "shapes_frame: n_slots differs from shapes_set_hulls"; return SHAPES_E_ARG; }
@@ -1477,9 +1497,11 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     const bool p2p = c->world > 1 && c->peers_ready && c->use_p2p;
     if (c->world > 1) { P.box = c->d_box2[fpar]; P.rank_bounds = c->d_bounds2[fpar]; P.gkeys = c->d_gkeys2[fpar]; }
     P.n_peers = p2p ? c->world : 0;
+    P.remote_inputs = (p2p && own_slots_only) ? 1 : 0;
     for (int r = 0; r < c->world && p2p; ++r) {
         P.peer_box[r] = c->peer_box2[fpar][r]; P.peer_bounds[r] = c->peer_bounds2[fpar][r]; P.peer_flags[r] = c->peer_flags[r];
         P.peer_keys[r] = c->peer_keys2[fpar][r];
+        for (int k = 0; k < 7; ++k) P.peer_in[k][r] = c->peer_in2[fpar][k][r];
     }
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
@@ -1583,7 +1605,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
-    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p; key.cell_limit = P.cell_limit;
+    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0;
     const int64_t launches_before = c->launches;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
     // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
@@ -1846,19 +1868,25 @@ int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const doub
     CU_TRY(c, cudaEventRecord(t0, c->stream));
     const double *host[7] = { pos_x, pos_y, rot, cos_rot, sin_rot, inv_lin, inv_rot };
     const double *dev[7];
+    // With the peer exchange every rank uploads only ITS slots (kernels pull foreign bodies from
+    // their owners' columns); otherwise the whole world is uploaded on every rank.
+    const bool own_only = c->world > 1 && c->peers_ready && c->use_p2p;
+    const int fpar = (int)((c->frame_no + 1) & 1);
+    const int64_t lo = own_only ? std::min<int64_t>(c->rank * c->chunk, n_slots) : 0;
+    const int64_t hi = own_only ? std::min<int64_t>((c->rank + 1) * c->chunk, n_slots) : n_slots;
     for (int k = 0; k < 7; ++k) {
         dev[k] = nullptr;
-        if (host[k] && n_slots > 0) {
-            CU_TRY(c, cudaMemcpyAsync(c->d_in[k], host[k], sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, c->stream));
-            dev[k] = c->d_in[k];
-        } else if (host[k]) dev[k] = c->d_in[k];
+        double *dst = c->world > 1 ? c->d_in2[fpar][k] : c->d_in[k];
+        if (host[k] && hi > lo)
+            CU_TRY(c, cudaMemcpyAsync(dst + lo, host[k] + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+        if (host[k]) dev[k] = dst;
     }
     const bool want_world = out->world_x && out->world_y;
     if (want_world && !c->d_world_x) {
         int rc = dev_alloc(c, &c->d_world_x, (size_t)c->max_verts); if (rc) return rc;
         rc = dev_alloc(c, &c->d_world_y, (size_t)c->max_verts); if (rc) return rc;
     }
-    int rc = run_frame(c, n_slots, dev, dt, baumgarte, slop, want_world, out);
+    int rc = run_frame(c, n_slots, dev, dt, baumgarte, slop, want_world, out, own_only);
     if (rc == SHAPES_OK) rc = shapes_fetch(c, out);
     cudaEventRecord(t1, c->stream);
     cudaEventSynchronize(t1);
@@ -1922,7 +1950,9 @@ int shapes_ipc_export(shapes_ctx *c, void *out)
 {
     if (!c || !out) return SHAPES_E_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h[7];
+    cudaIpcMemHandle_t h[21];
+    for (int par = 0; par < 2; ++par)
+        for (int k = 0; k < 7; ++k) CU_TRY(c, cudaIpcGetMemHandle(&h[7 + par * 7 + k], c->d_in2[par][k]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[0], c->d_box2[0]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[1], c->d_box2[1]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[2], c->d_bounds2[0]));
@@ -1946,12 +1976,14 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
             c->peer_bounds2[0][r] = c->d_bounds2[0]; c->peer_bounds2[1][r] = c->d_bounds2[1];
             c->peer_flags[r] = c->d_flags;
             c->peer_keys2[0][r] = c->d_gkeys2[0]; c->peer_keys2[1][r] = c->d_gkeys2[1];
+            for (int par = 0; par < 2; ++par)
+                for (int k = 0; k < 7; ++k) c->peer_in2[par][k][r] = c->d_in2[par][k];
             continue;
         }
-        cudaIpcMemHandle_t h[7];
+        cudaIpcMemHandle_t h[21];
         std::memcpy(h, static_cast<const char *>(all_blobs) + (size_t)r * SHAPES_IPC_BYTES, sizeof(h));
-        void *p[7];
-        for (int q = 0; q < 7; ++q) {
+        void *p[21];
+        for (int q = 0; q < 21; ++q) {
             CU_TRY(c, cudaIpcOpenMemHandle(&p[q], h[q], cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(p[q]);
         }
@@ -1960,6 +1992,8 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
         c->peer_bounds2[1][r] = static_cast<unsigned long long *>(p[3]);
         c->peer_flags[r] = static_cast<unsigned long long *>(p[4]);
         c->peer_keys2[0][r] = static_cast<uint32_t *>(p[5]); c->peer_keys2[1][r] = static_cast<uint32_t *>(p[6]);
+        for (int par = 0; par < 2; ++par)
+            for (int k = 0; k < 7; ++k) c->peer_in2[par][k][r] = static_cast<const double *>(p[7 + par * 7 + k]);
     }
     c->peers_ready = true;
     return SHAPES_OK;
