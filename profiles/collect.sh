@@ -7,11 +7,11 @@ TAG=${1:-r1}; shift || true
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 200 > gpurun_out/clocks_$TAG.csv 2>/dev/null &
 SMI=$!
-timeout 400 python bench.py --steps 20 --warmup 5 "$@" > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 400 python bench.py --steps 300 --warmup 10 "$@" > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 kill $SMI 2>/dev/null
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e "$@" > gpurun_out/ncu_launches_$TAG.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_rows|k_manifolds|k_sweep|k_transform_aabb|k_row_map" -s 10 -c 6 \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_rows|k_manifolds|k_sweep|k_transform_aabb|k_row_map|k_bin|k_scatter_sorted|k_keys" -s 14 -c 9 \
     -o gpurun_out/prof_$TAG -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e "$@" > gpurun_out/ncu_full_$TAG.log 2>&1
 python profiles/_stage.py gpurun_out/bench_$TAG.json
 tail -2 gpurun_out/bench_$TAG.err
