@@ -151,6 +151,18 @@ int  shapes_set_hulls(shapes_ctx *, int64_t n_slots, const uint8_t *alive,
                       const double *local_x, const double *local_y,
                       const int32_t *ext_min, const int32_t *ext_max);
 
+/* Same, for worlds that also contain CircleShapes (Contact.hs:19,
+ * Contact/Circle.hs:16-22, Engine.makeCircle Engine.hs:53-54): radius[s] >= 0 makes slot s a
+ * circle of that radius (its CSR vertex range must be empty), radius[s] < 0 a hull; radius == NULL
+ * is shapes_set_hulls.  Frames then follow the full generateContacts dispatch (Contact.hs:22-40):
+ * circle/circle (key (0,0), Same), circle/hull (key (0, hull feature), Same) and hull/circle
+ * (key (hull feature, 0), Flip) through GJK closestSimplex, hull/hull through SAT. */
+int  shapes_set_shapes(shapes_ctx *, int64_t n_slots, const uint8_t *alive,
+                       const int32_t *vert_offset,
+                       const double *local_x, const double *local_y,
+                       const int32_t *ext_min, const int32_t *ext_max,
+                       const double *radius);
+
 /* Broadphase cell edge; <= 0 restores the automatic choice made by
  * shapes_set_hulls.  Performance only: results do not depend on it. */
 int  shapes_set_cell_size(shapes_ctx *, double cell_size);

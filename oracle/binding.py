@@ -143,8 +143,22 @@ def unordered_pairs(n: int):
     return xs[:k], ys[:k]
 
 
-def contacts(world, pair_i, pair_j, wx, wy, nx, ny, ext_min, ext_max, dt, baumgarte, slop):
-    """prepareFrame + constraintGen over the given pairs -> dict of columns."""
+def move_circles(world, cos_rot, sin_rot):
+    n = world.n_slots
+    cx = np.zeros(n); cy = np.zeros(n)
+    lib().orc_move_circles(C.c_int64(n), _p(world.alive, _u8p), _f(world.radius), _f(world.pos_x), _f(world.pos_y),
+                           _f(cos_rot), _f(sin_rot), _f(cx), _f(cy))
+    return cx, cy
+
+
+def aabbs_circles(world, cx, cy, boxes):
+    lib().orc_aabbs_circles(C.c_int64(world.n_slots), _p(world.alive, _u8p), _f(world.radius), _f(cx), _f(cy),
+                            *[_f(b) for b in boxes])
+
+
+def contacts(world, pair_i, pair_j, wx, wy, nx, ny, ext_min, ext_max, dt, baumgarte, slop, circles=None):
+    """prepareFrame + constraintGen over the given pairs -> dict of columns.
+    circles = (centre_x, centre_y) when the world has CircleShapes (full generateContacts dispatch)."""
     cap = max(16, 2 * int(pair_i.shape[0]))
     cols = {k: np.zeros(cap, np.int32) for k in CONTACT_I32}
     cols["flip"] = np.zeros(cap, np.uint8)
@@ -163,10 +177,14 @@ def contacts(world, pair_i, pair_j, wx, wy, nx, ny, ext_min, ext_max, dt, baumga
         else:
             setattr(out, k, _f(cols[k]))
     pi = np.ascontiguousarray(pair_i, np.int32); pj = np.ascontiguousarray(pair_j, np.int32)
-    n = lib().orc_contacts(C.c_int64(pi.shape[0]), _p(pi, _i32p), _p(pj, _i32p), _p(world.vert_offset, _i32p),
-                           _f(wx), _f(wy), _f(nx), _f(ny), _p(ext_min, _i32p), _p(ext_max, _i32p),
-                           _f(world.pos_x), _f(world.pos_y), _f(world.inv_lin), _f(world.inv_rot),
-                           C.c_double(dt), C.c_double(baumgarte), C.c_double(slop), C.byref(out))
+    rad = world.radius if circles is not None else None
+    ccx, ccy = circles if circles is not None else (None, None)
+    lib().orc_contacts_shapes.restype = C.c_int64
+    n = lib().orc_contacts_shapes(C.c_int64(pi.shape[0]), _p(pi, _i32p), _p(pj, _i32p), _p(world.vert_offset, _i32p),
+                                  _f(wx), _f(wy), _f(nx), _f(ny), _p(ext_min, _i32p), _p(ext_max, _i32p),
+                                  _f(rad), _f(ccx), _f(ccy),
+                                  _f(world.pos_x), _f(world.pos_y), _f(world.inv_lin), _f(world.inv_rot),
+                                  C.c_double(dt), C.c_double(baumgarte), C.c_double(slop), C.byref(out))
     assert n <= cap
     return {k: v[:n].copy() for k, v in cols.items()}
 
@@ -179,12 +197,16 @@ def frame(world, cos_rot=None, sin_rot=None, dt=0.01, baumgarte=0.01, slop=0.02,
     emin, emax = ext if ext is not None else hull_extents(world)
     wx, wy, nx, ny = move_shapes(world, cos_rot, sin_rot)
     boxes = aabbs(world, wx, wy)
+    circles = None
+    if getattr(world, "radius", None) is not None:
+        circles = move_circles(world, cos_rot, sin_rot)          # setCircleTransform
+        aabbs_circles(world, circles[0], circles[1], boxes)      # circleToAabb
     static = is_static(world)
     if broadphase == "auto":
         broadphase = "aabb" if world.n_slots <= 3000 else "sweep"
     fn = {"aabb": culled_keys_aabb, "sweep": culled_keys_sweep, "grid": culled_keys_grid}[broadphase]
     pi, pj = fn(world, boxes, static)
-    res = contacts(world, pi, pj, wx, wy, nx, ny, emin, emax, dt, baumgarte, slop)
+    res = contacts(world, pi, pj, wx, wy, nx, ny, emin, emax, dt, baumgarte, slop, circles=circles)
     res.update(pair_i=pi, pair_j=pj, aabb_min_x=boxes[0], aabb_max_x=boxes[1], aabb_min_y=boxes[2],
                aabb_max_y=boxes[3], world_x=wx, world_y=wy, normal_wx=nx, normal_wy=ny,
                ext_min=emin, ext_max=emax, is_static=static)

@@ -612,6 +612,164 @@ static manifold_t hull_vs_hull(const hull_t *a, const hull_t *b)
 }
 
 /* ------------------------------------------------------------------ */
+/* Circles: Physics.Contact.Circle, CircleVsHull, GJK                   */
+/* ------------------------------------------------------------------ */
+
+/* Circle.contact circleA circleB (shapes/src/Physics/Contact/Circle.hs:30-53): A is the penetratee,
+ * the normal points out of A.  The flattened key is (0, 0), Same (Contact.hs:25-29). */
+static manifold_t circle_vs_circle(v2 a, double ra, v2 b, double rb)
+{
+    manifold_t m;
+    memset(&m, 0, sizeof m);
+    v2 ab = sub2(b, a);                                /* diffP2 b a */
+    double rab = ra + rb;
+    double ab_sq = (ab.x * ab.x) + (ab.y * ab.y);       /* sqLengthV2 */
+    if (!(rab * rab >= ab_sq)) return m;
+    double ab_len = sqrt(ab_sq);
+    v2 abn = { ab.x / ab_len, ab.y / ab_len };         /* abLength `sdivV2` ab */
+    v2 a1 = { (abn.x * ra) + a.x, (abn.y * ra) + a.y };        /* (ra `smulV2` abN) `vplusP2` a */
+    double nrb = -rb;
+    v2 b1 = { (abn.x * nrb) + b.x, (abn.y * nrb) + b.y };      /* ((-rb) `smulV2` abN) `vplusP2` b */
+    m.n = 1;
+    m.flip = 0;
+    m.edge = 0;
+    m.pen[0] = 0;
+    m.normal = abn;
+    m.center[0].x = (a1.x + b1.x) / 2.0;               /* midpointP2: 2 `sdivV2` (v0 `plusV2` v1) */
+    m.center[0].y = (a1.y + b1.y) / 2.0;
+    m.depth[0] = (ra + rb) - ab_len;
+    return m;
+}
+
+/* support (ConvexHull.hs:124-128): first maximum of dir . v */
+static int hull_support(const hull_t *h, v2 dir)
+{
+    int best = 0;
+    double bd = dot2(hull_vertex(h, 0), dir);
+    for (int k = 1; k < h->n; ++k) {
+        double d = dot2(hull_vertex(h, k), dir);
+        if (d > bd) { bd = d; best = k; }
+    }
+    return best;
+}
+
+static inline int same_direction(v2 a, v2 b) { return dot2(a, b) > 0.0; } /* GJK.hs:138-139 */
+/* crossV2V2 (Linear.hs:135-139) */
+static inline v2 cross_v2v2(v2 a, v2 b, v2 c)
+{
+    double abz = (a.x * b.y) - (a.y * b.x);
+    v2 r = { -(abz * c.y), abz * c.x };
+    return r;
+}
+
+#define GJK_MAX_ITER 64 /* the reference loops until a support vertex repeats; bounded here */
+
+/* closestSimplex hull origin (GJK.hs:52-69).  Returns the simplex size (1, 2; 3 = encloses the
+ * target; 0 = iteration cap hit) and its vertex indices, most recently added first. */
+static int gjk_closest_simplex(const hull_t *h, v2 origin, int idx[3])
+{
+    int n = 1;
+    idx[0] = 0;
+    v2 d = sub2(origin, hull_vertex(h, 0));
+    for (int it = 0; it < GJK_MAX_ITER; ++it) {
+        int aa = hull_support(h, d);
+        /* extendSimplex (GJK.hs:71-90): a repeated vertex ends the search */
+        if (n == 1) { if (idx[0] == aa) return 1; idx[1] = idx[0]; idx[0] = aa; n = 2; }
+        else { if (idx[0] == aa || idx[1] == aa) return 2; idx[2] = idx[1]; idx[1] = idx[0]; idx[0] = aa; n = 3; }
+        v2 a = hull_vertex(h, idx[0]), b = hull_vertex(h, idx[1]);
+        v2 ab = sub2(b, a), ao = sub2(origin, a);
+        if (n == 2) {
+            /* shiftSimplex2 (GJK.hs:98-112) */
+            if (same_direction(ab, ao)) d = cross_v2v2(ab, ao, ab);
+            else { n = 1; d = ao; }
+        } else {
+            /* shiftSimplex3 (GJK.hs:114-136) */
+            v2 c = hull_vertex(h, idx[2]);
+            v2 ac = sub2(c, a);
+            double abc = cross2(ab, ac);
+            v2 abcac = { -(abc * ac.y), abc * ac.x };   /* abc `zcrossV2` ac (Linear.hs:126-129) */
+            v2 ababc = { ab.y * abc, -(ab.x * abc) };   /* ab `crosszV2` abc (Linear.hs:121-124) */
+            int star = 0;
+            if (same_direction(abcac, ao)) {
+                if (same_direction(ac, ao)) { idx[1] = idx[2]; n = 2; d = cross_v2v2(ac, ao, ac); }
+                else star = 1;
+            } else if (same_direction(ababc, ao)) star = 1;
+            else return 3; /* simplex encloses the origin */
+            if (star) {
+                if (same_direction(ab, ao)) { n = 2; d = cross_v2v2(ab, ao, ab); }
+                else { n = 1; d = ao; }
+            }
+        }
+    }
+    return 0;
+}
+
+/* CircleVsHull.generateContacts (CircleVsHull.hs:18-69): the circle is always the penetrator.
+ * flip = 0: (CircleShape a, HullShape b) -> ((0, hullFeature), Same contact);
+ * flip = 1: (HullShape a, CircleShape b) -> ((hullFeature, 0), Flip contact)  (Contact.hs:30-39). */
+static manifold_t circle_vs_hull(v2 center, double r, const hull_t *h, int flip)
+{
+    manifold_t m;
+    memset(&m, 0, sizeof m);
+    int idx[3] = { 0, 0, 0 };
+    int n = gjk_closest_simplex(h, center, idx);
+    if (n != 1 && n != 2) return m;            /* Simplex3' (deep overlap) => Nothing (CircleVsHull.hs:29) */
+    v2 a = hull_vertex(h, idx[0]);
+    if (n == 2) {
+        /* closestAlong (CircleVsHull.hs:60-69); the feature is the most recently added vertex */
+        v2 b = hull_vertex(h, idx[1]);
+        v2 ao = sub2(center, a), ab = sub2(b, a);
+        v2 abn = normalize2(ab);
+        double s = dot2(ao, abn);
+        v2 along = { abn.x * s, abn.y * s };
+        a.x = along.x + a.x; a.y = along.y + a.y;
+    }
+    /* processSimplex_ (CircleVsHull.hs:42-58) */
+    double sq_radius = r * r;
+    v2 ab = sub2(center, a);
+    double ab_sq = (ab.x * ab.x) + (ab.y * ab.y);
+    if (sq_radius < ab_sq) return m;
+    double ab_len = sqrt(ab_sq);
+    v2 normal = { ab.x / ab_len, ab.y / ab_len };
+    m.n = 1;
+    m.flip = flip;
+    m.edge = 0;
+    m.pen[0] = idx[0];
+    m.normal = neg2(normal);
+    m.center[0] = a;
+    m.depth[0] = r - ab_len;
+    return m;
+}
+
+void orc_move_circles(int64_t n_slots, const uint8_t *alive, const double *radius,
+                      const double *pos_x, const double *pos_y,
+                      const double *cos_rot, const double *sin_rot,
+                      double *center_x, double *center_y)
+{
+    /* setCircleTransform (Circle.hs:55-59): Circle (fromLocalSpace zeroP2) radius */
+    for (int64_t s = 0; s < n_slots; ++s) {
+        if ((alive && !alive[s]) || !(radius[s] >= 0.0)) continue;
+        double t[9];
+        to_transform(pos_x[s], pos_y[s], cos_rot[s], sin_rot[s], t);
+        v2 zero = { 0.0, 0.0 };
+        v2 c = afmul(t, zero);
+        center_x[s] = c.x; center_y[s] = c.y;
+    }
+}
+
+void orc_aabbs_circles(int64_t n_slots, const uint8_t *alive, const double *radius,
+                       const double *center_x, const double *center_y,
+                       double *min_x, double *max_x, double *min_y, double *max_y)
+{
+    /* circleToAabb (Aabb.hs:86-88) */
+    for (int64_t s = 0; s < n_slots; ++s) {
+        if ((alive && !alive[s]) || !(radius[s] >= 0.0)) continue;
+        double x = center_x[s], y = center_y[s], r = radius[s];
+        min_x[s] = x - r; max_x[s] = x + r; min_y[s] = y - r; max_y[s] = y + r;
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* Constraint generators                                               */
 /* ------------------------------------------------------------------ */
 
@@ -651,11 +809,12 @@ static double eff_mass(const double j[6], const double im[6])
 
 #define PUT(arr, row, val) do { if (out->arr) out->arr[row] = (val); } while (0)
 
-int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair_j,
+int64_t orc_contacts_shapes(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair_j,
                      const int32_t *vert_offset,
                      const double *world_x, const double *world_y,
                      const double *normal_x, const double *normal_y,
                      const int32_t *ext_min, const int32_t *ext_max,
+                     const double *radius, const double *circle_x, const double *circle_y,
                      const double *pos_x, const double *pos_y,
                      const double *inv_lin, const double *inv_rot,
                      double dt, double baumgarte, double slop,
@@ -675,7 +834,19 @@ int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair
 
         /* keyedContacts (Constraints/Contact.hs:49-56) -> generateContacts
          * (Contact.hs:40, HullVsHull.hs:85-89) */
-        manifold_t m = hull_vs_hull(&ha, &hb);
+        /* generateContacts dispatch (shapes/src/Physics/Contact.hs:22-40) */
+        const int ca = radius && radius[i] >= 0.0, cb = radius && radius[j] >= 0.0;
+        manifold_t m;
+        if (ca && cb) {
+            v2 pa = { circle_x[i], circle_y[i] }, pb = { circle_x[j], circle_y[j] };
+            m = circle_vs_circle(pa, radius[i], pb, radius[j]);          /* ((0,0), Same contact) */
+        } else if (ca) {
+            v2 pa = { circle_x[i], circle_y[i] };
+            m = circle_vs_hull(pa, radius[i], &hb, 0);                   /* ((0, hullFeature), Same contact) */
+        } else if (cb) {
+            v2 pb = { circle_x[j], circle_y[j] };
+            m = circle_vs_hull(pb, radius[j], &ha, 1);                   /* ((hullFeature, 0), Flip contact) */
+        } else m = hull_vs_hull(&ha, &hb);
         v2 xi = { pos_x[i], pos_y[i] }, xj = { pos_x[j], pos_y[j] };
         for (int k = 0; k < m.n; ++k, ++row) {
             if (!out || row >= out->cap) continue;
@@ -718,6 +889,22 @@ int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair
         }
     }
     return row;
+}
+
+
+int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair_j,
+                     const int32_t *vert_offset,
+                     const double *world_x, const double *world_y,
+                     const double *normal_x, const double *normal_y,
+                     const int32_t *ext_min, const int32_t *ext_max,
+                     const double *pos_x, const double *pos_y,
+                     const double *inv_lin, const double *inv_rot,
+                     double dt, double baumgarte, double slop,
+                     orc_contacts_out *out)
+{
+    return orc_contacts_shapes(n_pairs, pair_i, pair_j, vert_offset, world_x, world_y, normal_x, normal_y,
+                               ext_min, ext_max, NULL, NULL, NULL, pos_x, pos_y, inv_lin, inv_rot,
+                               dt, baumgarte, slop, out);
 }
 
 void orc_solve_constraint(const double *j6, double b, const double *inv_mass6, double *vel6)

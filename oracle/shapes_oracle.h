@@ -121,6 +121,36 @@ int64_t orc_contacts(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair
                      double dt, double baumgarte, double slop,
                      orc_contacts_out *out);
 
+/* ---- circles ------------------------------------------------
+ * A slot with radius[s] >= 0 is a CircleShape of that radius (its CSR vertex range is empty);
+ * radius == NULL or radius[s] < 0 means HullShape.
+ *
+ * orc_move_circles: setCircleTransform (shapes/src/Physics/Contact/Circle.hs:55-59): the world
+ * centre is the transform applied to the local origin (afmul with the same toTransform matrix).
+ * orc_aabbs_circles: circleToAabb (shapes/src/Physics/Broadphase/Aabb.hs:86-88), overwrites the
+ * AABB entries of the circle slots.
+ * orc_contacts_shapes: prepareFrame + constraintGen with the full dispatch of
+ * Physics.Contact.generateContacts (shapes/src/Physics/Contact.hs:22-40): circle/circle
+ * (Circle.hs:30-53), circle/hull and hull/circle through GJK closestSimplex
+ * (Contact/GJK.hs:52-146, Contact/CircleVsHull.hs:18-69), hull/hull as orc_contacts. */
+void orc_move_circles(int64_t n_slots, const uint8_t *alive, const double *radius,
+                      const double *pos_x, const double *pos_y,
+                      const double *cos_rot, const double *sin_rot,
+                      double *center_x, double *center_y);
+void orc_aabbs_circles(int64_t n_slots, const uint8_t *alive, const double *radius,
+                       const double *center_x, const double *center_y,
+                       double *min_x, double *max_x, double *min_y, double *max_y);
+int64_t orc_contacts_shapes(int64_t n_pairs, const int32_t *pair_i, const int32_t *pair_j,
+                            const int32_t *vert_offset,
+                            const double *world_x, const double *world_y,
+                            const double *normal_x, const double *normal_y,
+                            const int32_t *ext_min, const int32_t *ext_max,
+                            const double *radius, const double *circle_x, const double *circle_y,
+                            const double *pos_x, const double *pos_y,
+                            const double *inv_lin, const double *inv_rot,
+                            double dt, double baumgarte, double slop,
+                            orc_contacts_out *out);
+
 /* The cache join of applyCachedSlns (shapes/src/Physics/Solvers/Contact.hs:84-121): descZipVector
  * (shapes/src/Utils/Descending.hs:47-71) walks this frame's contacts (descending ObjectFeatureKey)
  * against the previous frame's (key, ContactLagrangian) cache (descending): keys equal => useCache

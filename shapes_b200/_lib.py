@@ -72,6 +72,8 @@ SYMBOLS = {
     "shapes_last_error": (C.c_char_p, [C.c_void_p]),
     "shapes_set_hulls": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "shapes_set_shapes": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "shapes_set_cell_size": (C.c_int, [C.c_void_p, C.c_double]),
     "shapes_frame": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
     "shapes_frame_device": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),

@@ -172,6 +172,8 @@ struct Params {
     const double2 *local;       // interleaved local vertices
     const int32_t *ext_min, *ext_max;   // per edge (hull-relative)
     const unsigned long long *ext_packed; // per slot, 3+3 bits per edge, hulls with <= 8 vertices
+    const double *radius;       // per slot: >= 0 = CircleShape of that radius (no vertices), < 0 = hull; NULL = no circles
+    double2 *circ;              // world centre of the owned circle slots (setCircleTransform)
     // per-frame inputs
     const double *pos_x, *pos_y, *rot, *cos_rot, *sin_rot, *inv_lin, *inv_rot;
     double dt, baumgarte, slop;
@@ -316,6 +318,15 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
         const int n = P.vert_offset[s + 1] - o;
         const Aff m = to_transform(px, py, c, sn);
         Box b;
+        const double rad = P.radius ? P.radius[s] : -1.0;
+        if (rad >= 0.0) {
+            // setCircleTransform (Circle.hs:55-59): centre = transform applied to the local origin;
+            // circleToAabb (Aabb.hs:86-88)
+            const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
+            P.circ[s] = make_double2(ctr.x, ctr.y);
+            b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
+            b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+        }
         for (int k = 0; k < n; ++k) {
             double2 l = __ldg(&P.local[o + k]);
             V2 w = afmul(m, V2{ l.x, l.y });
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             }
         }
         // setHullTransform (ConvexHull.hs:193-194): unit edge normals recomputed from the NEW vertices
-        double2 v0 = P.wv[o], va = v0;
+        double2 v0 = n > 0 ? P.wv[o] : make_double2(0.0, 0.0), va = v0;
         for (int k = 0; k < n; ++k) {
             const double2 vb = (k + 1 < n) ? P.wv[o + k + 1] : v0;
             const V2 nn = unit_edge_normal(V2{ va.x, va.y }, V2{ vb.x, vb.y });
@@ -816,6 +827,118 @@ struct ContactKernel {
         if (e == 0 || depth < best.depth) { best.edge = e; best.depth = depth; best.pen = p_idx; }
         return false;
     }
+
+    // ---- circles: Circle.contact, GJK closestSimplex, CircleVsHull ----
+
+    // world centre of a circle slot: K0's value for owned slots, else setCircleTransform here
+    __device__ __forceinline__ V2 circle_center(int slot) const
+    {
+        if (slot >= P.own_lo && slot < P.own_hi) { const double2 c = P.circ[slot]; return V2{ c.x, c.y }; }
+        const Xf x = slot_xf(P, slot);
+        return afmul(to_transform(x.px, x.py, x.c, x.s), V2{ 0.0, 0.0 });
+    }
+
+    // support (ConvexHull.hs:124-128): first maximum of dir . v
+    __device__ __forceinline__ int support(const HullAcc &h, V2 dir) const
+    {
+        int best = 0;
+        double bd = dot2(vtx(h, 0), dir);
+#pragma unroll 1
+        for (int k = 1; k < h.n; ++k) {
+            const double d = dot2(vtx(h, k), dir);
+            if (d > bd) { bd = d; best = k; }
+        }
+        return best;
+    }
+
+    // closestSimplex hull origin (GJK.hs:52-69): size of the final simplex (1, 2; 3 = encloses the
+    // target; 0 = iteration cap) and its vertex indices, most recently added first.
+    __device__ int closest_simplex(const HullAcc &h, V2 origin, int &i0, int &i1) const
+    {
+        int n = 1, i2 = 0;
+        i0 = 0; i1 = 0;
+        V2 d = sub2(origin, vtx(h, 0));
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it) {
+            const int aa = support(h, d);
+            // extendSimplex (GJK.hs:71-90): a repeated vertex ends the search
+            if (n == 1) { if (i0 == aa) return 1; i1 = i0; i0 = aa; n = 2; }
+            else { if (i0 == aa || i1 == aa) return 2; i2 = i1; i1 = i0; i0 = aa; n = 3; }
+            const V2 a = vtx(h, i0), b = vtx(h, i1);
+            const V2 ab = sub2(b, a), ao = sub2(origin, a);
+            if (n == 2) { // shiftSimplex2 (GJK.hs:98-112)
+                if (dot2(ab, ao) > 0.0) d = cross_v2v2(ab, ao, ab);
+                else { n = 1; d = ao; }
+            } else {      // shiftSimplex3 (GJK.hs:114-136)
+                const V2 c = vtx(h, i2);
+                const V2 ac = sub2(c, a);
+                const double abc = cross2(ab, ac);
+                const V2 abcac{ -fmul(abc, ac.y), fmul(abc, ac.x) };  // abc `zcrossV2` ac (Linear.hs:126-129)
+                const V2 ababc{ fmul(ab.y, abc), -fmul(ab.x, abc) };  // ab `crosszV2` abc (Linear.hs:121-124)
+                bool star = false;
+                if (dot2(abcac, ao) > 0.0) {
+                    if (dot2(ac, ao) > 0.0) { i1 = i2; n = 2; d = cross_v2v2(ac, ao, ac); }
+                    else star = true;
+                } else if (dot2(ababc, ao) > 0.0) star = true;
+                else return 3; // the simplex encloses the target
+                if (star) {
+                    if (dot2(ab, ao) > 0.0) { n = 2; d = cross_v2v2(ab, ao, ab); }
+                    else { n = 1; d = ao; }
+                }
+            }
+        }
+        return 0;
+    }
+    // crossV2V2 (Linear.hs:135-139)
+    __device__ __forceinline__ static V2 cross_v2v2(V2 a, V2 b, V2 c)
+    {
+        const double abz = fsub(fmul(a.x, b.y), fmul(a.y, b.x));
+        return V2{ -fmul(abz, c.y), fmul(abz, c.x) };
+    }
+
+    // Circle.contact circleA circleB (Circle.hs:30-53): A is the penetratee, normal out of A.
+    __device__ bool circle_circle(V2 a, double ra, V2 b, double rb, V2 &normal, V2 &center, double &depth) const
+    {
+        const V2 ab = sub2(b, a);
+        const double rab = fadd(ra, rb);
+        const double ab_sq = fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y));
+        if (!(fmul(rab, rab) >= ab_sq)) return false;
+        const double ab_len = __dsqrt_rn(ab_sq);
+        normal = V2{ fdiv(ab.x, ab_len), fdiv(ab.y, ab_len) };
+        const V2 a1{ fadd(fmul(normal.x, ra), a.x), fadd(fmul(normal.y, ra), a.y) };
+        const double nrb = -rb;
+        const V2 b1{ fadd(fmul(normal.x, nrb), b.x), fadd(fmul(normal.y, nrb), b.y) };
+        center = V2{ fdiv(fadd(a1.x, b1.x), 2.0), fdiv(fadd(a1.y, b1.y), 2.0) }; // midpointP2
+        depth = fsub(fadd(ra, rb), ab_len);
+        return true;
+    }
+
+    // CircleVsHull.generateContacts (CircleVsHull.hs:18-69): the circle is always the penetrator
+    __device__ bool circle_hull(V2 ctr, double r, const HullAcc &h, int &feature, V2 &normal, V2 &point, double &depth) const
+    {
+        int i0, i1;
+        const int n = closest_simplex(h, ctr, i0, i1);
+        if (n != 1 && n != 2) return false; // Simplex3' (deep overlap) => Nothing (CircleVsHull.hs:29)
+        V2 a = vtx(h, i0);
+        if (n == 2) { // closestAlong (CircleVsHull.hs:60-69)
+            const V2 b = vtx(h, i1);
+            const V2 ao = sub2(ctr, a), ab = sub2(b, a);
+            const double len = __dsqrt_rn(fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y)));
+            const V2 abn{ fdiv(ab.x, len), fdiv(ab.y, len) };      // normalizeV2
+            const double sc = dot2(ao, abn);
+            a = V2{ fadd(fmul(abn.x, sc), a.x), fadd(fmul(abn.y, sc), a.y) };
+        }
+        // processSimplex_ (CircleVsHull.hs:42-58)
+        const V2 ab = sub2(ctr, a);
+        const double ab_sq = fadd(fmul(ab.x, ab.x), fmul(ab.y, ab.y));
+        if (fmul(r, r) < ab_sq) return false;
+        const double ab_len = __dsqrt_rn(ab_sq);
+        normal = V2{ -fdiv(ab.x, ab_len), -fdiv(ab.y, ab_len) };   // negateV2 normal
+        point = a;
+        depth = fsub(r, ab_len);
+        feature = i0;
+        return true;
+    }
 };
 
 enum { CLIP_LEFT = 0, CLIP_RIGHT = 1, CLIP_BOTH = 2, CLIP_NONE = 3 };
@@ -842,7 +965,7 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
 #ifndef CT_MIN_BLOCKS_GENERAL
 #define CT_MIN_BLOCKS_GENERAL 4
 #endif
-template <int MAXV>
+template <int MAXV, bool CIRCLES>
 __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN_BLOCKS_GENERAL) k_manifolds(Params P)
 {
     __shared__ double2 s_verts[CT_THREADS / 32][2][MAXV][32];
@@ -861,6 +984,36 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
         B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
         A.ext = P.ext_packed[i];
         B.ext = P.ext_packed[j];
+        if (CIRCLES) {
+            // generateContacts dispatch (shapes/src/Physics/Contact.hs:22-40)
+            const double ra = P.radius[i], rb = P.radius[j];
+            if (ra >= 0.0 || rb >= 0.0) {
+                V2 normal{ 0.0, 0.0 }, center{ 0.0, 0.0 };
+                double depth = 0.0;
+                int feature = 0, flip = 0;
+                bool hit;
+                if (ra >= 0.0 && rb >= 0.0) {            // ((0, 0), Same contact)
+                    hit = K.circle_circle(K.circle_center(i), ra, K.circle_center(j), rb, normal, center, depth);
+                } else if (ra >= 0.0) {                   // ((0, hullFeature), Same contact)
+                    K.stage(B);
+                    hit = K.circle_hull(K.circle_center(i), ra, B, feature, normal, center, depth);
+                } else {                                  // ((hullFeature, 0), Flip contact)
+                    K.stage(A);
+                    hit = K.circle_hull(K.circle_center(j), rb, A, feature, normal, center, depth);
+                    flip = 1;
+                }
+                if (hit) {
+                    ManRec rec;
+                    rec.nx = normal.x; rec.ny = normal.y;
+                    rec.ref_d = depth;                    // explicit depth (bit 61): not derived from a reference edge
+                    rec.c0x = center.x; rec.c0y = center.y; rec.c1x = 0.0; rec.c1y = 0.0;
+                    rec.bits = ((unsigned long long)(unsigned)feature << 20) | ((unsigned long long)flip << 60) | (1ull << 61);
+                    P.man[p] = rec;
+                }
+                P.ccnt[p] = hit ? 1u : 0u;
+                continue;
+            }
+        }
         K.stage(A);
         K.stage(B);
         unsigned cnt = 0;
@@ -982,7 +1135,8 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const V2 c = k ? V2{ rec.c1x, rec.c1y } : V2{ rec.c0x, rec.c0y };
         const V2 pos_i{ xi.x, xi.y }, pos_j{ xj.x, xj.y };
         // contactDepth_ (HullVsHull.hs:30-37): f v - f p, f = afdot' n
-        const double d = fsub(rec.ref_d, dot2(c, n));
+        // circle contacts carry their depth (Circle.hs:53, CircleVsHull.hs:54) instead of a reference edge
+        const double d = ((rec.bits >> 61) & 1u) ? rec.ref_d : fsub(rec.ref_d, dot2(c, n));
         P.key_i[row] = i; P.key_j[row] = j;
         // flipExtractPair fst (HullVsHull.hs:73-75, Utils.hs:184-186)
         P.feat_a[row] = flip ? pen : edge;
@@ -1222,7 +1376,9 @@ struct shapes_ctx {
     int64_t geometry_version = 0;
     int max_hull_verts = 0;
     unsigned cell_limit = 0;     // sticky per-frame cell budget (0 = not chosen yet)
-    int ct_blocks[2] = { 4, 4 }; // resident k_manifolds blocks per SM (boxes / general)
+    int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
+    bool has_circles = false;
+    double *d_radius = nullptr;
     int rows_blocks = 4;         // resident k_rows blocks per SM
     double auto_cell = 1.0, user_cell = 0.0;
     int64_t launches = 0;
@@ -1374,6 +1530,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     P.chunk = (int)std::max<int64_t>(c->chunk, 1);
     TRY_CREATE(dev_alloc(c, &P.wv, V));
     TRY_CREATE(dev_alloc(c, &P.wn, V));
+    TRY_CREATE(dev_alloc(c, &P.circ, N));
+    TRY_CREATE(dev_alloc(c, &c->d_radius, N));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
     TRY_CREATE(dev_alloc(c, &P.rank, N));
@@ -1433,9 +1591,11 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     c->scan_tmp_bytes = cb;
     {   // grid-stride k_manifolds grid: the number of co-resident blocks
         int b4 = 0, b8 = 0;
-        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_manifolds<4>, CT_THREADS, 0), "occupancy"));
-        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b8, k_manifolds<MAX_STAGED_VERTS>, CT_THREADS, 0), "occupancy"));
-        c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1);
+        int bc = 0;
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, k_manifolds<4, false>, CT_THREADS, 0), "occupancy"));
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b8, k_manifolds<MAX_STAGED_VERTS, false>, CT_THREADS, 0), "occupancy"));
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_manifolds<MAX_STAGED_VERTS, true>, CT_THREADS, 0), "occupancy"));
+        c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1); c->ct_blocks[2] = std::max(bc, 1);
         int br = 0;
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_rows, 256, 0), "occupancy"));
         c->rows_blocks = std::max(br, 1);
@@ -1574,8 +1734,9 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         }
         STAGE_MARK(); // 8: manifolds (SAT + clipping)
         if (N > 0) {
-            if (c->max_hull_verts <= 4) k_manifolds<4><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
-            else k_manifolds<MAX_STAGED_VERTS><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
+            if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
+            else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
+            else k_manifolds<MAX_STAGED_VERTS, false><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
             ++c->launches;
         }
         STAGE_MARK(); // 9: contact row offsets
@@ -1721,10 +1882,18 @@ const char *shapes_last_error(const shapes_ctx *c) { return c ? c->err.c_str() :
 int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const int32_t *vert_offset,
                      const double *local_x, const double *local_y, const int32_t *ext_min, const int32_t *ext_max)
 {
+    return shapes_set_shapes(c, n_slots, alive, vert_offset, local_x, local_y, ext_min, ext_max, nullptr);
+}
+
+int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const int32_t *vert_offset,
+                      const double *local_x, const double *local_y, const int32_t *ext_min, const int32_t *ext_max,
+                      const double *radius)
+{
     if (!c) return SHAPES_E_ARG;
-    if (n_slots < 0 || n_slots > c->max_shapes || (n_slots > 0 && (!vert_offset || !local_x || !local_y)) ||
+    if (n_slots < 0 || n_slots > c->max_shapes || (n_slots > 0 && !vert_offset) ||
+        (n_slots > 0 && vert_offset[n_slots] > 0 && (!local_x || !local_y)) ||
         ((ext_min == nullptr) != (ext_max == nullptr))) {
-        c->err = "shapes_set_hulls: bad argument";
+        c->err = "shapes_set_shapes: bad argument";
         return SHAPES_E_ARG;
     }
     CU_TRY(c, cudaSetDevice(c->device));
@@ -1740,9 +1909,18 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
     std::vector<double> diam;
     diam.reserve((size_t)n_slots);
     int max_verts_seen = 0;
+    bool any_circle = false;
     for (int64_t s = 0; s < n_slots; ++s) {
         const int32_t o = vert_offset[s], n = vert_offset[s + 1] - o;
-        if (n < 0 || (live[s] && n < 1)) { c->err = "shapes_set_hulls: a filled slot has no vertices"; return SHAPES_E_ARG; }
+        const bool circle = radius && radius[s] >= 0.0;
+        if (n < 0 || (live[s] && !circle && n < 1) || (circle && n != 0)) {
+            c->err = "shapes_set_shapes: a filled hull slot has no vertices (or a circle slot has some)";
+            return SHAPES_E_ARG;
+        }
+        if (circle) { // Circle (Contact/Circle.hs:16-19): diameter 2r for the cell-size estimate
+            if (live[s]) { any_circle = true; if (std::isfinite(radius[s])) diam.push_back(2.0 * radius[s]); }
+            continue;
+        }
         if (live[s] && n > max_verts_seen) max_verts_seen = n;
         double r2 = 0.0;
         for (int32_t k = 0; k < n; ++k) {
@@ -1770,6 +1948,7 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
         CU_TRY(c, cudaMemcpyAsync(c->d_alive, live.data(), (size_t)n_slots, cudaMemcpyHostToDevice, s));
         CU_TRY(c, cudaMemcpyAsync(c->d_vert_offset, vert_offset, sizeof(int32_t) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, s));
         if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+        if (any_circle) CU_TRY(c, cudaMemcpyAsync(c->d_radius, radius, sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
         if (ext_min) {
             for (int64_t v = 0; v < n_verts; ++v) {
                 // _hullExtents entries index the hull's own vertices
@@ -1788,6 +1967,8 @@ int shapes_set_hulls(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, const
     CU_TRY(c, cudaStreamSynchronize(s));
     c->n_slots = n_slots; c->n_verts = n_verts;
     c->max_hull_verts = max_verts_seen;
+    c->has_circles = any_circle;
+    c->P.radius = any_circle ? c->d_radius : nullptr;
     c->hulls_set = true;
     c->have_frame = false;
     ++c->geometry_version;

@@ -224,8 +224,10 @@ class Engine:
         emin = emax = None
         if ext is not None:
             emin = np.ascontiguousarray(ext[0], np.int32); emax = np.ascontiguousarray(ext[1], np.int32)
-        self._check(self.lib.shapes_set_hulls(self.ctx, world.n_slots, _ptr(world.alive), _ptr(world.vert_offset),
-                                              _ptr(world.local_x), _ptr(world.local_y), _ptr(emin), _ptr(emax)))
+        radius = getattr(world, "radius", None)
+        self._check(self.lib.shapes_set_shapes(self.ctx, world.n_slots, _ptr(world.alive), _ptr(world.vert_offset),
+                                               _ptr(world.local_x), _ptr(world.local_y), _ptr(emin), _ptr(emax),
+                                               _ptr(radius)))
         self.world = world
 
     def set_lagrangian_cache(self, lambda_np: np.ndarray, lambda_f: np.ndarray):

@@ -93,6 +93,46 @@ def broadphase_bench_world(spacing=0.0, dims=(30, 30)) -> World:
     return World.from_objects(_stacks((0.2, 0.2), (0.0, -4.5), spacing, dims), name="bp_bench")
 
 
+def balls_scene(dims=(10, 10), diameter=0.5, spacing=0.0) -> World:
+    """Balls.makeScene dims diameter spacing (shapes/src/Physics/Scenes/Balls.hs:69-72): the floor plus
+    columns that alternate circle stacks and box stacks (stacks_ not, :36-57), repeated additions."""
+    n_w, n_h = dims
+    left = 0.0 - (diameter * float(n_w - 1) / 2.0)
+    objs = [_box_floor()]
+    is_circle = True
+    for _ in range(n_w):
+        y = -4.5
+        for _ in range(n_h):
+            shape = diameter / 2.0 if is_circle else rectangle_vertices(diameter, diameter)
+            objs.append((shape, (left, y), 0.0, _BOX_MASS))
+            y = y + (diameter + spacing)
+        left = left + diameter
+        is_circle = not is_circle
+    w = World.from_objects(objs, name=f"balls{n_w}x{n_h}")
+    w.meta.update(dt=0.01, baumgarte=0.01, slop=0.02)
+    return w
+
+
+def random_circles_and_polygons(n=10_000, circle_frac=0.5, density=1.5, static_frac=0.05, config=6) -> World:
+    """Circles (radius U[0.2, 0.5]) mixed with convex polygons, uniform density."""
+    rng = SplitMix64(SEED_BASE + config)
+    is_c = rng.uniform(n) < circle_frac
+    n_poly = int((~is_c).sum())
+    off_p, lx, ly = _polygons(rng, n_poly)
+    nv = np.zeros(n, np.int64)
+    nv[~is_c] = np.diff(off_p)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(nv, out=off[1:])
+    radius = np.where(is_c, rng.uniform(n, 0.2, 0.5), -1.0)
+    side = math.sqrt(n / density)
+    px = rng.uniform(n, 0.0, side); py = rng.uniform(n, 0.0, side)
+    rot = rng.uniform(n, 0.0, 2.0 * math.pi)
+    static = rng.uniform(n) < static_frac
+    w = _finish(f"circles_polygons{n}", off, lx, ly, px, py, rot, static, {"config": config})
+    w.radius = np.ascontiguousarray(radius, np.float64)
+    return w.validate()
+
+
 def test_opt_boxes() -> World:
     """testOptBoxes (shapes/bench/Physics/Contact/Benchmark.hs:16-27): a 4x4 box at (0,0)
     and a 2x2 box at (1,3).  S.contact a b takes a = first, so the 4x4 box gets the larger

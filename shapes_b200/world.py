@@ -37,6 +37,7 @@ class World:
     rot: np.ndarray            # f64    [n]      _physObjRotPos
     inv_lin: np.ndarray        # f64    [n]      _physObjInvMass
     inv_rot: np.ndarray
+    radius: "np.ndarray | None" = None   # f64 [n]: >= 0 marks a CircleShape of that radius (no vertices); < 0 / None = hull
     name: str = "world"
     meta: dict = field(default_factory=dict)
 
@@ -56,6 +57,9 @@ class World:
             assert a.shape == (n,) and a.dtype == np.float64
         for a in (self.local_x, self.local_y):
             assert a.shape == (self.n_verts,) and a.dtype == np.float64
+        if self.radius is not None:
+            assert self.radius.shape == (n,) and self.radius.dtype == np.float64
+            assert np.all(np.diff(self.vert_offset)[self.radius >= 0] == 0), "a circle slot owns no vertices"
         return self
 
     def delete(self, slots: Iterable[int]) -> "World":
@@ -67,7 +71,7 @@ class World:
     @staticmethod
     def from_objects(objs: Sequence[tuple[Sequence[tuple[float, float]], tuple[float, float], float,
                                           tuple[float, float]]], name: str = "world") -> "World":
-        """objs: (local CCW vertices, position, rotation, (linear mass, rotational mass)),
+        """objs: (local CCW vertices | circle radius, position, rotation, (linear mass, rotational mass)),
         appended in order like World.fromList (World.hs:111-116)."""
         n = len(objs)
         off = np.zeros(n + 1, np.int32)
@@ -75,11 +79,15 @@ class World:
         ly: list[float] = []
         px = np.zeros(n); py = np.zeros(n); rot = np.zeros(n)
         il = np.zeros(n); ir = np.zeros(n)
+        radius = np.full(n, -1.0)
         for s, (verts, pos, r, mass) in enumerate(objs):
+            if isinstance(verts, (int, float)):      # makeCircle radius (Engine.hs:53-54)
+                radius[s] = float(verts)
+                verts = ()
             for (x, y) in verts:
                 lx.append(float(x)); ly.append(float(y))
             off[s + 1] = len(lx)
             px[s], py[s], rot[s] = pos[0], pos[1], r
             il[s], ir[s] = to_inv_mass2(mass)
         return World(np.ones(n, np.uint8), off, np.asarray(lx, np.float64), np.asarray(ly, np.float64),
-                     px, py, rot, il, ir, name=name).validate()
+                     px, py, rot, il, ir, radius=radius if (radius >= 0).any() else None, name=name).validate()

@@ -181,3 +181,41 @@ def test_warm_join_desc_zip_vector_semantics(oracle):
     empty = {k: np.zeros(0, np.int32) for k in this}
     assert oracle.warm_join(this, empty, np.zeros(0), np.zeros(0))[2].tolist() == [0] * 6
     assert len(oracle.warm_join(empty, that, np.ones(5), np.ones(5))[2]) == 0
+
+
+def test_kat4_kat5_circles(oracle, kat):
+    """Circle.contact and CircleVsHull/GJK on hand-derived vectors (tests/golden/README.md)."""
+    from shapes_b200.world import World, rectangle_vertices
+    k4 = kat["kat4_circle_circle"]
+    w = World.from_objects([(k4["b"]["radius"], tuple(k4["b"]["center"]), 0.0, (1.0, 1.0)),
+                            (k4["a"]["radius"], tuple(k4["a"]["center"]), 0.0, (1.0, 1.0))])
+    r = oracle.frame(w)
+    c = k4["contact"]
+    assert len(r["key_i"]) == 1 and [r["feat_a"][0], r["feat_b"][0]] == c["feat"] and r["flip"][0] == c["flip"]
+    assert [r["normal_x"][0], r["normal_y"][0]] == c["normal"] and [r["center_x"][0], r["center_y"][0]] == c["center"]
+    assert r["depth"][0] == c["depth"]
+    k5 = kat["kat5_circle_hull"]
+    box = (rectangle_vertices(*k5["box"]["size"]), tuple(k5["box"]["center"]), 0.0, (1.0, 1.0))
+    cir = (k5["circle"]["radius"], tuple(k5["circle"]["center"]), 0.0, (1.0, 1.0))
+    for objs, name in (([box, cir], "circle_is_a"), ([cir, box], "hull_is_a")):
+        r = oracle.frame(World.from_objects(objs))
+        c = k5[name]
+        assert len(r["key_i"]) == 1 and [r["feat_a"][0], r["feat_b"][0]] == c["feat"] and r["flip"][0] == c["flip"]
+        assert [r["normal_x"][0], r["normal_y"][0]] == c["normal"] and [r["center_x"][0], r["center_y"][0]] == c["center"]
+        assert r["depth"][0] == c["depth"]
+        if "rn" in c:
+            assert [r["rn_x"][0], r["rn_y"][0]] == c["rn"]
+
+
+def test_circle_worlds_oracle_invariants(oracle):
+    """Balls.makeScene and a random circle/polygon world: brute force == sweep == grid, unit normals."""
+    for w in (scenes.balls_scene((8, 6), 0.5, 0.0), scenes.random_circles_and_polygons(1500, config=60)):
+        a = oracle.frame(w, broadphase="aabb")
+        s_ = oracle.frame(w, broadphase="sweep")
+        assert np.array_equal(a["pair_i"], s_["pair_i"]) and np.array_equal(a["pair_j"], s_["pair_j"])
+        assert len(a["key_i"]) > 0
+        assert np.allclose(a["normal_x"] ** 2 + a["normal_y"] ** 2, 1.0)
+        ck = (a["key_i"].astype(np.int64) << 32) | a["key_j"]
+        assert np.all(ck[:-1] >= ck[1:])
+    w = scenes.balls_scene((4, 3), 0.5, 0.0)
+    assert w.radius is not None and (w.radius >= 0).sum() == 6 and w.n_slots == 13
