@@ -5,7 +5,7 @@
 // names and argument meaning:
 //
 //   shapes::World            Physics.World.World          (shapes/src/Physics/World.hs:46-84)
-//   shapes::makeRectangleHull / makeHull                  (shapes/src/Physics/Engine.hs:47-51)
+//   shapes::makeRectangleHull / makeHull / makeCircle      (shapes/src/Physics/Engine.hs:47-54)
 //   shapes::makePhysicalObj  + toInvMass2                 (Engine.hs:32-39, Constraint.hs:79-83)
 //   shapes::culledKeys       Aabb.culledKeys / Grid.culledKeys   (Broadphase/Aabb.hs:168-183)
 //   shapes::prepareFrame     Solvers.Contact.prepareFrame        (Solvers/Contact.hs:40-52)
@@ -56,6 +56,9 @@ inline Hull makeRectangleHull(double w, double h)
     return Hull{ { w2, h2 }, { -w2, h2 }, { -w2, -h2 }, { w2, -h2 } };
 }
 inline Hull makeHull(std::vector<V2> vertices) { return vertices; }
+// makeCircle (Engine.hs:53-54): CircleShape (circleWithRadius r)
+struct Circle { double radius; };
+inline Circle makeCircle(double radius) { return Circle{ radius }; }
 
 // World: SoA body columns + CSR hull geometry + EmptiesVector filled flags.
 class World {
@@ -64,6 +67,8 @@ public:
     std::vector<int32_t> vert_offset{ 0 };
     std::vector<double> local_x, local_y;
     std::vector<double> pos_x, pos_y, rot, inv_lin, inv_rot;
+    std::vector<double> radius;   // >= 0: CircleShape of that radius (no vertices); < 0: HullShape
+    bool has_circles = false;
     bool geometry_dirty = true;
 
     // World.append (World.hs:77-84): returns the new object's key
@@ -72,10 +77,18 @@ public:
         for (const V2 &v : hull) { local_x.push_back(v.x); local_y.push_back(v.y); }
         vert_offset.push_back((int32_t)local_x.size());
         alive.push_back(1);
+        radius.push_back(-1.0);
         pos_x.push_back(obj.pos.x); pos_y.push_back(obj.pos.y); rot.push_back(obj.rotPos);
         inv_lin.push_back(obj.invLin); inv_rot.push_back(obj.invRot);
         geometry_dirty = true;
         return (int)alive.size() - 1;
+    }
+    int append(const PhysicalObj &obj, const Circle &circle)
+    {
+        const int key = append(obj, Hull{});
+        radius.back() = circle.radius;
+        has_circles = true;
+        return key;
     }
     // World.delete (World.hs:86-87): the slot stays, keys remain sparse
     void remove(int key) { alive.at((size_t)key) = 0; geometry_dirty = true; }
@@ -207,8 +220,8 @@ private:
     {
         if (!ctx_ || w.slots() > cap_slots_ || (int64_t)w.local_x.size() > cap_verts_) { create(w); w.geometry_dirty = true; }
         if (w.geometry_dirty) {
-            const int rc = shapes_set_hulls(ctx_, w.slots(), w.alive.data(), w.vert_offset.data(), w.local_x.data(),
-                                            w.local_y.data(), nullptr, nullptr);
+            const int rc = shapes_set_shapes(ctx_, w.slots(), w.alive.data(), w.vert_offset.data(), w.local_x.data(),
+                                             w.local_y.data(), nullptr, nullptr, w.has_circles ? w.radius.data() : nullptr);
             if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
             w.geometry_dirty = false;
         }

@@ -56,6 +56,28 @@ int main()
                 CHECK(c0.normal.x == -0.0 && c0.normal.y == 1.0);         // Restitution: -n for Flip
             }
         }
+        {   // KAT-4 / KAT-5: circles (Circle.contact; CircleVsHull through GJK)
+            World w;
+            w.append(makePhysicalObj({ 3.0, 0.0 }, 0.0, { 1.0, 1.0 }), makeCircle(1.5));
+            w.append(makePhysicalObj({ 0.0, 0.0 }, 0.0, { 1.0, 1.0 }), makeCircle(2.0));
+            auto cs = prepareFrame(eng, w);
+            CHECK(cs.size() == 1);
+            if (cs.size() == 1) {
+                CHECK(cs[0].featA == 0 && cs[0].featB == 0 && !cs[0].flip);
+                CHECK(cs[0].normal.x == 1.0 && cs[0].normal.y == 0.0);
+                CHECK(cs[0].center.x == 1.75 && cs[0].center.y == 0.0 && cs[0].depth == 0.5);
+            }
+            World w2;
+            w2.append(makePhysicalObj({ 0.0, 1.4 }, 0.0, { 1.0, 1.0 }), makeCircle(0.5));
+            w2.append(makePhysicalObj({ 0.0, 0.0 }, 0.0, { 1.0, 1.0 }), makeRectangleHull(2.0, 2.0));
+            auto c2 = prepareFrame(eng, w2);      // hull = shape a (larger key) => ((hullFeature, 0), Flip)
+            CHECK(c2.size() == 1);
+            if (c2.size() == 1) {
+                CHECK(c2[0].featA == 1 && c2[0].featB == 0 && c2[0].flip);
+                CHECK(c2[0].normal.x == 0.0 && c2[0].normal.y == -1.0);
+                CHECK(c2[0].center.x == 0.0 && c2[0].center.y == 1.0 && c2[0].depth == 0.10000000000000009);
+            }
+        }
         {   // KAT-3
             World w;
             stacks(w, 0.2, 0.2, 0.0, -4.5, 0.0, 30, 30);
