@@ -228,6 +228,76 @@ int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
 int  shapes_ipc_export(shapes_ctx *, void *out_blob /* SHAPES_IPC_BYTES */);
 int  shapes_ipc_import(shapes_ctx *, const void *all_blobs /* world_size x SHAPES_IPC_BYTES */);
 
+/* ---- device-resident world ---------------------------- */
+
+/* The rest of Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) on the GPU: the body state
+ * (_wPhysObjs, _wMaterials; World.hs:46-52) lives in HBM, and one shapes_world_step call runs
+ *   culledKeys -> applyExternal -> prepareFrame -> applyCachedSlns -> improveWorld x iterations
+ *   -> advance -> moveShapes
+ * without any per-frame host<->device traffic.  The solver reproduces the reference's SEQUENTIAL
+ * Gauss-Seidel walk bit for bit: contacts are executed as the dependency graph that walk defines
+ * (a contact waits only for the previous contact on either of its two bodies), so every body sees
+ * its velocity updates in the reference's order.  Opt-in: a host that keeps its own solver simply
+ * never calls these functions.  Single-GPU ctxs only.
+ *
+ * Rotation: moveShapes needs cos/sin of the advanced rotation; the device uses shapes_sincos
+ * (include/shapes_sincos.h), a plain-IEEE routine the host can call too (same bits on both sides,
+ * <= 1 ulp from libm).  A step sequence is therefore bit-identical to the reference's updateWorld
+ * evaluated with shapes_sincos in place of libm's cos/sin in rotate22 (Linear.hs:353-357). */
+
+#define SHAPES_EXT_NONE  0
+#define SHAPES_EXT_ACCEL 1   /* constantAccel (World/External.hs:23-27) */
+#define SHAPES_EXT_FORCE 2   /* constantForce (World/External.hs:16-20), as the reference parses it */
+
+typedef struct shapes_step_config {
+    double dt;                 /* _engineTimestep (Engine/Main.hs:34-37) */
+    double baumgarte, slop;    /* ContactBehavior (Contact/Types.hs:20-25) */
+    int32_t external_kind;     /* SHAPES_EXT_* : the External applied each frame (World.hs:32-33) */
+    int32_t solver_iterations; /* improveWorld sweeps; updateWorld runs 2 (Engine/Main.hs:82-83) */
+    double external_x, external_y;
+    int32_t warm_start;        /* 1 = applyCachedSlns against the previous step's cache (updateWorld);
+                                  0 = every contact starts from ContactLagrangian 0 0 */
+    int32_t reserved;
+} shapes_step_config;
+
+typedef struct shapes_step_stats {
+    int64_t n_pairs, n_contacts;
+    int64_t solver_nodes;      /* (sweep, contact pair) nodes executed */
+    int64_t queue_pushes;      /* nodes that went through the ready queue instead of being chained */
+    int64_t body_chains;       /* dynamic bodies with at least one contact */
+    int32_t warm;              /* 1 = the cache join ran (sweep 0 applied cached Lagrangians) */
+    int32_t reserved;
+    float   frame_ms;          /* the hot path (K0..K3 + join), device time */
+    float   chains_ms;         /* external + dependency chains (sort + links) */
+    float   solve_ms;          /* k_solve */
+    float   integrate_ms;      /* advance + cache hand-over */
+    float   total_ms;          /* whole step, device time */
+} shapes_step_stats;
+
+/* Host columns of the n_slots objects: velocity, position, rotation (PhysicalObj, Constraint.hs:52-63),
+ * inverse masses, materials (mu = _mMu, bounce = _mBounce, World.hs:36-40).  cos_rot / sin_rot: the
+ * rotation the shapes were last moved with (makeWorldObj's moveShape); both NULL = shapes_sincos(rot).
+ * Requires shapes_set_hulls / shapes_set_shapes.  Resets the EngineCache (initEngine). */
+int  shapes_world_upload(shapes_ctx *, int64_t n_slots,
+                         const double *vel_x, const double *vel_y, const double *rot_vel,
+                         const double *pos_x, const double *pos_y, const double *rot,
+                         const double *cos_rot, const double *sin_rot,
+                         const double *inv_lin, const double *inv_rot,
+                         const double *mu, const double *bounce);
+/* Copy the body state back; any pointer may be NULL. */
+int  shapes_world_download(shapes_ctx *, int64_t n_slots,
+                           double *vel_x, double *vel_y, double *rot_vel,
+                           double *pos_x, double *pos_y, double *rot,
+                           double *cos_rot, double *sin_rot);
+/* One updateWorld.  SHAPES_E_CAPACITY (required counts in stats->n_pairs / n_contacts) leaves the
+ * world untouched.  Afterwards shapes_fetch / shapes_device_view_get describe the frame the step
+ * generated its contacts from; warm_hit is the cache join, warm_np / warm_f are the Lagrangians
+ * the solver LEFT (= the EngineCache the next step joins against). */
+int  shapes_world_step(shapes_ctx *, const shapes_step_config *cfg, shapes_step_stats *stats /* may be NULL */);
+
+/* Host-side evaluation of the shared cos/sin (include/shapes_sincos.h). Needs no GPU. */
+void shapes_sincos(int64_t n, const double *rot, double *cos_out, double *sin_out);
+
 /* ---- helpers ----------------------------------------------------------- */
 
 void *shapes_host_alloc(size_t bytes);     /* pinned host memory, NULL on failure */

@@ -37,10 +37,9 @@ class ContactsOut(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_DIR, "shapes_oracle.c")
-    hdr = os.path.join(_DIR, "shapes_oracle.h")
+    deps = [os.path.join(_DIR, f) for f in ("shapes_oracle.c", "shapes_oracle_step.c", "shapes_oracle.h", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or \
-            max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(LIB_PATH):
+            max(os.path.getmtime(d) for d in deps) > os.path.getmtime(LIB_PATH):
         subprocess.run(["make", "-C", _DIR, "-B", "libshapes_oracle.so"], check=True,
                        stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -52,8 +51,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()
         _lib = C.CDLL(LIB_PATH)
         _lib.orc_culled_keys_aabb.restype = C.c_int64
         _lib.orc_culled_keys_grid.restype = C.c_int64
@@ -223,3 +221,74 @@ def warm_join(this, that, that_np, that_f):
     lib().orc_warm_join(C.c_int64(n), *[_p(x, _i32p) for x in a], C.c_int64(m), *[_p(x, _i32p) for x in b],
                         _f(tn), _f(tf), _f(out_np), _f(out_f), _p(hit, _u8p))
     return out_np, out_f, hit
+
+
+# ---- the rest of updateWorld (shapes_oracle_step.c) ---------------------------------------------
+
+EXT_NONE, EXT_ACCEL, EXT_FORCE = 0, 1, 2
+
+
+def apply_external(world, vel_x, vel_y, kind, ex, ey, dt):
+    """applyExternal (World.hs:156-158), in place on vel_x / vel_y."""
+    lib().orc_apply_external(C.c_int64(world.n_slots), _p(world.alive, _u8p), C.c_int(kind), C.c_double(ex),
+                             C.c_double(ey), C.c_double(dt), _f(world.inv_lin), _f(vel_x), _f(vel_y))
+
+
+def advance(world, vel_x, vel_y, rot_vel, dt):
+    """advance (World.hs:167-169), in place on world.pos_x / pos_y / rot."""
+    lib().orc_advance(C.c_int64(world.n_slots), _p(world.alive, _u8p), C.c_double(dt), _f(vel_x), _f(vel_y),
+                      _f(rot_vel), _f(world.pos_x), _f(world.pos_y), _f(world.rot))
+
+
+def _cols6(fr, prefix):
+    arr = (_f64p * 6)()
+    keep = []
+    for q in range(6):
+        a = np.ascontiguousarray(fr[f"{prefix}{q}"], np.float64)
+        keep.append(a)
+        arr[q] = _f(a)
+    return arr, keep
+
+
+def apply_cached(world, fr, hit, lam_np, lam_f, vel_x, vel_y, rot_vel):
+    """useCache's applySln for the rows the join hit (Solvers/Contact.hs:99-112)."""
+    jn, k1 = _cols6(fr, "j_np"); jf, k2 = _cols6(fr, "j_f")
+    lib().orc_apply_cached(C.c_int64(len(fr["key_i"])), _p(fr["key_i"], _i32p), _p(fr["key_j"], _i32p),
+                           _p(hit, _u8p), _f(lam_np), _f(lam_f), jn, jf, _f(world.inv_lin), _f(world.inv_rot),
+                           _f(vel_x), _f(vel_y), _f(rot_vel))
+
+
+def improve_world(world, fr, mu, bounce, vel_x, vel_y, rot_vel, lam_np, lam_f):
+    """One improveWorld solutionProcessor sweep (Solvers/Contact.hs:146-157), in place."""
+    jn, k1 = _cols6(fr, "j_np"); jf, k2 = _cols6(fr, "j_f")
+    lib().orc_improve_world(C.c_int64(len(fr["key_i"])), _p(fr["key_i"], _i32p), _p(fr["key_j"], _i32p),
+                            jn, _f(fr["b_np"]), _f(fr["ra_x"]), _f(fr["ra_y"]), _f(fr["rb_x"]), _f(fr["rb_y"]),
+                            _f(fr["rn_x"]), _f(fr["rn_y"]), jf, _f(mu), _f(bounce),
+                            _f(world.inv_lin), _f(world.inv_rot), _f(vel_x), _f(vel_y), _f(rot_vel),
+                            _f(lam_np), _f(lam_f))
+
+
+def update_world(world, bodies, cache, cos_rot, sin_rot, dt=0.01, baumgarte=0.01, slop=0.02,
+                 external=(EXT_NONE, 0.0, 0.0), iterations=2, sincos=None, broadphase="auto"):
+    """Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) on the CPU, one frame, in place:
+    culledKeys -> applyExternal -> prepareFrame -> applyCachedSlns -> improveWorld x iterations ->
+    advance -> moveShapes.  `bodies` carries vel_x, vel_y, rot_vel, mu, bounce (numpy columns);
+    `cache` is the EngineCache: None or (keys dict, lam_np, lam_f) from the previous frame;
+    cos_rot / sin_rot are the rotation columns the shapes were last moved with; `sincos` maps the
+    new rot column to (cos, sin) -- libm (the reference's rotate22) when None.
+    Returns (frame dict, new cache, new cos, new sin)."""
+    fr = frame(world, cos_rot, sin_rot, dt=dt, baumgarte=baumgarte, slop=slop, broadphase=broadphase)
+    apply_external(world, bodies.vel_x, bodies.vel_y, external[0], external[1], external[2], dt)
+    n = len(fr["key_i"])
+    if cache is not None:
+        lam_np, lam_f, hit = warm_join(fr, cache[0], cache[1], cache[2])
+    else:
+        lam_np, lam_f, hit = np.zeros(n), np.zeros(n), np.zeros(n, np.uint8)
+    apply_cached(world, fr, hit, lam_np, lam_f, bodies.vel_x, bodies.vel_y, bodies.rot_vel)
+    for _ in range(iterations):
+        improve_world(world, fr, bodies.mu, bodies.bounce, bodies.vel_x, bodies.vel_y, bodies.rot_vel, lam_np, lam_f)
+    advance(world, bodies.vel_x, bodies.vel_y, bodies.rot_vel, dt)
+    c, s = (sincos or cos_sin)(world.rot)
+    keys = {k: fr[k] for k in ("key_i", "key_j", "feat_a", "feat_b")}
+    fr["warm_hit"] = hit
+    return fr, (keys, lam_np, lam_f), c, s

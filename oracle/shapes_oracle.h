@@ -173,6 +173,34 @@ void orc_mul2x2x2(const double *a, const double *b, double *out);
 void orc_solve_constraint(const double *j6, double b, const double *inv_mass6,
                           double *vel6);
 
+/* ---- the rest of updateWorld: shapes_oracle_step.c -------
+ * applyExternal (World.hs:156-158) with constantAccel (kind 1) / constantForce (kind 2)
+ * (World/External.hs:16-28); kind 0 = no external. */
+void orc_apply_external(int64_t n_slots, const uint8_t *alive, int kind, double ex, double ey, double dt,
+                        const double *inv_lin, double *vel_x, double *vel_y);
+/* advance (World.hs:167-169, advanceObj Constraint.hs:225-229). */
+void orc_advance(int64_t n_slots, const uint8_t *alive, double dt,
+                 const double *vel_x, const double *vel_y, const double *rot_vel,
+                 double *pos_x, double *pos_y, double *rot);
+/* useCache's applySln over the rows the warm join hit (Solvers/Contact.hs:54-65,99-112). */
+void orc_apply_cached(int64_t n_contacts, const int32_t *key_i, const int32_t *key_j, const uint8_t *hit,
+                      const double *lam_np, const double *lam_f,
+                      const double *const j_np[6], const double *const j_f[6],
+                      const double *inv_lin, const double *inv_rot,
+                      double *vel_x, double *vel_y, double *rot_vel);
+/* One improveWorld solutionProcessor sweep (Solvers/Contact.hs:124-157, Constraints/Contact.hs:74-110,
+ * SolutionProcessors.hs:12-53, Restitution.hs:34-47); lam_np / lam_f are the EngineCache values,
+ * updated in place. */
+void orc_improve_world(int64_t n_contacts, const int32_t *key_i, const int32_t *key_j,
+                       const double *const j_np[6], const double *b_np,
+                       const double *ra_x, const double *ra_y, const double *rb_x, const double *rb_y,
+                       const double *rn_x, const double *rn_y,
+                       const double *const j_f[6],
+                       const double *mu, const double *bounce,
+                       const double *inv_lin, const double *inv_rot,
+                       double *vel_x, double *vel_y, double *rot_vel,
+                       double *lam_np, double *lam_f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,29 @@ class DeviceView(C.Structure):
     ]
 
 
+class StepConfig(C.Structure):
+    """shapes_step_config"""
+    _fields_ = [
+        ("dt", C.c_double), ("baumgarte", C.c_double), ("slop", C.c_double),
+        ("external_kind", C.c_int32), ("solver_iterations", C.c_int32),
+        ("external_x", C.c_double), ("external_y", C.c_double),
+        ("warm_start", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class StepStats(C.Structure):
+    """shapes_step_stats"""
+    _fields_ = [
+        ("n_pairs", C.c_int64), ("n_contacts", C.c_int64),
+        ("solver_nodes", C.c_int64), ("queue_pushes", C.c_int64), ("body_chains", C.c_int64),
+        ("warm", C.c_int32), ("reserved", C.c_int32),
+        ("frame_ms", C.c_float), ("chains_ms", C.c_float), ("solve_ms", C.c_float),
+        ("integrate_ms", C.c_float), ("total_ms", C.c_float),
+    ]
+
+
+EXT_NONE, EXT_ACCEL, EXT_FORCE = 0, 1, 2
+
 # every symbol include/shapes_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "shapes_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
@@ -85,6 +108,10 @@ SYMBOLS = {
     "shapes_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "shapes_rank_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "shapes_world_upload": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 12),
+    "shapes_world_download": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 8),
+    "shapes_world_step": (C.c_int, [C.c_void_p, C.POINTER(StepConfig), C.POINTER(StepStats)]),
+    "shapes_sincos": (None, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "shapes_host_alloc": (C.c_void_p, [C.c_size_t]),
     "shapes_host_free": (None, [C.c_void_p]),
     "shapes_stream": (C.c_void_p, [C.c_void_p]),

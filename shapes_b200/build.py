@@ -30,8 +30,8 @@ def nvcc_command(out: str = LIB, extra: list[str] | None = None) -> list[str]:
         nvcc_path(), "-O3", "-std=c++17",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-lineinfo", "-fmad=false",
-        "-Xcompiler", "-fPIC", "-shared",
-        "-I", INC, "-o", out, SRC, "-ldl",
+        "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
+        "-I", INC, "-I", os.path.dirname(SRC), "-o", out, SRC, "-ldl",
     ] + (extra or [])
 
 
@@ -39,7 +39,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [SRC, os.path.join(INC, "shapes_b200.h")]
+    deps = [SRC, os.path.join(os.path.dirname(SRC), "world_step.cuh"),
+            os.path.join(INC, "shapes_b200.h"), os.path.join(INC, "shapes_sincos.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1355,7 +1355,10 @@ struct FrameKey {   // everything a captured frame graph bakes in
     int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote; int64_t geometry, n_prev; unsigned cell_limit;
 };
 
+struct WorldStep;   // device-resident world (world_step.cuh)
+
 struct shapes_ctx {
+    WorldStep *ws = nullptr;
     int device = 0;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -1828,7 +1831,11 @@ int fetch_col(shapes_ctx *c, T *dst, const T *src, int64_t n)
     return SHAPES_OK;
 }
 
+void world_free(shapes_ctx *c);
+
 } // namespace
+
+#include "world_step.cuh"
 
 extern "C" {
 
@@ -1867,6 +1874,7 @@ void shapes_destroy(shapes_ctx *c)
     for (int q = 0; q < 2; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl_api().CommDestroy(c->comm);
+    world_free(c);
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_counts) cudaFreeHost(c->h_counts);

@@ -335,6 +335,41 @@ class Engine:
                 self.grow(e.n_pairs, e.n_contacts)
         return self.frame(**kw)
 
+    # -- device-resident world ---------------------------------------------
+    def world_upload(self, bodies, cos_sin: Optional[tuple[np.ndarray, np.ndarray]] = None):
+        """shapes_world_upload: the world's PhysicalObj / Material columns move to HBM.
+        `bodies` is a world.Bodies; positions and inverse masses come from self.world."""
+        w = self.world
+        cols = [np.ascontiguousarray(a, np.float64) for a in
+                (bodies.vel_x, bodies.vel_y, bodies.rot_vel, w.pos_x, w.pos_y, w.rot)]
+        cs = [None, None]
+        if cos_sin is not None:
+            cs = [np.ascontiguousarray(cos_sin[0], np.float64), np.ascontiguousarray(cos_sin[1], np.float64)]
+        rest = [np.ascontiguousarray(a, np.float64) for a in (w.inv_lin, w.inv_rot, bodies.mu, bodies.bounce)]
+        self._check(self.lib.shapes_world_upload(self.ctx, w.n_slots, *[_ptr(a) for a in cols], _ptr(cs[0]), _ptr(cs[1]),
+                                                 *[_ptr(a) for a in rest]))
+
+    def world_download(self) -> dict[str, np.ndarray]:
+        """shapes_world_download: vel_x, vel_y, rot_vel, pos_x, pos_y, rot, cos_rot, sin_rot."""
+        n = self.world.n_slots
+        names = ("vel_x", "vel_y", "rot_vel", "pos_x", "pos_y", "rot", "cos_rot", "sin_rot")
+        out = {k: np.empty(n) for k in names}
+        self._check(self.lib.shapes_world_download(self.ctx, n, *[_ptr(out[k]) for k in names]))
+        return out
+
+    def world_step(self, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02,
+                   external=(_lib.EXT_NONE, 0.0, 0.0), iterations: int = 2, warm_start: bool = True) -> _lib.StepStats:
+        """shapes_world_step: one Physics.Engine.Main.updateWorld on the device."""
+        cfg = _lib.StepConfig(dt, baumgarte, slop, int(external[0]), int(iterations), float(external[1]),
+                              float(external[2]), 1 if warm_start else 0, 0)
+        stats = _lib.StepStats()
+        rc = self.lib.shapes_world_step(self.ctx, C.byref(cfg), C.byref(stats))
+        if rc == _lib.E_CAPACITY:
+            msg = self.lib.shapes_last_error(self.ctx)
+            raise CapacityError(msg.decode() if msg else "", int(stats.n_pairs), int(stats.n_contacts))
+        self._check(rc)
+        return stats
+
     def set_profiling(self, on: bool = True):
         self._check(self.lib.shapes_set_profiling(self.ctx, 1 if on else 0))
 
@@ -365,6 +400,20 @@ def nccl_unique_id() -> bytes:
 # ---------------------------------------------------------------------------
 # the reference's entry points, by name
 # ---------------------------------------------------------------------------
+
+def sincos(rot: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """shapes_sincos on the host: the cos/sin the device-resident world uses (same bits as the GPU)."""
+    r = np.ascontiguousarray(rot, np.float64)
+    c = np.empty_like(r); s = np.empty_like(r)
+    _lib.load().shapes_sincos(r.shape[0], _ptr(r), _ptr(c), _ptr(s))
+    return c, s
+
+
+def updateWorld(engine: Engine, dt: float, beh: "ContactBehavior", external=(_lib.EXT_NONE, 0.0, 0.0)) -> _lib.StepStats:
+    """Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) on a world uploaded with world_upload."""
+    return engine.world_step(dt=dt, baumgarte=beh.contactBaumgarte, slop=beh.contactPenetrationSlop, external=external,
+                             iterations=2)
+
 
 def culledKeys(engine: Engine, cos_sin=None) -> np.ndarray:
     """Aabb.culledKeys world :: Descending (Int, Int) -- (n_pairs, 2), descending."""

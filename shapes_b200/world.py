@@ -26,6 +26,25 @@ def to_inv_mass2(mass: tuple[float, float]) -> tuple[float, float]:
 
 
 @dataclass
+class Bodies:
+    """Velocity and material columns of the world's objects: the part of PhysicalObj
+    (shapes/src/Physics/Constraint.hs:52-63) and Material (World.hs:36-40) that only the solver and
+    the integrator touch.  Used by the device-resident world step (Engine.world_upload / updateWorld)."""
+    vel_x: np.ndarray          # f64 [n]  _physObjVel
+    vel_y: np.ndarray
+    rot_vel: np.ndarray        # f64 [n]  _physObjRotVel
+    mu: np.ndarray             # f64 [n]  _mMu
+    bounce: np.ndarray         # f64 [n]  _mBounce
+
+    @staticmethod
+    def at_rest(n: int, mu: float = 0.2, bounce: float = 0.2) -> "Bodies":
+        return Bodies(np.zeros(n), np.zeros(n), np.zeros(n), np.full(n, float(mu)), np.full(n, float(bounce)))
+
+    def copy(self) -> "Bodies":
+        return Bodies(*(a.copy() for a in (self.vel_x, self.vel_y, self.rot_vel, self.mu, self.bounce)))
+
+
+@dataclass
 class World:
     """n_slots slots; slot s owns vertices [vert_offset[s], vert_offset[s+1])."""
     alive: np.ndarray          # uint8  [n]      EmptiesVector filled flags
