@@ -225,7 +225,7 @@ struct Params {
     // warm start (descZipVector): previous frame's keys + the host solver's Lagrangian cache for them
     const int32_t *pk_i, *pk_j, *pk_fa, *pk_fb;
     const double *cache_np, *cache_f;
-    long long n_prev;
+    const long long *n_prev;    // device word, set outside the captured graph (the count changes every frame)
     double *warm_np, *warm_f;
     uint8_t *warm_hit;
     FrameState *st;
@@ -270,6 +270,8 @@ __device__ __forceinline__ Box box_of(const Params &P, int s)
 // ---------------------------------------------------------------------------------------------
 // K0: moveShapes + toAabb
 // ---------------------------------------------------------------------------------------------
+
+__global__ void k_set_i64(long long *p, long long v) { *p = v; }
 
 __global__ void k_reset_state(FrameState *st)
 {
@@ -1210,7 +1212,7 @@ __global__ void __launch_bounds__(256) k_warm_join(Params P)
     const FrameState *st = P.st;
     if (st->error) return;
     const long long n_rows = st->n_contacts < P.max_contacts ? st->n_contacts : P.max_contacts;
-    const long long n_prev = P.n_prev;
+    const long long n_prev = *P.n_prev;
     for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
          row += (long long)gridDim.x * blockDim.x) {
         const unsigned long long key = ((unsigned long long)(unsigned)P.key_i[row] << 32) | (unsigned)P.key_j[row];
@@ -1397,6 +1399,7 @@ struct shapes_ctx {
     void *d_scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     FrameState *h_state = nullptr; // pinned
+    long long *d_n_prev = nullptr; // rows of the previous frame's key columns (read by k_warm_join)
     int64_t *d_counts = nullptr;   // world x 2 (pairs, contacts), all-gathered
     int64_t *h_counts = nullptr;   // pinned
     Params P{};
@@ -1577,6 +1580,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     for (int q = 0; q < 6; ++q) { TRY_CREATE(dev_alloc(c, &P.j_np[q], C)); TRY_CREATE(dev_alloc(c, &P.j_f[q], C)); }
     TRY_CREATE(dev_alloc(c, &P.st, 1));
     TRY_CREATE(dev_alloc(c, &c->d_counts, 2 * world));
+    TRY_CREATE(dev_alloc(c, &c->d_n_prev, 1));
     TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
     TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 2 * world), "cudaMallocHost"));
     // library scratch: radix sort of (cell key, slot) and the offset scan
@@ -1643,7 +1647,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     const bool warm = c->cache_valid && c->n_prev_keys >= 0;
     P.pk_i = c->alt_key[0]; P.pk_j = c->alt_key[1]; P.pk_fa = c->alt_key[2]; P.pk_fb = c->alt_key[3];
     P.cache_np = c->d_cache_np; P.cache_f = c->d_cache_f;
-    P.n_prev = warm ? c->n_prev_keys : 0;
+    const long long n_prev_now = warm ? c->n_prev_keys : 0;
+    P.n_prev = c->d_n_prev;
     // Cell budget of this frame: the scan and the clear cover exactly this many cells, so it follows
     // the grid the last frame needed (x2 head-room) instead of the table capacity; the planner coarsens
     // the cells if the world outgrows it within one frame (results do not depend on the cell size).
@@ -1769,9 +1774,10 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
-    key.warm = warm; key.n_prev = P.n_prev; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0;
-    const int64_t launches_before = c->launches;
+    key.warm = warm; key.n_prev = 0; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
+    k_set_i64<<<1, 1, 0, s>>>(c->d_n_prev, n_prev_now); ++c->launches;   // outside the graph: varies per frame
+    const int64_t launches_before = c->launches;
     // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
     if (!c->use_graph || c->profiling || c->world > 1) { // per-stage events cannot be timed from inside a graph
         const int rc = issue();

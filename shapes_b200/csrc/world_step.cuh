@@ -38,18 +38,40 @@ constexpr unsigned SOLVE_NODE_MASK = (1u << SOLVE_PASS_SHIFT) - 1u;
 constexpr int SOLVE_THREADS = 128;
 constexpr unsigned long long SOLVE_IDLE_LIMIT_NS = 4000000000ull;   // a thread idle for ~4 s of sleeps gives up
 
-struct SolveState {
+// Shared scheduler words, one 128 B line each: the idle pollers, the pushers and the chain ends
+// must not queue up behind each other on one L2 sector.
+struct __align__(128) SolveState {
     unsigned long long head;      // next queue slot to claim
+    unsigned long long pad0[15];
     unsigned long long tail;      // next queue slot to fill
+    unsigned long long pad1[15];
     unsigned done;                // body chains that finished their last sweep
+    unsigned pad2[31];
     unsigned expected;            // body chains that exist (dynamic bodies with at least one contact)
+    int overflow;                 // 1 = queue overflow, 2 = idle time-out (both are internal errors)
     unsigned long long nodes_run; // statistics
     unsigned long long queue_cap;
-    int overflow;
+    unsigned long long pad3[13];
 };
+
+// Everything static a node needs, one 32 B sector: bodies, first contact row, successor links.
+struct __align__(32) NodeRec {
+    int i, j;                     // pair_i (larger key), pair_j
+    unsigned r0;                  // first contact row of the pair
+    unsigned flags;               // rows [0,2) | body i dynamic [2] | body j dynamic [3]
+    int next_i, next_j;           // >= 0: next node on that body in this sweep; < 0: -1 - (first node of the body's chain)
+    unsigned succ_r0_i, succ_r0_j; // first contact row of those two successor nodes (so their rows can be prefetched a node ahead)
+};
+// One contact row as the solver reads it (array of structures, 192 B = 6 sectors): the SoA result
+// columns stay the product's output; this copy is packed by k_pack_rows for the gather-heavy solver.
+constexpr int ROW_DOUBLES = 24;   // jn[6] jf[6] b_np inv_eff_np inv_eff_f ra[2] rb[2] rn[2] hit pad[2]
+struct __align__(32) BodyRec { double inv_lin, inv_rot, mu, bounce; };
 
 struct SolveParams {
     const FrameState *st;
+    NodeRec *node;
+    double *rows;                 // n_contacts x ROW_DOUBLES
+    const BodyRec *body;
     const int32_t *pair_i, *pair_j;
     const uint32_t *ccnt, *coff;
     const double *j_np[6], *b_np, *ra_x, *ra_y, *rb_x, *rb_y, *rn_x, *rn_y, *j_f[6], *inv_eff_np, *inv_eff_f;
@@ -66,6 +88,11 @@ struct SolveParams {
     SolveState *ss;
     int n_slots;
     int p_begin, p_end;           // sweeps [p_begin, p_end): 0 = applyCachedSlns, >= 1 = improveWorld
+    unsigned long long queue_cap;
+    int lanes;                    // executor lanes per warp (the others exit at once)
+    unsigned sleep_cap;           // longest idle back-off in ns (0 = spin)
+    unsigned claim_after;         // iterations an idle lane of a busy warp waits for a sibling's hand-over before it claims a queue slot
+    int prefer_i;                 // both successors ready: 1 = continue on body i's chain, 0 = on body j's
 };
 
 __device__ __forceinline__ bool body_dynamic(double2 m) { return !(m.x == 0.0 && m.y == 0.0); }   // not isStatic (Constraint.hs:123-125)
@@ -137,6 +164,43 @@ __global__ void __launch_bounds__(256) k_advance(int n, const uint8_t *alive, do
     c[s] = cc; sn[s] = ss;
 }
 
+__global__ void __launch_bounds__(256) k_pack_body(int n, const double *inv_lin, const double *inv_rot, const double *mu,
+                                                   const double *bounce, BodyRec *body)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    body[s] = BodyRec{ inv_lin[s], inv_rot[s], mu[s], bounce[s] };
+}
+
+// Contact rows, SoA columns -> 192 B records.  A warp transposes 32 rows through shared memory:
+// coalesced column reads, coalesced record writes.
+constexpr int PACK_WARPS = 4;
+__global__ void __launch_bounds__(PACK_WARPS * 32) k_pack_rows(SolveParams S)
+{
+    __shared__ double tile[PACK_WARPS][32][ROW_DOUBLES + 1];
+    const long long n_rows = S.st->n_contacts;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long n_tiles = (n_rows + 31) / 32;
+    for (long long t = (long long)blockIdx.x * PACK_WARPS + wid; t < n_tiles; t += (long long)gridDim.x * PACK_WARPS) {
+        const long long r = t * 32 + lane;
+        double (*T)[ROW_DOUBLES + 1] = tile[wid];
+        if (r < n_rows) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { T[lane][k] = S.j_np[k][r]; T[lane][6 + k] = S.j_f[k][r]; }
+            T[lane][12] = S.b_np[r]; T[lane][13] = S.inv_eff_np[r]; T[lane][14] = S.inv_eff_f[r];
+            T[lane][15] = S.ra_x[r]; T[lane][16] = S.ra_y[r]; T[lane][17] = S.rb_x[r]; T[lane][18] = S.rb_y[r];
+            T[lane][19] = S.rn_x[r]; T[lane][20] = S.rn_y[r];
+            T[lane][21] = S.hit[r] ? 1.0 : 0.0; T[lane][22] = 0.0; T[lane][23] = 0.0;
+        }
+        __syncwarp();
+        const long long base = t * 32 * ROW_DOUBLES;                 // doubles
+        const long long limit = n_rows * ROW_DOUBLES;
+        for (int e = lane; e < 32 * ROW_DOUBLES; e += 32)
+            if (base + e < limit) S.rows[base + e] = T[e / ROW_DOUBLES][e % ROW_DOUBLES];
+        __syncwarp();
+    }
+}
+
 // ---- dependency chains -----------------------------------------------------------------------------
 // Body b is touched, in list order, first by the pairs where it is the SMALLER key (pair_j == b:
 // they belong to larger first keys, which come earlier in the descending list) and then by its own
@@ -195,6 +259,13 @@ __global__ void __launch_bounds__(256) k_chain_finish(SolveParams S)
         }
         const int deps = ((dyn_i && head_i != (int)q) ? 1 : 0) + ((dyn_j && head_j != (int)q) ? 1 : 0);
         S.cnt[q] = deps;
+        NodeRec rec;
+        rec.i = i; rec.j = j; rec.r0 = S.coff[q];
+        rec.flags = (S.ccnt[q] & 3u) | (dyn_i ? 4u : 0u) | (dyn_j ? 8u : 0u);
+        rec.next_i = S.next_i[q]; rec.next_j = S.next_j[q];
+        rec.succ_r0_i = S.coff[rec.next_i >= 0 ? rec.next_i : -1 - rec.next_i];
+        rec.succ_r0_j = S.coff[rec.next_j >= 0 ? rec.next_j : -1 - rec.next_j];
+        S.node[q] = rec;
         if (chains) atomicAdd(&ss->expected, chains);
         if (deps == 0) {
             const unsigned long long slot = atomicAdd(&ss->tail, 1ull);
@@ -224,130 +295,227 @@ __device__ __forceinline__ void apply_lagrangian(double l, const double *j, cons
 __device__ __forceinline__ double hs_max(double x, double y) { return (x <= y) ? y : x; }
 __device__ __forceinline__ double hs_min(double x, double y) { return (x <= y) ? x : y; }
 
-// One node: the (at most two) contacts of pair q, in row order, for sweep `pass`.
-__device__ __forceinline__ void solve_pair(const SolveParams &S, unsigned q, int pass, int i, int j, double2 mi, double2 mj,
-                                           bool dyn_i, bool dyn_j)
+__device__ __forceinline__ NodeRec load_node(const NodeRec *p)
 {
-    const unsigned m = S.ccnt[q], r0 = S.coff[q];
-    const double2 a0 = __ldcg(&S.vel[2 * i]), a1 = __ldcg(&S.vel[2 * i + 1]);
-    const double2 b0 = __ldcg(&S.vel[2 * j]), b1 = __ldcg(&S.vel[2 * j + 1]);
-    double v[6] = { a0.x, a0.y, a1.x, b0.x, b0.y, b1.x };
-    const double im[6] = { mi.x, mi.x, mi.y, mj.x, mj.x, mj.y };     // invMassM2 (Constraint.hs:118-120)
-    if (pass == 0) {
-        // useCache (Solvers/Contact.hs:99-112): applySln with the cached ContactLagrangian
-        for (unsigned k = 0; k < m; ++k) {
-            const unsigned r = r0 + k;
-            if (!S.hit[r]) continue;
-            double jn[6], jf[6];
-#pragma unroll
-            for (int t = 0; t < 6; ++t) { jn[t] = S.j_np[t][r]; jf[t] = S.j_f[t][r]; }
-            apply_lagrangian(__ldcg(&S.lam_np[r]), jn, im, v);
-            apply_lagrangian(__ldcg(&S.lam_f[r]), jf, im, v);
-        }
-    } else {
-        // improveContactSln (Solvers/Contact.hs:124-143)
-        const double bounciness = hs_min(S.bounce[i], S.bounce[j]);            // uncurry min (Restitution.hs:47)
-        const double pair_mu = fdiv(fadd(S.mu[i], S.mu[j]), 2.0);               // pairMu (Friction.hs:46-48)
-        for (unsigned k = 0; k < m; ++k) {
-            const unsigned r = r0 + k;
-            double jn[6], jf[6];
-#pragma unroll
-            for (int t = 0; t < 6; ++t) { jn[t] = S.j_np[t][r]; jf[t] = S.j_f[t][r]; }
-            const double b_np = S.b_np[r], en = S.inv_eff_np[r], ef = S.inv_eff_f[r];
-            const double rax = S.ra_x[r], ray = S.ra_y[r], rbx = S.rb_x[r], rby = S.rb_y[r], rnx = S.rn_x[r], rny = S.rn_y[r];
-            const double cached_np = __ldcg(&S.lam_np[r]), cached_f = __ldcg(&S.lam_f[r]);
-            // bounceB (Restitution.hs:34-47)
-            const double nwa = -v[2];
-            const double nwa_x = -fmul(nwa, ray), nwa_y = fmul(nwa, rax);       // zcrossV2 (Linear.hs:127-130)
-            const double wb_x = -fmul(v[5], rby), wb_y = fmul(v[5], rbx);
-            const double cv_x = fadd(fadd(fadd(-v[0], nwa_x), v[3]), wb_x);
-            const double cv_y = fadd(fadd(fadd(-v[1], nwa_y), v[4]), wb_y);
-            const double bounce_b = hs_min(0.0, fmul(bounciness, fadd(fmul(cv_x, rnx), fmul(cv_y, rny))));
-            // contactLagrangian (Constraints/Contact.hs:87-97) = lagrangian2 (Constraint.hs:164-169) twice,
-            // both from the velocities read above; effMassM2 is the velocity-independent column K3 wrote
-            const double new_np = fdiv(-fadd(dot6(jn, v), fadd(b_np, bounce_b)), en);
-            const double new_f = fdiv(-fadd(dot6(jf, v), 0.0), ef);
-            // solutionProcessor (Constraints/Contact.hs:99-110): positive, then clampAbs
-            const double apply_np = hs_max(new_np, -cached_np);
-            const double cache_np = fadd(cached_np, apply_np);
-            const double max_thresh = fmul(cache_np, pair_mu), min_thresh = -max_thresh;
-            const double accum = fadd(cached_f, new_f);
-            const double accum2 = (accum > max_thresh) ? max_thresh : ((accum < min_thresh) ? min_thresh : accum);
-            const double apply_f = fsub(accum2, cached_f);
-            // applySln (Solvers/Contact.hs:54-65): non-penetration first, then friction
-            apply_lagrangian(apply_np, jn, im, v);
-            apply_lagrangian(apply_f, jf, im, v);
-            __stcg(&S.lam_np[r], cache_np);
-            __stcg(&S.lam_f[r], accum2);
-        }
-    }
-    if (dyn_i) { __stcg(&S.vel[2 * i], make_double2(v[0], v[1])); __stcg(&S.vel[2 * i + 1], make_double2(v[2], 0.0)); }
-    if (dyn_j) { __stcg(&S.vel[2 * j], make_double2(v[3], v[4])); __stcg(&S.vel[2 * j + 1], make_double2(v[5], 0.0)); }
+    const int4 a = __ldg(reinterpret_cast<const int4 *>(p)), b = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+    NodeRec r;
+    r.i = a.x; r.j = a.y; r.r0 = (unsigned)a.z; r.flags = (unsigned)a.w;
+    r.next_i = b.x; r.next_j = b.y; r.succ_r0_i = (unsigned)b.z; r.succ_r0_j = (unsigned)b.w;
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// release fence: the velocity / lambda / counter stores before it are visible device-wide before
+// the counter decrements after it
+__device__ __forceinline__ void fence_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+
+// One contact row against the pair's velocities v (improveContactSln, Solvers/Contact.hs:124-143).
+// R = the packed row (ROW_DOUBLES doubles).  Returns the new cached Lagrangians.
+__device__ __forceinline__ void improve_row(const double2 *R, const double *im, double bounciness, double pair_mu,
+                                            double cached_np, double cached_f, double *v, double *out_np, double *out_f)
+{
+    const double jn[6] = { R[0].x, R[0].y, R[1].x, R[1].y, R[2].x, R[2].y };
+    const double jf[6] = { R[3].x, R[3].y, R[4].x, R[4].y, R[5].x, R[5].y };
+    const double b_np = R[6].x, en = R[6].y, ef = R[7].x;
+    const double rax = R[7].y, ray = R[8].x, rbx = R[8].y, rby = R[9].x, rnx = R[9].y, rny = R[10].x;
+    // bounceB (Restitution.hs:34-47)
+    const double nwa = -v[2];
+    const double nwa_x = -fmul(nwa, ray), nwa_y = fmul(nwa, rax);       // zcrossV2 (Linear.hs:127-130)
+    const double wb_x = -fmul(v[5], rby), wb_y = fmul(v[5], rbx);
+    const double cv_x = fadd(fadd(fadd(-v[0], nwa_x), v[3]), wb_x);
+    const double cv_y = fadd(fadd(fadd(-v[1], nwa_y), v[4]), wb_y);
+    const double bounce_b = hs_min(0.0, fmul(bounciness, fadd(fmul(cv_x, rnx), fmul(cv_y, rny))));
+    // contactLagrangian (Constraints/Contact.hs:87-97) = lagrangian2 (Constraint.hs:164-169) twice, both
+    // from the velocities as read; effMassM2 is the velocity-independent value K3 computed
+    const double new_np = fdiv(-fadd(dot6(jn, v), fadd(b_np, bounce_b)), en);
+    const double new_f = fdiv(-fadd(dot6(jf, v), 0.0), ef);
+    // solutionProcessor (Constraints/Contact.hs:99-110): positive, then clampAbs
+    const double apply_np = hs_max(new_np, -cached_np);
+    const double cache_np = fadd(cached_np, apply_np);
+    const double max_thresh = fmul(cache_np, pair_mu), min_thresh = -max_thresh;
+    const double accum = fadd(cached_f, new_f);
+    const double accum2 = (accum > max_thresh) ? max_thresh : ((accum < min_thresh) ? min_thresh : accum);
+    const double apply_f = fsub(accum2, cached_f);
+    // applySln (Solvers/Contact.hs:54-65): non-penetration first, then friction
+    apply_lagrangian(apply_np, jn, im, v);
+    apply_lagrangian(apply_f, jf, im, v);
+    *out_np = cache_np; *out_f = accum2;
 }
 
-// Persistent dataflow executor.  A thread runs a node, publishes its results (fence), decrements
-// the dependency counters of the node's two successors (the next contact pair on body i, on body
-// j), continues with a successor it made ready and queues the other one.  Idle threads each wait
-// on their own queue slot.  No thread ever waits for a particular other thread, so residency and
-// scheduling order cannot deadlock it.
+// useCache (Solvers/Contact.hs:99-112): applySln with the cached ContactLagrangian, rows the join hit
+__device__ __forceinline__ void cached_row(const double2 *R, const double *im, double l_np, double l_f, double *v)
+{
+    if (R[10].y == 0.0) return;                                           // newCache: nothing to apply
+    const double jn[6] = { R[0].x, R[0].y, R[1].x, R[1].y, R[2].x, R[2].y };
+    const double jf[6] = { R[3].x, R[3].y, R[4].x, R[4].y, R[5].x, R[5].y };
+    apply_lagrangian(l_np, jn, im, v);
+    apply_lagrangian(l_f, jf, im, v);
+}
+
+// Persistent dataflow executor.  A thread runs a node, publishes its results (release fence),
+// decrements the dependency counters of the node's two successors (the next contact pair on body
+// i, on body j), continues with a successor it made ready and queues the other one.  Idle threads
+// each wait on their own queue slot.  No thread ever waits for a particular other thread, so
+// residency and scheduling order cannot deadlock it.
+//
+// The critical path of a step is the longest dependency chain (thousands of nodes in a pile), so
+// the loop is organised around the latency of ONE hop: every static datum of a node sits in one
+// NodeRec sector and 192 B row records; the NodeRecs of both successors are fetched while the
+// current node computes and their rows are pulled into L2, so that after the counter decrement
+// only L2 hits (velocities of the other body, prefetched rows) separate a thread from the math.
+// Mutable data (velocities, Lagrangians, counters, queue) is only ever accessed at L2
+// (ld.cg / st.cg / atomics / volatile), never through the non-coherent L1.
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams S)
 {
     SolveState *ss = S.ss;
     const unsigned expected = ss->expected;
     if (expected == 0 || ss->overflow) return;
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool executor = lane < S.lanes;
+    const double2 *rows = reinterpret_cast<const double2 *>(S.rows);
+    const double2 *body = reinterpret_cast<const double2 *>(S.body);
     unsigned node = SOLVE_NONE;
+    NodeRec rec = {};
     int pass = 0;
     long long my_slot = -1;
     unsigned backoff = 32;
+    unsigned idle_iters = 0;
     unsigned long long ran = 0, idle_ns = 0;
+    // The warp stays converged: every lane takes part in the votes of each iteration, lanes with a
+    // node run it in lock step (their loads overlap), a lane that made two successors ready hands
+    // the second one to an idle sibling through shuffles (no memory round trip) and only queues it
+    // globally when the warp has no free lane.  Only a warp with no work at all sleeps -- a
+    // sleeping lane in a busy warp would hold its siblings back.
     for (;;) {
-        if (node == SOLVE_NONE) {
-            if (my_slot < 0) my_slot = (long long)atomicAdd(&ss->head, 1ull);
-            unsigned e = SOLVE_NONE;
-            if ((unsigned long long)my_slot < ss->queue_cap) e = ld_volatile_u32(&S.queue[my_slot]);
-            if (e != SOLVE_NONE) {
-                __threadfence();
-                node = e & SOLVE_NODE_MASK; pass = (int)(e >> SOLVE_PASS_SHIFT);
-                my_slot = -1; backoff = 32; idle_ns = 0;
-            } else {
-                if (*reinterpret_cast<volatile unsigned *>(&ss->done) >= expected) break;
-                if (*reinterpret_cast<volatile int *>(&ss->overflow)) break;
-                __nanosleep(backoff);
-                idle_ns += backoff;
-                if (backoff < 1024) backoff <<= 1;
-                if (idle_ns > SOLVE_IDLE_LIMIT_NS) { ss->overflow = 2; break; }   // never spin forever: the host reports it
-                continue;
+        __syncwarp();
+        // idle lanes: a claimed queue slot is polled once per iteration; a slot is claimed when the
+        // whole warp is idle (see below) or after a few iterations without a sibling's hand-over
+        if (node == SOLVE_NONE && executor) {
+            if (my_slot < 0 && idle_iters >= S.claim_after) my_slot = (long long)atomicAdd(&ss->head, 1ull);
+            if (my_slot >= 0) {
+                unsigned e = SOLVE_NONE;
+                if ((unsigned long long)my_slot < S.queue_cap) e = ld_volatile_u32(&S.queue[my_slot]);
+                if (e != SOLVE_NONE) {
+                    node = e & SOLVE_NODE_MASK; pass = (int)(e >> SOLVE_PASS_SHIFT);
+                    rec = load_node(&S.node[node]);
+                    my_slot = -1;
+                }
             }
         }
-        const unsigned q = node;
-        const int i = S.pair_i[q], j = S.pair_j[q];
-        const double2 mi = S.mass[i], mj = S.mass[j];
-        const bool dyn_i = body_dynamic(mi), dyn_j = body_dynamic(mj);
-        solve_pair(S, q, pass, i, j, mi, mj, dyn_i, dyn_j);
-        ++ran;
-        const int li = S.next_i[q], lj = S.next_j[q];
-        if (pass + 1 < S.p_end) S.cnt[q] = (dyn_i ? 1 : 0) + (dyn_j ? 1 : 0);   // re-arm for the next sweep
-        __threadfence();                                                         // release: velocities, lambdas, counter
-        unsigned ready[2]; int ready_pass[2]; int n_ready = 0;
+        const unsigned busy = __ballot_sync(0xffffffffu, node != SOLVE_NONE);
+        if (busy == 0) {
+            int stop = 0;
+            if (lane == 0) {
+                if (*reinterpret_cast<volatile unsigned *>(&ss->done) >= expected) stop = 1;
+                else if (*reinterpret_cast<volatile int *>(&ss->overflow)) stop = 1;
+                else if (idle_ns > SOLVE_IDLE_LIMIT_NS) { ss->overflow = 2; stop = 1; }   // never spin forever: the host reports it
+            }
+            stop = __shfl_sync(0xffffffffu, stop, 0);
+            if (stop) break;
+            idle_iters = S.claim_after;                 // an idle warp listens to the global queue
+            if (S.sleep_cap) __nanosleep(backoff);
+            idle_ns += backoff;
+            if (backoff < S.sleep_cap) backoff <<= 1;
+            continue;
+        }
+        backoff = 32; idle_ns = 0;
+        // what this lane offers to / continues with after the iteration
+        unsigned spare = SOLVE_NONE; int spare_pass = 0; NodeRec spare_rec = {};
+        if (node == SOLVE_NONE) ++idle_iters;
+        else {
+            idle_iters = 0;
+            const unsigned q = node;
+            const int i = rec.i, j = rec.j;
+            const unsigned m = rec.flags & 3u, r0 = rec.r0;
+            const bool dyn_i = (rec.flags & 4u) != 0, dyn_j = (rec.flags & 8u) != 0;
+            // ---- every load of this node, issued together
+            double2 R0[11], R1[11];
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            if (!(side == 0 ? dyn_i : dyn_j)) continue;
-            const int link = side == 0 ? li : lj;
-            unsigned succ; int sp;
-            if (link >= 0) { succ = (unsigned)link; sp = pass; }
-            else {
-                succ = (unsigned)(-1 - link); sp = pass + 1;
-                if (sp >= S.p_end) { atomicAdd(&ss->done, 1u); continue; }       // this body's chain is finished
+            for (int t = 0; t < 11; ++t) R0[t] = __ldg(&rows[(size_t)r0 * (ROW_DOUBLES / 2) + t]);
+            if (m > 1) {
+#pragma unroll
+                for (int t = 0; t < 11; ++t) R1[t] = __ldg(&rows[(size_t)(r0 + 1) * (ROW_DOUBLES / 2) + t]);
             }
-            if (atomicSub(&S.cnt[succ], 1) == 1) { ready[n_ready] = succ; ready_pass[n_ready] = sp; ++n_ready; }
+            const double2 a0 = __ldcg(&S.vel[2 * i]), a1 = __ldcg(&S.vel[2 * i + 1]);
+            const double2 b0 = __ldcg(&S.vel[2 * j]), b1 = __ldcg(&S.vel[2 * j + 1]);
+            const double2 mi = __ldg(&body[2 * i]), ui = __ldg(&body[2 * i + 1]);
+            const double2 mj = __ldg(&body[2 * j]), uj = __ldg(&body[2 * j + 1]);
+            double l0n = __ldcg(&S.lam_np[r0]), l0f = __ldcg(&S.lam_f[r0]), l1n = 0.0, l1f = 0.0;
+            if (m > 1) { l1n = __ldcg(&S.lam_np[r0 + 1]); l1f = __ldcg(&S.lam_f[r0 + 1]); }
+            // both successors' records (static), needed only after the math below
+            const int li = rec.next_i, lj = rec.next_j;
+            const unsigned si = (unsigned)(li >= 0 ? li : -1 - li), sj = (unsigned)(lj >= 0 ? lj : -1 - lj);
+            const NodeRec rsi = load_node(&S.node[si]), rsj = load_node(&S.node[sj]);
+            // ... and their rows / Lagrangians start moving towards L2 now, a whole node ahead of their use
+            // (nothing should be in flight to DRAM when the release fence below drains the memory pipeline)
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? dyn_i : dyn_j)) continue;
+                const unsigned sr = side == 0 ? rec.succ_r0_i : rec.succ_r0_j;
+                const double2 *p = &rows[(size_t)sr * (ROW_DOUBLES / 2)];
+                prefetch_l2(p); prefetch_l2(p + 8); prefetch_l2(p + 16);
+                prefetch_l2(&S.lam_np[sr]); prefetch_l2(&S.lam_f[sr]);
+            }
+            // ---- the node
+            double v[6] = { a0.x, a0.y, a1.x, b0.x, b0.y, b1.x };
+            const double im[6] = { mi.x, mi.x, mi.y, mj.x, mj.x, mj.y };     // invMassM2 (Constraint.hs:118-120)
+            if (pass == 0) {
+                cached_row(R0, im, l0n, l0f, v);
+                if (m > 1) cached_row(R1, im, l1n, l1f, v);
+            } else {
+                const double bounciness = hs_min(ui.y, uj.y);                    // uncurry min (Restitution.hs:47)
+                const double pair_mu = fdiv(fadd(ui.x, uj.x), 2.0);              // pairMu (Friction.hs:46-48)
+                improve_row(R0, im, bounciness, pair_mu, l0n, l0f, v, &l0n, &l0f);
+                __stcg(&S.lam_np[r0], l0n); __stcg(&S.lam_f[r0], l0f);
+                if (m > 1) {
+                    improve_row(R1, im, bounciness, pair_mu, l1n, l1f, v, &l1n, &l1f);
+                    __stcg(&S.lam_np[r0 + 1], l1n); __stcg(&S.lam_f[r0 + 1], l1f);
+                }
+            }
+            if (dyn_i) { __stcg(&S.vel[2 * i], make_double2(v[0], v[1])); __stcg(&S.vel[2 * i + 1], make_double2(v[2], 0.0)); }
+            if (dyn_j) { __stcg(&S.vel[2 * j], make_double2(v[3], v[4])); __stcg(&S.vel[2 * j + 1], make_double2(v[5], 0.0)); }
+            ++ran;
+            if (pass + 1 < S.p_end) S.cnt[q] = (dyn_i ? 1 : 0) + (dyn_j ? 1 : 0);   // re-arm for the next sweep
+            fence_release();
+            // both counter decrements are issued before either result is looked at (one L2 round trip, not two)
+            const bool wrap_i = li < 0, wrap_j = lj < 0;
+            const int sp_i = pass + (wrap_i ? 1 : 0), sp_j = pass + (wrap_j ? 1 : 0);
+            const bool end_i = dyn_i && sp_i >= S.p_end, end_j = dyn_j && sp_j >= S.p_end;   // the body's chain is finished
+            const bool go_i = dyn_i && !end_i, go_j = dyn_j && !end_j;
+            int old_i = 0, old_j = 0;
+            if (go_i) old_i = atomicSub(&S.cnt[si], 1);
+            if (go_j) old_j = atomicSub(&S.cnt[sj], 1);
+            if (end_i || end_j) atomicAdd(&ss->done, (end_i ? 1u : 0u) + (end_j ? 1u : 0u));
+            const bool rdy_i = go_i && old_i == 1, rdy_j = go_j && old_j == 1;
+            // continue along one ready successor; a second one is offered to the warp
+            node = SOLVE_NONE;
+            if (rdy_i || rdy_j) {
+                const bool take_i = rdy_i && (!rdy_j || S.prefer_i);
+                node = take_i ? si : sj; pass = take_i ? sp_i : sp_j; rec = take_i ? rsi : rsj;
+                if (rdy_i && rdy_j) { spare = take_i ? sj : si; spare_pass = take_i ? sp_j : sp_i; spare_rec = take_i ? rsj : rsi; }
+            }
         }
-        node = SOLVE_NONE;
-        if (n_ready > 0) {
-            __threadfence();                                                     // acquire: the other predecessor's results
-            node = ready[0]; pass = ready_pass[0];
-            if (n_ready > 1) {
+        // ---- hand spare nodes to free sibling lanes (k-th spare to the k-th free lane); the rest is queued
+        const unsigned spare_mask = __ballot_sync(0xffffffffu, spare != SOLVE_NONE);
+        if (spare_mask) {
+            const unsigned free_mask = __ballot_sync(0xffffffffu, executor && node == SOLVE_NONE && my_slot < 0);
+            const int n_free = __popc(free_mask);
+            const bool i_am_free = ((free_mask >> lane) & 1u) != 0;
+            const int my_rank = i_am_free ? __popc(free_mask & lt_mask) : __popc(spare_mask & lt_mask);
+            // a free lane of rank r reads from the r-th spare holder (if there is one)
+            const int src = (i_am_free && my_rank < __popc(spare_mask)) ? (int)__fns(spare_mask, 0, my_rank + 1) : lane;
+            const unsigned g_node = __shfl_sync(0xffffffffu, spare, src);
+            const int g_pass = __shfl_sync(0xffffffffu, spare_pass, src);
+            NodeRec g;
+            g.i = __shfl_sync(0xffffffffu, spare_rec.i, src); g.j = __shfl_sync(0xffffffffu, spare_rec.j, src);
+            g.r0 = __shfl_sync(0xffffffffu, spare_rec.r0, src); g.flags = __shfl_sync(0xffffffffu, spare_rec.flags, src);
+            g.next_i = __shfl_sync(0xffffffffu, spare_rec.next_i, src); g.next_j = __shfl_sync(0xffffffffu, spare_rec.next_j, src);
+            g.succ_r0_i = __shfl_sync(0xffffffffu, spare_rec.succ_r0_i, src); g.succ_r0_j = __shfl_sync(0xffffffffu, spare_rec.succ_r0_j, src);
+            if (i_am_free && src != lane) { node = g_node; pass = g_pass; rec = g; idle_iters = 0; }
+            else if (spare != SOLVE_NONE && my_rank >= n_free) {
                 const unsigned long long slot = atomicAdd(&ss->tail, 1ull);
-                if (slot < ss->queue_cap) st_volatile_u32(&S.queue[slot], ready[1] | ((unsigned)ready_pass[1] << SOLVE_PASS_SHIFT));
+                if (slot < S.queue_cap) st_volatile_u32(&S.queue[slot], spare | ((unsigned)spare_pass << SOLVE_PASS_SHIFT));
                 else ss->overflow = 1;
             }
         }
@@ -368,6 +536,9 @@ struct WorldStep {
     double2 *vel = nullptr;
     double *tmp[3] = {};           // unpack scratch
     int32_t *next_i = nullptr, *next_j = nullptr, *first_i = nullptr, *first_j = nullptr, *cnt = nullptr;
+    NodeRec *node = nullptr;
+    double *rows = nullptr;
+    BodyRec *body = nullptr;
     uint32_t *sort_key[2] = {}, *sort_val[2] = {};
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
@@ -377,6 +548,10 @@ struct WorldStep {
     SolveState *h_ss = nullptr;    // pinned
     cudaEvent_t ev[5] = {};
     int solve_blocks = 0;
+    int lanes = 32;
+    unsigned sleep_cap = 1024;
+    int prefer_i = 1;
+    unsigned claim_after = 0;
     int64_t steps = 0;
 };
 
@@ -399,6 +574,9 @@ int world_alloc(shapes_ctx *c)
     for (int k = 0; k < 3; ++k) WS_ALLOC(&w->tmp[k], N);
     WS_ALLOC(&w->vel, 2 * N);
     WS_ALLOC(&w->next_i, P); WS_ALLOC(&w->next_j, P); WS_ALLOC(&w->cnt, P);
+    WS_ALLOC(&w->node, P);
+    WS_ALLOC(&w->rows, (size_t)std::max<int64_t>(c->max_contacts, 1) * ROW_DOUBLES);
+    WS_ALLOC(&w->body, N);
     WS_ALLOC(&w->first_i, N); WS_ALLOC(&w->first_j, N);
     for (int k = 0; k < 2; ++k) { WS_ALLOC(&w->sort_key[k], P); WS_ALLOC(&w->sort_val[k], P); }
     CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, w->sort_tmp_bytes, w->sort_key[0], w->sort_key[1], w->sort_val[0],
@@ -406,6 +584,10 @@ int world_alloc(shapes_ctx *c)
     WS_ALLOC(reinterpret_cast<uint8_t **>(&w->sort_tmp), w->sort_tmp_bytes);
     int per_sm = 2;
     if (const char *e = std::getenv("SHAPES_B200_SOLVE_BLOCKS_PER_SM")) per_sm = std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("SHAPES_B200_SOLVE_LANES")) w->lanes = std::min(32, std::max(1, std::atoi(e)));
+    if (const char *e = std::getenv("SHAPES_B200_SOLVE_CLAIM_AFTER")) w->claim_after = (unsigned)std::max(0, std::atoi(e));
+    if (const char *e = std::getenv("SHAPES_B200_SOLVE_PREFER_I")) w->prefer_i = std::atoi(e) ? 1 : 0;
+    if (const char *e = std::getenv("SHAPES_B200_SOLVE_SLEEP")) w->sleep_cap = (unsigned)std::max(0, std::atoi(e));
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, SOLVE_THREADS, 0));
     per_sm = std::min(per_sm, std::max(occ, 1));
@@ -464,6 +646,7 @@ int shapes_world_upload(shapes_ctx *c, int64_t n_slots, const double *vel_x, con
         const double *vsrc[3] = { vel_x, vel_y, rot_vel };
         for (int k = 0; k < 3; ++k) CU_TRY(c, cudaMemcpyAsync(w->tmp[k], vsrc[k], bytes, cudaMemcpyHostToDevice, s));
         k_pack_vel<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(N, w->tmp[0], w->tmp[1], w->tmp[2], w->vel); ++c->launches;
+        k_pack_body<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(N, w->col[5], w->col[6], w->col[7], w->col[8], w->body); ++c->launches;
         if (!cos_rot) { k_sincos<<<grid_for(N, 256, 1 << 30), 256, 0, s>>>(N, w->col[2], w->col[3], w->col[4]); ++c->launches; }
         CU_TRY(c, cudaGetLastError());
     }
@@ -543,10 +726,12 @@ int shapes_world_step(shapes_ctx *c, const shapes_step_config *cfg, shapes_step_
     S.inv_eff_np = P.inv_eff_np; S.inv_eff_f = P.inv_eff_f;
     S.hit = P.warm_hit; S.lam_np = P.warm_np; S.lam_f = P.warm_f;
     S.vel = w->vel; S.mass = P.mass; S.mu = w->col[7]; S.bounce = w->col[8];
+    S.node = w->node; S.rows = w->rows; S.body = w->body;
     S.next_i = w->next_i; S.next_j = w->next_j; S.first_i = w->first_i; S.first_j = w->first_j; S.cnt = w->cnt;
     for (int k = 0; k < 2; ++k) { S.sort_key[k] = w->sort_key[k]; S.sort_val[k] = w->sort_val[k]; }
     S.queue = w->queue; S.ss = w->ss; S.n_slots = N;
     S.p_begin = warm ? 0 : 1; S.p_end = 1 + cfg->solver_iterations;
+    S.lanes = w->lanes; S.sleep_cap = w->sleep_cap; S.queue_cap = w->queue_cap; S.prefer_i = w->prefer_i; S.claim_after = w->claim_after;
     const bool solve = n_contacts > 0 && n_pairs > 0 && S.p_begin < S.p_end;
     if (solve) {
         const int sms = c->sm_count;
@@ -566,6 +751,7 @@ int shapes_world_step(shapes_ctx *c, const shapes_step_config *cfg, shapes_step_
         CU_TRY(c, cub::DeviceRadixSort::SortPairs(w->sort_tmp, tb, dk, dv, (int)n_pairs, 0, bits, s));
         k_chain_links<<<sms * 8, 256, 0, s>>>(S, dk.Current(), dv.Current()); ++c->launches;
         k_chain_finish<<<sms * 8, 256, 0, s>>>(S); ++c->launches;
+        k_pack_rows<<<sms * 8, PACK_WARPS * 32, 0, s>>>(S); ++c->launches;
     }
     CU_TRY(c, cudaEventRecord(w->ev[2], s));
     if (solve) { k_solve<<<w->solve_blocks, SOLVE_THREADS, 0, s>>>(S); ++c->launches; }
