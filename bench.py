@@ -167,6 +167,65 @@ def cpu_sample(workload: str, budget_frames: int = 3):
                     f"{'Aabb.culledKeys (n^2)' if w.n_slots <= 3000 else 'Grid.culledKeys restatement, unit cells'}"}
 
 
+def world_step_leg(eng, world, args, bracket):
+    """shapes_world_step: the whole Physics.Engine.Main.updateWorld on the device (body state resident in HBM,
+    applyExternal, applyCachedSlns, 2 improveWorld sweeps executed as the sequential walk's dependency
+    graph, advance), next to the oracle's sequential solver on a bounded sample."""
+    from shapes_b200.world import Bodies
+    n = world.n_slots
+    rng = np.random.default_rng(11)
+    bodies = Bodies(rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), np.full(n, 0.2), np.zeros(n))
+    eng.world = world
+    eng.world_upload(bodies)
+    ext = (1, 0.0, -2.0)                       # Stacks.externals: constantAccel (0, -2)
+    for _ in range(3):
+        eng.world_step(external=ext)
+    steps = max(3, min(args.steps, 10))
+    rows = []
+    bracket()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st = eng.world_step(external=ext)
+        rows.append((st.frame_ms, st.chains_ms, st.solve_ms, st.integrate_ms, st.total_ms))
+    bracket()
+    wall_ms = (time.perf_counter() - t0) / steps * 1e3
+    med = np.median(np.asarray(rows), axis=0)
+    res = {"api": "shapes_world_step (no per-frame host<->device traffic)", "steps": steps, "ms_per_step": wall_ms,
+           "device_ms": {"hot_path": float(med[0]), "chains": float(med[1]), "solver": float(med[2]), "integrate": float(med[3]),
+                         "total": float(med[4])},
+           "pairs": int(st.n_pairs), "contacts": int(st.n_contacts), "solver_nodes": int(st.solver_nodes),
+           "solver_iterations": 2, "warm_start": bool(st.warm),
+           "parity": "bit-identical to the sequential oracle (tests/test_gpu_world.py)"}
+    if not args.no_cpu_baseline:
+        from oracle import binding as orc
+        from shapes_b200 import scenes
+        ws = scenes.box_pile(1000, 100) if args.workload == "pile" else make_world(args.workload, 100_000, 1)[0]
+        ns = ws.n_slots
+        bs = Bodies(rng.uniform(-0.1, 0.1, ns), rng.uniform(-0.1, 0.1, ns), rng.uniform(-0.1, 0.1, ns), np.full(ns, 0.2), np.zeros(ns))
+        c, s = orc.cos_sin(ws.rot)
+        cache, ts, nrow = None, [], 0
+        for _ in range(3):
+            fr = orc.frame(ws, c, s, broadphase="sweep")
+            t0 = time.perf_counter()
+            orc.apply_external(ws, bs.vel_x, bs.vel_y, 1, 0.0, -2.0, 0.01)
+            nrow = len(fr["key_i"])
+            lam_np, lam_f, hit = (orc.warm_join(fr, *cache) if cache else (np.zeros(nrow), np.zeros(nrow), np.zeros(nrow, np.uint8)))
+            orc.apply_cached(ws, fr, hit, lam_np, lam_f, bs.vel_x, bs.vel_y, bs.rot_vel)
+            for _ in range(2):
+                orc.improve_world(ws, fr, bs.mu, bs.bounce, bs.vel_x, bs.vel_y, bs.rot_vel, lam_np, lam_f)
+            orc.advance(ws, bs.vel_x, bs.vel_y, bs.rot_vel, 0.01)
+            c, s = orc.cos_sin(ws.rot)
+            ts.append((time.perf_counter() - t0) * 1e3)
+            cache = ({q: fr[q] for q in ("key_i", "key_j", "feat_a", "feat_b")}, lam_np, lam_f)
+        per = float(np.median(ts))
+        res["cpu_solver"] = {"kind": "port", "cores": 1, "sample_shapes": ns, "sample_contacts": nrow, "ms_per_step_of_sample": per,
+                             "ns_per_contact": per * 1e6 / max(nrow, 1),
+                             "extrapolated_ms_at_bench_contacts": per / max(nrow, 1) * int(st.n_contacts),
+                             "note": "oracle: applyExternal + join + applyCachedSlns + 2 improveWorld sweeps + advance + libm "
+                                     "cos/sin, sequential like the reference; contact generation excluded"}
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on host cores.  The
     Haskell reference cannot be compiled here (no GHC), so this is the oracle port; it is
@@ -210,6 +269,7 @@ def main():
     ap.add_argument("--shapes-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-world-step", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -378,6 +438,11 @@ def main():
                "steps": e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "shapes_frame (pinned host buffers, all result columns fetched)"}
 
+    # ---- whole updateWorld on the device (not part of the headline metric) ----
+    world_step = None
+    if world_size == 1 and not args.no_world_step:
+        world_step = world_step_leg(eng, world, args, bracket)
+
     if rank != 0:
         eng.close()
         if dist is not None:
@@ -434,7 +499,7 @@ def main():
         "warm_start": {"ms_per_step_with_cache_join": warm_ms, "join_kernel_ms": warm_join_ms, "steps": warm_steps,
                        "note": "descZipVector join of this frame's keys with the previous frame's Lagrangian cache "
                                "(device resident); includes one 2 x 8 B x contacts D2D cache copy per step"},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "world_step": world_step,
     }
     emit(line)
     eng.close()

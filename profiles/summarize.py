@@ -122,6 +122,29 @@ def main():
                        "workload": d["config"]["workload"] if os.path.exists(bj) else None,
                        "shapes": d["config"]["shapes"] if os.path.exists(bj) else None,
                        "dram_bytes_per_launch": traffic}, f, indent=1)
+    # ---- device-resident world step (shapes_world_step)
+    wj = [os.path.join(OUT, f"world_{tag}.json"), os.path.join(OUT, f"world_poly_{tag}.json")]
+    if any(os.path.exists(x) for x in wj):
+        md += ["## shapes_world_step (whole updateWorld on the device; profiles/world_step.py, CUDA events)", ""]
+        for x in wj:
+            if not os.path.exists(x):
+                continue
+            lines = [l for l in open(x).read().splitlines() if l.startswith("{")]
+            if lines:
+                w = json.loads(lines[-1])
+                md += [f"* {w['workload']}: {json.dumps(w['ms_median'])} ms (median of {w['steps']} steps); {w['pairs']} pairs, "
+                       f"{w['contacts']} contacts, {w['solver_nodes']} solver nodes, {w['queue_pushes']} queue pushes; "
+                       f"cpu_solver: {json.dumps(w.get('cpu_solver'))}"]
+        if os.path.exists(bj) and d.get("world_step"):
+            md += [f"* bench.py `world_step` key: {json.dumps(d['world_step'])}"]
+        md += [""]
+    lw = os.path.join(OUT, f"launches_world_{tag}.csv")
+    if os.path.exists(lw):
+        table, tot = launches_table(lw)
+        md += ["### ncu launch list of the step's own kernels (solver side)", "", table, ""]
+    repw = os.path.join(OUT, f"prof_world_{tag}.ncu-rep")
+    if os.path.exists(repw):
+        md += ["### ncu --set full capture of `k_solve` (1M-box pile)", "", raw_tables(repw, {}), ""]
     path = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
     with open(path, "w") as f:
         f.write("\n".join(md))

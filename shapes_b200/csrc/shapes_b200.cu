@@ -1776,7 +1776,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
     key.warm = warm; key.n_prev = 0; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
-    k_set_i64<<<1, 1, 0, s>>>(c->d_n_prev, n_prev_now); ++c->launches;   // outside the graph: varies per frame
+    if (warm) { k_set_i64<<<1, 1, 0, s>>>(c->d_n_prev, n_prev_now); ++c->launches; }   // outside the graph: varies per frame
     const int64_t launches_before = c->launches;
     // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
     if (!c->use_graph || c->profiling || c->world > 1) { // per-stage events cannot be timed from inside a graph
