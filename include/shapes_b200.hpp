@@ -8,6 +8,7 @@
 //   shapes::makeRectangleHull / makeHull / makeCircle      (shapes/src/Physics/Engine.hs:47-54)
 //   shapes::makePhysicalObj  + toInvMass2                 (Engine.hs:32-39, Constraint.hs:79-83)
 //   shapes::culledKeys       Aabb.culledKeys / Grid.culledKeys   (Broadphase/Aabb.hs:168-183)
+//   shapes::updateWorld      Physics.Engine.Main.updateWorld     (Engine/Main.hs:71-86), on device-resident bodies
 //   shapes::prepareFrame     Solvers.Contact.prepareFrame        (Solvers/Contact.hs:40-52)
 //   shapes::constraintGen    Constraints.Contact.constraintGen   (Constraints/Contact.hs:60-72)
 //
@@ -38,13 +39,20 @@ struct V2 { double x, y; };
 struct ContactBehavior { double contactBaumgarte = 0.0, contactPenetrationSlop = 0.0; };
 
 // PhysicalObj, position part + inverse mass (Constraint.hs:52-63); velocities stay with the host solver
-struct PhysicalObj { V2 pos; double rotPos; double invLin, invRot; };
+struct PhysicalObj { V2 pos; double rotPos; double invLin, invRot; V2 vel{ 0.0, 0.0 }; double rotVel = 0.0; };
 
 // toInvMass2 (Constraint.hs:79-83): mass 0 means infinite mass
 inline PhysicalObj makePhysicalObj(V2 pos, double rotPos, std::pair<double, double> mass)
 {
     auto inv = [](double m) { return m == 0.0 ? 0.0 : 1.0 / m; };
     return PhysicalObj{ pos, rotPos, inv(mass.first), inv(mass.second) };
+}
+// makePhysicalObj vel rotvel pos rotpos mass (Engine.hs:32-39), the reference's argument order
+inline PhysicalObj makePhysicalObj(V2 vel, double rotVel, V2 pos, double rotPos, std::pair<double, double> mass)
+{
+    PhysicalObj o = makePhysicalObj(pos, rotPos, mass);
+    o.vel = vel; o.rotVel = rotVel;
+    return o;
 }
 
 using Hull = std::vector<V2>;    // CCW local vertices (_hullLocalVertices)
@@ -67,6 +75,8 @@ public:
     std::vector<int32_t> vert_offset{ 0 };
     std::vector<double> local_x, local_y;
     std::vector<double> pos_x, pos_y, rot, inv_lin, inv_rot;
+    std::vector<double> vel_x, vel_y, rot_vel;   // _physObjVel, _physObjRotVel (used by the device-resident world step)
+    std::vector<double> mu, bounce;               // Material (World.hs:36-40)
     std::vector<double> radius;   // >= 0: CircleShape of that radius (no vertices); < 0: HullShape
     bool has_circles = false;
     bool geometry_dirty = true;
@@ -78,6 +88,8 @@ public:
         vert_offset.push_back((int32_t)local_x.size());
         alive.push_back(1);
         radius.push_back(-1.0);
+        vel_x.push_back(obj.vel.x); vel_y.push_back(obj.vel.y); rot_vel.push_back(obj.rotVel);
+        mu.push_back(0.0); bounce.push_back(0.0);
         pos_x.push_back(obj.pos.x); pos_y.push_back(obj.pos.y); rot.push_back(obj.rotPos);
         inv_lin.push_back(obj.invLin); inv_rot.push_back(obj.invRot);
         geometry_dirty = true;
@@ -147,6 +159,43 @@ public:
         }
     }
 
+    // ---- device-resident world: the whole updateWorld on the GPU -------
+    // shapes_world_upload: the bodies of `w` move to HBM (and the EngineCache starts empty)
+    void worldUpload(World &w)
+    {
+        ensure(w);
+        const int rc = shapes_world_upload(ctx_, w.slots(), w.vel_x.data(), w.vel_y.data(), w.rot_vel.data(), w.pos_x.data(),
+                                           w.pos_y.data(), w.rot.data(), nullptr, nullptr, w.inv_lin.data(), w.inv_rot.data(),
+                                           w.mu.data(), w.bounce.data());
+        if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
+        uploaded_ = &w;
+    }
+    // shapes_world_step: one updateWorld; grows the ctx and re-uploads on SHAPES_E_CAPACITY (the step
+    // leaves the world untouched in that case, so the last downloaded/uploaded state is still current)
+    shapes_step_stats worldStep(World &w, const shapes_step_config &cfg)
+    {
+        if (uploaded_ != &w) worldUpload(w);
+        for (int attempt = 0;; ++attempt) {
+            shapes_step_stats st{};
+            const int rc = shapes_world_step(ctx_, &cfg, &st);
+            if (rc == SHAPES_E_CAPACITY && attempt < 4) {
+                worldDownload(w);
+                grow(w, st.n_pairs, st.n_contacts);
+                worldUpload(w);
+                continue;
+            }
+            if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
+            return st;
+        }
+    }
+    // shapes_world_download: velocities, positions and rotations back into `w`
+    void worldDownload(World &w)
+    {
+        const int rc = shapes_world_download(ctx_, w.slots(), w.vel_x.data(), w.vel_y.data(), w.rot_vel.data(), w.pos_x.data(),
+                                             w.pos_y.data(), w.rot.data(), nullptr, nullptr);
+        if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
+    }
+
 private:
     struct Columns {
         std::vector<int32_t> pi, pj, ki, kj, fa, fb;
@@ -211,6 +260,7 @@ private:
     void create(const World &w)
     {
         if (ctx_) { shapes_destroy(ctx_); ctx_ = nullptr; }
+        uploaded_ = nullptr;
         cap_slots_ = std::max<int64_t>(w.slots(), 1);
         cap_verts_ = std::max<int64_t>((int64_t)w.local_x.size(), 1);
         const int rc = shapes_create(&ctx_, device_, cap_slots_, cap_verts_, max_pairs_, max_contacts_);
@@ -236,6 +286,7 @@ private:
     }
 
     shapes_ctx *ctx_ = nullptr;
+    World *uploaded_ = nullptr;
     int device_;
     int64_t max_pairs_, max_contacts_, cap_slots_ = 0, cap_verts_ = 0;
 };
@@ -256,6 +307,23 @@ inline std::vector<KeyedContact> prepareFrame(Engine &e, World &w)
 inline Frame constraintGen(Engine &e, const ContactBehavior &beh, double dt, World &w)
 {
     return e.frame(w, beh, dt, true, true);
+}
+
+// External (World.hs:32-33): the two the reference defines (World/External.hs:16-28)
+struct External { int kind = SHAPES_EXT_NONE; V2 v{ 0.0, 0.0 }; };
+inline External makeConstantAccel(V2 a) { return External{ SHAPES_EXT_ACCEL, a }; }     // Engine.hs:44-45
+inline External makeConstantForce(V2 f) { return External{ SHAPES_EXT_FORCE, f }; }
+
+// Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) on the device-resident copy of `w`:
+// culledKeys, applyExternal, prepareFrame, applyCachedSlns, improveWorld x2, advance, moveShapes.
+// The bodies stay in HBM between calls; Engine::worldDownload brings them back into `w`.
+inline shapes_step_stats updateWorld(Engine &e, World &w, double dt, const ContactBehavior &beh, const External &ext)
+{
+    shapes_step_config cfg{};
+    cfg.dt = dt; cfg.baumgarte = beh.contactBaumgarte; cfg.slop = beh.contactPenetrationSlop;
+    cfg.external_kind = ext.kind; cfg.external_x = ext.v.x; cfg.external_y = ext.v.y;
+    cfg.solver_iterations = 2; cfg.warm_start = 1;
+    return e.worldStep(w, cfg);
 }
 
 } // namespace shapes

@@ -2,9 +2,11 @@
 //   * testOptBoxes   (shapes/bench/Physics/Contact/Benchmark.hs:16-27)  -> KAT-1
 //   * testWorld      (shapes/bench/Physics/Broadphase/Benchmark.hs:50-52) -> KAT-3
 //   * Stacks.makeScene (30,30) 0 (shapes/src/Physics/Scenes/Stacks.hs:110-113) -> config 1 counts
+//   * updateWorld on the Stacks scene's floor + one box (device-resident world step)
 // Exit code 0 = all checks passed; 3 = no usable GPU (the library refuses, it never falls back).
 #include "shapes_b200.hpp"
 
+#include <cmath>
 #include <cstdio>
 
 using namespace shapes;
@@ -102,6 +104,29 @@ int main()
             auto keys = culledKeys(eng, w);
             for (auto &p : keys) CHECK(p.first != 900 && p.second != 900);
             CHECK(keys.size() < 3076);
+        }
+        {   // updateWorld (Engine/Main.hs:71-86) on device-resident bodies: Stacks' floor and one box
+            // (mu 0.2, bounce 0, gravity (0,-2), ContactBehavior 0.01 0.02, dt 0.01): the box lands and rests
+            World w;
+            w.append(makePhysicalObj({ 0.0, -6.0 }, 0.0, { 0.0, 0.0 }), makeRectangleHull(18.0, 1.0));
+            w.append(makePhysicalObj({ 0.0, 0.0 }, 0.0, { 0.0, -4.5 }, 0.0, { 2.0, 1.0 }), makeRectangleHull(0.2, 0.2));
+            w.mu = { 0.2, 0.2 }; w.bounce = { 0.0, 0.0 };
+            const External gravity = makeConstantAccel({ 0.0, -2.0 });
+            shapes_step_stats st{};
+            for (int f = 0; f < 400; ++f) st = updateWorld(eng, w, 0.01, ContactBehavior{ 0.01, 0.02 }, gravity);
+            eng.worldDownload(w);
+            CHECK(st.n_pairs == 1 && st.n_contacts >= 1 && st.warm == 1);
+            CHECK(w.pos_y[0] == -6.0 && w.vel_y[0] == 0.0);                    // the static floor never moves
+            CHECK(std::fabs(w.pos_y[1] - (-6.0 + 0.5 + 0.1)) < 0.01);          // resting on the floor's top face
+            CHECK(std::fabs(w.vel_y[1]) < 0.02 && std::fabs(w.rot[1]) < 0.05);
+            // a capacity error inside a step grows the ctx and carries on from the same state
+            Engine small(0, 1, 1);
+            World w2;
+            w2.append(makePhysicalObj({ 0.0, -6.0 }, 0.0, { 0.0, 0.0 }), makeRectangleHull(18.0, 1.0));
+            stacks(w2, 0.2, 0.2, 0.0, -5.41, 0.0, 6, 4);
+            w2.mu.assign(w2.mu.size(), 0.2);
+            for (int f = 0; f < 5; ++f) st = updateWorld(small, w2, 0.01, ContactBehavior{ 0.01, 0.02 }, gravity);
+            CHECK(st.n_pairs > 1 && st.n_contacts > 1);
         }
     } catch (const Error &e) {
         std::printf("shapes::Error: %s\n", e.what());
