@@ -135,6 +135,42 @@ def test_step_needs_an_uploaded_world():
             eng.world_step()
 
 
+def test_worlds_without_contacts_and_tiny_worlds(oracle):
+    """No pairs at all (bodies far apart), a single body, a single touching pair: the solver kernels
+    are skipped or run with one node; integration still happens."""
+    from shapes_b200.world import World, rectangle_vertices
+    far = World.from_objects([(rectangle_vertices(1, 1), (10.0 * k, 0.0), 0.1 * k, (1.0, 1.0)) for k in range(50)])
+    st = run_both(oracle, far, random_bodies(50, 9), 3, external=(1, 0.0, -2.0))
+    assert st[-1].n_pairs == 0 and st[-1].solver_nodes == 0
+    one = World.from_objects([(rectangle_vertices(1, 1), (0.0, 0.0), 0.3, (2.0, 1.0))])
+    run_both(oracle, one, random_bodies(1, 10), 3, external=(2, 1.0, 0.0))
+    two = World.from_objects([(rectangle_vertices(4, 4), (0.0, 0.0), 0.0, (0.0, 0.0)),
+                              (rectangle_vertices(2, 2), (0.5, 2.9), 0.05, (1.0, 0.5))])
+    st = run_both(oracle, two, random_bodies(2, 11, mu=(0.3, 0.3)), 20, external=(1, 0.0, -2.0))
+    assert st[-1].n_contacts >= 1 and st[-1].body_chains == 1
+
+
+def test_hot_path_call_between_steps_resets_the_cache(oracle):
+    """shapes_frame between two world steps replaces 'the last frame': the next step then starts cold
+    (ContactLagrangian 0 0 everywhere), exactly like an engine whose cache was dropped."""
+    from shapes_b200 import engine
+    from shapes_b200.engine import Engine
+    w = scenes.box_pile(40, 30)
+    b = random_bodies(w.n_slots, 12)
+    wo = copy.deepcopy(w); bo = b.copy()
+    c, s = engine.sincos(wo.rot)
+    with Engine(w) as eng:
+        eng.world_upload(b)
+        eng.world_step(external=(1, 0.0, -2.0))
+        fr, cache, c, s = oracle.update_world(wo, bo, None, c, s, external=(1, 0.0, -2.0), sincos=engine.sincos)
+        eng.frame_grow(cos_sin=engine.sincos(w.rot))           # an unrelated hot-path call on the host copy
+        st = eng.world_step(external=(1, 0.0, -2.0))
+        assert st.warm == 0
+        fr, cache, c, s = oracle.update_world(wo, bo, None, c, s, external=(1, 0.0, -2.0), sincos=engine.sincos)
+        d = eng.world_download()
+        assert same(d["vel_x"], bo.vel_x) and same(d["rot_vel"], bo.rot_vel) and same(d["pos_y"], wo.pos_y)
+
+
 def test_schedule_independence(oracle):
     """Two runs of the same world give the same bits although the dataflow schedule differs."""
     from shapes_b200.engine import Engine
