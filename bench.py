@@ -270,6 +270,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-world-step", action="store_true")
+    ap.add_argument("--slot-order", default="generator", choices=["generator", "morton"],
+                    help="morton: slot keys assigned along a Z-curve of the positions (scenes.spatially_sorted)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -312,6 +314,10 @@ def main():
         dist.barrier()
 
     world, world_desc = make_world(args.workload, args.shapes_per_gpu, world_size)
+    if args.slot_order == "morton":
+        from shapes_b200 import scenes as _scenes
+        world = _scenes.spatially_sorted(world)
+        world_desc += ", slot keys in Morton order of position"
     n = world.n_slots
     vbar = world.n_verts / max(n, 1)
     cos_rot, sin_rot = np.cos(world.rot), np.sin(world.rot)

@@ -103,6 +103,8 @@ __device__ __forceinline__ bool bounds_overlap(double a, double b, double c, dou
     return !((c > b) || (d < a));
 }
 
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct __align__(32) Box { double min_x, max_x, min_y, max_y; };
 struct __align__(32) Xf { double px, py, c, s; };
 
@@ -962,12 +964,108 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
     return CLIP_NONE;
 }
 
+// The clipped manifold of an overlapping hull pair (both SAT directions found no separating axis):
+// penetratedEdge / penetratingEdge (SAT.hs:152-171), clipEdge (SAT.hs:190-218), flattenContactPoints
+// (SAT.hs:181-187).  E = penetrated hull, Pn = penetrating hull; `acc` supplies their world vertices and
+// the unit normal of E's edge.  Writes the ManRec when the pair has contacts; returns their number.
+template <typename Acc>
+__device__ __forceinline__ unsigned emit_manifold(const Params &P, long long p, const Acc &acc, int e_n, int pn_n,
+                                                  int edge, int pen, bool same)
+{
+    unsigned cnt = 0;
+    const V2 n = acc.normal_e(edge); // overlapNormal (SAT.hs:98-100)
+    // penetratedEdge (SAT.hs:169-171)
+    const int e1 = (edge < e_n - 1) ? edge + 1 : 0;
+    const V2 ra = acc.ve(edge), rb = acc.ve(e1);
+    // penetratingEdge (SAT.hs:152-166)
+    const int ib = pen;
+    const int ic = (ib < pn_n - 1) ? ib + 1 : 0;
+    const int ia = (ib > 0) ? ib - 1 : pn_n - 1;
+    const V2 va = acc.vp(ia), vb = acc.vp(ib), vc = acc.vp(ic);
+    const double abn = fabs(dot2(sub2(vb, va), n));
+    const double bcn = fabs(dot2(sub2(vc, vb), n));
+    V2 q0, q1;
+    int i0, i1;
+    if (bcn < abn) { q0 = vb; i0 = ib; q1 = vc; i1 = ic; }
+    else { q0 = va; i0 = ia; q1 = vb; i1 = ib; }
+    // clipEdge (SAT.hs:190-218)
+    const V2 inc_n = clockwise2(sub2(q1, q0)); // toLine2 c d, unclipped endpoints
+    const double inc_b = dot2(q0, inc_n);
+    V2 x;
+    bool alive = true;
+    int r = clip_segment(ra, sub2(rb, ra), inc_n, inc_b, q0, q1, x); // perpLine2 a b
+    if (r == CLIP_BOTH) alive = false;
+    else if (r == CLIP_LEFT) q0 = x;
+    else if (r == CLIP_RIGHT) q1 = x;
+    if (alive) {
+        r = clip_segment(rb, sub2(ra, rb), inc_n, inc_b, q0, q1, x); // perpLine2 b a
+        if (r == CLIP_BOTH) alive = false;
+        else if (r == CLIP_LEFT) q0 = x;
+        else if (r == CLIP_RIGHT) q1 = x;
+    }
+    if (alive) {
+        r = clip_segment(ra, neg2(n), inc_n, inc_b, q0, q1, x); // Line2 a (negateV2 n)
+        // applyClip'' (Linear.hs:285-292) removes the clipped endpoint;
+        // flattenContactPoints (SAT.hs:181-187): descending feature index
+        V2 c0 = q0, c1 = q1;
+        int p0 = i0, p1 = i1;
+        if (r == CLIP_LEFT) { cnt = 1; c0 = q1; p0 = i1; }
+        else if (r == CLIP_RIGHT) { cnt = 1; }
+        else if (r == CLIP_NONE) {
+            cnt = 2;
+            if (!(i0 > i1)) { c0 = q1; p0 = i1; c1 = q0; p1 = i0; }
+        }
+        if (cnt) {
+            ManRec rec;
+            rec.nx = n.x; rec.ny = n.y;
+            rec.ref_d = dot2(ra, n); // contactDepth_ (HullVsHull.hs:30-37): f v, f = afdot' n
+            rec.c0x = c0.x; rec.c0y = c0.y; rec.c1x = c1.x; rec.c1y = c1.y;
+            rec.bits = (unsigned long long)(unsigned)edge | ((unsigned long long)(unsigned)p0 << 20) |
+                       ((unsigned long long)(unsigned)p1 << 40) | ((unsigned long long)(same ? 0 : 1) << 60);
+            P.man[p] = rec;
+        }
+    }
+    return cnt;
+}
+
+// Accessor over the per-thread kernel's staged hulls
+template <int MAXV>
+struct StagedAcc {
+    const ContactKernel<MAXV> &K;
+    const HullAcc &E, &Pn;
+    __device__ __forceinline__ V2 normal_e(int e) const { return K.normal(E, e); }
+    __device__ __forceinline__ V2 ve(int k) const { return K.vtx(E, k); }
+    __device__ __forceinline__ V2 vp(int k) const { return K.vtx(Pn, k); }
+};
+
+// One hull pair on ONE thread: stage both hulls, SAT both ways, clip.  Returns the contact count.
+template <int MAXV>
+__device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV> &K, const Params &P, long long p, HullAcc &A, HullAcc &B)
+{
+    K.stage(A);
+    K.stage(B);
+    // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
+    // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
+    const bool boxes = (A.n == 4) & (B.n == 4);
+    const SatRes ab = boxes ? K.template min_overlap<4, 4>(A, B) : K.template min_overlap<0, 0>(A, B);
+    if (ab.sep) return 0;
+    const SatRes ba = boxes ? K.template min_overlap<4, 4>(B, A) : K.template min_overlap<0, 0>(B, A);
+    if (ba.sep) return 0;
+    const bool same = ab.depth < ba.depth;
+    const HullAcc &E = same ? A : B;
+    const HullAcc &Pn = same ? B : A;
+    const SatRes ov = same ? ab : ba;
+    return emit_manifold(P, p, StagedAcc<MAXV>{ K, E, Pn }, E.n, Pn.n, ov.edge, ov.pen, same);
+}
+
 // K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
 // count and, when it has contacts, its manifold record.  No ordering between pairs.
 #ifndef CT_MIN_BLOCKS_GENERAL
 #define CT_MIN_BLOCKS_GENERAL 4
 #endif
-template <int MAXV, bool CIRCLES>
+constexpr unsigned CCNT_FALLBACK = 0xffffffffu;   // k_manifolds_coop: "left to the per-thread kernel"
+
+template <int MAXV, bool CIRCLES, bool FLAGGED_ONLY = false>
 __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN_BLOCKS_GENERAL) k_manifolds(Params P)
 {
     __shared__ double2 s_verts[CT_THREADS / 32][2][MAXV][32];
@@ -980,6 +1078,7 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
 
     for (long long p = (long long)blockIdx.x * CT_THREADS + threadIdx.x; p < n_pairs;
          p += (long long)gridDim.x * CT_THREADS) {
+        if (FLAGGED_ONLY && P.ccnt[p] != CCNT_FALLBACK) continue;   // second pass after k_manifolds_coop
         const int i = P.pair_i[p], j = P.pair_j[p];
         HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
         A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
@@ -1016,75 +1115,153 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
                 continue;
             }
         }
-        K.stage(A);
-        K.stage(B);
-        unsigned cnt = 0;
-        // contactDebug (SAT.hs:238-248): eitherBranchBoth (Utils.hs:230-235) -- a separating
-        // axis on either side means no contact; else depth_ab < depth_ba ? Same : Flip.
-        const bool boxes = (A.n == 4) & (B.n == 4);
-        const SatRes ab = boxes ? K.template min_overlap<4, 4>(A, B) : K.template min_overlap<0, 0>(A, B);
-        if (!ab.sep) {
-            const SatRes ba = boxes ? K.template min_overlap<4, 4>(B, A) : K.template min_overlap<0, 0>(B, A);
-            if (!ba.sep) {
-                const bool same = ab.depth < ba.depth;
-                const HullAcc &E = same ? A : B;
-                const HullAcc &Pn = same ? B : A;
-                const SatRes ov = same ? ab : ba;
-                const V2 n = K.normal(E, ov.edge); // overlapNormal (SAT.hs:98-100)
-                // penetratedEdge (SAT.hs:169-171)
-                const int e1 = (ov.edge < E.n - 1) ? ov.edge + 1 : 0;
-                const V2 ra = K.vtx(E, ov.edge), rb = K.vtx(E, e1);
-                // penetratingEdge (SAT.hs:152-166)
-                const int ib = ov.pen;
-                const int ic = (ib < Pn.n - 1) ? ib + 1 : 0;
-                const int ia = (ib > 0) ? ib - 1 : Pn.n - 1;
-                const V2 va = K.vtx(Pn, ia), vb = K.vtx(Pn, ib), vc = K.vtx(Pn, ic);
-                const double abn = fabs(dot2(sub2(vb, va), n));
-                const double bcn = fabs(dot2(sub2(vc, vb), n));
-                V2 q0, q1;
-                int i0, i1;
-                if (bcn < abn) { q0 = vb; i0 = ib; q1 = vc; i1 = ic; }
-                else { q0 = va; i0 = ia; q1 = vb; i1 = ib; }
-                // clipEdge (SAT.hs:190-218)
-                const V2 inc_n = clockwise2(sub2(q1, q0)); // toLine2 c d, unclipped endpoints
-                const double inc_b = dot2(q0, inc_n);
-                V2 x;
-                bool alive = true;
-                int r = clip_segment(ra, sub2(rb, ra), inc_n, inc_b, q0, q1, x); // perpLine2 a b
-                if (r == CLIP_BOTH) alive = false;
-                else if (r == CLIP_LEFT) q0 = x;
-                else if (r == CLIP_RIGHT) q1 = x;
-                if (alive) {
-                    r = clip_segment(rb, sub2(ra, rb), inc_n, inc_b, q0, q1, x); // perpLine2 b a
-                    if (r == CLIP_BOTH) alive = false;
-                    else if (r == CLIP_LEFT) q0 = x;
-                    else if (r == CLIP_RIGHT) q1 = x;
+        P.ccnt[p] = hull_pair_manifold<MAXV>(K, P, p, A, B);
+    }
+}
+
+
+// K3a for general convex polygons (hulls of 3..8 vertices): 16 lanes per pair.
+// In `k_manifolds` a thread walks (edges of A) x (vertices of B) + (edges of B) x (vertices of A) on its
+// own; with 3..8 vertices per hull the trip counts differ from lane to lane (14.9 of 32 threads active
+// per instruction in ncu) and every lane stages two whole hulls.  Here lane (dir, e) of a half warp owns
+// ONE candidate axis: the unit normal of edge e of the penetrated hull of direction dir (0: A <- B,
+// 1: B <- A).  It projects the other hull's <= 8 vertices (one batch of loads, the same addresses
+// across the 8 lanes of a direction), and the minOverlap fold (SAT.hs:121-143) runs over the eight
+// per-edge results by shuffles IN EDGE ORDER, so ties, NaNs and the first-minimum rule behave exactly
+// like the sequential fold.  A warp does its 32 pairs two at a time (phase 1), then every lane clips
+// one pair (phase 2, `emit_manifold`).  Pairs with a hull of more than 8 vertices, or a hull whose world
+// vertices were not materialised on this rank, are flagged and finished by a second, per-thread pass.
+constexpr int CO_WARPS = 4;
+enum { CO_NONE = 0, CO_SAME = 1, CO_FLIP = 2, CO_FALLBACK = 3 };
+
+struct GlobalAcc {      // emit_manifold over K0's world vertices / normals in global memory
+    const Params &P;
+    int e_off, pn_off;
+    __device__ __forceinline__ V2 normal_e(int e) const { const double2 v = P.wn[e_off + e]; return V2{ v.x, v.y }; }
+    __device__ __forceinline__ V2 ve(int k) const { const double2 v = P.wv[e_off + k]; return V2{ v.x, v.y }; }
+    __device__ __forceinline__ V2 vp(int k) const { const double2 v = P.wv[pn_off + k]; return V2{ v.x, v.y }; }
+};
+
+__global__ void __launch_bounds__(CO_WARPS * 32, 4) k_manifolds_coop(Params P)
+{
+    __shared__ int s_out[CO_WARPS][32][3];                           // phase 1 -> phase 2: outcome, edge, penetrator
+
+    const FrameState *st = P.st;
+    if (st->error) return;
+    const long long n_pairs = st->n_pairs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, dir = (lane >> 3) & 1, e = lane & 7;
+    const int group_base = lane & ~7;                 // first lane of my (pair, direction) group
+    const long long n_tiles = (n_pairs + 31) / 32;
+
+    for (long long tile = (long long)blockIdx.x * CO_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * CO_WARPS) {
+        const long long base = tile * 32;
+        // ---- prologue: lane L reads the indices of pair base + L (coalesced), so the 16 steps below get them by
+        // shuffle instead of a dependent load chain each, and pulls both hulls' vertex / normal lines towards L2
+        // (partners are scattered in memory on worlds whose keys are unrelated to position).
+        // Prefetching one or two tiles further ahead (a software pipeline over the warp's tiles) was built and
+        // measured SLOWER (1M polygons: 0.283 / 0.288 ms vs 0.262 ms; 4M mixed: 1.44 vs 1.22 ms): with ~2400
+        // resident warps and ~24 KB of hull lines per tile the prefetched footprint no longer fits the 126 MB L2.
+        int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
+        if (base + lane < n_pairs) {
+            my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane];
+            my_oa = P.vert_offset[my_i]; my_na = P.vert_offset[my_i + 1] - my_oa;
+            my_ob = P.vert_offset[my_j]; my_nb = P.vert_offset[my_j + 1] - my_ob;
+            pf_l2(&P.wv[my_oa]); pf_l2(&P.wn[my_oa]); pf_l2(&P.wv[my_ob]); pf_l2(&P.wn[my_ob]);
+            if (my_na > 1) { pf_l2(&P.wv[my_oa + my_na - 1]); pf_l2(&P.wn[my_oa + my_na - 1]); }
+            if (my_nb > 1) { pf_l2(&P.wv[my_ob + my_nb - 1]); pf_l2(&P.wn[my_ob + my_nb - 1]); }
+            pf_l2(&P.ext_packed[my_i]); pf_l2(&P.ext_packed[my_j]);
+        }
+        // ---- phase 1: SAT, two pairs per step
+#pragma unroll 1
+        for (int t = 0; t < 16; ++t) {
+            const int src = 2 * t + half;
+            const long long p = base + src;
+            const bool valid = p < n_pairs;
+            const int i = __shfl_sync(0xffffffffu, my_i, src), j = __shfl_sync(0xffffffffu, my_j, src);
+            const int oa = __shfl_sync(0xffffffffu, my_oa, src), na = __shfl_sync(0xffffffffu, my_na, src);
+            const int ob = __shfl_sync(0xffffffffu, my_ob, src), nb = __shfl_sync(0xffffffffu, my_nb, src);
+            const bool own = i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi;
+            const bool coop = valid && own && na >= 1 && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
+            // my direction: E = penetrated hull (its edge normals are the axes), Pn = the other hull
+            const int e_slot = dir ? j : i, e_off = dir ? ob : oa, e_n = dir ? nb : na;
+            const int pn_off = dir ? oa : ob, pn_n = dir ? na : nb;
+            const bool active = coop && e < e_n;
+            bool sep = false;
+            double depth = 0.0;
+            int pen = 0;
+            if (active) {
+                // overlap sEdge edge sPen (SAT.hs:103-117)
+                const double2 dn = P.wn[e_off + e];
+                const unsigned bits = (unsigned)(P.ext_packed[e_slot] >> (6 * e));
+                const double2 vmin = P.wv[e_off + (bits & 7)], vmax = P.wv[e_off + ((bits >> 3) & 7)];
+                double2 pv[MAX_STAGED_VERTS];
+#pragma unroll
+                for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = P.wv[pn_off + k];
+                const V2 d{ dn.x, dn.y };
+                // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
+                const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
+                // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
+                double p_min = dot2(V2{ pv[0].x, pv[0].y }, d), p_max = p_min;
+#pragma unroll
+                for (int k = 1; k < MAX_STAGED_VERTS; ++k) {
+                    if (k >= pn_n) break;
+                    const double q = dot2(V2{ pv[k].x, pv[k].y }, d);
+                    if (q < p_min) { p_min = q; pen = k; }
+                    if (q > p_max) p_max = q;
                 }
-                if (alive) {
-                    r = clip_segment(ra, neg2(n), inc_n, inc_b, q0, q1, x); // Line2 a (negateV2 n)
-                    // applyClip'' (Linear.hs:285-292) removes the clipped endpoint;
-                    // flattenContactPoints (SAT.hs:181-187): descending feature index
-                    V2 c0 = q0, c1 = q1;
-                    int p0 = i0, p1 = i1;
-                    if (r == CLIP_LEFT) { cnt = 1; c0 = q1; p0 = i1; }
-                    else if (r == CLIP_RIGHT) { cnt = 1; }
-                    else if (r == CLIP_NONE) {
-                        cnt = 2;
-                        if (!(i0 > i1)) { c0 = q1; p0 = i1; c1 = q0; p1 = i0; }
-                    }
-                    if (cnt) {
-                        ManRec rec;
-                        rec.nx = n.x; rec.ny = n.y;
-                        rec.ref_d = dot2(ra, n); // contactDepth_ (HullVsHull.hs:30-37): f v, f = afdot' n
-                        rec.c0x = c0.x; rec.c0y = c0.y; rec.c1x = c1.x; rec.c1y = c1.y;
-                        rec.bits = (unsigned long long)(unsigned)ov.edge | ((unsigned long long)(unsigned)p0 << 20) |
-                                   ((unsigned long long)(unsigned)p1 << 40) | ((unsigned long long)(same ? 0 : 1) << 60);
-                        P.man[p] = rec;
-                    }
+                sep = (p_min > s_max) || (p_max < s_min);        // overlapTest (SAT.hs:74-83)
+                depth = fsub(s_max, p_min);                       // overlapAmount (SAT.hs:86-96)
+            }
+            // a separating axis on either side means no contact (contactDebug, SAT.hs:238-248)
+            const unsigned sep_mask = __ballot_sync(0xffffffffu, sep);
+            const bool pair_sep = ((sep_mask >> (16 * half)) & 0xffffu) != 0;
+            // minOverlap' (SAT.hs:121-143) over my direction's edges: edge 0 first, a later edge replaces the
+            // best one only with a strictly smaller depth.  That fold equals the lexicographic minimum of
+            // (depth, edge) with a NaN depth treated as +inf -- unless edge 0's depth is NaN, in which case
+            // nothing ever replaces edge 0.  Three butterfly steps over the 8 lanes of the direction.
+            const double d0 = __shfl_sync(0xffffffffu, depth, group_base);
+            double best_key = (active && !(depth != depth)) ? depth : __longlong_as_double(0x7ff0000000000000ll);
+            double best_depth = depth;
+            int best_ep = e | (pen << 8);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const double k2 = __shfl_xor_sync(0xffffffffu, best_key, o);
+                const double d2 = __shfl_xor_sync(0xffffffffu, best_depth, o);
+                const int ep2 = __shfl_xor_sync(0xffffffffu, best_ep, o);
+                if (k2 < best_key || (k2 == best_key && (ep2 & 0xff) < (best_ep & 0xff))) { best_key = k2; best_depth = d2; best_ep = ep2; }
+            }
+            const int ep0 = __shfl_sync(0xffffffffu, e | (pen << 8), group_base);
+            if (d0 != d0) { best_depth = d0; best_ep = ep0; }
+            const int best_edge = best_ep & 0xff, best_pen = best_ep >> 8;
+            // direction 1's result moves to the lanes of direction 0
+            const double o_depth = __shfl_sync(0xffffffffu, best_depth, lane ^ 8);
+            const int o_edge = __shfl_sync(0xffffffffu, best_edge, lane ^ 8), o_pen = __shfl_sync(0xffffffffu, best_pen, lane ^ 8);
+            if ((lane & 15) == 0) {
+                int outcome = CO_NONE, edge = 0, pn = 0;
+                if (valid && !coop) outcome = CO_FALLBACK;
+                else if (coop && !pair_sep) {
+                    const bool same = best_depth < o_depth;       // depth_ab < depth_ba ? Same : Flip (ties: Flip)
+                    outcome = same ? CO_SAME : CO_FLIP;
+                    edge = same ? best_edge : o_edge; pn = same ? best_pen : o_pen;
                 }
+                s_out[warp][2 * t + half][0] = outcome; s_out[warp][2 * t + half][1] = edge; s_out[warp][2 * t + half][2] = pn;
             }
         }
-        P.ccnt[p] = cnt;
+        __syncwarp();
+        // ---- phase 2: one pair per lane
+        const long long p = base + lane;
+        if (p < n_pairs) {
+            const int outcome = s_out[warp][lane][0], edge = s_out[warp][lane][1], pn = s_out[warp][lane][2];
+            unsigned cnt = 0;
+            if (outcome == CO_SAME || outcome == CO_FLIP) {
+                const int oa = my_oa, na = my_na, ob = my_ob, nb = my_nb;
+                const bool same = outcome == CO_SAME;
+                cnt = emit_manifold(P, p, GlobalAcc{ P, same ? oa : ob, same ? ob : oa }, same ? na : nb, same ? nb : na, edge, pn, same);
+            } else if (outcome == CO_FALLBACK) cnt = CCNT_FALLBACK;   // finished by k_manifolds<.., FLAGGED_ONLY>
+            P.ccnt[p] = cnt;
+        }
+        __syncwarp();
     }
 }
 
@@ -1382,6 +1559,8 @@ struct shapes_ctx {
     int max_hull_verts = 0;
     unsigned cell_limit = 0;     // sticky per-frame cell budget (0 = not chosen yet)
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
+    int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
+    bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
     bool has_circles = false;
     double *d_radius = nullptr;
     int rows_blocks = 4;         // resident k_rows blocks per SM
@@ -1603,6 +1782,10 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b8, k_manifolds<MAX_STAGED_VERTS, false>, CT_THREADS, 0), "occupancy"));
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_manifolds<MAX_STAGED_VERTS, true>, CT_THREADS, 0), "occupancy"));
         c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1); c->ct_blocks[2] = std::max(bc, 1);
+        int bco = 0;
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop, CO_WARPS * 32, 0), "occupancy"));
+        c->coop_blocks = std::max(bco, 1);
+        c->use_coop = std::getenv("SHAPES_B200_NO_COOP") == nullptr;
         int br = 0;
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_rows, 256, 0), "occupancy"));
         c->rows_blocks = std::max(br, 1);
@@ -1744,6 +1927,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         if (N > 0) {
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
+            else if (c->use_coop) {
+                k_manifolds_coop<<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                // hulls with more than 8 vertices / foreign hulls (multi-rank): per-thread pass over the flagged pairs
+                if (c->max_hull_verts > MAX_STAGED_VERTS || c->world > 1) {
+                    k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
+                }
+            }
             else k_manifolds<MAX_STAGED_VERTS, false><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
             ++c->launches;
         }

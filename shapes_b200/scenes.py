@@ -262,3 +262,36 @@ def gaussian_blob(n=1_000_000, density=1.0, peak_factor=4.0, static_frac=0.02, c
     rot = rng.uniform(n, 0.0, 2.0 * math.pi)
     static = rng.uniform(n) < static_frac
     return _finish(f"blob{n}", off, lx, ly, px, py, rot, static, {"config": config, "sigma": sigma})
+
+
+def spatially_sorted(world: World, cell: float = 2.0) -> World:
+    """The same objects with slot keys assigned in Morton (Z-curve) order of their positions.
+
+    Keys are the host's choice (World.append hands them out in insertion order, World.hs:77-84); an engine
+    that inserts objects region by region gets this layout.  It matters for performance only: partner hulls
+    of a pair sit close in memory, and with several GPUs each rank's slot range is a compact region, so
+    the multi-rank cell filter keeps only the neighbourhood of that region."""
+    gx = np.floor((world.pos_x - np.nanmin(world.pos_x)) / cell).astype(np.uint64)
+    gy = np.floor((world.pos_y - np.nanmin(world.pos_y)) / cell).astype(np.uint64)
+
+    def spread(v):
+        v = v & np.uint64(0xFFFFFFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+
+    order = np.argsort(spread(gx) | (spread(gy) << np.uint64(1)), kind="stable")
+    nv = np.diff(world.vert_offset).astype(np.int64)[order]
+    off = np.zeros(world.n_slots + 1, np.int64)
+    np.cumsum(nv, out=off[1:])
+    src = np.repeat(world.vert_offset[:-1].astype(np.int64)[order] - off[:-1], nv) + np.arange(off[-1])
+    out = World(world.alive[order].copy(), off.astype(np.int32), world.local_x[src].copy(), world.local_y[src].copy(),
+                world.pos_x[order].copy(), world.pos_y[order].copy(), world.rot[order].copy(),
+                world.inv_lin[order].copy(), world.inv_rot[order].copy(),
+                radius=None if world.radius is None else world.radius[order].copy(), name=world.name + "_morton")
+    out.meta.update(world.meta)
+    out.meta["slot_order"] = "morton"
+    return out.validate()
