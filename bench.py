@@ -447,7 +447,10 @@ def main():
     # ---- whole updateWorld on the device (not part of the headline metric) ----
     world_step = None
     if world_size == 1 and not args.no_world_step:
-        world_step = world_step_leg(eng, world, args, bracket)
+        try:
+            world_step = world_step_leg(eng, world, args, bracket)
+        except Exception as e:     # an extra leg must never cost the headline line
+            world_step = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         eng.close()

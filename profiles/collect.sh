@@ -22,3 +22,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_s
     -o gpurun_out/prof_world_$TAG -f python profiles/world_step.py --workload pile --nx 1000 --ny 1000 --steps 1 --warmup 1 > gpurun_out/ncu_full_world_$TAG.log 2>&1
 python profiles/_stage.py gpurun_out/bench_$TAG.json
 tail -2 gpurun_out/bench_$TAG.err
+# general polygons: one full capture of the 16-lanes-per-pair SAT kernel on config 2 at 1M polygons
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_manifolds_coop" -s 3 -c 1 -o gpurun_out/prof_coop_$TAG -f \
+    python bench.py --workload polygons --shapes-per-gpu 1000000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-world-step > gpurun_out/ncu_coop_$TAG.log 2>&1

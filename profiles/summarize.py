@@ -145,6 +145,9 @@ def main():
     repw = os.path.join(OUT, f"prof_world_{tag}.ncu-rep")
     if os.path.exists(repw):
         md += ["### ncu --set full capture of `k_solve` (1M-box pile)", "", raw_tables(repw, {}), ""]
+    repc = os.path.join(OUT, f"prof_coop_{tag}.ncu-rep")
+    if os.path.exists(repc):
+        md += ["### ncu --set full capture of `k_manifolds_coop` (config 2 at 1M polygons)", "", raw_tables(repc, {}), ""]
     path = os.path.join(ROOT, "profiles", f"{tag}_summary.md")
     with open(path, "w") as f:
         f.write("\n".join(md))
