@@ -1,0 +1,115 @@
+"""Two restatements of the reference, written separately and structured differently, must agree bit for bit:
+oracle/shapes_oracle.c (+ _step.c: index arithmetic over SoA columns) against oracle/hs_mirror.py (the
+reference's own Neighborhood / Maybe / Either / foldl1 shapes, function by function).  This catches
+transcription slips in either; it does not pin them to the Haskell program's outputs (no GHC here).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hs_mirror as hs
+from shapes_b200 import scenes
+from shapes_b200.world import Bodies, World, rectangle_vertices
+
+COLS_J = [f"j_np{q}" for q in range(6)]
+COLS_F = [f"j_f{q}" for q in range(6)]
+
+
+def same(a, b):
+    return a == b or (a != a and b != b)
+
+
+def compare_frame(oracle, w, dt=0.01, beh=(0.01, 0.02)):
+    c, s = oracle.cos_sin(w.rot)
+    fr = oracle.frame(w, c, s, dt=dt, baumgarte=beh[0], slop=beh[1], broadphase="aabb")
+    hulls = hs.hulls_of(w, c, s)
+    # world vertices, normals, frozen extents
+    for slot, h in enumerate(hulls):
+        if h is None:
+            continue
+        o = int(w.vert_offset[slot])
+        for k in range(h.count):
+            assert same(h.vertices[k][0], fr["world_x"][o + k]) and same(h.vertices[k][1], fr["world_y"][o + k]), (slot, k)
+            assert same(h.edge_normals[k][0], fr["normal_wx"][o + k]) and same(h.edge_normals[k][1], fr["normal_wy"][o + k])
+            assert h.extents[k] == (int(fr["ext_min"][o + k]), int(fr["ext_max"][o + k])), (slot, k)
+    pairs = list(zip(fr["pair_i"].tolist(), fr["pair_j"].tolist()))
+    rows = hs.prepare_frame(w, hulls, pairs, beh, dt)
+    assert len(rows) == len(fr["key_i"]), (len(rows), len(fr["key_i"]))
+    for k, r in enumerate(rows):
+        assert r["key"] == (fr["key_i"][k], fr["key_j"][k], fr["feat_a"][k], fr["feat_b"][k]), k
+        assert r["flip"] == fr["flip"][k]
+        ct = r["contact"]
+        assert same(ct["normal"][0], fr["normal_x"][k]) and same(ct["normal"][1], fr["normal_y"][k]), k
+        assert same(ct["center"][0], fr["center_x"][k]) and same(ct["center"][1], fr["center_y"][k]), k
+        assert same(ct["depth"], fr["depth"][k]), k
+        jn, bn = r["constraint"]["nonpen"]
+        jf, bf = r["constraint"]["friction"]
+        ra, rb, rn = r["constraint"]["restitution"]
+        for q in range(6):
+            assert same(jn[q], fr[COLS_J[q]][k]) and same(jf[q], fr[COLS_F[q]][k]), (k, q)
+        assert same(bn, fr["b_np"][k]) and bf == 0.0
+        assert same(ra[0], fr["ra_x"][k]) and same(ra[1], fr["ra_y"][k]) and same(rb[0], fr["rb_x"][k]) and same(rb[1], fr["rb_y"][k])
+        assert same(rn[0], fr["rn_x"][k]) and same(rn[1], fr["rn_y"][k])
+        i, j = r["key"][0], r["key"][1]
+        a = {"inv": (w.inv_lin[i], w.inv_rot[i])}
+        b = {"inv": (w.inv_lin[j], w.inv_rot[j])}
+        assert same(hs.effMassM2(jn, a, b), fr["inv_eff_np"][k]) and same(hs.effMassM2(jf, a, b), fr["inv_eff_f"][k])
+    return fr, rows
+
+
+def test_kat1_through_the_mirror():
+    """testOptBoxes (bench/Physics/Contact/Benchmark.hs:16-27), the hand trace of tests/golden/README.md."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")) as f:
+        kat = json.load(f)["kat1_testOptBoxes"]
+    a = hs.ConvexHull(rectangle_vertices(4, 4)).setHullTransform(lambda p: hs.afmul(hs.toTransform((0.0, 0.0), (1.0, 0.0)), p))
+    b = hs.ConvexHull(rectangle_vertices(2, 2)).setHullTransform(lambda p: hs.afmul(hs.toTransform((1.0, 3.0), (1.0, 0.0)), p))
+    got = hs.generateContacts(a, b)
+    assert len(got) == len(kat["contacts"])
+    for (feat, (flipping, c)), want in zip(got, kat["contacts"]):
+        assert list(feat) == want["feat"] and (0 if flipping == "Same" else 1) == want["flip"]
+        assert list(c["normal"]) == want["normal"] and list(c["center"]) == want["center"] and c["depth"] == want["depth"]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_polygon_worlds(oracle, seed):
+    w = scenes.random_polygons(260, density=2.5, config=300 + seed)
+    fr, rows = compare_frame(oracle, w)
+    assert len(rows) > 40 and {r["flip"] for r in rows} == {0, 1}
+
+
+def test_stacks_pile_and_touching_boxes(oracle):
+    """Axis-aligned boxes: parallel reference / incident edges (det = 0, NaN-driven ClipNone), exact ties."""
+    w = scenes.stacks_scene((6, 5), 0.0)
+    w.pos_y[1:] -= 0.905
+    fr, rows = compare_frame(oracle, w)
+    assert len(rows) > 50
+    compare_frame(oracle, scenes.box_pile(12, 9))
+    t = World.from_objects([(rectangle_vertices(4, 4), (0.0, 0.0), 0.0, (1.0, 1.0)),
+                            (rectangle_vertices(2, 2), (1.0, 3.0), 0.0, (1.0, 1.0)),
+                            (rectangle_vertices(2, 2), (3.0, 0.0), 0.0, (0.0, 0.0))])
+    compare_frame(oracle, t, dt=0.02, beh=(0.2, 0.001))
+
+
+def test_solver_sweeps_agree(oracle):
+    """improveWorld (two sweeps) over a frame's contacts: the C loop against improveContactSln of the mirror."""
+    w = scenes.random_polygons(160, density=3.0, config=310)
+    fr, rows = compare_frame(oracle, w)
+    n = w.n_slots
+    rng = np.random.default_rng(3)
+    b = Bodies(rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(0, 0.6, n), rng.uniform(0, 0.5, n))
+    objs = [{"vel": (b.vel_x[s], b.vel_y[s]), "rotvel": b.rot_vel[s], "pos": (w.pos_x[s], w.pos_y[s]),
+             "inv": (w.inv_lin[s], w.inv_rot[s])} for s in range(n)]
+    lam = [(0.0, 0.0)] * len(rows)
+    lam_np, lam_f = np.zeros(len(rows)), np.zeros(len(rows))
+    for sweep in range(2):
+        oracle.improve_world(w, fr, b.mu, b.bounce, b.vel_x, b.vel_y, b.rot_vel, lam_np, lam_f)
+        for k, r in enumerate(rows):
+            i, j = r["key"][0], r["key"][1]
+            (objs[i], objs[j]), lam[k] = hs.improveContactSln(r["constraint"], lam[k], (b.mu[i], b.mu[j]),
+                                                                (b.bounce[i], b.bounce[j]), (objs[i], objs[j]))
+        for s in range(n):
+            assert same(objs[s]["vel"][0], b.vel_x[s]) and same(objs[s]["vel"][1], b.vel_y[s]) and same(objs[s]["rotvel"], b.rot_vel[s]), (sweep, s)
+        for k in range(len(rows)):
+            assert same(lam[k][0], lam_np[k]) and same(lam[k][1], lam_f[k]), (sweep, k)
+    assert np.abs(lam_np).max() > 0.0
