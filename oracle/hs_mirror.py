@@ -431,3 +431,180 @@ def prepare_frame(world, hulls, pairs, beh, dt):
             rows.append({"key": ij + feat, "flip": 0 if fc[0] == "Same" else 1, "contact": fc[1],
                          "constraint": constraintGen(beh, dt, fc, (a, b))})
     return rows
+
+
+# ---- circles: Physics.Contact.Circle / GJK / CircleVsHull, Physics.Contact.generateContacts ----------
+
+def sdivV2(s, v): return (_div(v[0], s), _div(v[1], s))              # Linear.hs:80-82  liftV2 (/## s)
+def sqLengthV2(v): return (v[0] * v[0]) + (v[1] * v[1])              # :175-176
+def crosszV2(a, bz): return (a[1] * bz, -(a[0] * bz))                # :121-124
+def sameDirection(a, b): return dotV2(a, b) > 0.0                    # GJK.hs:138-139
+
+
+def crossV2V2(a, b, c):                                              # Linear.hs:135-139
+    abz = (a[0] * b[1]) - (a[1] * b[0])
+    return (-(abz * c[1]), abz * c[0])
+
+
+def circle_contact(ca, ra, cb, rb):                                  # Circle.contact (Circle.hs:30-53); A = penetratee
+    ab = minusV2(cb, ca)
+    rab = ra + rb
+    ab_sq = sqLengthV2(ab)
+    if not (rab * rab >= ab_sq):
+        return None
+    ab_len = math.sqrt(ab_sq)
+    ab_n = sdivV2(ab_len, ab)
+    a1 = plusV2(smulV2(ra, ab_n), ca)
+    b1 = plusV2(smulV2(-rb, ab_n), cb)
+    return {"normal": ab_n, "center": sdivV2(2, plusV2(a1, b1)), "depth": ra + rb - ab_len}
+
+
+def support(hull, d):                                                # ConvexHull.hs:124-128: first maximum
+    acc = (dotV2(hull.neighborhoods[0].center, d), hull.neighborhoods[0])
+    for n in hull.neighborhoods[1:]:
+        dist = dotV2(n.center, d)
+        if dist > acc[0]:
+            acc = (dist, n)
+    return acc[1]
+
+
+def closestSimplex(hull, origin):                                    # GJK.hs:52-69
+    simplex = [hull.neighborhoods[0]]                                # Left (Simplex1 a); most recent vertex first
+    d = minusV2(origin, simplex[0].center)
+    for _ in range(64):                                              # the reference loops until a repeat; bounded here like the C oracle
+        aa = support(hull, d)
+        if any(aa.index == s.index for s in simplex):                # extendSimplex1/2: a repeat ends the search
+            return ("Simplex12", simplex)
+        simplex = [aa] + simplex
+        a = simplex[0].center
+        ao = minusV2(origin, a)
+        ab = minusV2(simplex[1].center, a)
+        if len(simplex) == 2:                                        # shiftSimplex2 (:98-112)
+            if sameDirection(ab, ao):
+                d = crossV2V2(ab, ao, ab)
+            else:
+                simplex, d = [simplex[0]], ao
+        else:                                                        # shiftSimplex3 (:114-136)
+            ac = minusV2(simplex[2].center, a)
+            abc = crossV2(ab, ac)
+            abcac = zcrossV2(abc, ac)
+            ababc = crosszV2(ab, abc)
+            star = None
+            if sameDirection(abcac, ao):
+                if sameDirection(ac, ao):
+                    simplex, d = [simplex[0], simplex[2]], crossV2V2(ac, ao, ac)
+                else:
+                    star = True
+            elif sameDirection(ababc, ao):
+                star = True
+            else:
+                return ("Simplex3", simplex)                         # encloses the target
+            if star:
+                if sameDirection(ab, ao):
+                    simplex, d = [simplex[0], simplex[1]], crossV2V2(ab, ao, ab)
+                else:
+                    simplex, d = [simplex[0]], ao
+    return ("Simplex12", None)
+
+
+def circle_hull_contacts(center, radius, hull):                      # CircleVsHull.generateContacts (:18-69)
+    kind, simplex = closestSimplex(hull, center)
+    if kind != "Simplex12" or simplex is None:
+        return None                                                  # Simplex3': deep overlap -> Nothing
+    feature = simplex[0]
+    a = feature.center
+    if len(simplex) == 2:                                            # closestAlong (:60-69)
+        b = simplex[1].center
+        ao, ab = minusV2(center, a), minusV2(b, a)
+        ab_norm = normalizeV2(ab)
+        a = plusV2(smulV2(dotV2(ao, ab_norm), ab_norm), a)
+    ab = minusV2(center, a)                                          # processSimplex_ (:42-58)
+    ab_sq = sqLengthV2(ab)
+    if radius * radius < ab_sq:
+        return None
+    ab_len = math.sqrt(ab_sq)
+    return feature.index, {"normal": negateV2(sdivV2(ab_len, ab)), "center": a, "depth": radius - ab_len}
+
+
+def generateContactsShapes(sa, sb):                                  # Physics.Contact.generateContacts (Contact.hs:22-40)
+    """A shape is ("hull", ConvexHull) or ("circle", centre, radius)."""
+    if sa[0] == "circle" and sb[0] == "circle":
+        c = circle_contact(sa[1], sa[2], sb[1], sb[2])
+        return [] if c is None else [((0, 0), ("Same", c))]
+    if sa[0] == "circle":
+        r = circle_hull_contacts(sa[1], sa[2], sb[1])
+        return [] if r is None else [((0, r[0]), ("Same", r[1]))]
+    if sb[0] == "circle":
+        r = circle_hull_contacts(sb[1], sb[2], sa[1])
+        return [] if r is None else [((r[0], 0), ("Flip", r[1]))]
+    return generateContacts(sa[1], sb[1])
+
+
+# ---- Physics.Broadphase.Aabb -------------------------------------------------------------------------
+
+def mergeRange(x, y):                                                # Aabb.hs:104-110
+    (a, b), (c, d) = x, y
+    return (a if a < c else c, b if b > d else d)
+
+
+def hullToAabb(hull):                                                # :81-84: foldl1 mergeAabb over the vertices
+    acc = ((hull.vertices[0][0],) * 2, (hull.vertices[0][1],) * 2)
+    for v in hull.vertices[1:]:
+        acc = (mergeRange(acc[0], (v[0], v[0])), mergeRange(acc[1], (v[1], v[1])))
+    return acc
+
+
+def circleToAabb(center, r):                                         # :86-88
+    return ((center[0] - r, center[0] + r), (center[1] - r, center[1] + r))
+
+
+def boundsOverlap(x, y):                                             # :69-72
+    (a, b), (c, d) = x, y
+    return not (c > b or d < a)
+
+
+def aabbCheck(p, q): return boundsOverlap(p[0], q[0]) and boundsOverlap(p[1], q[1])   # :75-78
+
+
+def unorderedPairs(n):                                               # :155-163
+    out = []
+    if n < 2:
+        return out
+    x, y = n - 1, n - 2
+    while True:
+        out.append((x, y))
+        if (x, y) == (1, 0):
+            return out
+        if y == 0:
+            x, y = x - 1, x - 2
+        else:
+            y -= 1
+
+
+def culledKeys(tagged):                                              # :168-183; tagged = [(key, aabb, isStatic)] in traversal order
+    out = []
+    for (i, j) in unorderedPairs(len(tagged)):
+        ki, a, sa = tagged[i]
+        kj, b, sb = tagged[j]
+        if not (sa and sb) and aabbCheck(a, b):
+            out.append((ki, kj))
+    return out
+
+
+# ---- Utils.Descending.descZipVector as applyCachedSlns uses it ----------------------------------------
+
+def descZipVector(these, those):                                     # Descending.hs:47-71 -> per `this`: matching `that` index or None
+    out, that_i = [], 0
+    for this_key in these:
+        match = None
+        while that_i < len(those):
+            that_key = those[that_i]
+            if this_key < that_key:
+                that_i += 1                                          # keep looking
+                continue
+            if this_key == that_key:
+                match = that_i
+                that_i += 1
+            break
+        out.append(match)
+    return out

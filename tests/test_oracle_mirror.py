@@ -113,3 +113,73 @@ def test_solver_sweeps_agree(oracle):
         for k in range(len(rows)):
             assert same(lam[k][0], lam_np[k]) and same(lam[k][1], lam_f[k]), (sweep, k)
     assert np.abs(lam_np).max() > 0.0
+
+
+def mirror_world(w, c, s):
+    """Shapes (hulls and circles), tagged AABBs in traversal order, as the reference's World holds them."""
+    hulls = hs.hulls_of(w, c, s)
+    shapes, tagged = {}, []
+    for slot in range(w.n_slots):
+        if not w.alive[slot]:
+            continue
+        if w.radius is not None and w.radius[slot] >= 0:
+            m = hs.toTransform((float(w.pos_x[slot]), float(w.pos_y[slot])), (float(c[slot]), float(s[slot])))
+            centre = hs.afmul(m, (0.0, 0.0))                         # setCircleTransform (Circle.hs:55-59)
+            shapes[slot] = ("circle", centre, float(w.radius[slot]))
+            box = hs.circleToAabb(centre, float(w.radius[slot]))
+        else:
+            shapes[slot] = ("hull", hulls[slot])
+            box = hs.hullToAabb(hulls[slot])
+        tagged.append((slot, box, w.inv_lin[slot] == 0.0 and w.inv_rot[slot] == 0.0))
+    return shapes, tagged
+
+
+@pytest.mark.parametrize("scene", ["balls", "mixed", "deleted"])
+def test_circles_broadphase_and_dispatch(oracle, scene):
+    """Aabb.culledKeys (unorderedPairs order, static/static dropped) and the four-way generateContacts
+    dispatch (Circle.contact, GJK closestSimplex, CircleVsHull) against the C oracle."""
+    if scene == "balls":
+        w = scenes.balls_scene((7, 6), 0.5, 0.0)
+        w.pos_y[1:] -= 0.55
+    else:
+        w = scenes.random_circles_and_polygons(240, config=320)
+        if scene == "deleted":
+            w.delete([3, 17, 100, 101])
+    c, s = oracle.cos_sin(w.rot)
+    fr = oracle.frame(w, c, s, broadphase="aabb")
+    shapes, tagged = mirror_world(w, c, s)
+    for slot, box, _ in tagged:
+        assert box == ((fr["aabb_min_x"][slot], fr["aabb_max_x"][slot]), (fr["aabb_min_y"][slot], fr["aabb_max_y"][slot])), slot
+    pairs = hs.culledKeys(tagged)
+    assert pairs == list(zip(fr["pair_i"].tolist(), fr["pair_j"].tolist()))
+    k = 0
+    kinds = set()
+    for (i, j) in pairs:
+        for feat, (flipping, ct) in hs.generateContactsShapes(shapes[i], shapes[j]):
+            assert (i, j) + feat == (fr["key_i"][k], fr["key_j"][k], fr["feat_a"][k], fr["feat_b"][k]), k
+            assert (0 if flipping == "Same" else 1) == fr["flip"][k]
+            assert same(ct["normal"][0], fr["normal_x"][k]) and same(ct["normal"][1], fr["normal_y"][k]), k
+            assert same(ct["center"][0], fr["center_x"][k]) and same(ct["center"][1], fr["center_y"][k]), k
+            assert same(ct["depth"], fr["depth"][k]), k
+            kinds.add((shapes[i][0], shapes[j][0]))
+            k += 1
+    assert k == len(fr["key_i"]) and k > 10
+    if scene == "mixed":
+        assert len(kinds) == 4                                       # all four shape-pair kinds produced contacts
+
+
+def test_desc_zip_vector_agrees(oracle):
+    rng = np.random.default_rng(9)
+    def keys(n):
+        ks = sorted({(int(a), int(b), int(c), int(d)) for a, b, c, d in rng.integers(0, 6, (n, 4))}, reverse=True)
+        return ks
+    for trial in range(20):
+        these, those = keys(40), keys(40)
+        want = hs.descZipVector(these, those)
+        cols = lambda ks: {n: np.array([k[q] for k in ks], np.int32) for q, n in enumerate(("key_i", "key_j", "feat_a", "feat_b"))}
+        lam_np = np.arange(len(those), dtype=np.float64) + 1.0
+        lam_f = -np.arange(len(those), dtype=np.float64) - 1.0
+        o_np, o_f, hit = oracle.warm_join(cols(these), cols(those), lam_np, lam_f)
+        for k, m in enumerate(want):
+            assert bool(hit[k]) == (m is not None)
+            assert (o_np[k], o_f[k]) == ((lam_np[m], lam_f[m]) if m is not None else (0.0, 0.0))
