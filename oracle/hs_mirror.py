@@ -608,3 +608,49 @@ def descZipVector(these, those):                                     # Descendin
             break
         out.append(match)
     return out
+
+
+# ---- Physics.Broadphase.Grid (the variant updateWorld calls, Engine/Main.hs:75) ------------------------
+
+def axialIndex(axis, val):                                           # Grid.hs:124-127; axis = (length, unit, origin)
+    return math.floor(_div(val - axis[2], axis[1]))
+
+
+def boxIndices(axes, box):                                           # :129-141
+    x_axis, y_axis = axes
+    xs = range(axialIndex(x_axis, box[0][0]), axialIndex(x_axis, box[0][1]) + 1)
+    ys = range(axialIndex(y_axis, box[1][0]), axialIndex(y_axis, box[1][1]) + 1)
+    return [x + (y * x_axis[0]) for x in xs for y in ys]              # flattenIndex' (:117-118)
+
+
+def fromTaggedAabbs(axes, tagged):                                   # :96-105: IntMap (IntMap TaggedAabb)
+    grid = {}
+    for key, box, is_static in tagged:
+        for index in boxIndices(axes, box):
+            grid.setdefault(index, {})[key] = (is_static, box)
+    return grid
+
+
+def allPairs(xs):                                                    # :84-89 (the accumulation order does not survive the sort)
+    out = []
+    for a in range(len(xs)):
+        for b in range(a + 1, len(xs)):
+            out.append((xs[a], xs[b]))
+    return out
+
+
+def grid_culledKeys(axes, tagged):                                   # toGrid + culledKeys + culledKeys' + uniq (:67-95)
+    pairs = []
+    for square in fromTaggedAabbs(axes, tagged).values():
+        desc = sorted(square.items(), key=lambda kv: -kv[0])         # IM.toDescList
+        for (a, (sa, box_a)), (b, (sb, box_b)) in allPairs(desc):
+            if sa and sb:
+                continue                                             # two static shapes
+            if aabbCheck(box_a, box_b):
+                pairs.append((a, b))
+    pairs.sort(reverse=True)                                         # sortBy (flip compare)
+    out = []
+    for p in pairs:                                                  # uniq
+        if not out or out[-1] != p:
+            out.append(p)
+    return out

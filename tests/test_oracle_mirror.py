@@ -183,3 +183,20 @@ def test_desc_zip_vector_agrees(oracle):
         for k, m in enumerate(want):
             assert bool(hit[k]) == (m is not None)
             assert (o_np[k], o_f[k]) == ((lam_np[m], lam_f[m]) if m is not None else (0.0, 0.0))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_grid_culled_keys_agrees(oracle, seed):
+    """Grid.toGrid / culledKeys (Grid.hs:67-141, what updateWorld calls) == Aabb.culledKeys == the C oracle's
+    grid restatement, on worlds inside and partly outside the engine's 20x20 grid (gridAxes, Engine/Main.hs:39-40)."""
+    w = scenes.random_polygons(220, density=0.7, config=330 + seed)
+    w.pos_x -= 9.0; w.pos_y -= 9.0                                    # the square [0, 17.7]^2 -> [-9, 8.7]^2 (+ overhang)
+    c, s = oracle.cos_sin(w.rot)
+    shapes, tagged = mirror_world(w, c, s)
+    axes = ((20, 1.0, -10.0), (20, 1.0, -10.0))
+    got = hs.grid_culledKeys(axes, tagged)
+    assert got == hs.culledKeys(tagged)
+    wx, wy, _, _ = oracle.move_shapes(w, c, s)
+    boxes = oracle.aabbs(w, wx, wy)
+    pi, pj = oracle.culled_keys_grid(w, boxes, oracle.is_static(w))
+    assert got == list(zip(pi.tolist(), pj.tolist())) and len(got) > 20
