@@ -213,6 +213,7 @@ struct Params {
     int my_rank;
     unsigned long long frame_no;
     unsigned long long *cnt, *off; // per query slot, indexed own_hi-1-i
+    unsigned long long *hitmask;   // per sorted position: k_sweep<count>'s hits, replayed by k_sweep<emit>
     int64_t max_pairs, max_contacts;
     int32_t *pair_i, *pair_j;
     // contacts
@@ -576,6 +577,43 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         ++count;
     };
 
+    // The count pass leaves a bit per candidate (in enumeration order: the three runs, then the big list)
+    // so that the emit pass revisits only the hits -- no AABB records, no overlap tests.  Bit 63 = more than
+    // 63 candidates: the emit pass then repeats the tests.
+    unsigned long long mask = 0;
+    unsigned cand = 0;
+    const unsigned long long want = EMIT ? P.hitmask[p] : 0ull;
+    const bool replay = EMIT && !(want >> 63);
+    const unsigned n_big = st->n_big;
+    if (replay) {
+        unsigned long long m = want;
+        unsigned seen = 0;
+        for (int dy = -1; dy <= 1 && m; ++dy) {
+            const int ny = cy + dy;
+            if (ny < 0 || ny >= H) continue;
+            const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
+            const unsigned q_lo = __ldg(&P.cell_begin[(size_t)ny * W + x_lo]);
+            const unsigned q_hi = __ldg(&P.cell_begin[(size_t)ny * W + x_hi + 1]);
+            const unsigned len = q_hi - q_lo;
+            // bits [seen, seen + len) belong to this run
+            unsigned long long run = (len >= 64u - seen) ? (m >> seen) : ((m >> seen) & ((1ull << len) - 1ull));
+            while (run) {
+                const int b = __ffsll((long long)run) - 1;
+                run &= run - 1;
+                hit((int)(__ldg(&P.smeta[q_lo + (unsigned)b]) & 0x7fffffffu));
+            }
+            seen += len;
+            if (seen >= 63u) break;
+        }
+        if (seen < 63u) {
+            unsigned long long run = (want & 0x7fffffffffffffffull) >> seen;
+            while (run) {
+                const int b = __ffsll((long long)run) - 1;
+                run &= run - 1;
+                hit((int)P.big_idx[b]);
+            }
+        }
+    } else {
     for (int dy = -1; dy <= 1; ++dy) {
         const int ny = cy + dy;
         if (ny < 0 || ny >= H) continue;
@@ -583,23 +621,24 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
         const unsigned q_lo = __ldg(&P.cell_begin[(size_t)ny * W + x_lo]);
         const unsigned q_hi = __ldg(&P.cell_begin[(size_t)ny * W + x_hi + 1]);
-        for (unsigned q = q_lo; q < q_hi; ++q) {
+        for (unsigned q = q_lo; q < q_hi; ++q, ++cand) {
             const uint32_t m = __ldg(&P.smeta[q]);
             const int j = (int)(m & 0x7fffffffu);
             if (j >= i) continue;
             if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
             const Box bj = P.sbox[q];
-            if (aabb_check(bi, bj)) hit(j);
+            if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
         }
     }
-    const unsigned n_big = st->n_big;
-    for (unsigned b = 0; b < n_big; ++b) {
+    for (unsigned b = 0; b < n_big; ++b, ++cand) {
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
         if (si && slot_static(P, j)) continue;
         const Box bj = box_of(P, j);
-        if (aabb_check(bi, bj)) hit(j);
+        if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
     }
+    }
+    if (!EMIT) P.hitmask[p] = (cand > 63u) ? (1ull << 63) : mask;
 
     if (!EMIT) { P.cnt[r] = count; continue; }
     if (count == 0) continue;
@@ -1739,6 +1778,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     c->use_p2p = std::getenv("SHAPES_B200_NO_P2P") == nullptr;
     TRY_CREATE(dev_alloc(c, &P.cnt, N));
     TRY_CREATE(dev_alloc(c, &P.off, N));
+    TRY_CREATE(dev_alloc(c, &P.hitmask, N));
     TRY_CREATE(dev_alloc(c, &P.pair_i, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.pair_j, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.man, max_pairs));
