@@ -36,7 +36,7 @@ constexpr unsigned SOLVE_NONE = 0xffffffffu;     // "no node" / empty queue slot
 constexpr int SOLVE_PASS_SHIFT = 28;             // queue entry = node | pass << 28
 constexpr unsigned SOLVE_NODE_MASK = (1u << SOLVE_PASS_SHIFT) - 1u;
 constexpr int SOLVE_THREADS = 128;
-constexpr unsigned long long SOLVE_IDLE_LIMIT_NS = 4000000000ull;   // a thread idle for ~4 s of sleeps gives up
+constexpr unsigned long long SOLVE_IDLE_LIMIT_NS = 15000000000ull;  // a warp idle for ~15 s of sleeps gives up
 
 // Shared scheduler words, one 128 B line each: the idle pollers, the pushers and the chain ends
 // must not queue up behind each other on one L2 sector.
@@ -543,7 +543,8 @@ struct WorldStep {
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     uint32_t *queue = nullptr;
-    size_t queue_cap = 0;
+    size_t queue_alloc = 0;        // slots allocated
+    size_t queue_cap = 0;          // slots this step may use (pairs x sweeps + threads)
     SolveState *ss = nullptr;
     SolveState *h_ss = nullptr;    // pinned
     cudaEvent_t ev[5] = {};
@@ -592,9 +593,10 @@ int world_alloc(shapes_ctx *c)
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve, SOLVE_THREADS, 0));
     per_sm = std::min(per_sm, std::max(occ, 1));
     w->solve_blocks = c->sm_count * per_sm;
-    // every node is queued at most once per sweep, every idle thread holds at most one claimed slot
-    w->queue_cap = P * (size_t)3 + (size_t)w->solve_blocks * SOLVE_THREADS + 64;
-    WS_ALLOC(&w->queue, w->queue_cap);
+    // every node is queued at most once per sweep, every idle thread holds at most one claimed slot;
+    // sized for updateWorld's 3 sweeps here, re-allocated by shapes_world_step when a step needs more
+    w->queue_alloc = P * (size_t)3 + (size_t)w->solve_blocks * SOLVE_THREADS + 64;
+    WS_ALLOC(&w->queue, w->queue_alloc);
     WS_ALLOC(&w->ss, 1);
 #undef WS_ALLOC
     CU_TRY(c, cudaMallocHost(&w->h_ss, sizeof(SolveState)));
@@ -737,6 +739,16 @@ int shapes_world_step(shapes_ctx *c, const shapes_step_config *cfg, shapes_step_
         const int sms = c->sm_count;
         SolveState init;
         std::memset(&init, 0, sizeof(init));
+        // queue slots this step can need: one per (sweep, pair) + one claimed slot per thread
+        const size_t need = (size_t)n_pairs * (size_t)(S.p_end - S.p_begin) + (size_t)w->solve_blocks * SOLVE_THREADS + 64;
+        if (need > w->queue_alloc) {
+            uint32_t *bigger = nullptr;
+            CU_TRY(c, cudaStreamSynchronize(s));
+            CU_TRY(c, cudaMalloc(&bigger, sizeof(uint32_t) * need));
+            for (void *&q : c->allocs) if (q == w->queue) { cudaFree(q); q = bigger; }
+            w->queue = bigger; w->queue_alloc = need; S.queue = bigger;
+        }
+        w->queue_cap = need; S.queue_cap = need;
         init.queue_cap = w->queue_cap;
         *w->h_ss = init;
         CU_TRY(c, cudaMemcpyAsync(w->ss, w->h_ss, sizeof(SolveState), cudaMemcpyHostToDevice, s));

@@ -94,7 +94,7 @@ def test_random_polygons_and_circles(oracle):
     run_both(oracle, w, random_bodies(w.n_slots, 3, speed=1.0), 4, external=(1, 0.0, -2.0))
 
 
-@pytest.mark.parametrize("iterations,warm", [(0, True), (1, True), (5, True), (2, False)])
+@pytest.mark.parametrize("iterations,warm", [(0, True), (1, True), (5, True), (12, True), (2, False)])
 def test_solver_sweeps_and_cold_start(oracle, iterations, warm):
     w = scenes.box_pile(60, 40)
     run_both(oracle, w, random_bodies(w.n_slots, 4), 3, external=(1, 0.0, -2.0), iterations=iterations, warm_start=warm)
