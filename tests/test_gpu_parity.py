@@ -111,6 +111,33 @@ def test_mixed_and_blob(oracle):
     check_world(oracle, scenes.gaussian_blob(30_000, density=1.0))
 
 
+def test_tie_heavy_lattice_world(oracle):
+    """Shapes from a small pool placed on a lattice of quarter units with rotations by multiples of 90 degrees
+    (exact cos/sin): equal depths, touching edges, coincident vertices and parallel clip planes everywhere --
+    every tie-break of the SAT fold, the incident-edge choice and the NaN-driven ClipNone at once, through both
+    contact kernels (boxes only / hulls of up to 8 vertices)."""
+    rng = np.random.default_rng(33)
+    boxes = [rectangle_vertices(w, h) for w in (0.5, 1.0, 2.0) for h in (0.5, 1.0, 1.5)]
+    polys = [[(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)], [(0.5, 0.0), (0.0, 0.75), (-0.5, 0.0)],
+             [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)],
+             [(1.0, 0.5), (0.0, 1.0), (-1.0, 0.5), (-1.0, -0.5), (0.0, -1.0), (1.0, -0.5)],
+             [(1.0, 0.0), (0.75, 0.75), (0.0, 1.0), (-0.75, 0.75), (-1.0, 0.0), (-0.75, -0.75), (0.0, -1.0), (0.75, -0.75)]]
+    quarter = [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)]
+    for pool in (boxes, boxes + polys):
+        objs = []
+        for k in range(4000):
+            v = pool[rng.integers(len(pool))]
+            pos = (float(rng.integers(-160, 161)) * 0.25, float(rng.integers(-160, 161)) * 0.25)
+            objs.append((v, pos, 0.0, (1.0, 1.0) if rng.random() < 0.9 else (0.0, 0.0)))
+        w = World.from_objects(objs)
+        rot = rng.integers(0, 4, w.n_slots)
+        cs = (np.array([quarter[r][0] for r in rot]), np.array([quarter[r][1] for r in rot]))
+        want = oracle.frame(w, cs[0], cs[1], broadphase="sweep")
+        got = gpu_frame(w, cs)
+        assert_frames_match(got, want)
+        assert len(want["key_i"]) > 3000 and want["flip"].sum() > 0     # axis-aligned boxes: depth ties everywhere, ties are Flip
+
+
 def test_deleted_slots_and_all_static(oracle):
     w = scenes.random_polygons(3000, density=2.5, static_frac=0.3, config=31)
     w.delete(list(range(0, 3000, 7)))

@@ -200,3 +200,50 @@ def test_grid_culled_keys_agrees(oracle, seed):
     boxes = oracle.aabbs(w, wx, wy)
     pi, pj = oracle.culled_keys_grid(w, boxes, oracle.is_static(w))
     assert got == list(zip(pi.tolist(), pj.tolist())) and len(got) > 20
+
+
+def test_differential_fuzz_on_tie_heavy_pairs(oracle):
+    """Coordinates on a coarse lattice (multiples of 1/4, rotations by multiples of 90 degrees) make exact
+    ties, touching edges, coincident vertices and parallel clip planes the norm rather than the exception;
+    non-finite and huge positions ride along.  Both restatements must still agree on every row."""
+    rng = np.random.default_rng(21)
+    boxes = [rectangle_vertices(w, h) for w in (0.5, 1.0, 2.0) for h in (0.5, 1.0, 1.5)]
+    tri = [[(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)], [(0.5, 0.0), (0.0, 0.75), (-0.5, 0.0)], [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)],
+           [(1.0, 0.5), (0.0, 1.0), (-1.0, 0.5), (-1.0, -0.5), (0.0, -1.0), (1.0, -0.5)]]
+    shapes_pool = boxes + tri
+    quarter = [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)]
+    n_rows = n_flip = n_one = 0
+    for trial in range(60):
+        objs = []
+        for k in range(12):
+            v = shapes_pool[rng.integers(len(shapes_pool))]
+            pos = (float(rng.integers(-6, 7)) * 0.25, float(rng.integers(-6, 7)) * 0.25)
+            objs.append((v, pos, 0.0, (1.0, 1.0) if rng.random() < 0.8 else (0.0, 0.0)))
+        w = World.from_objects(objs)
+        rot = rng.integers(0, 4, w.n_slots)
+        c = np.array([quarter[r][0] for r in rot]); s = np.array([quarter[r][1] for r in rot])
+        if trial % 10 == 9:                                           # non-finite / huge bodies
+            w.pos_x[3] = np.inf; w.pos_y[5] = np.nan; w.pos_x[7] = 1e300
+        fr = oracle.frame(w, c, s, broadphase="aabb")
+        hulls = hs.hulls_of(w, c, s)
+        pairs = list(zip(fr["pair_i"].tolist(), fr["pair_j"].tolist()))
+        shapes, tagged = mirror_world(w, c, s)
+        assert hs.culledKeys(tagged) == pairs
+        rows = hs.prepare_frame(w, hulls, pairs, (0.01, 0.02), 0.01)
+        assert len(rows) == len(fr["key_i"]), trial
+        for k, r in enumerate(rows):
+            assert r["key"] == (fr["key_i"][k], fr["key_j"][k], fr["feat_a"][k], fr["feat_b"][k]) and r["flip"] == fr["flip"][k], (trial, k)
+            ct = r["contact"]
+            assert same(ct["normal"][0], fr["normal_x"][k]) and same(ct["normal"][1], fr["normal_y"][k])
+            assert same(ct["center"][0], fr["center_x"][k]) and same(ct["center"][1], fr["center_y"][k]) and same(ct["depth"], fr["depth"][k])
+            jn, bn = r["constraint"]["nonpen"]
+            jf, _ = r["constraint"]["friction"]
+            for q in range(6):
+                assert same(jn[q], fr[COLS_J[q]][k]) and same(jf[q], fr[COLS_F[q]][k]), (trial, k, q)
+            assert same(bn, fr["b_np"][k])
+        n_rows += len(rows); n_flip += sum(r["flip"] for r in rows)
+        counts = {}
+        for r in rows:
+            counts[r["key"][:2]] = counts.get(r["key"][:2], 0) + 1
+        n_one += sum(1 for v in counts.values() if v == 1)
+    assert n_rows > 1500 and 0 < n_flip < n_rows and n_one > 20      # both branches, one- and two-point manifolds
