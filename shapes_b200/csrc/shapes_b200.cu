@@ -1181,7 +1181,7 @@ struct GlobalAcc {      // emit_manifold over K0's world vertices / normals in g
     __device__ __forceinline__ V2 vp(int k) const { const double2 v = P.wv[pn_off + k]; return V2{ v.x, v.y }; }
 };
 
-__global__ void __launch_bounds__(CO_WARPS * 32, 4) k_manifolds_coop(Params P)
+__global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
 {
     __shared__ int s_out[CO_WARPS][32][3];                           // phase 1 -> phase 2: outcome, edge, penetrator
 
