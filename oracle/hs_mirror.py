@@ -654,3 +654,63 @@ def grid_culledKeys(axes, tagged):                                   # toGrid + 
         if not out or out[-1] != p:
             out.append(p)
     return out
+
+
+# ---- Physics.Engine.Main.updateWorld, assembled from the pieces above ---------------------------------
+
+def constantAccel(a):                                                # World/External.hs:23-27
+    def ext(dt, o):
+        if 0.0 == o["inv"][0]:                                       # isStaticLin
+            return o
+        return dict(o, vel=plusV2(o["vel"], smulV2(dt, a)))
+    return ext
+
+
+def advanceObj(o, dt):                                               # Constraint.hs:225-229
+    return dict(o, pos=plusV2(smulV2(dt, o["vel"]), o["pos"]), rot=(dt * o["rotvel"]) + o["rot"])
+
+
+def applySln(lagr, cc, ab):                                          # Solvers/Contact.hs:54-65: applyFriction . applyNonPen
+    ab = applyLagrangian(lagr[0], cc["nonpen"], ab)
+    return applyLagrangian(lagr[1], cc["friction"], ab)
+
+
+def updateWorld(objs, hulls_local, mats, cache, ext, dt, beh, sincos, grid_axes=None):
+    """One Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86).
+    objs: list of dicts {vel, rotvel, pos, rot, inv, cs=(cos, sin) the shape was last moved with} (all slots filled);
+    hulls_local: local CCW vertices per object; mats: [(mu, bounce)]; cache: [(key, (lam_np, lam_f))] descending.
+    Returns the new cache; objs are updated in place."""
+    n = len(objs)
+    # the shapes as moveShapes left them (World.hs:132-140)
+    hulls = [ConvexHull(hulls_local[k]).setHullTransform(lambda p, m=toTransform(objs[k]["pos"], objs[k]["cs"]): afmul(m, p))
+             for k in range(n)]
+    tagged = [(k, hullToAabb(hulls[k]), objs[k]["inv"] == (0.0, 0.0)) for k in range(n)]
+    keys = grid_culledKeys(grid_axes, tagged) if grid_axes else culledKeys(tagged)      # :75
+    for k in range(n):                                               # applyExternal (:76, World.hs:156-158)
+        objs[k] = ext(dt, objs[k])
+    k_contacts = []                                                  # prepareFrame (:77)
+    for (i, j) in keys:
+        k_contacts += keyedContacts((i, j), (hulls[i], hulls[j]))
+    # applyCachedSlns (:78-80, Solvers/Contact.hs:74-121)
+    this_keys = [ij + feat for (ij, feat), _ in k_contacts]
+    match = descZipVector(this_keys, [k for k, _ in cache])
+    lagrangians, constraints = [], []
+    for (key, fc), m in zip(k_contacts, match):
+        (i, j), _ = key
+        cc = constraintGen(beh, dt, fc, (objs[i], objs[j]))
+        if m is None:
+            lagrangians.append((key[0] + key[1], (0.0, 0.0)))        # newCache
+        else:
+            objs[i], objs[j] = applySln(cache[m][1], cc, (objs[i], objs[j]))   # useCache
+            lagrangians.append(cache[m])
+        constraints.append(cc)
+    for _ in range(2):                                               # improveWorld x2 (:81-82)
+        for k, (key, _) in enumerate(k_contacts):
+            (i, j), _ = key
+            (objs[i], objs[j]), lam = improveContactSln(constraints[k], lagrangians[k][1], (mats[i][0], mats[j][0]),
+                                                         (mats[i][1], mats[j][1]), (objs[i], objs[j]))
+            lagrangians[k] = (lagrangians[k][0], lam)
+    for k in range(n):                                               # advance (:83) + moveShapes (:84)
+        objs[k] = advanceObj(objs[k], dt)
+        objs[k]["cs"] = sincos(objs[k]["rot"])
+    return lagrangians

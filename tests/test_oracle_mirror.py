@@ -247,3 +247,40 @@ def test_differential_fuzz_on_tie_heavy_pairs(oracle):
             counts[r["key"][:2]] = counts.get(r["key"][:2], 0) + 1
         n_one += sum(1 for v in counts.values() if v == 1)
     assert n_rows > 1500 and 0 < n_flip < n_rows and n_one > 20      # both branches, one- and two-point manifolds
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")   # numpy scalars warn on the 1/0 of parallel clip planes; the NaN is the point
+def test_update_world_assembly_agrees(oracle):
+    """Whole frames of Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) -- culledKeys, applyExternal,
+    prepareFrame, applyCachedSlns (join + applySln), improveWorld x2, advance, moveShapes -- assembled twice:
+    the C oracle's update_world against the mirror's updateWorld, 25 frames of boxes landing on the floor."""
+    import math
+    w = scenes.stacks_scene((4, 3), 0.0)
+    w.pos_y[1:] -= 0.85
+    n = w.n_slots
+    b = Bodies.at_rest(n, 0.2, 0.0)
+    rng = np.random.default_rng(5)
+    b.vel_x[1:] = rng.uniform(-0.3, 0.3, n - 1); b.rot_vel[1:] = rng.uniform(-0.5, 0.5, n - 1)
+    libm = lambda r: (math.cos(r), math.sin(r))
+    c, s = oracle.cos_sin(w.rot)
+    objs = [{"vel": (b.vel_x[k], b.vel_y[k]), "rotvel": b.rot_vel[k], "pos": (w.pos_x[k], w.pos_y[k]), "rot": w.rot[k],
+             "inv": (w.inv_lin[k], w.inv_rot[k]), "cs": (c[k], s[k])} for k in range(n)]
+    local = [[(w.local_x[v], w.local_y[v]) for v in range(w.vert_offset[k], w.vert_offset[k + 1])] for k in range(n)]
+    mats = [(b.mu[k], b.bounce[k]) for k in range(n)]
+    cache_o, cache_m = None, []
+    saw_contacts = saw_hits = False
+    for f in range(25):
+        fr, cache_o, c, s = oracle.update_world(w, b, cache_o, c, s, external=(oracle.EXT_ACCEL, 0.0, -2.0), broadphase="aabb")
+        cache_m = hs.updateWorld(objs, local, mats, cache_m, hs.constantAccel((0.0, -2.0)), 0.01, (0.01, 0.02), libm)
+        assert len(cache_m) == len(cache_o[1]), f
+        for k, (key, lam) in enumerate(cache_m):
+            assert key == (cache_o[0]["key_i"][k], cache_o[0]["key_j"][k], cache_o[0]["feat_a"][k], cache_o[0]["feat_b"][k]), (f, k)
+            assert same(lam[0], cache_o[1][k]) and same(lam[1], cache_o[2][k]), (f, k)
+        for k in range(n):
+            o = objs[k]
+            assert same(o["vel"][0], b.vel_x[k]) and same(o["vel"][1], b.vel_y[k]) and same(o["rotvel"], b.rot_vel[k]), (f, k)
+            assert same(o["pos"][0], w.pos_x[k]) and same(o["pos"][1], w.pos_y[k]) and same(o["rot"], w.rot[k]), (f, k)
+            assert same(o["cs"][0], c[k]) and same(o["cs"][1], s[k]), (f, k)
+        saw_contacts |= len(cache_m) > 0
+        saw_hits |= bool(fr["warm_hit"].any())
+    assert saw_contacts and saw_hits
