@@ -149,6 +149,7 @@ struct FrameState {
     int error;
     long long n_pairs;
     long long n_contacts;
+    unsigned long long work_cursor; // sorted mode: next free entry of the cell-ordered SAT work list
 };
 
 struct Params;
@@ -185,6 +186,16 @@ struct Params {
     Box *box;                   // per slot
     double *world_x, *world_y;  // optional debug output
     double2 *wv, *wn;           // world vertices / unit edge normals of the OWNED slots (moveShapes result)
+    // Sorted mode (general polygon worlds): the moveShapes result is materialised in CELL order instead --
+    // position p of the counting sort owns the fixed-stride record shv/shn[8p .. 8p+8) -- and the SAT stage
+    // visits the pairs in cell order through a work list, so both hulls of a pair sit next to the hulls of
+    // the neighbouring pairs whatever the host's slot numbering is.
+    int sorted_mode;
+    const int32_t *vert_slot;   // per static vertex: the slot it belongs to
+    uint32_t *pos_of;           // per slot: its position (grid shapes in cell order, then the big list); ~0u = none
+    unsigned long long *shull;  // per position: packed extents [0,48) | vertex count [48,56) | materialised [56]
+    double2 *shv, *shn;         // per position x 8: world vertices / unit edge normals (hulls of <= 8 vertices)
+    uint32_t *w_dst, *w_pi, *w_pj; // SAT work list, cell order: output pair index, positions of both hulls
     uint32_t *keys, *keys_sorted; // cell key per slot / per sorted position
     uint32_t *rank;             // per slot: arrival order within its cell (counting sort)
     Box *sbox;                  // AABB records in sorted order
@@ -289,6 +300,7 @@ __global__ void k_reset_state(FrameState *st)
     st->error = 0;
     st->n_pairs = 0;
     st->n_contacts = 0;
+    st->work_cursor = 0ull;
 }
 
 __device__ __forceinline__ double warp_min(double v)
@@ -332,10 +344,11 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
             b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
         }
+        const bool keep = !P.sorted_mode;   // sorted mode: k_hulls_scatter materialises the hulls in cell order
         for (int k = 0; k < n; ++k) {
             double2 l = __ldg(&P.local[o + k]);
             V2 w = afmul(m, V2{ l.x, l.y });
-            P.wv[o + k] = make_double2(w.x, w.y);
+            if (keep) P.wv[o + k] = make_double2(w.x, w.y);
             if (P.world_x) { P.world_x[o + k] = w.x; P.world_y[o + k] = w.y; }
             if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
             else {
@@ -346,8 +359,8 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             }
         }
         // setHullTransform (ConvexHull.hs:193-194): unit edge normals recomputed from the NEW vertices
-        double2 v0 = n > 0 ? P.wv[o] : make_double2(0.0, 0.0), va = v0;
-        for (int k = 0; k < n; ++k) {
+        double2 v0 = (keep && n > 0) ? P.wv[o] : make_double2(0.0, 0.0), va = v0;
+        for (int k = 0; keep && k < n; ++k) {
             const double2 vb = (k + 1 < n) ? P.wv[o + k + 1] : v0;
             const V2 nn = unit_edge_normal(V2{ va.x, va.y }, V2{ vb.x, vb.y });
             P.wn[o + k] = make_double2(nn.x, nn.y);
@@ -515,6 +528,7 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
         if (key == P.key_none + 1u) {
             const unsigned pos = atomicAdd(&P.st->n_big, 1u);
             P.big_idx[pos] = (uint32_t)s;
+            P.rank[s] = pos;
             key = P.key_none;
         } else if (key < P.key_none) {
             const bool own = s >= P.own_lo && s < P.own_hi;
@@ -529,13 +543,53 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
 // and keys in sorted order, contiguous per cell and per grid row.
 __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 {
+    const unsigned n_sorted = P.sorted_mode ? P.cell_begin[P.st->n_cells] : 0u;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
         const uint32_t key = P.keys[s];
-        if (key >= P.key_none) continue;
+        if (key >= P.key_none) {
+            if (P.sorted_mode) {
+                // big shapes take the positions after the grid's, in big-list order; everything else has none
+                const bool big = P.gkeys[s] == P.key_none + 1u;
+                const uint32_t p = big ? n_sorted + P.rank[s] : 0xffffffffu;
+                P.pos_of[s] = p;
+                if (big) P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
+            }
+            continue;
+        }
         const uint32_t p = P.cell_begin[key] + P.rank[s];
         P.sbox[p] = box_of(P, s);
         P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
         P.keys_sorted[p] = key;
+        if (P.sorted_mode) P.pos_of[s] = p;
+    }
+}
+
+// Sorted mode, K1c: moveShapes (World.hs:132-140) straight into cell order.  One thread per static vertex v
+// of a kept hull: world vertex = afmul (toTransform pos rot) local (setHullTransform, ConvexHull.hs:184-195) and
+// the unit normal of the edge that starts there, recomputed from the NEW vertices (ConvexHull.hs:193-194,
+// 218-226), written to the hull's fixed-stride record at its sorted position.  Reads are in slot order
+// (coalesced), the stores of one hull are one contiguous run.  Hulls of more than 8 vertices get no record
+// (their pairs are finished by the per-thread pass from the local vertices).
+__global__ void __launch_bounds__(256) k_hulls_scatter(Params P, int n_verts)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_verts; v += gridDim.x * blockDim.x) {
+        const int s = __ldg(&P.vert_slot[v]);
+        const uint32_t p = P.pos_of[s];
+        if (p == 0xffffffffu || !P.alive[s]) continue;
+        const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
+        const int k = v - o;
+        const bool mat = n <= MAX_STAGED_VERTS;
+        if (k == 0)
+            P.shull[p] = (mat ? (P.ext_packed[s] & 0xffffffffffffull) | (1ull << 56) : 0ull) | ((unsigned long long)(n > 255 ? 255 : n) << 48);
+        if (!mat) continue;
+        const Xf x = slot_xf(P, s);
+        const Aff m = to_transform(x.px, x.py, x.c, x.s);
+        const double2 la = __ldg(&P.local[v]);
+        const double2 lb = __ldg(&P.local[(k + 1 < n) ? v + 1 : o]);   // nextIndex (ConvexHull.hs:228-230)
+        const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
+        const V2 nn = unit_edge_normal(wa, wb);
+        P.shv[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(wa.x, wa.y);
+        P.shn[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(nn.x, nn.y);
     }
 }
 
@@ -547,32 +601,74 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 
 constexpr int EMIT_LOCAL = 24;
 
+// Exclusive prefix sum of one value per thread over a 128-thread block; `total` = the block's sum.
+__device__ __forceinline__ unsigned long long block128_exclusive(unsigned long long v, unsigned long long &total)
+{
+    __shared__ unsigned long long s_warp[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();            // s_warp may still be read by the previous call
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0;
+    total = 0;
+    for (int w = 0; w < 4; ++w) { if (w < warp) before += s_warp[w]; total += s_warp[w]; }
+    return before + inc - v;
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(128) k_sweep(Params P)
 {
     const FrameState *st = P.st;
     if (EMIT && st->error) return;
     const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sorted; p += gridDim.x * blockDim.x) {
-    const uint32_t meta = P.smeta[p];
-    const int i = (int)(meta & 0x7fffffffu);
+    const bool sorted = P.sorted_mode != 0;
+    __shared__ unsigned long long s_wbase;
+    // blocks walk whole 128-position tiles, so that the work-list reservation below is block uniform
+    for (unsigned tile = blockIdx.x * 128u; tile < n_sorted; tile += gridDim.x * 128u) {
+    const unsigned p = tile + threadIdx.x;
+    uint32_t meta = 0;
+    int i = -1;
+    bool query = false;
+    if (p < n_sorted) {
+        meta = P.smeta[p];
+        i = (int)(meta & 0x7fffffffu);
+        query = i >= P.own_lo && i < P.own_hi;
+    }
+    const int r = P.own_hi - 1 - i;
+    // Sorted mode, emit pass: the SAT stage visits the pairs in CELL order.  Each tile reserves a run of the
+    // work list (one atomic per 128 queries; tiles are handed out in launch order, so the list follows the
+    // cell order closely) and every query writes (output index, position of i, position of j) per partner.
+    unsigned long long wbase = 0;
+    if (EMIT && sorted) {
+        unsigned long long total;
+        const unsigned long long mine = query ? P.cnt[r] : 0ull;
+        const unsigned long long before = block128_exclusive(mine, total);
+        if (threadIdx.x == 0) s_wbase = total ? atomicAdd(&P.st->work_cursor, total) : 0ull;
+        __syncthreads();
+        wbase = s_wbase + before;
+    }
+    if (!query) continue;
     const bool si = (meta >> 31) != 0;
-    if (i < P.own_lo || i >= P.own_hi) continue;
     const Box bi = P.sbox[p];
     const uint32_t key = P.keys_sorted[p];
     const int W = st->W, H = st->H;
     const int cy = (int)(key / (uint32_t)W), cx = (int)(key % (uint32_t)W);
-    const int r = P.own_hi - 1 - i;
 
     unsigned long long count = 0;
     int local[EMIT_LOCAL];
+    unsigned local_q[EMIT_LOCAL];
     unsigned long long base = 0;
     if (EMIT) base = P.off[r];
 
-    auto hit = [&](int j) {
+    auto hit = [&](int j, unsigned q) {
         if (EMIT) {
-            if (count < EMIT_LOCAL) local[count] = j;
-            else P.pair_j[base + count] = j;
+            if (count < EMIT_LOCAL) { local[count] = j; local_q[count] = q; }
+            else { P.pair_j[base + count] = j; if (sorted) P.w_pj[wbase + count] = q; }
         }
         ++count;
     };
@@ -600,7 +696,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             while (run) {
                 const int b = __ffsll((long long)run) - 1;
                 run &= run - 1;
-                hit((int)(__ldg(&P.smeta[q_lo + (unsigned)b]) & 0x7fffffffu));
+                hit((int)(__ldg(&P.smeta[q_lo + (unsigned)b]) & 0x7fffffffu), q_lo + (unsigned)b);
             }
             seen += len;
             if (seen >= 63u) break;
@@ -610,7 +706,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             while (run) {
                 const int b = __ffsll((long long)run) - 1;
                 run &= run - 1;
-                hit((int)P.big_idx[b]);
+                hit((int)P.big_idx[b], n_sorted + (unsigned)b);
             }
         }
     } else {
@@ -627,7 +723,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             if (j >= i) continue;
             if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
             const Box bj = P.sbox[q];
-            if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
+            if (aabb_check(bi, bj)) { hit(j, q); if (cand < 63u) mask |= 1ull << cand; }
         }
     }
     for (unsigned b = 0; b < n_big; ++b, ++cand) {
@@ -635,7 +731,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         if (j >= i) continue;
         if (si && slot_static(P, j)) continue;
         const Box bj = box_of(P, j);
-        if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
+        if (aabb_check(bi, bj)) { hit(j, n_sorted + b); if (cand < 63u) mask |= 1ull << cand; }
     }
     }
     if (!EMIT) P.hitmask[p] = (cand > 63u) ? (1ull << 63) : mask;
@@ -645,21 +741,33 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
     if (count <= EMIT_LOCAL) {
         const int n = (int)count;
         for (int a = 1; a < n; ++a) { // insertion sort, descending
-            int v = local[a], b2 = a - 1;
-            while (b2 >= 0 && local[b2] < v) { local[b2 + 1] = local[b2]; --b2; }
-            local[b2 + 1] = v;
+            const int v = local[a];
+            const unsigned vq = local_q[a];
+            int b2 = a - 1;
+            while (b2 >= 0 && local[b2] < v) { local[b2 + 1] = local[b2]; local_q[b2 + 1] = local_q[b2]; --b2; }
+            local[b2 + 1] = v; local_q[b2 + 1] = vq;
         }
         for (int a = 0; a < n; ++a) { P.pair_i[base + a] = i; P.pair_j[base + a] = local[a]; }
+        if (sorted)
+            for (int a = 0; a < n; ++a) {
+                P.w_dst[wbase + a] = (uint32_t)(base + a); P.w_pi[wbase + a] = p; P.w_pj[wbase + a] = local_q[a];
+            }
     } else {
         for (int a = 0; a < EMIT_LOCAL; ++a) P.pair_j[base + a] = local[a];
+        if (sorted) for (int a = 0; a < EMIT_LOCAL; ++a) P.w_pj[wbase + a] = local_q[a];
         int32_t *seg = P.pair_j + base;
+        uint32_t *segq = P.w_pj + wbase;
         for (unsigned long long a = 1; a < count; ++a) {
-            int v = seg[a];
+            const int v = seg[a];
+            const uint32_t vq = sorted ? segq[a] : 0u;
             long long b2 = (long long)a - 1;
-            while (b2 >= 0 && seg[b2] < v) { seg[b2 + 1] = seg[b2]; --b2; }
+            while (b2 >= 0 && seg[b2] < v) { seg[b2 + 1] = seg[b2]; if (sorted) segq[b2 + 1] = segq[b2]; --b2; }
             seg[b2 + 1] = v;
+            if (sorted) segq[b2 + 1] = vq;
         }
         for (unsigned long long a = 0; a < count; ++a) P.pair_i[base + a] = i;
+        if (sorted)
+            for (unsigned long long a = 0; a < count; ++a) { P.w_dst[wbase + a] = (uint32_t)(base + a); P.w_pi[wbase + a] = p; }
     }
     }
 }
@@ -671,7 +779,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
     const FrameState *st = P.st;
     if (EMIT && st->error) return;
     __shared__ unsigned s_warp[8];
-    __shared__ unsigned long long s_run;
+    __shared__ unsigned long long s_run, s_wbase;
     const unsigned n_big = st->n_big;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned b = blockIdx.x; b < n_big; b += gridDim.x) {
@@ -681,8 +789,14 @@ __global__ void __launch_bounds__(256) k_big(Params P)
         const bool si = slot_static(P, i);
         const int r = P.own_hi - 1 - i;
         const unsigned long long base = EMIT ? P.off[r] : 0ull;
-        if (threadIdx.x == 0) s_run = 0;
+        if (threadIdx.x == 0) {
+            s_run = 0;
+            // sorted mode: this query's run of the SAT work list (see k_sweep)
+            if (EMIT && P.sorted_mode) { const unsigned long long n = P.cnt[r]; s_wbase = n ? atomicAdd(&P.st->work_cursor, n) : 0ull; }
+        }
         __syncthreads();
+        const unsigned long long wbase = (EMIT && P.sorted_mode) ? s_wbase : 0ull;
+        const unsigned pi_pos = (EMIT && P.sorted_mode) ? P.pos_of[i] : 0u;
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
@@ -697,6 +811,10 @@ __global__ void __launch_bounds__(256) k_big(Params P)
                 const unsigned long long pos = base + run + before + __popc(bal & ((1u << lane) - 1u));
                 P.pair_i[pos] = i;
                 P.pair_j[pos] = j;
+                if (P.sorted_mode) {
+                    const unsigned long long w = wbase + (pos - base);
+                    P.w_dst[w] = (uint32_t)pos; P.w_pi[w] = pi_pos; P.w_pj[w] = P.pos_of[j];
+                }
             }
             __syncthreads();
             if (threadIdx.x == 0) s_run = run + total;
@@ -763,7 +881,7 @@ struct ContactKernel {
     }
     __device__ __forceinline__ void stage(HullAcc &h) const
     {
-        h.owned = h.slot >= P.own_lo && h.slot < P.own_hi;
+        h.owned = !P.sorted_mode && h.slot >= P.own_lo && h.slot < P.own_hi;
         if (h.n <= MAXV) {
             if (h.owned) {
                 if (MAXV > 4) {
@@ -1173,14 +1291,18 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
 constexpr int CO_WARPS = 4;
 enum { CO_NONE = 0, CO_SAME = 1, CO_FLIP = 2, CO_FALLBACK = 3 };
 
-struct GlobalAcc {      // emit_manifold over K0's world vertices / normals in global memory
-    const Params &P;
+struct GlobalAcc {      // emit_manifold over materialised world vertices / normals in global memory
+    const double2 *wv, *wn;
     int e_off, pn_off;
-    __device__ __forceinline__ V2 normal_e(int e) const { const double2 v = P.wn[e_off + e]; return V2{ v.x, v.y }; }
-    __device__ __forceinline__ V2 ve(int k) const { const double2 v = P.wv[e_off + k]; return V2{ v.x, v.y }; }
-    __device__ __forceinline__ V2 vp(int k) const { const double2 v = P.wv[pn_off + k]; return V2{ v.x, v.y }; }
+    __device__ __forceinline__ V2 normal_e(int e) const { const double2 v = wn[e_off + e]; return V2{ v.x, v.y }; }
+    __device__ __forceinline__ V2 ve(int k) const { const double2 v = wv[e_off + k]; return V2{ v.x, v.y }; }
+    __device__ __forceinline__ V2 vp(int k) const { const double2 v = wv[pn_off + k]; return V2{ v.x, v.y }; }
 };
 
+// SORTED: the tile's 32 pairs come from the cell-ordered work list (w_dst / w_pi / w_pj) and both hulls are
+// read from the cell-ordered records shv / shn / shull, so neighbouring tiles touch neighbouring memory
+// whatever the slot numbering; results still go to the pair's place in the reference order (w_dst).
+template <bool SORTED>
 __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
 {
     __shared__ int s_out[CO_WARPS][32][3];                           // phase 1 -> phase 2: outcome, edge, penetrator
@@ -1188,6 +1310,8 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
     const FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = st->n_pairs;
+    const double2 *const WV = SORTED ? P.shv : P.wv;
+    const double2 *const WN = SORTED ? P.shn : P.wn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, dir = (lane >> 3) & 1, e = lane & 7;
     const int group_base = lane & ~7;                 // first lane of my (pair, direction) group
@@ -1202,14 +1326,27 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
         // measured SLOWER (1M polygons: 0.283 / 0.288 ms vs 0.262 ms; 4M mixed: 1.44 vs 1.22 ms): with ~2400
         // resident warps and ~24 KB of hull lines per tile the prefetched footprint no longer fits the 126 MB L2.
         int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
+        long long my_dst = base + lane;
+        unsigned long long my_xa = 0, my_xb = 0;    // SORTED: packed extents of both hulls
         if (base + lane < n_pairs) {
-            my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane];
-            my_oa = P.vert_offset[my_i]; my_na = P.vert_offset[my_i + 1] - my_oa;
-            my_ob = P.vert_offset[my_j]; my_nb = P.vert_offset[my_j + 1] - my_ob;
-            pf_l2(&P.wv[my_oa]); pf_l2(&P.wn[my_oa]); pf_l2(&P.wv[my_ob]); pf_l2(&P.wn[my_ob]);
-            if (my_na > 1) { pf_l2(&P.wv[my_oa + my_na - 1]); pf_l2(&P.wn[my_oa + my_na - 1]); }
-            if (my_nb > 1) { pf_l2(&P.wv[my_ob + my_nb - 1]); pf_l2(&P.wn[my_ob + my_nb - 1]); }
-            pf_l2(&P.ext_packed[my_i]); pf_l2(&P.ext_packed[my_j]);
+            if (SORTED) {
+                my_dst = (long long)P.w_dst[base + lane];
+                my_i = (int)P.w_pi[base + lane]; my_j = (int)P.w_pj[base + lane];   // POSITIONS, not slots
+                my_xa = P.shull[my_i]; my_xb = P.shull[my_j];
+                my_oa = my_i * MAX_STAGED_VERTS; my_ob = my_j * MAX_STAGED_VERTS;
+                // hulls without a record (more than 8 vertices) send the pair to the per-thread pass
+                my_na = ((my_xa >> 56) & 1ull) ? (int)((my_xa >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
+                my_nb = ((my_xb >> 56) & 1ull) ? (int)((my_xb >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
+                pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
+            } else {
+                my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane];
+                my_oa = P.vert_offset[my_i]; my_na = P.vert_offset[my_i + 1] - my_oa;
+                my_ob = P.vert_offset[my_j]; my_nb = P.vert_offset[my_j + 1] - my_ob;
+                pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
+                if (my_na > 1) { pf_l2(&WV[my_oa + my_na - 1]); pf_l2(&WN[my_oa + my_na - 1]); }
+                if (my_nb > 1) { pf_l2(&WV[my_ob + my_nb - 1]); pf_l2(&WN[my_ob + my_nb - 1]); }
+                pf_l2(&P.ext_packed[my_i]); pf_l2(&P.ext_packed[my_j]);
+            }
         }
         // ---- phase 1: SAT, two pairs per step
 #pragma unroll 1
@@ -1220,10 +1357,15 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
             const int i = __shfl_sync(0xffffffffu, my_i, src), j = __shfl_sync(0xffffffffu, my_j, src);
             const int oa = __shfl_sync(0xffffffffu, my_oa, src), na = __shfl_sync(0xffffffffu, my_na, src);
             const int ob = __shfl_sync(0xffffffffu, my_ob, src), nb = __shfl_sync(0xffffffffu, my_nb, src);
-            const bool own = i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi;
+            const bool own = SORTED || (i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi);
             const bool coop = valid && own && na >= 1 && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
             // my direction: E = penetrated hull (its edge normals are the axes), Pn = the other hull
             const int e_slot = dir ? j : i, e_off = dir ? ob : oa, e_n = dir ? nb : na;
+            unsigned long long e_ext = 0;
+            if (SORTED) {
+                const unsigned long long xa = __shfl_sync(0xffffffffu, my_xa, src), xb = __shfl_sync(0xffffffffu, my_xb, src);
+                e_ext = dir ? xb : xa;
+            }
             const int pn_off = dir ? oa : ob, pn_n = dir ? na : nb;
             const bool active = coop && e < e_n;
             bool sep = false;
@@ -1231,12 +1373,12 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
             int pen = 0;
             if (active) {
                 // overlap sEdge edge sPen (SAT.hs:103-117)
-                const double2 dn = P.wn[e_off + e];
-                const unsigned bits = (unsigned)(P.ext_packed[e_slot] >> (6 * e));
-                const double2 vmin = P.wv[e_off + (bits & 7)], vmax = P.wv[e_off + ((bits >> 3) & 7)];
+                const double2 dn = WN[e_off + e];
+                const unsigned bits = (unsigned)((SORTED ? e_ext : P.ext_packed[e_slot]) >> (6 * e));
+                const double2 vmin = WV[e_off + (bits & 7)], vmax = WV[e_off + ((bits >> 3) & 7)];
                 double2 pv[MAX_STAGED_VERTS];
 #pragma unroll
-                for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = P.wv[pn_off + k];
+                for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = WV[pn_off + k];
                 const V2 d{ dn.x, dn.y };
                 // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
                 const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
@@ -1289,14 +1431,14 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
         }
         __syncwarp();
         // ---- phase 2: one pair per lane
-        const long long p = base + lane;
-        if (p < n_pairs) {
+        if (base + lane < n_pairs) {
+            const long long p = my_dst;     // the pair's index in the reference order
             const int outcome = s_out[warp][lane][0], edge = s_out[warp][lane][1], pn = s_out[warp][lane][2];
             unsigned cnt = 0;
             if (outcome == CO_SAME || outcome == CO_FLIP) {
                 const int oa = my_oa, na = my_na, ob = my_ob, nb = my_nb;
                 const bool same = outcome == CO_SAME;
-                cnt = emit_manifold(P, p, GlobalAcc{ P, same ? oa : ob, same ? ob : oa }, same ? na : nb, same ? nb : na, edge, pn, same);
+                cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? oa : ob, same ? ob : oa }, same ? na : nb, same ? nb : na, edge, pn, same);
             } else if (outcome == CO_FALLBACK) cnt = CCNT_FALLBACK;   // finished by k_manifolds<.., FLAGGED_ONLY>
             P.ccnt[p] = cnt;
         }
@@ -1570,7 +1712,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote; int64_t geometry, n_prev; unsigned cell_limit;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote, sorted; int64_t geometry, n_prev; unsigned cell_limit;
 };
 
 struct WorldStep;   // device-resident world (world_step.cuh)
@@ -1600,6 +1742,8 @@ struct shapes_ctx {
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
+    bool use_sorted = true;       // general polygons: hull records + SAT work list in cell order (SHAPES_B200_NO_SORTED=1: slot order)
+    int32_t *d_vert_slot = nullptr;
     bool has_circles = false;
     double *d_radius = nullptr;
     int rows_blocks = 4;         // resident k_rows blocks per SM
@@ -1755,6 +1899,16 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.wv, V));
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.circ, N));
+    c->use_sorted = std::getenv("SHAPES_B200_NO_SORTED") == nullptr;
+    TRY_CREATE(dev_alloc(c, &c->d_vert_slot, V));
+    TRY_CREATE(dev_alloc(c, &P.pos_of, N));
+    TRY_CREATE(dev_alloc(c, &P.shull, N));
+    TRY_CREATE(dev_alloc(c, &P.shv, c->use_sorted ? (size_t)N * MAX_STAGED_VERTS : 1));
+    TRY_CREATE(dev_alloc(c, &P.shn, c->use_sorted ? (size_t)N * MAX_STAGED_VERTS : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_dst, c->use_sorted ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_pi, c->use_sorted ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_pj, c->use_sorted ? max_pairs : 1));
+    P.vert_slot = c->d_vert_slot;
     TRY_CREATE(dev_alloc(c, &c->d_radius, N));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
@@ -1823,7 +1977,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_manifolds<MAX_STAGED_VERTS, true>, CT_THREADS, 0), "occupancy"));
         c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1); c->ct_blocks[2] = std::max(bc, 1);
         int bco = 0;
-        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop, CO_WARPS * 32, 0), "occupancy"));
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop<true>, CO_WARPS * 32, 0), "occupancy"));
         c->coop_blocks = std::max(bco, 1);
         c->use_coop = std::getenv("SHAPES_B200_NO_COOP") == nullptr;
         int br = 0;
@@ -1860,6 +2014,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.inv_lin = in[5]; P.inv_rot = in[6];
     P.dt = dt; P.baumgarte = baumgarte; P.slop = slop;
     P.cell_size = c->user_cell > 0.0 ? c->user_cell : c->auto_cell;
+    // general polygon worlds on one rank: hull records and the SAT work list in cell order
+    P.sorted_mode = (c->use_sorted && c->use_coop && c->world == 1 && !c->has_circles && c->max_hull_verts > 4) ? 1 : 0;
     // the previous frame's key columns become the join's "that" side; this frame writes the other set
     if (c->have_frame) {
         std::swap(P.key_i, c->alt_key[0]); std::swap(P.key_j, c->alt_key[1]);
@@ -1944,7 +2100,12 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cell_count, P.cell_begin, (int)P.cell_limit + 1, s));
         }
         STAGE_MARK(); // 4: scatter into cell order
-        if (N > 0) { k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
+        if (N > 0) {
+            k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+            if (P.sorted_mode && c->n_verts > 0) {
+                k_hulls_scatter<<<grid_for(c->n_verts, 256, sms * 16), 256, 0, s>>>(P, (int)c->n_verts); ++c->launches;
+            }
+        }
         STAGE_MARK(); // 5: sweep count
         if (N > 0) {
             k_sweep<false><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
@@ -1968,7 +2129,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
             else if (c->use_coop) {
-                k_manifolds_coop<<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                if (P.sorted_mode) k_manifolds_coop<true><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                else k_manifolds_coop<false><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
                 // hulls with more than 8 vertices / foreign hulls (multi-rank): per-thread pass over the flagged pairs
                 if (c->max_hull_verts > MAX_STAGED_VERTS || c->world > 1) {
                     k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
@@ -2004,7 +2166,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.n = n_slots; for (int k = 0; k < 7; ++k) key.in[k] = in[k];
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
-    key.warm = warm; key.n_prev = 0; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0;
+    key.warm = warm; key.n_prev = 0; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0; key.sorted = P.sorted_mode != 0;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
     if (warm) { k_set_i64<<<1, 1, 0, s>>>(c->d_n_prev, n_prev_now); ++c->launches; }   // outside the graph: varies per frame
     const int64_t launches_before = c->launches;
@@ -2150,6 +2312,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     if (alive) std::memcpy(live.data(), alive, (size_t)n_slots);
     // layout conversion (interleave x/y) and the static cell-size estimate: hull diameters
     std::vector<double2> inter((size_t)n_verts);
+    std::vector<int32_t> vslot((size_t)n_verts);
     std::vector<double> diam;
     diam.reserve((size_t)n_slots);
     int max_verts_seen = 0;
@@ -2169,6 +2332,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         double r2 = 0.0;
         for (int32_t k = 0; k < n; ++k) {
             inter[o + k] = make_double2(local_x[o + k], local_y[o + k]);
+            vslot[o + k] = (int32_t)s;
             const double d2 = local_x[o + k] * local_x[o + k] + local_y[o + k] * local_y[o + k];
             if (d2 > r2) r2 = d2;
         }
@@ -2193,6 +2357,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         CU_TRY(c, cudaMemcpyAsync(c->d_vert_offset, vert_offset, sizeof(int32_t) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, s));
         if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
         if (any_circle) CU_TRY(c, cudaMemcpyAsync(c->d_radius, radius, sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
+        if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_vert_slot, vslot.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
         if (ext_min) {
             for (int64_t v = 0; v < n_verts; ++v) {
                 // _hullExtents entries index the hull's own vertices

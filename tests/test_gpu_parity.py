@@ -274,3 +274,59 @@ def test_config3_full_size_pile(oracle):
     want = oracle.frame(w, c, s, broadphase="sweep")
     assert_frames_match(got, want)
     assert len(want["pair_i"]) > 3_500_000
+
+
+# ---- cell-ordered hull records + SAT work list (general polygon worlds) -------------------------
+
+def _polygon_world_with_big_shapes(seed=41, n=3000):
+    """Random polygons (some with more than 8 vertices) plus big shapes of every kind: two static floors,
+    a big dynamic polygon over many cells, a big 12-gon -- all on the big list, as queries and as partners."""
+    rng = np.random.default_rng(seed)
+    objs = []
+    side = 40.0
+    for k in range(n):
+        nv = int(rng.integers(3, 9)) if k % 11 else int(rng.integers(9, 14))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+        r = rng.uniform(0.3, 0.5)
+        verts = [(r * np.cos(a), r * np.sin(a)) for a in ang]
+        objs.append((verts, (rng.uniform(0, side), rng.uniform(0, side)), rng.uniform(0, 6.28),
+                     (0.0, 0.0) if k % 23 == 0 else (1.0, 1.0)))
+    big = [(rectangle_vertices(side + 2.0, 1.0), (side / 2, 0.2), 0.0, (0.0, 0.0)),
+           (rectangle_vertices(1.0, side), (side / 3, side / 2), 0.1, (0.0, 0.0)),
+           ([(6.0, 0.0), (0.0, 5.0), (-6.0, 0.0), (0.0, -5.0)], (side / 2, side / 2), 0.3, (1.0, 1.0)),
+           ([(7 * np.cos(a), 7 * np.sin(a)) for a in np.linspace(0, 2 * np.pi, 12, endpoint=False)],
+            (side * 0.7, side * 0.6), 0.2, (1.0, 1.0))]
+    # big shapes at both ends and in the middle of the key range
+    objs = big[:1] + objs[: n // 2] + big[1:3] + objs[n // 2:] + big[3:]
+    return World.from_objects(objs)
+
+
+def test_sorted_mode_big_shapes_and_long_hulls(oracle):
+    got, want = check_world(oracle, _polygon_world_with_big_shapes(), broadphase="aabb")
+    assert got["_n_big"] >= 4 and len(want["key_i"]) > 500
+
+
+def test_sorted_mode_crowded_cells(oracle):
+    """More than 24 partners per query (the emit pass's global-memory sort) and more than 63 candidates (no
+    hit-mask replay) with the work list in play."""
+    w = scenes.random_polygons(1500, density=60.0, static_frac=0.05, config=43)
+    got, want = check_world(oracle, w, broadphase="aabb")
+    per_query = np.bincount(want["pair_i"], minlength=w.n_slots)
+    assert per_query.max() > 40 and len(want["pair_i"]) > 30_000
+
+
+@pytest.mark.parametrize("which", ["polygons", "big", "crowded", "nonfinite"])
+def test_slot_order_path_still_matches(oracle, monkeypatch, which):
+    """SHAPES_B200_NO_SORTED=1: hull records in slot order, SAT in the reference's pair order (the r1 path)."""
+    monkeypatch.setenv("SHAPES_B200_NO_SORTED", "1")
+    if which == "polygons":
+        check_world(oracle, scenes.random_polygons(10_000), broadphase="sweep")
+    elif which == "big":
+        check_world(oracle, _polygon_world_with_big_shapes(seed=42), broadphase="aabb")
+    elif which == "crowded":
+        check_world(oracle, scenes.random_polygons(1200, density=60.0, static_frac=0.05, config=44), broadphase="aabb")
+    else:
+        w = scenes.random_polygons(1500, density=2.0, static_frac=0.1, config=33)
+        w.pos_x[40] = w.pos_y[40] = np.nan
+        w.pos_y[41] = np.inf
+        check_world(oracle, w, broadphase="aabb")
