@@ -308,6 +308,18 @@ void *shapes_stream(shapes_ctx *);
 int64_t shapes_launch_count(const shapes_ctx *);
 const char *shapes_version(void);
 
+/* Statistics of the last completed frame (bench / profiling; nothing here changes results). */
+#define SHAPES_SAT_PER_THREAD_BOXES   0  /* k_manifolds<4>: boxes-only worlds, one thread per pair            */
+#define SHAPES_SAT_PER_THREAD         1  /* k_manifolds<8>: one thread per pair                               */
+#define SHAPES_SAT_PER_THREAD_CIRCLES 2  /* k_manifolds<8, circles>: the full generateContacts dispatch       */
+#define SHAPES_SAT_COOP               3  /* k_manifolds_coop: 16 lanes per pair (general polygon worlds)      */
+typedef struct shapes_frame_info {
+    int64_t pairs_with_contacts;   /* broadphase pairs whose narrow phase produced at least one contact */
+    int32_t sorted_mode;           /* 1 = hull records and the SAT work list are kept in grid-cell order */
+    int32_t sat_kernel;            /* SHAPES_SAT_* */
+} shapes_frame_info;
+int  shapes_last_frame_info(shapes_ctx *, shapes_frame_info *info);
+
 /* Per-stage device timing (CUDA events on the ctx stream between the stages of a frame).
  * Off by default; when on, shapes_stage_ms fills SHAPES_N_STAGES milliseconds of the last
  * frame, in the order shapes_stage_name reports. */

@@ -83,6 +83,13 @@ class StepStats(C.Structure):
     ]
 
 
+class FrameInfo(C.Structure):
+    """shapes_frame_info"""
+    _fields_ = [("pairs_with_contacts", C.c_int64), ("sorted_mode", C.c_int32), ("sat_kernel", C.c_int32)]
+
+
+SAT_KERNEL_NAMES = {0: "k_manifolds<4>", 1: "k_manifolds<8>", 2: "k_manifolds<8,circles>", 3: "k_manifolds_coop"}
+
 EXT_NONE, EXT_ACCEL, EXT_FORCE = 0, 1, 2
 
 # every symbol include/shapes_b200.h declares: name -> (restype, argtypes)
@@ -117,6 +124,7 @@ SYMBOLS = {
     "shapes_stream": (C.c_void_p, [C.c_void_p]),
     "shapes_launch_count": (C.c_int64, [C.c_void_p]),
     "shapes_version": (C.c_char_p, []),
+    "shapes_last_frame_info": (C.c_int, [C.c_void_p, C.POINTER(FrameInfo)]),
     "shapes_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "shapes_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "shapes_stage_name": (C.c_char_p, [C.c_int]),

@@ -150,6 +150,7 @@ struct FrameState {
     long long n_pairs;
     long long n_contacts;
     unsigned long long work_cursor; // sorted mode: next free entry of the cell-ordered SAT work list
+    unsigned long long n_pairs_hit; // pairs with at least one contact (statistics: the roofline accounting)
 };
 
 struct Params;
@@ -192,6 +193,7 @@ struct Params {
     // the neighbouring pairs whatever the host's slot numbering is.
     int sorted_mode;
     const int32_t *vert_slot;   // per static vertex: the slot it belongs to
+    const int32_t *vert_next;   // per static vertex: the next vertex of its hull (wraps)
     uint32_t *pos_of;           // per slot: its position (grid shapes in cell order, then the big list); ~0u = none
     unsigned long long *shull;  // per position: packed extents [0,48) | vertex count [48,56) | materialised [56]
     double2 *shv, *shn;         // per position x 8: world vertices / unit edge normals (hulls of <= 8 vertices)
@@ -301,6 +303,7 @@ __global__ void k_reset_state(FrameState *st)
     st->n_pairs = 0;
     st->n_contacts = 0;
     st->work_cursor = 0ull;
+    st->n_pairs_hit = 0ull;
 }
 
 __device__ __forceinline__ double warp_min(double v)
@@ -572,25 +575,31 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 // (their pairs are finished by the per-thread pass from the local vertices).
 __global__ void __launch_bounds__(256) k_hulls_scatter(Params P, int n_verts)
 {
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_verts; v += gridDim.x * blockDim.x) {
-        const int s = __ldg(&P.vert_slot[v]);
-        const uint32_t p = P.pos_of[s];
-        if (p == 0xffffffffu || !P.alive[s]) continue;
-        const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
-        const int k = v - o;
-        const bool mat = n <= MAX_STAGED_VERTS;
-        if (k == 0)
-            P.shull[p] = (mat ? (P.ext_packed[s] & 0xffffffffffffull) | (1ull << 56) : 0ull) | ((unsigned long long)(n > 255 ? 255 : n) << 48);
-        if (!mat) continue;
-        const Xf x = slot_xf(P, s);
-        const Aff m = to_transform(x.px, x.py, x.c, x.s);
-        const double2 la = __ldg(&P.local[v]);
-        const double2 lb = __ldg(&P.local[(k + 1 < n) ? v + 1 : o]);   // nextIndex (ConvexHull.hs:228-230)
-        const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
-        const V2 nn = unit_edge_normal(wa, wb);
-        P.shv[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(wa.x, wa.y);
-        P.shn[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(nn.x, nn.y);
-    }
+    // One vertex per thread and no branch between the loads: the r2a version (early exits between dependent
+    // loads, 6 levels deep) sat on long-scoreboard stalls for 0.136 ms at 1M polygons; here level 1 is the
+    // vertex's static columns, level 2 everything that hangs off its slot.
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_verts) return;
+    const int s = __ldg(&P.vert_slot[v]);
+    const int vn = __ldg(&P.vert_next[v]);                 // nextIndex (ConvexHull.hs:228-230), static
+    const double2 la = __ldg(&P.local[v]);
+    const uint32_t p = P.pos_of[s];
+    const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
+    const bool live = P.alive[s] != 0;
+    const unsigned long long xp = P.ext_packed[s];
+    const Xf x = slot_xf(P, s);
+    const double2 lb = __ldg(&P.local[vn]);
+    if (p == 0xffffffffu || !live) return;
+    const int k = v - o;
+    const bool mat = n <= MAX_STAGED_VERTS;
+    if (k == 0)
+        P.shull[p] = (mat ? (xp & 0xffffffffffffull) | (1ull << 56) : 0ull) | ((unsigned long long)(n > 255 ? 255 : n) << 48);
+    if (!mat) return;
+    const Aff m = to_transform(x.px, x.py, x.c, x.s);
+    const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
+    const V2 nn = unit_edge_normal(wa, wb);
+    P.shv[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(wa.x, wa.y);
+    P.shn[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(nn.x, nn.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1277,17 +1286,20 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
 }
 
 
-// K3a for general convex polygons (hulls of 3..8 vertices): 16 lanes per pair.
+// K3a for general convex polygons (hulls of 3..8 vertices): 8 lanes per pair.
 // In `k_manifolds` a thread walks (edges of A) x (vertices of B) + (edges of B) x (vertices of A) on its
 // own; with 3..8 vertices per hull the trip counts differ from lane to lane (14.9 of 32 threads active
-// per instruction in ncu) and every lane stages two whole hulls.  Here lane (dir, e) of a half warp owns
-// ONE candidate axis: the unit normal of edge e of the penetrated hull of direction dir (0: A <- B,
-// 1: B <- A).  It projects the other hull's <= 8 vertices (one batch of loads, the same addresses
-// across the 8 lanes of a direction), and the minOverlap fold (SAT.hs:121-143) runs over the eight
-// per-edge results by shuffles IN EDGE ORDER, so ties, NaNs and the first-minimum rule behave exactly
-// like the sequential fold.  A warp does its 32 pairs two at a time (phase 1), then every lane clips
-// one pair (phase 2, `emit_manifold`).  Pairs with a hull of more than 8 vertices, or a hull whose world
-// vertices were not materialised on this rank, are flagged and finished by a second, per-thread pass.
+// per instruction in ncu) and every lane stages two whole hulls.  Here lane e of an 8-lane group owns
+// candidate axis e of BOTH directions (0: A penetrated by B, 1: B penetrated by A): the unit normal of
+// edge e of the penetrated hull, against which it projects the other hull's <= 8 vertices (one batch of
+// loads, the same addresses across the 8 lanes).  The minOverlap fold (SAT.hs:121-143) over the eight
+// per-edge results is a shuffle minimum of the depths followed by a ballot that picks the FIRST edge holding
+// that minimum -- the sequential fold's strict `<`, with its NaN behaviour kept (see fold_min_overlap).
+// A warp does its 32 pairs four at a time (phase 1, 8 steps), then every lane clips one pair (phase 2,
+// `emit_manifold`).  Pairs with a hull of more than 8 vertices, or a hull whose world vertices were not
+// materialised on this rank, are flagged and finished by a second, per-thread pass.
+// (r1 ran 16 lanes per pair, one direction per lane, 16 steps per tile: 285 warp instructions per step of
+// two pairs, a third of them the lexicographic shuffle fold and the index shuffles -- profiles/r2_summary.md.)
 constexpr int CO_WARPS = 4;
 enum { CO_NONE = 0, CO_SAME = 1, CO_FLIP = 2, CO_FALLBACK = 3 };
 
@@ -1299,13 +1311,65 @@ struct GlobalAcc {      // emit_manifold over materialised world vertices / norm
     __device__ __forceinline__ V2 vp(int k) const { const double2 v = wv[pn_off + k]; return V2{ v.x, v.y }; }
 };
 
+// overlap sEdge edge sPen (SAT.hs:103-117) for ONE edge of the penetrated hull E (this lane's), against all
+// vertices of the penetrating hull.  Returns true when the axis separates; else depth / penetrator.
+__device__ __forceinline__ bool coop_edge(const double2 *__restrict__ WV, const double2 *__restrict__ WN, int e_off, int e,
+                                          unsigned long long e_ext, int pn_off, int pn_n, double &depth, int &pen)
+{
+    const double2 dn = WN[e_off + e];
+    const unsigned bits = (unsigned)(e_ext >> (6 * e));
+    const double2 vmin = WV[e_off + (bits & 7)], vmax = WV[e_off + ((bits >> 3) & 7)];
+    double2 pv[MAX_STAGED_VERTS];
+#pragma unroll
+    for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = WV[pn_off + k];
+    const V2 d{ dn.x, dn.y };
+    // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
+    const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
+    // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
+    double p_min = dot2(V2{ pv[0].x, pv[0].y }, d), p_max = p_min;
+    pen = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_STAGED_VERTS; ++k) {
+        if (k >= pn_n) break;
+        const double q = dot2(V2{ pv[k].x, pv[k].y }, d);
+        if (q < p_min) { p_min = q; pen = k; }
+        if (q > p_max) p_max = q;
+    }
+    depth = fsub(s_max, p_min);                              // overlapAmount (SAT.hs:86-96)
+    return (p_min > s_max) || (p_max < s_min);               // overlapTest (SAT.hs:74-83)
+}
+
+// minOverlap' (SAT.hs:121-143) over the edges held by the 8 lanes of my group: edge 0 first, a later edge replaces
+// the best one only with a strictly smaller depth.  That fold equals "the first edge holding the minimum depth, a
+// NaN depth counting as +inf" -- unless edge 0's depth is NaN, in which case nothing ever replaces edge 0.
+// (A NaN lane can only be the first holder of the minimum when that minimum is +inf and lane 0 is not itself
+// +inf / NaN -- impossible, lane 0 would hold it first.)  Returns the winning edge; depth / pen come from its lane.
+__device__ __forceinline__ int fold_min_overlap(bool active, double depth, int group_base)
+{
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const bool is_nan = depth != depth;
+    const double key = (active && !is_nan) ? depth : inf;
+    double kmin = key;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const double k2 = __shfl_xor_sync(0xffffffffu, kmin, o);
+        kmin = (k2 < kmin) ? k2 : kmin;
+    }
+    const unsigned holders = (__ballot_sync(0xffffffffu, active && key == kmin) >> group_base) & 0xffu;
+    const unsigned nans = (__ballot_sync(0xffffffffu, active && is_nan) >> group_base) & 0xffu;
+    if ((nans & 1u) || holders == 0u) return 0;
+    return __ffs((int)holders) - 1;
+}
+
 // SORTED: the tile's 32 pairs come from the cell-ordered work list (w_dst / w_pi / w_pj) and both hulls are
 // read from the cell-ordered records shv / shn / shull, so neighbouring tiles touch neighbouring memory
 // whatever the slot numbering; results still go to the pair's place in the reference order (w_dst).
 template <bool SORTED>
 __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
 {
-    __shared__ int s_out[CO_WARPS][32][3];                           // phase 1 -> phase 2: outcome, edge, penetrator
+    __shared__ int4 s_meta[CO_WARPS][32];                 // per pair of the tile: offset / count of hull A, of hull B
+    __shared__ ulonglong2 s_ext[CO_WARPS][32];            // packed extents of both hulls
+    __shared__ int s_out[CO_WARPS][32];                   // phase 1 -> phase 2: outcome | edge << 8 | penetrator << 16
 
     const FrameState *st = P.st;
     if (st->error) return;
@@ -1313,127 +1377,86 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
     const double2 *const WV = SORTED ? P.shv : P.wv;
     const double2 *const WN = SORTED ? P.shn : P.wn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = lane >> 4, dir = (lane >> 3) & 1, e = lane & 7;
-    const int group_base = lane & ~7;                 // first lane of my (pair, direction) group
+    const int grp = lane >> 3, e = lane & 7;
+    const int group_base = lane & ~7;                 // first lane of my pair's group
     const long long n_tiles = (n_pairs + 31) / 32;
 
     for (long long tile = (long long)blockIdx.x * CO_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * CO_WARPS) {
         const long long base = tile * 32;
-        // ---- prologue: lane L reads the indices of pair base + L (coalesced), so the 16 steps below get them by
-        // shuffle instead of a dependent load chain each, and pulls both hulls' vertex / normal lines towards L2
-        // (partners are scattered in memory on worlds whose keys are unrelated to position).
+        // ---- prologue: lane L reads the indices of pair base + L (coalesced) into shared memory, so the 8 steps
+        // below get them with two broadcast loads instead of a dependent chain each, and pulls both hulls'
+        // vertex / normal lines towards L2.
         // Prefetching one or two tiles further ahead (a software pipeline over the warp's tiles) was built and
-        // measured SLOWER (1M polygons: 0.283 / 0.288 ms vs 0.262 ms; 4M mixed: 1.44 vs 1.22 ms): with ~2400
-        // resident warps and ~24 KB of hull lines per tile the prefetched footprint no longer fits the 126 MB L2.
-        int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
+        // measured SLOWER in r1 (1M polygons: 0.283 / 0.288 ms vs 0.262 ms): with ~2400 resident warps and
+        // ~24 KB of hull lines per tile the prefetched footprint no longer fits the 126 MB L2.
+        int my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
         long long my_dst = base + lane;
-        unsigned long long my_xa = 0, my_xb = 0;    // SORTED: packed extents of both hulls
+        unsigned long long my_xa = 0, my_xb = 0;
         if (base + lane < n_pairs) {
             if (SORTED) {
                 my_dst = (long long)P.w_dst[base + lane];
-                my_i = (int)P.w_pi[base + lane]; my_j = (int)P.w_pj[base + lane];   // POSITIONS, not slots
-                my_xa = P.shull[my_i]; my_xb = P.shull[my_j];
-                my_oa = my_i * MAX_STAGED_VERTS; my_ob = my_j * MAX_STAGED_VERTS;
+                const int pa = (int)P.w_pi[base + lane], pb = (int)P.w_pj[base + lane];   // POSITIONS, not slots
+                my_xa = P.shull[pa]; my_xb = P.shull[pb];
+                my_oa = pa * MAX_STAGED_VERTS; my_ob = pb * MAX_STAGED_VERTS;
                 // hulls without a record (more than 8 vertices) send the pair to the per-thread pass
                 my_na = ((my_xa >> 56) & 1ull) ? (int)((my_xa >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
                 my_nb = ((my_xb >> 56) & 1ull) ? (int)((my_xb >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
                 pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
             } else {
-                my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane];
-                my_oa = P.vert_offset[my_i]; my_na = P.vert_offset[my_i + 1] - my_oa;
-                my_ob = P.vert_offset[my_j]; my_nb = P.vert_offset[my_j + 1] - my_ob;
-                pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
-                if (my_na > 1) { pf_l2(&WV[my_oa + my_na - 1]); pf_l2(&WN[my_oa + my_na - 1]); }
-                if (my_nb > 1) { pf_l2(&WV[my_ob + my_nb - 1]); pf_l2(&WN[my_ob + my_nb - 1]); }
-                pf_l2(&P.ext_packed[my_i]); pf_l2(&P.ext_packed[my_j]);
+                const int i = P.pair_i[base + lane], j = P.pair_j[base + lane];
+                my_oa = P.vert_offset[i]; my_na = P.vert_offset[i + 1] - my_oa;
+                my_ob = P.vert_offset[j]; my_nb = P.vert_offset[j + 1] - my_ob;
+                if (i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi) {
+                    pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
+                    if (my_na > 1) { pf_l2(&WV[my_oa + my_na - 1]); pf_l2(&WN[my_oa + my_na - 1]); }
+                    if (my_nb > 1) { pf_l2(&WV[my_ob + my_nb - 1]); pf_l2(&WN[my_ob + my_nb - 1]); }
+                    my_xa = P.ext_packed[i]; my_xb = P.ext_packed[j];
+                } else my_na = MAX_STAGED_VERTS + 1;      // a hull of another rank: per-thread pass
             }
         }
-        // ---- phase 1: SAT, two pairs per step
+        s_meta[warp][lane] = make_int4(my_oa, my_na, my_ob, my_nb);
+        s_ext[warp][lane] = make_ulonglong2(my_xa, my_xb);
+        __syncwarp();
+        // ---- phase 1: SAT, four pairs per step
 #pragma unroll 1
-        for (int t = 0; t < 16; ++t) {
-            const int src = 2 * t + half;
-            const long long p = base + src;
-            const bool valid = p < n_pairs;
-            const int i = __shfl_sync(0xffffffffu, my_i, src), j = __shfl_sync(0xffffffffu, my_j, src);
-            const int oa = __shfl_sync(0xffffffffu, my_oa, src), na = __shfl_sync(0xffffffffu, my_na, src);
-            const int ob = __shfl_sync(0xffffffffu, my_ob, src), nb = __shfl_sync(0xffffffffu, my_nb, src);
-            const bool own = SORTED || (i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi);
-            const bool coop = valid && own && na >= 1 && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
-            // my direction: E = penetrated hull (its edge normals are the axes), Pn = the other hull
-            const int e_slot = dir ? j : i, e_off = dir ? ob : oa, e_n = dir ? nb : na;
-            unsigned long long e_ext = 0;
-            if (SORTED) {
-                const unsigned long long xa = __shfl_sync(0xffffffffu, my_xa, src), xb = __shfl_sync(0xffffffffu, my_xb, src);
-                e_ext = dir ? xb : xa;
-            }
-            const int pn_off = dir ? oa : ob, pn_n = dir ? na : nb;
-            const bool active = coop && e < e_n;
+        for (int t = 0; t < 8; ++t) {
+            const int src = 4 * t + grp;
+            const bool valid = base + src < n_pairs;
+            const int4 m = s_meta[warp][src];
+            const ulonglong2 x = s_ext[warp][src];
+            const int oa = m.x, na = m.y, ob = m.z, nb = m.w;
+            const bool coop = valid && na >= 1 && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
+            // direction 0: A is the penetrated hull (its edge normals are the axes), B the penetrating one; then 1
+            const bool act0 = coop && e < na, act1 = coop && e < nb;
+            double depth0 = 0.0, depth1 = 0.0;
+            int pen0 = 0, pen1 = 0;
             bool sep = false;
-            double depth = 0.0;
-            int pen = 0;
-            if (active) {
-                // overlap sEdge edge sPen (SAT.hs:103-117)
-                const double2 dn = WN[e_off + e];
-                const unsigned bits = (unsigned)((SORTED ? e_ext : P.ext_packed[e_slot]) >> (6 * e));
-                const double2 vmin = WV[e_off + (bits & 7)], vmax = WV[e_off + ((bits >> 3) & 7)];
-                double2 pv[MAX_STAGED_VERTS];
-#pragma unroll
-                for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = WV[pn_off + k];
-                const V2 d{ dn.x, dn.y };
-                // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
-                const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
-                // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
-                double p_min = dot2(V2{ pv[0].x, pv[0].y }, d), p_max = p_min;
-#pragma unroll
-                for (int k = 1; k < MAX_STAGED_VERTS; ++k) {
-                    if (k >= pn_n) break;
-                    const double q = dot2(V2{ pv[k].x, pv[k].y }, d);
-                    if (q < p_min) { p_min = q; pen = k; }
-                    if (q > p_max) p_max = q;
-                }
-                sep = (p_min > s_max) || (p_max < s_min);        // overlapTest (SAT.hs:74-83)
-                depth = fsub(s_max, p_min);                       // overlapAmount (SAT.hs:86-96)
-            }
+            if (act0) sep = coop_edge(WV, WN, oa, e, x.x, ob, nb, depth0, pen0);
+            if (act1) sep |= coop_edge(WV, WN, ob, e, x.y, oa, na, depth1, pen1);
             // a separating axis on either side means no contact (contactDebug, SAT.hs:238-248)
-            const unsigned sep_mask = __ballot_sync(0xffffffffu, sep);
-            const bool pair_sep = ((sep_mask >> (16 * half)) & 0xffffu) != 0;
-            // minOverlap' (SAT.hs:121-143) over my direction's edges: edge 0 first, a later edge replaces the
-            // best one only with a strictly smaller depth.  That fold equals the lexicographic minimum of
-            // (depth, edge) with a NaN depth treated as +inf -- unless edge 0's depth is NaN, in which case
-            // nothing ever replaces edge 0.  Three butterfly steps over the 8 lanes of the direction.
-            const double d0 = __shfl_sync(0xffffffffu, depth, group_base);
-            double best_key = (active && !(depth != depth)) ? depth : __longlong_as_double(0x7ff0000000000000ll);
-            double best_depth = depth;
-            int best_ep = e | (pen << 8);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                const double k2 = __shfl_xor_sync(0xffffffffu, best_key, o);
-                const double d2 = __shfl_xor_sync(0xffffffffu, best_depth, o);
-                const int ep2 = __shfl_xor_sync(0xffffffffu, best_ep, o);
-                if (k2 < best_key || (k2 == best_key && (ep2 & 0xff) < (best_ep & 0xff))) { best_key = k2; best_depth = d2; best_ep = ep2; }
-            }
-            const int ep0 = __shfl_sync(0xffffffffu, e | (pen << 8), group_base);
-            if (d0 != d0) { best_depth = d0; best_ep = ep0; }
-            const int best_edge = best_ep & 0xff, best_pen = best_ep >> 8;
-            // direction 1's result moves to the lanes of direction 0
-            const double o_depth = __shfl_sync(0xffffffffu, best_depth, lane ^ 8);
-            const int o_edge = __shfl_sync(0xffffffffu, best_edge, lane ^ 8), o_pen = __shfl_sync(0xffffffffu, best_pen, lane ^ 8);
-            if ((lane & 15) == 0) {
-                int outcome = CO_NONE, edge = 0, pn = 0;
-                if (valid && !coop) outcome = CO_FALLBACK;
+            const bool pair_sep = ((__ballot_sync(0xffffffffu, sep) >> group_base) & 0xffu) != 0u;
+            const int edge0 = fold_min_overlap(act0, depth0, group_base);
+            const int edge1 = fold_min_overlap(act1, depth1, group_base);
+            const double best0 = __shfl_sync(0xffffffffu, depth0, group_base + edge0);
+            const double best1 = __shfl_sync(0xffffffffu, depth1, group_base + edge1);
+            const int bpen0 = __shfl_sync(0xffffffffu, pen0, group_base + edge0);
+            const int bpen1 = __shfl_sync(0xffffffffu, pen1, group_base + edge1);
+            if (e == 0) {
+                int out = CO_NONE;
+                if (valid && !coop) out = CO_FALLBACK;
                 else if (coop && !pair_sep) {
-                    const bool same = best_depth < o_depth;       // depth_ab < depth_ba ? Same : Flip (ties: Flip)
-                    outcome = same ? CO_SAME : CO_FLIP;
-                    edge = same ? best_edge : o_edge; pn = same ? best_pen : o_pen;
+                    const bool same = best0 < best1;              // depth_ab < depth_ba ? Same : Flip (ties: Flip)
+                    out = same ? (CO_SAME | (edge0 << 8) | (bpen0 << 16)) : (CO_FLIP | (edge1 << 8) | (bpen1 << 16));
                 }
-                s_out[warp][2 * t + half][0] = outcome; s_out[warp][2 * t + half][1] = edge; s_out[warp][2 * t + half][2] = pn;
+                s_out[warp][src] = out;
             }
         }
         __syncwarp();
         // ---- phase 2: one pair per lane
         if (base + lane < n_pairs) {
             const long long p = my_dst;     // the pair's index in the reference order
-            const int outcome = s_out[warp][lane][0], edge = s_out[warp][lane][1], pn = s_out[warp][lane][2];
+            const int packed = s_out[warp][lane];
+            const int outcome = packed & 0xff, edge = (packed >> 8) & 0xff, pn = (packed >> 16) & 0xff;
             unsigned cnt = 0;
             if (outcome == CO_SAME || outcome == CO_FLIP) {
                 const int oa = my_oa, na = my_na, ob = my_ob, nb = my_nb;
@@ -1453,8 +1476,10 @@ __global__ void __launch_bounds__(256) k_row_map(Params P)
     FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = st->n_pairs;
+    unsigned hit = 0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
         const unsigned cnt = P.ccnt[p], off = P.coff[p];
+        hit += cnt ? 1u : 0u;
         for (unsigned k = 0; k < cnt; ++k)
             if ((long long)off + k < P.max_contacts) P.row_map[off + k] = (uint32_t)((p << 1) | k);
         if (p == n_pairs - 1) {
@@ -1463,6 +1488,8 @@ __global__ void __launch_bounds__(256) k_row_map(Params P)
             if (total > P.max_contacts) atomicOr(&st->error, ERR_CONTACT_CAP);
         }
     }
+    for (int o = 16; o > 0; o >>= 1) hit += __shfl_xor_sync(0xffffffffu, hit, o);
+    if ((threadIdx.x & 31) == 0 && hit) atomicAdd(&st->n_pairs_hit, (unsigned long long)hit);
 }
 
 // K3b: one lane per contact ROW, warps own 32 ALIGNED rows.  Every column store of a warp is a
@@ -1743,7 +1770,7 @@ struct shapes_ctx {
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
     bool use_sorted = true;       // general polygons: hull records + SAT work list in cell order (SHAPES_B200_NO_SORTED=1: slot order)
-    int32_t *d_vert_slot = nullptr;
+    int32_t *d_vert_slot = nullptr, *d_vert_next = nullptr;
     bool has_circles = false;
     double *d_radius = nullptr;
     int rows_blocks = 4;         // resident k_rows blocks per SM
@@ -1901,6 +1928,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.circ, N));
     c->use_sorted = std::getenv("SHAPES_B200_NO_SORTED") == nullptr;
     TRY_CREATE(dev_alloc(c, &c->d_vert_slot, V));
+    TRY_CREATE(dev_alloc(c, &c->d_vert_next, V));
+    P.vert_next = c->d_vert_next;
     TRY_CREATE(dev_alloc(c, &P.pos_of, N));
     TRY_CREATE(dev_alloc(c, &P.shull, N));
     TRY_CREATE(dev_alloc(c, &P.shv, c->use_sorted ? (size_t)N * MAX_STAGED_VERTS : 1));
@@ -2103,7 +2132,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         if (N > 0) {
             k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
             if (P.sorted_mode && c->n_verts > 0) {
-                k_hulls_scatter<<<grid_for(c->n_verts, 256, sms * 16), 256, 0, s>>>(P, (int)c->n_verts); ++c->launches;
+                k_hulls_scatter<<<grid_for(c->n_verts, 256, 1 << 30), 256, 0, s>>>(P, (int)c->n_verts); ++c->launches;
             }
         }
         STAGE_MARK(); // 5: sweep count
@@ -2312,7 +2341,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     if (alive) std::memcpy(live.data(), alive, (size_t)n_slots);
     // layout conversion (interleave x/y) and the static cell-size estimate: hull diameters
     std::vector<double2> inter((size_t)n_verts);
-    std::vector<int32_t> vslot((size_t)n_verts);
+    std::vector<int32_t> vslot((size_t)n_verts), vnext((size_t)n_verts);
     std::vector<double> diam;
     diam.reserve((size_t)n_slots);
     int max_verts_seen = 0;
@@ -2333,6 +2362,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         for (int32_t k = 0; k < n; ++k) {
             inter[o + k] = make_double2(local_x[o + k], local_y[o + k]);
             vslot[o + k] = (int32_t)s;
+            vnext[o + k] = (k + 1 < n) ? o + k + 1 : o;
             const double d2 = local_x[o + k] * local_x[o + k] + local_y[o + k] * local_y[o + k];
             if (d2 > r2) r2 = d2;
         }
@@ -2357,7 +2387,10 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         CU_TRY(c, cudaMemcpyAsync(c->d_vert_offset, vert_offset, sizeof(int32_t) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, s));
         if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
         if (any_circle) CU_TRY(c, cudaMemcpyAsync(c->d_radius, radius, sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
-        if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_vert_slot, vslot.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+        if (n_verts > 0) {
+            CU_TRY(c, cudaMemcpyAsync(c->d_vert_slot, vslot.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+            CU_TRY(c, cudaMemcpyAsync(c->d_vert_next, vnext.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
+        }
         if (ext_min) {
             for (int64_t v = 0; v < n_verts; ++v) {
                 // _hullExtents entries index the hull's own vertices
@@ -2613,6 +2646,17 @@ void shapes_host_free(void *p) { if (p) cudaFreeHost(p); }
 void *shapes_stream(shapes_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int64_t shapes_launch_count(const shapes_ctx *c) { return c ? c->launches : 0; }
+
+int shapes_last_frame_info(shapes_ctx *c, shapes_frame_info *info)
+{
+    if (!c || !info) return SHAPES_E_ARG;
+    if (!c->have_frame) { c->err = "shapes_last_frame_info: no completed frame"; return SHAPES_E_ARG; }
+    info->pairs_with_contacts = (int64_t)c->h_state->n_pairs_hit;
+    info->sorted_mode = c->P.sorted_mode;
+    info->sat_kernel = c->has_circles ? SHAPES_SAT_PER_THREAD_CIRCLES : c->max_hull_verts <= 4 ? SHAPES_SAT_PER_THREAD_BOXES
+                     : c->use_coop ? SHAPES_SAT_COOP : SHAPES_SAT_PER_THREAD;
+    return SHAPES_OK;
+}
 
 int shapes_set_profiling(shapes_ctx *c, int enabled)
 {

@@ -28,6 +28,11 @@ CONTACT_I32 = ("key_i", "key_j", "feat_a", "feat_b")
 CONTACT_F64 = ("normal_x", "normal_y", "center_x", "center_y", "depth")
 CONSTRAINT_F64 = (tuple(f"j_np{q}" for q in range(6)) + ("b_np", "ra_x", "ra_y", "rb_x", "rb_y", "rn_x", "rn_y")
                   + tuple(f"j_f{q}" for q in range(6)) + ("b_f", "inv_eff_np", "inv_eff_f"))
+# Compact wire format of the constraint rows: the columns that carry arithmetic of their own.  The other sixteen
+# are sign copies of the contact normal (j_np / j_f entries 0, 1, 3, 4; rn), c - pos (ra, rb) and a constant (b_f);
+# `expand_rows` rebuilds them bit for bit (IEEE negation and subtraction are exact), so a host that asks for these
+# only moves 113 instead of 225 bytes per row over PCIe.
+CONSTRAINT_COMPACT_F64 = ("j_np2", "j_np5", "b_np", "j_f2", "j_f5", "inv_eff_np", "inv_eff_f")
 WARM_F64 = ("warm_np", "warm_f")
 AABB_COLS = ("aabb_min_x", "aabb_max_x", "aabb_min_y", "aabb_max_y")
 WORLD_COLS = ("world_x", "world_y")
@@ -89,6 +94,9 @@ class _HostBuffers:
         if "constraints" in want:
             for k in CONSTRAINT_F64:
                 self.cols[k] = alloc(max_contacts, np.float64)
+        if "constraints_compact" in want:
+            for k in CONSTRAINT_COMPACT_F64:
+                self.cols[k] = alloc(max_contacts, np.float64)
         if "warm" in want:
             for k in WARM_F64:
                 self.cols[k] = alloc(max_contacts, np.float64)
@@ -136,6 +144,7 @@ class Frame:
         self.device_ms = float(out.device_ms)
         self.total_ms = float(out.total_ms)
         self.cols = {}
+        self.d2h_bytes = bufs.bytes_for(self.n_pairs, self.n_contacts, n_slots, n_verts)
         for k, a in bufs.cols.items():
             n = (self.n_pairs if k in PAIR_COLS else n_slots if k in AABB_COLS else n_verts if k in WORLD_COLS
                  else self.n_contacts)
@@ -257,9 +266,19 @@ class Engine:
 
     def frame(self, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02,
               cos_sin: Optional[tuple[np.ndarray, np.ndarray]] = None,
-              want=("pairs", "contacts", "constraints"), pinned: bool = False) -> Frame:
-        """One frame through shapes_frame with host buffers (H2D + kernels + D2H)."""
+              want=("pairs", "contacts", "constraints"), pinned: bool = False,
+              compact: bool = False, expand: bool = True) -> Frame:
+        """One frame through shapes_frame with host buffers (H2D + kernels + D2H).
+
+        compact: fetch the constraint rows in the compact wire format (CONSTRAINT_COMPACT_F64: NULL pointers for
+        the sixteen derived columns, so the library copies 113 instead of 225 bytes per row); with `expand` the
+        derived columns are rebuilt on the host (`expand_rows`), bit-identical to the full fetch."""
         w = self.world
+        if compact and "constraints" in want:
+            want = tuple(k for k in want if k != "constraints") + ("contacts", "constraints_compact")
+            want = tuple(dict.fromkeys(want))
+        else:
+            compact = False
         bufs = self._buffers(want, pinned)
         out = FrameOut()
         bufs.fill(out)
@@ -271,7 +290,10 @@ class Engine:
                                    _ptr(cos_rot), _ptr(sin_rot), _ptr(w.inv_lin), _ptr(w.inv_rot),
                                    dt, baumgarte, slop, C.byref(out))
         self._check(rc, out)
-        return Frame(out, bufs, w.n_slots, w.n_verts)
+        fr = Frame(out, bufs, w.n_slots, w.n_verts)
+        if compact and expand:
+            expand_rows(fr.cols, w.pos_x, w.pos_y)
+        return fr
 
     def frame_device(self, pos_x: int, pos_y: int, rot: int, cos_rot: int, sin_rot: int, inv_lin: int,
                      inv_rot: int, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02) -> FrameOut:
@@ -297,6 +319,21 @@ class Engine:
         v = _lib.DeviceView()
         self._check(self.lib.shapes_device_view_get(self.ctx, C.byref(v)))
         return v
+
+    def frame_info(self) -> _lib.FrameInfo:
+        """Statistics of the last completed frame (shapes_last_frame_info)."""
+        info = _lib.FrameInfo()
+        self._check(self.lib.shapes_last_frame_info(self.ctx, C.byref(info)))
+        return info
+
+    def pairs_with_contacts(self) -> int:
+        return int(self.frame_info().pairs_with_contacts)
+
+    def sorted_mode(self) -> bool:
+        return bool(self.frame_info().sorted_mode)
+
+    def sat_kernel_name(self) -> str:
+        return _lib.SAT_KERNEL_NAMES.get(int(self.frame_info().sat_kernel), "?")
 
     def ipc_export(self) -> bytes:
         """CUDA IPC handles of this rank's exchange buffers (shapes_ipc_export)."""
@@ -407,6 +444,28 @@ def sincos(rot: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     c = np.empty_like(r); s = np.empty_like(r)
     _lib.load().shapes_sincos(r.shape[0], _ptr(r), _ptr(c), _ptr(s))
     return c, s
+
+
+def expand_rows(cols: dict, pos_x: np.ndarray, pos_y: np.ndarray) -> dict:
+    """Rebuild the sixteen derived constraint columns from the compact wire format, in place and bit for bit.
+
+    With n the contact normal, t = clockwiseV2 n = (n.y, -n.x), c the contact centre and flip the Flipping tag:
+      j_np = (-n, x, n, x) and j_f = (-t, x, t, x) on (penetrated, penetrator), halves swapped back for Flip
+             (NonPenetration.hs:34-43, Friction.hs:31-44, Utils.hs:175-177,212-215) -- so entries 0, 1, 3, 4 are
+             +-n / +-t by the flip bit; the cross terms (entries 2, 5) are shipped;
+      ra = c - pos_i, rb = c - pos_j, rn = n for Same / -n for Flip (Restitution.hs:21-31);  b_f = 0 (Friction.hs:26-29).
+    Negation and one IEEE subtraction reproduce the device's bits exactly."""
+    nx, ny = cols["normal_x"], cols["normal_y"]
+    f = cols["flip"].astype(bool)
+    sx = np.where(f, nx, -nx); sy = np.where(f, ny, -ny)          # -n for Same, n for Flip
+    cols["j_np0"], cols["j_np1"], cols["j_np3"], cols["j_np4"] = sx, sy, -sx, -sy
+    cols["j_f0"], cols["j_f1"], cols["j_f3"], cols["j_f4"] = sy, -sx, -sy, sx
+    cols["rn_x"], cols["rn_y"] = -sx, -sy
+    ki, kj = cols["key_i"], cols["key_j"]
+    cols["ra_x"] = cols["center_x"] - pos_x[ki]; cols["ra_y"] = cols["center_y"] - pos_y[ki]
+    cols["rb_x"] = cols["center_x"] - pos_x[kj]; cols["rb_y"] = cols["center_y"] - pos_y[kj]
+    cols["b_f"] = np.zeros_like(nx)
+    return cols
 
 
 def updateWorld(engine: Engine, dt: float, beh: "ContactBehavior", external=(_lib.EXT_NONE, 0.0, 0.0)) -> _lib.StepStats:

@@ -330,3 +330,19 @@ def test_slot_order_path_still_matches(oracle, monkeypatch, which):
         w.pos_x[40] = w.pos_y[40] = np.nan
         w.pos_y[41] = np.inf
         check_world(oracle, w, broadphase="aabb")
+
+
+def test_compact_wire_format_expands_to_the_full_rows(oracle):
+    """shapes_frame with NULL pointers for the sixteen derived constraint columns (113 instead of 225 bytes per row
+    over PCIe) + engine.expand_rows == the full fetch == the oracle, bit for bit."""
+    from shapes_b200.engine import Engine
+    for w in (scenes.random_polygons(20_000, density=2.0, config=45), scenes.box_pile(100, 60)):
+        c, s = oracle.cos_sin(w.rot)
+        want = oracle.frame(w, c, s, broadphase="sweep")
+        with Engine(w) as eng:
+            fr = eng.frame_grow(cos_sin=(c, s), compact=True)
+            assert fr.d2h_bytes == 8 * fr.n_pairs + (17 + 12 * 8) * fr.n_contacts
+            assert_frames_match(fr.cols, want)
+            full = eng.frame(cos_sin=(c, s))
+            assert full.d2h_bytes == 8 * fr.n_pairs + (17 + 26 * 8) * fr.n_contacts
+            assert_frames_match(full.cols, want)

@@ -66,3 +66,24 @@ def test_world_delete_keeps_keys_sparse():
     w = World.from_objects([(rectangle_vertices(1, 1), (float(k), 0.0), 0.0, (1.0, 1.0)) for k in range(4)])
     w.delete([1])
     assert w.alive.tolist() == [1, 0, 1, 1] and w.n_slots == 4
+
+
+def test_expand_rows_rebuilds_the_derived_columns_bit_for_bit(oracle):
+    """Compact wire format (engine.CONSTRAINT_COMPACT_F64): the sixteen derived constraint columns are rebuilt
+    from the shipped ones exactly -- checked on the oracle's own rows (flips, signed zeros, clipped points)."""
+    import numpy as np
+    from shapes_b200 import engine, scenes
+    for w in (scenes.random_polygons(3000, density=3.0, static_frac=0.1, config=51), scenes.box_pile(40, 30),
+              scenes.stacks_scene((12, 8), 0.0)):
+        c, s = oracle.cos_sin(w.rot)
+        want = oracle.frame(w, c, s)
+        assert len(want["key_i"]) > 100
+        shipped = ("key_i", "key_j", "feat_a", "feat_b", "flip", "normal_x", "normal_y", "center_x", "center_y", "depth") \
+            + engine.CONSTRAINT_COMPACT_F64
+        cols = {k: np.array(want[k]) for k in shipped}
+        engine.expand_rows(cols, w.pos_x, w.pos_y)
+        for k in engine.CONSTRAINT_F64:
+            a, b = cols[k], np.asarray(want[k])
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64)), k
+        if w.name.startswith("polygons"):
+            assert want["flip"].any() and not want["flip"].all()
