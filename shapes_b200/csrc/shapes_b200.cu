@@ -187,17 +187,13 @@ struct Params {
     Box *box;                   // per slot
     double *world_x, *world_y;  // optional debug output
     double2 *wv, *wn;           // world vertices / unit edge normals of the OWNED slots (moveShapes result)
-    // Sorted mode (general polygon worlds): the moveShapes result is materialised in CELL order instead --
-    // position p of the counting sort owns the fixed-stride record shv/shn[8p .. 8p+8) -- and the SAT stage
-    // visits the pairs in cell order through a work list, so both hulls of a pair sit next to the hulls of
-    // the neighbouring pairs whatever the host's slot numbering is.
+    const uint4 *hh;            // per slot, static: CSR offset, vertex count, packed extents (lo, hi) -- one 16 B gather per hull
+    // Sorted mode (general polygon worlds): the SAT stage visits the pairs in grid-CELL order through a work
+    // list written by the (single pass) sweep, so the hulls a tile of pairs touches are shared with the
+    // neighbouring tiles whatever the host's slot numbering is; results go to the pair's place in the
+    // reference order, off[r(i)] + a.
     int sorted_mode;
-    const int32_t *vert_slot;   // per static vertex: the slot it belongs to
-    const int32_t *vert_next;   // per static vertex: the next vertex of its hull (wraps)
-    uint32_t *pos_of;           // per slot: its position (grid shapes in cell order, then the big list); ~0u = none
-    unsigned long long *shull;  // per position: packed extents [0,48) | vertex count [48,56) | materialised [56]
-    double2 *shv, *shn;         // per position x 8: world vertices / unit edge normals (hulls of <= 8 vertices)
-    uint32_t *w_dst, *w_pi, *w_pj; // SAT work list, cell order: output pair index, positions of both hulls
+    uint32_t *w_i, *w_j, *w_a;  // SAT work list, cell order: both slots and the pair's rank among i's partners
     uint32_t *keys, *keys_sorted; // cell key per slot / per sorted position
     uint32_t *rank;             // per slot: arrival order within its cell (counting sort)
     Box *sbox;                  // AABB records in sorted order
@@ -327,18 +323,21 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
 {
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
-        double px = P.pos_x[s], py = P.pos_y[s];
+        // level 1: everything indexed by the slot, requested before anything is consumed
+        const double px = P.pos_x[s], py = P.pos_y[s];
+        const double il = P.inv_lin[s], ir = P.inv_rot[s];
+        const bool live = P.alive[s] != 0;
+        const int o = P.vert_offset[s];
+        const int n = P.vert_offset[s + 1] - o;
+        const double rad = P.radius ? P.radius[s] : -1.0;
         double c, sn;
         if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
         else sincos(P.rot[s], &sn, &c); // not bit-exact against libm (documented at the ABI)
         P.xf[s] = Xf{ px, py, c, sn };
-        P.mass[s] = make_double2(P.inv_lin[s], P.inv_rot[s]);
-        if (!P.alive[s]) continue;
-        const int o = P.vert_offset[s];
-        const int n = P.vert_offset[s + 1] - o;
+        P.mass[s] = make_double2(il, ir);
+        if (!live) continue;
         const Aff m = to_transform(px, py, c, sn);
         Box b;
-        const double rad = P.radius ? P.radius[s] : -1.0;
         if (rad >= 0.0) {
             // setCircleTransform (Circle.hs:55-59): centre = transform applied to the local origin;
             // circleToAabb (Aabb.hs:86-88)
@@ -347,27 +346,56 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
             b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
             b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
         }
-        const bool keep = !P.sorted_mode;   // sorted mode: k_hulls_scatter materialises the hulls in cell order
-        for (int k = 0; k < n; ++k) {
-            double2 l = __ldg(&P.local[o + k]);
-            V2 w = afmul(m, V2{ l.x, l.y });
-            if (keep) P.wv[o + k] = make_double2(w.x, w.y);
-            if (P.world_x) { P.world_x[o + k] = w.x; P.world_y[o + k] = w.y; }
-            if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
-            else {
-                b.min_x = (b.min_x < w.x) ? b.min_x : w.x;
-                b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
-                b.min_y = (b.min_y < w.y) ? b.min_y : w.y;
-                b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+        if (n <= MAX_STAGED_VERTS) {
+            // level 2: the hull's local vertices as ONE batch of loads; world vertices stay in registers for the
+            // normals (the r1 kernel re-read them from global memory after storing them, one dependent step per vertex)
+            double2 l[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < n) l[k] = __ldg(&P.local[o + k]);
+            V2 w[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                w[k] = afmul(m, V2{ l[k].x, l[k].y });
+                P.wv[o + k] = make_double2(w[k].x, w[k].y);
+                if (P.world_x) { P.world_x[o + k] = w[k].x; P.world_y[o + k] = w[k].y; }
+                if (k == 0) { b.min_x = b.max_x = w[k].x; b.min_y = b.max_y = w[k].y; }
+                else {
+                    b.min_x = (b.min_x < w[k].x) ? b.min_x : w[k].x;
+                    b.max_x = (b.max_x > w[k].x) ? b.max_x : w[k].x;
+                    b.min_y = (b.min_y < w[k].y) ? b.min_y : w[k].y;
+                    b.max_y = (b.max_y > w[k].y) ? b.max_y : w[k].y;
+                }
             }
-        }
-        // setHullTransform (ConvexHull.hs:193-194): unit edge normals recomputed from the NEW vertices
-        double2 v0 = (keep && n > 0) ? P.wv[o] : make_double2(0.0, 0.0), va = v0;
-        for (int k = 0; keep && k < n; ++k) {
-            const double2 vb = (k + 1 < n) ? P.wv[o + k + 1] : v0;
-            const V2 nn = unit_edge_normal(V2{ va.x, va.y }, V2{ vb.x, vb.y });
-            P.wn[o + k] = make_double2(nn.x, nn.y);
-            va = vb;
+            // setHullTransform (ConvexHull.hs:193-194): unit edge normals recomputed from the NEW vertices
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                const V2 nxt = (k + 1 < MAX_STAGED_VERTS && k + 1 < n) ? w[(k + 1) & (MAX_STAGED_VERTS - 1)] : w[0];
+                const V2 nn = unit_edge_normal(w[k], nxt);
+                P.wn[o + k] = make_double2(nn.x, nn.y);
+            }
+        } else {
+            for (int k = 0; k < n; ++k) {
+                double2 l = __ldg(&P.local[o + k]);
+                V2 w = afmul(m, V2{ l.x, l.y });
+                P.wv[o + k] = make_double2(w.x, w.y);
+                if (P.world_x) { P.world_x[o + k] = w.x; P.world_y[o + k] = w.y; }
+                if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                else {
+                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x;
+                    b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y;
+                    b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                }
+            }
+            double2 v0 = P.wv[o], va = v0;
+            for (int k = 0; k < n; ++k) {
+                const double2 vb = (k + 1 < n) ? P.wv[o + k + 1] : v0;
+                const V2 nn = unit_edge_normal(V2{ va.x, va.y }, V2{ vb.x, vb.y });
+                P.wn[o + k] = make_double2(nn.x, nn.y);
+                va = vb;
+            }
         }
         P.box[s] = b;
         if (finite4(b)) {
@@ -531,7 +559,6 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
         if (key == P.key_none + 1u) {
             const unsigned pos = atomicAdd(&P.st->n_big, 1u);
             P.big_idx[pos] = (uint32_t)s;
-            P.rank[s] = pos;
             key = P.key_none;
         } else if (key < P.key_none) {
             const bool own = s >= P.own_lo && s < P.own_hi;
@@ -546,60 +573,14 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
 // and keys in sorted order, contiguous per cell and per grid row.
 __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 {
-    const unsigned n_sorted = P.sorted_mode ? P.cell_begin[P.st->n_cells] : 0u;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
         const uint32_t key = P.keys[s];
-        if (key >= P.key_none) {
-            if (P.sorted_mode) {
-                // big shapes take the positions after the grid's, in big-list order; everything else has none
-                const bool big = P.gkeys[s] == P.key_none + 1u;
-                const uint32_t p = big ? n_sorted + P.rank[s] : 0xffffffffu;
-                P.pos_of[s] = p;
-                if (big) P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
-            }
-            continue;
-        }
+        if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
         P.sbox[p] = box_of(P, s);
         P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
         P.keys_sorted[p] = key;
-        if (P.sorted_mode) P.pos_of[s] = p;
     }
-}
-
-// Sorted mode, K1c: moveShapes (World.hs:132-140) straight into cell order.  One thread per static vertex v
-// of a kept hull: world vertex = afmul (toTransform pos rot) local (setHullTransform, ConvexHull.hs:184-195) and
-// the unit normal of the edge that starts there, recomputed from the NEW vertices (ConvexHull.hs:193-194,
-// 218-226), written to the hull's fixed-stride record at its sorted position.  Reads are in slot order
-// (coalesced), the stores of one hull are one contiguous run.  Hulls of more than 8 vertices get no record
-// (their pairs are finished by the per-thread pass from the local vertices).
-__global__ void __launch_bounds__(256) k_hulls_scatter(Params P, int n_verts)
-{
-    // One vertex per thread and no branch between the loads: the r2a version (early exits between dependent
-    // loads, 6 levels deep) sat on long-scoreboard stalls for 0.136 ms at 1M polygons; here level 1 is the
-    // vertex's static columns, level 2 everything that hangs off its slot.
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_verts) return;
-    const int s = __ldg(&P.vert_slot[v]);
-    const int vn = __ldg(&P.vert_next[v]);                 // nextIndex (ConvexHull.hs:228-230), static
-    const double2 la = __ldg(&P.local[v]);
-    const uint32_t p = P.pos_of[s];
-    const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
-    const bool live = P.alive[s] != 0;
-    const unsigned long long xp = P.ext_packed[s];
-    const Xf x = slot_xf(P, s);
-    const double2 lb = __ldg(&P.local[vn]);
-    if (p == 0xffffffffu || !live) return;
-    const int k = v - o;
-    const bool mat = n <= MAX_STAGED_VERTS;
-    if (k == 0)
-        P.shull[p] = (mat ? (xp & 0xffffffffffffull) | (1ull << 56) : 0ull) | ((unsigned long long)(n > 255 ? 255 : n) << 48);
-    if (!mat) return;
-    const Aff m = to_transform(x.px, x.py, x.c, x.s);
-    const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
-    const V2 nn = unit_edge_normal(wa, wb);
-    P.shv[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(wa.x, wa.y);
-    P.shn[(size_t)p * MAX_STAGED_VERTS + k] = make_double2(nn.x, nn.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -629,96 +610,18 @@ __device__ __forceinline__ unsigned long long block128_exclusive(unsigned long l
     return before + inc - v;
 }
 
-template <bool EMIT>
-__global__ void __launch_bounds__(128) k_sweep(Params P)
+enum { SWEEP_COUNT = 0, SWEEP_EMIT = 1, SWEEP_FUSED = 2 };
+
+// Candidates of query i (a small shape in cell (cx, cy), AABB bi, static flag si) in enumeration order: the three
+// grid-row runs of its 3x3 neighbourhood, then the big list.  `hit(j)` is called for every partner j < i whose
+// AABB passes aabbCheck; returns the hit mask (bit c = candidate c hit; bit 63 = more than 63 candidates, no mask).
+template <typename F>
+__device__ __forceinline__ unsigned long long sweep_test_all(const Params &P, const FrameState *st, int i, bool si, const Box &bi,
+                                                             int cx, int cy, F &&hit)
 {
-    const FrameState *st = P.st;
-    if (EMIT && st->error) return;
-    const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
-    const bool sorted = P.sorted_mode != 0;
-    __shared__ unsigned long long s_wbase;
-    // blocks walk whole 128-position tiles, so that the work-list reservation below is block uniform
-    for (unsigned tile = blockIdx.x * 128u; tile < n_sorted; tile += gridDim.x * 128u) {
-    const unsigned p = tile + threadIdx.x;
-    uint32_t meta = 0;
-    int i = -1;
-    bool query = false;
-    if (p < n_sorted) {
-        meta = P.smeta[p];
-        i = (int)(meta & 0x7fffffffu);
-        query = i >= P.own_lo && i < P.own_hi;
-    }
-    const int r = P.own_hi - 1 - i;
-    // Sorted mode, emit pass: the SAT stage visits the pairs in CELL order.  Each tile reserves a run of the
-    // work list (one atomic per 128 queries; tiles are handed out in launch order, so the list follows the
-    // cell order closely) and every query writes (output index, position of i, position of j) per partner.
-    unsigned long long wbase = 0;
-    if (EMIT && sorted) {
-        unsigned long long total;
-        const unsigned long long mine = query ? P.cnt[r] : 0ull;
-        const unsigned long long before = block128_exclusive(mine, total);
-        if (threadIdx.x == 0) s_wbase = total ? atomicAdd(&P.st->work_cursor, total) : 0ull;
-        __syncthreads();
-        wbase = s_wbase + before;
-    }
-    if (!query) continue;
-    const bool si = (meta >> 31) != 0;
-    const Box bi = P.sbox[p];
-    const uint32_t key = P.keys_sorted[p];
     const int W = st->W, H = st->H;
-    const int cy = (int)(key / (uint32_t)W), cx = (int)(key % (uint32_t)W);
-
-    unsigned long long count = 0;
-    int local[EMIT_LOCAL];
-    unsigned local_q[EMIT_LOCAL];
-    unsigned long long base = 0;
-    if (EMIT) base = P.off[r];
-
-    auto hit = [&](int j, unsigned q) {
-        if (EMIT) {
-            if (count < EMIT_LOCAL) { local[count] = j; local_q[count] = q; }
-            else { P.pair_j[base + count] = j; if (sorted) P.w_pj[wbase + count] = q; }
-        }
-        ++count;
-    };
-
-    // The count pass leaves a bit per candidate (in enumeration order: the three runs, then the big list)
-    // so that the emit pass revisits only the hits -- no AABB records, no overlap tests.  Bit 63 = more than
-    // 63 candidates: the emit pass then repeats the tests.
     unsigned long long mask = 0;
     unsigned cand = 0;
-    const unsigned long long want = EMIT ? P.hitmask[p] : 0ull;
-    const bool replay = EMIT && !(want >> 63);
-    const unsigned n_big = st->n_big;
-    if (replay) {
-        unsigned long long m = want;
-        unsigned seen = 0;
-        for (int dy = -1; dy <= 1 && m; ++dy) {
-            const int ny = cy + dy;
-            if (ny < 0 || ny >= H) continue;
-            const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
-            const unsigned q_lo = __ldg(&P.cell_begin[(size_t)ny * W + x_lo]);
-            const unsigned q_hi = __ldg(&P.cell_begin[(size_t)ny * W + x_hi + 1]);
-            const unsigned len = q_hi - q_lo;
-            // bits [seen, seen + len) belong to this run
-            unsigned long long run = (len >= 64u - seen) ? (m >> seen) : ((m >> seen) & ((1ull << len) - 1ull));
-            while (run) {
-                const int b = __ffsll((long long)run) - 1;
-                run &= run - 1;
-                hit((int)(__ldg(&P.smeta[q_lo + (unsigned)b]) & 0x7fffffffu), q_lo + (unsigned)b);
-            }
-            seen += len;
-            if (seen >= 63u) break;
-        }
-        if (seen < 63u) {
-            unsigned long long run = (want & 0x7fffffffffffffffull) >> seen;
-            while (run) {
-                const int b = __ffsll((long long)run) - 1;
-                run &= run - 1;
-                hit((int)P.big_idx[b], n_sorted + (unsigned)b);
-            }
-        }
-    } else {
     for (int dy = -1; dy <= 1; ++dy) {
         const int ny = cy + dy;
         if (ny < 0 || ny >= H) continue;
@@ -732,52 +635,148 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             if (j >= i) continue;
             if (si && (m >> 31)) continue; // never pair two static shapes (Aabb.hs:172-176)
             const Box bj = P.sbox[q];
-            if (aabb_check(bi, bj)) { hit(j, q); if (cand < 63u) mask |= 1ull << cand; }
+            if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
         }
     }
+    const unsigned n_big = st->n_big;
     for (unsigned b = 0; b < n_big; ++b, ++cand) {
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
         if (si && slot_static(P, j)) continue;
         const Box bj = box_of(P, j);
-        if (aabb_check(bi, bj)) { hit(j, n_sorted + b); if (cand < 63u) mask |= 1ull << cand; }
+        if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
     }
-    }
-    if (!EMIT) P.hitmask[p] = (cand > 63u) ? (1ull << 63) : mask;
+    return (cand > 63u) ? (1ull << 63) : mask;
+}
 
-    if (!EMIT) { P.cnt[r] = count; continue; }
-    if (count == 0) continue;
-    if (count <= EMIT_LOCAL) {
-        const int n = (int)count;
-        for (int a = 1; a < n; ++a) { // insertion sort, descending
-            const int v = local[a];
-            const unsigned vq = local_q[a];
-            int b2 = a - 1;
-            while (b2 >= 0 && local[b2] < v) { local[b2 + 1] = local[b2]; local_q[b2 + 1] = local_q[b2]; --b2; }
-            local[b2 + 1] = v; local_q[b2 + 1] = vq;
+// The same hits again from the mask sweep_test_all returned (bit 63 clear): no AABB records, no overlap tests.
+template <typename F>
+__device__ __forceinline__ void sweep_replay(const Params &P, const FrameState *st, int cx, int cy, unsigned long long want, F &&hit)
+{
+    const int W = st->W, H = st->H;
+    unsigned long long m = want;
+    unsigned seen = 0;
+    for (int dy = -1; dy <= 1 && m; ++dy) {
+        const int ny = cy + dy;
+        if (ny < 0 || ny >= H) continue;
+        const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, W - 1);
+        const unsigned q_lo = __ldg(&P.cell_begin[(size_t)ny * W + x_lo]);
+        const unsigned q_hi = __ldg(&P.cell_begin[(size_t)ny * W + x_hi + 1]);
+        const unsigned len = q_hi - q_lo;
+        // bits [seen, seen + len) belong to this run
+        unsigned long long run = (len >= 64u - seen) ? (m >> seen) : ((m >> seen) & ((1ull << len) - 1ull));
+        while (run) {
+            const int b = __ffsll((long long)run) - 1;
+            run &= run - 1;
+            hit((int)(__ldg(&P.smeta[q_lo + (unsigned)b]) & 0x7fffffffu));
         }
-        for (int a = 0; a < n; ++a) { P.pair_i[base + a] = i; P.pair_j[base + a] = local[a]; }
-        if (sorted)
-            for (int a = 0; a < n; ++a) {
-                P.w_dst[wbase + a] = (uint32_t)(base + a); P.w_pi[wbase + a] = p; P.w_pj[wbase + a] = local_q[a];
-            }
-    } else {
-        for (int a = 0; a < EMIT_LOCAL; ++a) P.pair_j[base + a] = local[a];
-        if (sorted) for (int a = 0; a < EMIT_LOCAL; ++a) P.w_pj[wbase + a] = local_q[a];
-        int32_t *seg = P.pair_j + base;
-        uint32_t *segq = P.w_pj + wbase;
-        for (unsigned long long a = 1; a < count; ++a) {
-            const int v = seg[a];
-            const uint32_t vq = sorted ? segq[a] : 0u;
-            long long b2 = (long long)a - 1;
-            while (b2 >= 0 && seg[b2] < v) { seg[b2 + 1] = seg[b2]; if (sorted) segq[b2 + 1] = segq[b2]; --b2; }
-            seg[b2 + 1] = v;
-            if (sorted) segq[b2 + 1] = vq;
-        }
-        for (unsigned long long a = 0; a < count; ++a) P.pair_i[base + a] = i;
-        if (sorted)
-            for (unsigned long long a = 0; a < count; ++a) { P.w_dst[wbase + a] = (uint32_t)(base + a); P.w_pi[wbase + a] = p; }
+        seen += len;
+        if (seen >= 63u) break;
     }
+    if (seen < 63u) {
+        unsigned long long run = (want & 0x7fffffffffffffffull) >> seen;
+        while (run) {
+            const int b = __ffsll((long long)run) - 1;
+            run &= run - 1;
+            hit((int)P.big_idx[b]);
+        }
+    }
+}
+
+// MODE SWEEP_COUNT / SWEEP_EMIT: the two-pass sweep -- counts per query, (scan in descending i), then the pairs
+// straight into their place of the reference order; the count pass leaves a hit mask per query so that the emit
+// pass revisits only the hits.
+// MODE SWEEP_FUSED (sorted mode): ONE pass.  A query counts its partners (mask in a register), the 128 queries of
+// a tile reserve a run of the cell-ordered SAT work list with one atomic (tiles are handed out in launch order, so
+// the list follows the cell order closely), and each query replays its hits into (i, j, a) entries, a = the rank
+// of j among i's partners in descending order.  The pair's index in the reference order is off[r(i)] + a, resolved
+// by the SAT stage after the scan; pair_i / pair_j are written there too.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_sweep(Params P)
+{
+    constexpr bool EMIT = MODE == SWEEP_EMIT, FUSED = MODE == SWEEP_FUSED;
+    const FrameState *st = P.st;
+    if (EMIT && st->error) return;
+    const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
+    __shared__ unsigned long long s_wbase;
+    // blocks walk whole 128-position tiles, so that the work-list reservation below is block uniform
+    for (unsigned tile = blockIdx.x * 128u; tile < n_sorted; tile += gridDim.x * 128u) {
+        const unsigned p = tile + threadIdx.x;
+        uint32_t meta = 0;
+        int i = -1;
+        bool query = false;
+        if (p < n_sorted) {
+            meta = P.smeta[p];
+            i = (int)(meta & 0x7fffffffu);
+            query = i >= P.own_lo && i < P.own_hi;
+        }
+        const int r = P.own_hi - 1 - i;
+        const bool si = (meta >> 31) != 0;
+        Box bi{ 0.0, 0.0, 0.0, 0.0 };
+        int cx = 0, cy = 0;
+        if (query) {
+            bi = P.sbox[p];
+            const uint32_t key = P.keys_sorted[p];
+            cy = (int)(key / (uint32_t)st->W); cx = (int)(key % (uint32_t)st->W);
+        }
+        unsigned long long count = 0, mask = 0;
+        if (query && !EMIT) {
+            mask = sweep_test_all(P, st, i, si, bi, cx, cy, [&](int) { ++count; });
+            P.cnt[r] = count;
+            if (!FUSED) P.hitmask[p] = mask;
+        }
+        if (MODE == SWEEP_COUNT) continue;
+
+        unsigned long long base = 0;      // first output (EMIT) / work-list (FUSED) index of this query
+        bool room = true;
+        if (FUSED) {
+            unsigned long long total;
+            const unsigned long long before = block128_exclusive(count, total);
+            if (threadIdx.x == 0) s_wbase = total ? atomicAdd(&P.st->work_cursor, total) : 0ull;
+            __syncthreads();
+            base = s_wbase + before;
+            room = s_wbase + total <= (unsigned long long)P.max_pairs;   // else k_finish_pairs raises the capacity error
+        } else if (query) {
+            base = P.off[r];
+            mask = P.hitmask[p];
+            count = 0;
+        }
+        if (!query || !room) continue;
+        if (FUSED && count == 0) continue;
+
+        int32_t *const out_j = FUSED ? reinterpret_cast<int32_t *>(P.w_j) : P.pair_j;
+        int local[EMIT_LOCAL];
+        unsigned long long n_hit = 0;
+        auto collect = [&](int j) {
+            if (n_hit < EMIT_LOCAL) local[n_hit] = j;
+            else out_j[base + n_hit] = j;
+            ++n_hit;
+        };
+        if (!(mask >> 63)) sweep_replay(P, st, cx, cy, mask, collect);
+        else sweep_test_all(P, st, i, si, bi, cx, cy, collect);
+        if (n_hit == 0) continue;
+        // each i's partners in descending order => Aabb.culledKeys order (Aabb.hs:155-183)
+        if (n_hit <= EMIT_LOCAL) {
+            const int n = (int)n_hit;
+            for (int a = 1; a < n; ++a) { // insertion sort, descending
+                const int v = local[a];
+                int b2 = a - 1;
+                while (b2 >= 0 && local[b2] < v) { local[b2 + 1] = local[b2]; --b2; }
+                local[b2 + 1] = v;
+            }
+            for (int a = 0; a < n; ++a) out_j[base + a] = local[a];
+        } else {
+            for (int a = 0; a < EMIT_LOCAL; ++a) out_j[base + a] = local[a];
+            int32_t *seg = out_j + base;
+            for (unsigned long long a = 1; a < n_hit; ++a) {
+                const int v = seg[a];
+                long long b2 = (long long)a - 1;
+                while (b2 >= 0 && seg[b2] < v) { seg[b2 + 1] = seg[b2]; --b2; }
+                seg[b2 + 1] = v;
+            }
+        }
+        if (FUSED) for (unsigned long long a = 0; a < n_hit; ++a) { P.w_i[base + a] = (uint32_t)i; P.w_a[base + a] = (uint32_t)a; }
+        else for (unsigned long long a = 0; a < n_hit; ++a) P.pair_i[base + a] = i;
     }
 }
 
@@ -805,7 +804,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
         }
         __syncthreads();
         const unsigned long long wbase = (EMIT && P.sorted_mode) ? s_wbase : 0ull;
-        const unsigned pi_pos = (EMIT && P.sorted_mode) ? P.pos_of[i] : 0u;
+        const bool room = wbase + (P.sorted_mode ? P.cnt[r] : 0ull) <= (unsigned long long)P.max_pairs;
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
@@ -818,11 +817,12 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             const unsigned long long run = s_run;
             if (EMIT && pred) {
                 const unsigned long long pos = base + run + before + __popc(bal & ((1u << lane) - 1u));
-                P.pair_i[pos] = i;
-                P.pair_j[pos] = j;
-                if (P.sorted_mode) {
-                    const unsigned long long w = wbase + (pos - base);
-                    P.w_dst[w] = (uint32_t)pos; P.w_pi[w] = pi_pos; P.w_pj[w] = P.pos_of[j];
+                if (P.sorted_mode) {   // work-list entry; the SAT stage writes pair_i / pair_j at off[r] + a
+                    const unsigned long long a = pos - base, w = wbase + a;
+                    if (room) { P.w_i[w] = (uint32_t)i; P.w_j[w] = (uint32_t)j; P.w_a[w] = (uint32_t)a; }
+                } else {
+                    P.pair_i[pos] = i;
+                    P.pair_j[pos] = j;
                 }
             }
             __syncthreads();
@@ -890,7 +890,7 @@ struct ContactKernel {
     }
     __device__ __forceinline__ void stage(HullAcc &h) const
     {
-        h.owned = !P.sorted_mode && h.slot >= P.own_lo && h.slot < P.own_hi;
+        h.owned = h.slot >= P.own_lo && h.slot < P.own_hi;
         if (h.n <= MAXV) {
             if (h.owned) {
                 if (MAXV > 4) {
@@ -1286,22 +1286,27 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
 }
 
 
-// K3a for general convex polygons (hulls of 3..8 vertices): 8 lanes per pair.
+// K3a for general convex polygons (hulls of 3..8 vertices): 16 lanes per pair.
 // In `k_manifolds` a thread walks (edges of A) x (vertices of B) + (edges of B) x (vertices of A) on its
 // own; with 3..8 vertices per hull the trip counts differ from lane to lane (14.9 of 32 threads active
-// per instruction in ncu) and every lane stages two whole hulls.  Here lane e of an 8-lane group owns
-// candidate axis e of BOTH directions (0: A penetrated by B, 1: B penetrated by A): the unit normal of
-// edge e of the penetrated hull, against which it projects the other hull's <= 8 vertices (one batch of
-// loads, the same addresses across the 8 lanes).  The minOverlap fold (SAT.hs:121-143) over the eight
-// per-edge results is a shuffle minimum of the depths followed by a ballot that picks the FIRST edge holding
-// that minimum -- the sequential fold's strict `<`, with its NaN behaviour kept (see fold_min_overlap).
-// A warp does its 32 pairs four at a time (phase 1, 8 steps), then every lane clips one pair (phase 2,
-// `emit_manifold`).  Pairs with a hull of more than 8 vertices, or a hull whose world vertices were not
-// materialised on this rank, are flagged and finished by a second, per-thread pass.
-// (r1 ran 16 lanes per pair, one direction per lane, 16 steps per tile: 285 warp instructions per step of
-// two pairs, a third of them the lexicographic shuffle fold and the index shuffles -- profiles/r2_summary.md.)
+// per instruction in ncu) and every lane stages two whole hulls.  Here lane (dir, e) of a half warp owns
+// ONE candidate axis: the unit normal of edge e of the penetrated hull of direction dir (0: A <- B,
+// 1: B <- A), against which it projects the other hull's <= 8 vertices.  A warp does its 32 pairs two at a
+// time (phase 1, 16 steps), then every lane clips one pair (phase 2, `emit_manifold`).
+//  * The 64 vertex / normal records of a step (2 pairs x 2 hulls x 16) are copied global -> shared with one
+//    16 B cp.async per lane and hull, one step AHEAD of their use (double buffer): the SAT arithmetic never waits
+//    for a global load, and its 11 operand loads per lane are LDS with immediate offsets.
+//  * The minOverlap fold (SAT.hs:121-143) over the eight per-edge results is a shuffle minimum of the depths
+//    followed by a ballot that picks the FIRST edge holding that minimum -- the sequential fold's strict `<`,
+//    with its NaN behaviour kept (see fold_min_overlap).
+//  * Each direction's winner goes to shared memory; the Same / Flip decision moves to phase 2.
+// Pairs with a hull of more than 8 vertices, or a hull whose world vertices were not materialised on this
+// rank, are flagged and finished by a second, per-thread pass.
+// History (1M random polygons, SAT stage): one thread per pair 0.381 ms; r1 16 lanes per pair with global operand
+// loads, a lexicographic shuffle fold and index shuffles 0.224 ms (285 warp instructions per step, 62 % issue
+// utilisation); 8 lanes per pair / both directions per lane 0.225 ms (fewer instructions, but two dependent load
+// batches per step and spills at 80 registers) -- profiles/r2_summary.md.
 constexpr int CO_WARPS = 4;
-enum { CO_NONE = 0, CO_SAME = 1, CO_FLIP = 2, CO_FALLBACK = 3 };
 
 struct GlobalAcc {      // emit_manifold over materialised world vertices / normals in global memory
     const double2 *wv, *wn;
@@ -1311,33 +1316,14 @@ struct GlobalAcc {      // emit_manifold over materialised world vertices / norm
     __device__ __forceinline__ V2 vp(int k) const { const double2 v = wv[pn_off + k]; return V2{ v.x, v.y }; }
 };
 
-// overlap sEdge edge sPen (SAT.hs:103-117) for ONE edge of the penetrated hull E (this lane's), against all
-// vertices of the penetrating hull.  Returns true when the axis separates; else depth / penetrator.
-__device__ __forceinline__ bool coop_edge(const double2 *__restrict__ WV, const double2 *__restrict__ WN, int e_off, int e,
-                                          unsigned long long e_ext, int pn_off, int pn_n, double &depth, int &pen)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    const double2 dn = WN[e_off + e];
-    const unsigned bits = (unsigned)(e_ext >> (6 * e));
-    const double2 vmin = WV[e_off + (bits & 7)], vmax = WV[e_off + ((bits >> 3) & 7)];
-    double2 pv[MAX_STAGED_VERTS];
-#pragma unroll
-    for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < pn_n) pv[k] = WV[pn_off + k];
-    const V2 d{ dn.x, dn.y };
-    // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
-    const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
-    // extentAlong (ConvexHull.hs:81-100): first minimum / first maximum win
-    double p_min = dot2(V2{ pv[0].x, pv[0].y }, d), p_max = p_min;
-    pen = 0;
-#pragma unroll
-    for (int k = 1; k < MAX_STAGED_VERTS; ++k) {
-        if (k >= pn_n) break;
-        const double q = dot2(V2{ pv[k].x, pv[k].y }, d);
-        if (q < p_min) { p_min = q; pen = k; }
-        if (q > p_max) p_max = q;
-    }
-    depth = fsub(s_max, p_min);                              // overlapAmount (SAT.hs:86-96)
-    return (p_min > s_max) || (p_max < s_min);               // overlapTest (SAT.hs:74-83)
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // minOverlap' (SAT.hs:121-143) over the edges held by the 8 lanes of my group: edge 0 first, a later edge replaces
 // the best one only with a strictly smaller depth.  That fold equals "the first edge holding the minimum depth, a
@@ -1361,108 +1347,142 @@ __device__ __forceinline__ int fold_min_overlap(bool active, double depth, int g
     return __ffs((int)holders) - 1;
 }
 
-// SORTED: the tile's 32 pairs come from the cell-ordered work list (w_dst / w_pi / w_pj) and both hulls are
-// read from the cell-ordered records shv / shn / shull, so neighbouring tiles touch neighbouring memory
-// whatever the slot numbering; results still go to the pair's place in the reference order (w_dst).
+struct __align__(16) CoopRes { double depth; int edge_pen; int flags; };   // per (pair, direction): minOverlap's winner
+enum { CO_F_SEP = 1, CO_F_FALLBACK = 2 };
+
+// SORTED: the tile's 32 pairs come from the cell-ordered work list (w_i / w_j / w_a), so neighbouring tiles touch
+// the same hulls whatever the slot numbering; results go to the pair's place in the reference order, off[r(i)] + a,
+// and pair_i / pair_j are written here.  Otherwise the tile is 32 consecutive pairs of the reference order.
 template <bool SORTED>
 __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
 {
     __shared__ int4 s_meta[CO_WARPS][32];                 // per pair of the tile: offset / count of hull A, of hull B
     __shared__ ulonglong2 s_ext[CO_WARPS][32];            // packed extents of both hulls
-    __shared__ int s_out[CO_WARPS][32];                   // phase 1 -> phase 2: outcome | edge << 8 | penetrator << 16
+    __shared__ double2 s_hull[CO_WARPS][2][2][32];        // [buffer][pair of the step][A verts, A normals, B verts, B normals]
+    __shared__ CoopRes s_res[CO_WARPS][32][2];            // phase 1 -> phase 2
 
     const FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = st->n_pairs;
-    const double2 *const WV = SORTED ? P.shv : P.wv;
-    const double2 *const WN = SORTED ? P.shn : P.wn;
+    const double2 *const WV = P.wv;
+    const double2 *const WN = P.wn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grp = lane >> 3, e = lane & 7;
-    const int group_base = lane & ~7;                 // first lane of my pair's group
+    const int half = lane >> 4, dir = (lane >> 3) & 1, e = lane & 7;
+    const int group_base = lane & ~7;                 // first lane of my (pair, direction) group
+    const int idx16 = lane & 15;                      // staging: element of the A / B half of my pair's record
+    const double2 *const src_arr = (idx16 < 8) ? WV : WN;
     const long long n_tiles = (n_pairs + 31) / 32;
+
+    // cp.async of step t's records into buffer t & 1: lane (q, idx16) copies element idx16 of hull A and of hull B
+    auto stage = [&](int t) {
+        const int src = 2 * t + half;
+        const int4 m = s_meta[warp][src];
+        const int k = idx16 & 7;
+        if (m.y >= 1 && m.w >= 1 && m.y <= MAX_STAGED_VERTS && m.w <= MAX_STAGED_VERTS) {
+            if (k < m.y) cp_async16(&s_hull[warp][t & 1][half][idx16], src_arr + m.x + k);
+            if (k < m.w) cp_async16(&s_hull[warp][t & 1][half][16 + idx16], src_arr + m.z + k);
+        }
+        cp_async_commit();
+    };
 
     for (long long tile = (long long)blockIdx.x * CO_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * CO_WARPS) {
         const long long base = tile * 32;
-        // ---- prologue: lane L reads the indices of pair base + L (coalesced) into shared memory, so the 8 steps
-        // below get them with two broadcast loads instead of a dependent chain each, and pulls both hulls'
-        // vertex / normal lines towards L2.
-        // Prefetching one or two tiles further ahead (a software pipeline over the warp's tiles) was built and
-        // measured SLOWER in r1 (1M polygons: 0.283 / 0.288 ms vs 0.262 ms): with ~2400 resident warps and
-        // ~24 KB of hull lines per tile the prefetched footprint no longer fits the 126 MB L2.
-        int my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
+        // ---- prologue: lane L reads the header of pair base + L into shared memory (vertex count 0 = no pair,
+        // MAX_STAGED_VERTS + 1 = leave it to the per-thread pass)
+        int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
         long long my_dst = base + lane;
         unsigned long long my_xa = 0, my_xb = 0;
         if (base + lane < n_pairs) {
             if (SORTED) {
-                my_dst = (long long)P.w_dst[base + lane];
-                const int pa = (int)P.w_pi[base + lane], pb = (int)P.w_pj[base + lane];   // POSITIONS, not slots
-                my_xa = P.shull[pa]; my_xb = P.shull[pb];
-                my_oa = pa * MAX_STAGED_VERTS; my_ob = pb * MAX_STAGED_VERTS;
-                // hulls without a record (more than 8 vertices) send the pair to the per-thread pass
-                my_na = ((my_xa >> 56) & 1ull) ? (int)((my_xa >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
-                my_nb = ((my_xb >> 56) & 1ull) ? (int)((my_xb >> 48) & 0xffull) : MAX_STAGED_VERTS + 1;
-                pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
-            } else {
-                const int i = P.pair_i[base + lane], j = P.pair_j[base + lane];
-                my_oa = P.vert_offset[i]; my_na = P.vert_offset[i + 1] - my_oa;
-                my_ob = P.vert_offset[j]; my_nb = P.vert_offset[j + 1] - my_ob;
-                if (i >= P.own_lo && i < P.own_hi && j >= P.own_lo && j < P.own_hi) {
-                    pf_l2(&WV[my_oa]); pf_l2(&WN[my_oa]); pf_l2(&WV[my_ob]); pf_l2(&WN[my_ob]);
-                    if (my_na > 1) { pf_l2(&WV[my_oa + my_na - 1]); pf_l2(&WN[my_oa + my_na - 1]); }
-                    if (my_nb > 1) { pf_l2(&WV[my_ob + my_nb - 1]); pf_l2(&WN[my_ob + my_nb - 1]); }
-                    my_xa = P.ext_packed[i]; my_xb = P.ext_packed[j];
-                } else my_na = MAX_STAGED_VERTS + 1;      // a hull of another rank: per-thread pass
-            }
+                my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane];
+                my_dst = (long long)(P.off[P.own_hi - 1 - my_i] + P.w_a[base + lane]);
+            } else { my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane]; }
+            const uint4 ha = __ldg(&P.hh[my_i]), hb = __ldg(&P.hh[my_j]);
+            my_oa = (int)ha.x; my_na = (int)ha.y; my_ob = (int)hb.x; my_nb = (int)hb.y;
+            my_xa = (unsigned long long)ha.z | ((unsigned long long)ha.w << 32);
+            my_xb = (unsigned long long)hb.z | ((unsigned long long)hb.w << 32);
+            const bool own = my_i >= P.own_lo && my_i < P.own_hi && my_j >= P.own_lo && my_j < P.own_hi;
+            if (!own || my_na > MAX_STAGED_VERTS || my_nb > MAX_STAGED_VERTS) my_na = MAX_STAGED_VERTS + 1;
         }
         s_meta[warp][lane] = make_int4(my_oa, my_na, my_ob, my_nb);
         s_ext[warp][lane] = make_ulonglong2(my_xa, my_xb);
         __syncwarp();
-        // ---- phase 1: SAT, four pairs per step
+        // ---- phase 1: SAT, two pairs per step, operands staged one step ahead
+        stage(0);
 #pragma unroll 1
-        for (int t = 0; t < 8; ++t) {
-            const int src = 4 * t + grp;
-            const bool valid = base + src < n_pairs;
+        for (int t = 0; t < 16; ++t) {
+            if (t + 1 < 16) { stage(t + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
+            const int src = 2 * t + half;
             const int4 m = s_meta[warp][src];
-            const ulonglong2 x = s_ext[warp][src];
-            const int oa = m.x, na = m.y, ob = m.z, nb = m.w;
-            const bool coop = valid && na >= 1 && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
-            // direction 0: A is the penetrated hull (its edge normals are the axes), B the penetrating one; then 1
-            const bool act0 = coop && e < na, act1 = coop && e < nb;
-            double depth0 = 0.0, depth1 = 0.0;
-            int pen0 = 0, pen1 = 0;
+            const int na = m.y, nb = m.w;
+            const bool valid = na >= 1;
+            const bool coop = valid && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
+            // my direction: E = penetrated hull (its edge normals are the axes), Pn = the other hull
+            const int e_n = dir ? nb : na, pn_n = dir ? na : nb;
+            const double2 *const rec = s_hull[warp][t & 1][half];
+            const double2 *const ev = rec + (dir ? 16 : 0), *const pvs = rec + (dir ? 0 : 16);
+            const bool active = coop && e < e_n;
             bool sep = false;
-            if (act0) sep = coop_edge(WV, WN, oa, e, x.x, ob, nb, depth0, pen0);
-            if (act1) sep |= coop_edge(WV, WN, ob, e, x.y, oa, na, depth1, pen1);
-            // a separating axis on either side means no contact (contactDebug, SAT.hs:238-248)
-            const bool pair_sep = ((__ballot_sync(0xffffffffu, sep) >> group_base) & 0xffu) != 0u;
-            const int edge0 = fold_min_overlap(act0, depth0, group_base);
-            const int edge1 = fold_min_overlap(act1, depth1, group_base);
-            const double best0 = __shfl_sync(0xffffffffu, depth0, group_base + edge0);
-            const double best1 = __shfl_sync(0xffffffffu, depth1, group_base + edge1);
-            const int bpen0 = __shfl_sync(0xffffffffu, pen0, group_base + edge0);
-            const int bpen1 = __shfl_sync(0xffffffffu, pen1, group_base + edge1);
-            if (e == 0) {
-                int out = CO_NONE;
-                if (valid && !coop) out = CO_FALLBACK;
-                else if (coop && !pair_sep) {
-                    const bool same = best0 < best1;              // depth_ab < depth_ba ? Same : Flip (ties: Flip)
-                    out = same ? (CO_SAME | (edge0 << 8) | (bpen0 << 16)) : (CO_FLIP | (edge1 << 8) | (bpen1 << 16));
+            double depth = 0.0;
+            int pen = 0;
+            if (active) {
+                // overlap sEdge edge sPen (SAT.hs:103-117)
+                const ulonglong2 x = s_ext[warp][src];
+                const unsigned bits = (unsigned)((dir ? x.y : x.x) >> (6 * e));
+                const double2 dn = ev[8 + e];
+                const double2 vmin = ev[bits & 7], vmax = ev[(bits >> 3) & 7];
+                const V2 d{ dn.x, dn.y };
+                // extentAlongSelf (ConvexHull.hs:111-118): the cached extreme vertices only
+                const double s_min = dot2(V2{ vmin.x, vmin.y }, d), s_max = dot2(V2{ vmax.x, vmax.y }, d);
+                // extentAlong (ConvexHull.hs:81-100): first minimum wins.  The maximum is only ever compared with
+                // s_min (overlapTest, SAT.hs:74-83: pMax < sMin), so instead of folding it, `below` keeps "every
+                // projection so far is < s_min or unordered" -- with the fold's NaN rules that is pMax < sMin
+                // exactly when the first projection and s_min are not NaN (a NaN start freezes the fold's maximum
+                // at NaN, later NaNs are skipped by its `>`).
+                const double2 p0 = pvs[0];
+                const double q0 = dot2(V2{ p0.x, p0.y }, d);
+                double p_min = q0;
+                bool below = !(q0 >= s_min);
+#pragma unroll
+                for (int k = 1; k < MAX_STAGED_VERTS; ++k) {
+                    if (k >= pn_n) break;
+                    const double2 pk = pvs[k];
+                    const double q = dot2(V2{ pk.x, pk.y }, d);
+                    if (q < p_min) { p_min = q; pen = k; }
+                    below = below && !(q >= s_min);
                 }
-                s_out[warp][src] = out;
+                sep = (p_min > s_max) || (below && q0 == q0 && s_min == s_min);   // overlapTest (SAT.hs:74-83)
+                depth = fsub(s_max, p_min);                                       // overlapAmount (SAT.hs:86-96)
             }
+            // a separating axis on either side means no contact (contactDebug, SAT.hs:238-248)
+            const unsigned sep_mask = __ballot_sync(0xffffffffu, sep);
+            const int edge = fold_min_overlap(active, depth, group_base);
+            const double best = __shfl_sync(0xffffffffu, depth, group_base + edge);
+            const int bpen = __shfl_sync(0xffffffffu, pen, group_base + edge);
+            if (e == 0) {
+                CoopRes r;
+                r.depth = best;
+                r.edge_pen = edge | (bpen << 8);
+                r.flags = (((sep_mask >> (16 * half)) & 0xffffu) ? CO_F_SEP : 0) | ((valid && !coop) ? CO_F_FALLBACK : 0);
+                s_res[warp][src][dir] = r;
+            }
+            __syncwarp();       // buffer t & 1 is free again before stage(t + 2) refills it
         }
-        __syncwarp();
         // ---- phase 2: one pair per lane
         if (base + lane < n_pairs) {
             const long long p = my_dst;     // the pair's index in the reference order
-            const int packed = s_out[warp][lane];
-            const int outcome = packed & 0xff, edge = (packed >> 8) & 0xff, pn = (packed >> 16) & 0xff;
+            if (SORTED) { P.pair_i[p] = my_i; P.pair_j[p] = my_j; }
+            const CoopRes r0 = s_res[warp][lane][0], r1 = s_res[warp][lane][1];
             unsigned cnt = 0;
-            if (outcome == CO_SAME || outcome == CO_FLIP) {
-                const int oa = my_oa, na = my_na, ob = my_ob, nb = my_nb;
-                const bool same = outcome == CO_SAME;
-                cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? oa : ob, same ? ob : oa }, same ? na : nb, same ? nb : na, edge, pn, same);
-            } else if (outcome == CO_FALLBACK) cnt = CCNT_FALLBACK;   // finished by k_manifolds<.., FLAGGED_ONLY>
+            if (r0.flags & CO_F_FALLBACK) cnt = CCNT_FALLBACK;          // finished by k_manifolds<.., FLAGGED_ONLY>
+            else if (!(r0.flags & CO_F_SEP)) {
+                const bool same = r0.depth < r1.depth;                  // depth_ab < depth_ba ? Same : Flip (ties: Flip)
+                const int ep = same ? r0.edge_pen : r1.edge_pen;
+                cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
+                                    same ? my_na : my_nb, same ? my_nb : my_na, ep & 0xff, (ep >> 8) & 0xff, same);
+            }
             P.ccnt[p] = cnt;
         }
         __syncwarp();
@@ -1671,7 +1691,7 @@ __global__ void k_hull_extents(int n_slots, const int32_t *vert_offset, const do
 }
 
 __global__ void k_pack_extents(int n_slots, const int32_t *vert_offset, const int32_t *ext_min,
-                               const int32_t *ext_max, unsigned long long *packed)
+                               const int32_t *ext_max, unsigned long long *packed, uint4 *hh)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
@@ -1681,6 +1701,7 @@ __global__ void k_pack_extents(int n_slots, const int32_t *vert_offset, const in
         for (int e = 0; e < n; ++e)
             w |= ((unsigned long long)(ext_min[o + e] & 7) | ((unsigned long long)(ext_max[o + e] & 7) << 3)) << (6 * e);
     packed[s] = w;
+    hh[s] = make_uint4((unsigned)o, (unsigned)n, (unsigned)w, (unsigned)(w >> 32));
 }
 
 __global__ void k_split_boxes(int n, const Box *box, double *a, double *b, double *c, double *d)
@@ -1769,8 +1790,8 @@ struct shapes_ctx {
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
-    bool use_sorted = true;       // general polygons: hull records + SAT work list in cell order (SHAPES_B200_NO_SORTED=1: slot order)
-    int32_t *d_vert_slot = nullptr, *d_vert_next = nullptr;
+    bool use_sorted = true;       // general polygons: single-pass sweep + SAT work list in cell order (SHAPES_B200_NO_SORTED=1: two-pass sweep, SAT in the reference's pair order)
+    uint4 *d_hh = nullptr;        // static hull headers (Params::hh)
     bool has_circles = false;
     double *d_radius = nullptr;
     int rows_blocks = 4;         // resident k_rows blocks per SM
@@ -1927,17 +1948,11 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.circ, N));
     c->use_sorted = std::getenv("SHAPES_B200_NO_SORTED") == nullptr;
-    TRY_CREATE(dev_alloc(c, &c->d_vert_slot, V));
-    TRY_CREATE(dev_alloc(c, &c->d_vert_next, V));
-    P.vert_next = c->d_vert_next;
-    TRY_CREATE(dev_alloc(c, &P.pos_of, N));
-    TRY_CREATE(dev_alloc(c, &P.shull, N));
-    TRY_CREATE(dev_alloc(c, &P.shv, c->use_sorted ? (size_t)N * MAX_STAGED_VERTS : 1));
-    TRY_CREATE(dev_alloc(c, &P.shn, c->use_sorted ? (size_t)N * MAX_STAGED_VERTS : 1));
-    TRY_CREATE(dev_alloc(c, &P.w_dst, c->use_sorted ? max_pairs : 1));
-    TRY_CREATE(dev_alloc(c, &P.w_pi, c->use_sorted ? max_pairs : 1));
-    TRY_CREATE(dev_alloc(c, &P.w_pj, c->use_sorted ? max_pairs : 1));
-    P.vert_slot = c->d_vert_slot;
+    TRY_CREATE(dev_alloc(c, &c->d_hh, N));
+    P.hh = c->d_hh;
+    TRY_CREATE(dev_alloc(c, &P.w_i, c->use_sorted ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_j, c->use_sorted ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_a, c->use_sorted ? max_pairs : 1));
     TRY_CREATE(dev_alloc(c, &c->d_radius, N));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
@@ -2129,15 +2144,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cell_count, P.cell_begin, (int)P.cell_limit + 1, s));
         }
         STAGE_MARK(); // 4: scatter into cell order
+        if (N > 0) { k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 5: sweep count (sorted mode: the whole single-pass sweep)
         if (N > 0) {
-            k_scatter_sorted<<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
-            if (P.sorted_mode && c->n_verts > 0) {
-                k_hulls_scatter<<<grid_for(c->n_verts, 256, 1 << 30), 256, 0, s>>>(P, (int)c->n_verts); ++c->launches;
-            }
-        }
-        STAGE_MARK(); // 5: sweep count
-        if (N > 0) {
-            k_sweep<false><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            const int g = grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30);
+            if (P.sorted_mode) k_sweep<SWEEP_FUSED><<<g, 128, 0, s>>>(P);
+            else k_sweep<SWEEP_COUNT><<<g, 128, 0, s>>>(P);
+            ++c->launches;
             k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 6: scan
@@ -2150,7 +2163,7 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         }
         STAGE_MARK(); // 7: sweep emit
         if (N > 0) {
-            k_sweep<true><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            if (!P.sorted_mode) { k_sweep<SWEEP_EMIT><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches; }
             k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 8: manifolds (SAT + clipping)
@@ -2341,7 +2354,6 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     if (alive) std::memcpy(live.data(), alive, (size_t)n_slots);
     // layout conversion (interleave x/y) and the static cell-size estimate: hull diameters
     std::vector<double2> inter((size_t)n_verts);
-    std::vector<int32_t> vslot((size_t)n_verts), vnext((size_t)n_verts);
     std::vector<double> diam;
     diam.reserve((size_t)n_slots);
     int max_verts_seen = 0;
@@ -2361,8 +2373,6 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         double r2 = 0.0;
         for (int32_t k = 0; k < n; ++k) {
             inter[o + k] = make_double2(local_x[o + k], local_y[o + k]);
-            vslot[o + k] = (int32_t)s;
-            vnext[o + k] = (k + 1 < n) ? o + k + 1 : o;
             const double d2 = local_x[o + k] * local_x[o + k] + local_y[o + k] * local_y[o + k];
             if (d2 > r2) r2 = d2;
         }
@@ -2387,10 +2397,6 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         CU_TRY(c, cudaMemcpyAsync(c->d_vert_offset, vert_offset, sizeof(int32_t) * (size_t)(n_slots + 1), cudaMemcpyHostToDevice, s));
         if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
         if (any_circle) CU_TRY(c, cudaMemcpyAsync(c->d_radius, radius, sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
-        if (n_verts > 0) {
-            CU_TRY(c, cudaMemcpyAsync(c->d_vert_slot, vslot.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
-            CU_TRY(c, cudaMemcpyAsync(c->d_vert_next, vnext.data(), sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
-        }
         if (ext_min) {
             for (int64_t v = 0; v < n_verts; ++v) {
                 // _hullExtents entries index the hull's own vertices
@@ -2402,7 +2408,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
             k_hull_extents<<<grid_for(n_slots, 128, 1 << 30), 128, 0, s>>>((int)n_slots, c->d_vert_offset, c->d_local, c->d_ext_min, c->d_ext_max);
             ++c->launches;
         }
-        k_pack_extents<<<grid_for(n_slots, 128, 1 << 30), 128, 0, s>>>((int)n_slots, c->d_vert_offset, c->d_ext_min, c->d_ext_max, c->d_ext_packed);
+        k_pack_extents<<<grid_for(n_slots, 128, 1 << 30), 128, 0, s>>>((int)n_slots, c->d_vert_offset, c->d_ext_min, c->d_ext_max, c->d_ext_packed, c->d_hh);
         ++c->launches;
         CU_TRY(c, cudaGetLastError());
     }
