@@ -136,6 +136,7 @@ constexpr int SHAPES_MAX_RANKS = 16;
 constexpr int ERR_PAIR_CAP = 1;
 constexpr int ERR_PEER_TIMEOUT = 4;
 constexpr int ERR_CONTACT_CAP = 2;
+constexpr int ERR_REPLAN = 8;       // plan-ahead: too many shapes fell outside the planned grid -- re-seed and redo the frame
 constexpr int MAX_STAGED_VERTS = 8; // hulls up to this many vertices are staged in shared memory
 
 // Device-resident per-frame state: lets every kernel be launched without a host round trip.
@@ -202,6 +203,8 @@ struct Params {
     uint32_t *cell_begin;       // exclusive scan of cell_count: cell c = sorted positions [begin[c], begin[c+1])
     uint8_t *cell_mark;         // multi-rank: cells inside the 3x3 neighbourhood of an owned shape
     int multi_rank;
+    int plan_ahead;             // 1 = the grid was planned from the PREVIOUS frame's bounds (k_begin_frame): K0 keys and bins
+    unsigned big_limit;         // plan-ahead: more big-list entries than this = the plan is stale (ERR_REPLAN)
     unsigned cell_cap;
     unsigned cell_limit;        // cells the planner may use this frame (<= cell_cap); what the scan covers
     uint32_t key_none;          // sort key of slots outside the grid (dead / big): first value past the cell table
@@ -302,6 +305,54 @@ __global__ void k_reset_state(FrameState *st)
     st->n_pairs_hit = 0ull;
 }
 
+// Choose origin, cell edge and grid extent for finite world bounds [bmin, bmax] (ordered-uint encodings in st).
+// The cell edge starts at the static estimate (largest hull diameter outside the big set) and doubles until the
+// table fits.  `margin` cells are added on every side (plan-ahead: shapes may have moved since the bounds were taken;
+// whatever still falls outside goes to the exact big-shape path, so results never depend on the plan).
+__device__ void plan_grid_from_bounds(FrameState *st, double cell_size, unsigned cell_limit, double margin)
+{
+    if (st->bmax_x == 0ull) { // no finite shape
+        st->ox = st->oy = 0.0; st->h = cell_size; st->W = st->H = 1; st->n_cells = 1;
+        return;
+    }
+    const double bx = dec_ordered(st->bmin_x), by = dec_ordered(st->bmin_y);
+    const double ex = dec_ordered(st->bmax_x) - bx, ey = dec_ordered(st->bmax_y) - by;
+    double h = cell_size;
+    double wx = 0.0, wy = 0.0;
+    bool ok = false;
+    for (int it = 0; it < 2200; ++it) {
+        wx = floor(ex / h) + 1.0 + 2.0 * margin;
+        wy = floor(ey / h) + 1.0 + 2.0 * margin;
+        if (isfinite(wx) && isfinite(wy) && wx < 1073741824.0 && wy < 1073741824.0 &&
+            wx * wy <= (double)cell_limit) { ok = true; break; }
+        h *= 2.0;
+    }
+    if (!ok) { wx = wy = 1.0; h = INFINITY; margin = 0.0; } // every finite shape lands in cell (0,0) or the big set
+    const double ox = bx - margin * h, oy = by - margin * h;
+    st->ox = isfinite(ox) ? ox : bx; st->oy = isfinite(oy) ? oy : by; st->h = h;
+    st->W = (int)wx; st->H = (int)wy;
+    st->n_cells = (unsigned)(st->W * st->H);
+}
+
+// Plan-ahead frames (single rank): first kernel of the frame, one thread.  The bounds K0 reduced in the PREVIOUS
+// frame (or the bounds-only pass after shapes_set_hulls) become this frame's grid, two cells of margin around
+// them; then the per-frame counters are reset.  K0 can therefore key and bin every shape as it computes its AABB:
+// no bounds -> plan -> keys dependency inside the frame.
+__global__ void k_begin_frame(Params P)
+{
+    FrameState *st = P.st;
+    plan_grid_from_bounds(st, P.cell_size, P.cell_limit, 2.0);
+    st->bmin_x = st->bmin_y = ~0ull;
+    st->bmax_x = st->bmax_y = 0ull;
+    st->n_big = 0;
+    st->n_small = 0;
+    st->error = 0;
+    st->n_pairs = 0;
+    st->n_contacts = 0;
+    st->work_cursor = 0ull;
+    st->n_pairs_hit = 0ull;
+}
+
 __device__ __forceinline__ double warp_min(double v)
 {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -319,10 +370,44 @@ __device__ __forceinline__ double warp_max(double v)
 // moveShape (World.hs:132-134) -> setHullTransform (ConvexHull.hs:184-195): world vertex =
 // afmul (toTransform pos rot) local; hullToAabb (Aabb.hs:81-84) = foldl1 mergeAabb with
 // mergeRange's `if a < c then a else c` / `if b > d then b else d` (Aabb.hs:104-110).
+__device__ __forceinline__ bool small_cell(const Box &b, const FrameState *st, int &cx, int &cy);
+
+// BOUNDS_ONLY: nothing is stored -- the pass that seeds the plan-ahead grid after shapes_set_hulls.
+template <bool BOUNDS_ONLY>
 __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi)
 {
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
+        if (BOUNDS_ONLY) {
+            if (!P.alive[s]) continue;
+            const double px = P.pos_x[s], py = P.pos_y[s];
+            double c, sn;
+            if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
+            else sincos(P.rot[s], &sn, &c);
+            const Aff m = to_transform(px, py, c, sn);
+            const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
+            const double rad = P.radius ? P.radius[s] : -1.0;
+            Box b{ 0.0, 0.0, 0.0, 0.0 };
+            if (rad >= 0.0) {
+                const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
+                b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
+                b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+            }
+            for (int k = 0; k < n; ++k) {
+                const double2 l = __ldg(&P.local[o + k]);
+                const V2 w = afmul(m, V2{ l.x, l.y });
+                if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                else {
+                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                }
+            }
+            if (finite4(b)) {
+                mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
+                mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+            }
+            continue;
+        }
         // level 1: everything indexed by the slot, requested before anything is consumed
         const double px = P.pos_x[s], py = P.pos_y[s];
         const double il = P.inv_lin[s], ir = P.inv_rot[s];
@@ -335,7 +420,7 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
         else sincos(P.rot[s], &sn, &c); // not bit-exact against libm (documented at the ABI)
         P.xf[s] = Xf{ px, py, c, sn };
         P.mass[s] = make_double2(il, ir);
-        if (!live) continue;
+        if (!live) { if (P.plan_ahead) P.keys[s] = P.key_none; continue; }
         const Aff m = to_transform(px, py, c, sn);
         Box b;
         if (rad >= 0.0) {
@@ -401,6 +486,22 @@ __global__ void __launch_bounds__(256) k_transform_aabb(Params P, int lo, int hi
         if (finite4(b)) {
             mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
             mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+        }
+        if (P.plan_ahead) {
+            // K0b/K1a fused (the grid of this frame was planned before the frame started): cell key of the min corner,
+            // histogram of the cell table (the arrival order is the counting sort's scatter slot); shapes outside the
+            // planned grid, spanning more than 2 cells or with non-finite bounds go to the big list
+            int cx, cy;
+            uint32_t key = P.key_none;
+            if (small_cell(b, P.st, cx, cy)) {
+                key = (uint32_t)cy * (uint32_t)P.st->W + (uint32_t)cx;
+                P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
+            } else {
+                const unsigned pos = atomicAdd(&P.st->n_big, 1u);
+                P.big_idx[pos] = (uint32_t)s;
+                if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);   // a stale plan must not turn into an O(N^2) frame
+            }
+            P.keys[s] = key;
         }
     }
     // block-level reduction, then one set of atomics per block
@@ -477,26 +578,7 @@ __global__ void k_plan_grid(Params P, int world)
         if (b[2] > st->bmax_x) st->bmax_x = b[2];
         if (b[3] > st->bmax_y) st->bmax_y = b[3];
     }
-    if (st->bmax_x == 0ull) { // no finite shape
-        st->ox = st->oy = 0.0; st->h = P.cell_size; st->W = st->H = 1; st->n_cells = 1;
-        return;
-    }
-    double ox = dec_ordered(st->bmin_x), oy = dec_ordered(st->bmin_y);
-    double ex = dec_ordered(st->bmax_x) - ox, ey = dec_ordered(st->bmax_y) - oy;
-    double h = P.cell_size;
-    double wx = 0.0, wy = 0.0;
-    bool ok = false;
-    for (int it = 0; it < 2200; ++it) {
-        wx = floor(ex / h) + 1.0;
-        wy = floor(ey / h) + 1.0;
-        if (isfinite(wx) && isfinite(wy) && wx < 1073741824.0 && wy < 1073741824.0 &&
-            wx * wy <= (double)P.cell_limit) { ok = true; break; }
-        h *= 2.0;
-    }
-    if (!ok) { wx = wy = 1.0; h = INFINITY; } // every finite shape lands in cell (0,0) or the big set
-    st->ox = ox; st->oy = oy; st->h = h;
-    st->W = (int)wx; st->H = (int)wy;
-    st->n_cells = (unsigned)(st->W * st->H);
+    plan_grid_from_bounds(st, P.cell_size, P.cell_limit, 0.0);
 }
 
 // Cell of an AABB's min corner if the box spans at most 2 cells per axis ("small"), else -1.
@@ -696,7 +778,7 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
 {
     constexpr bool EMIT = MODE == SWEEP_EMIT, FUSED = MODE == SWEEP_FUSED;
     const FrameState *st = P.st;
-    if (EMIT && st->error) return;
+    if ((EMIT && st->error) || (st->error & ERR_REPLAN)) return;
     const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
     __shared__ unsigned long long s_wbase;
     // blocks walk whole 128-position tiles, so that the work-list reservation below is block uniform
@@ -785,7 +867,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(256) k_big(Params P)
 {
     const FrameState *st = P.st;
-    if (EMIT && st->error) return;
+    if ((EMIT && st->error) || (st->error & ERR_REPLAN)) return;
     __shared__ unsigned s_warp[8];
     __shared__ unsigned long long s_run, s_wbase;
     const unsigned n_big = st->n_big;
@@ -1332,6 +1414,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // +inf / NaN -- impossible, lane 0 would hold it first.)  Returns the winning edge; depth / pen come from its lane.
 __device__ __forceinline__ int fold_min_overlap(bool active, double depth, int group_base)
 {
+#ifndef COOP_SHUFFLE_FOLD
+    // Depths that matter are >= 0 (no axis separates: pMin <= sMax) or NaN, so after folding -0 into +0 the bit
+    // pattern orders like the value and the minimum is two 32-bit warp reductions (REDUX) over the group's 8 lanes.
+    // (When some axis separates the depths may be negative and the winner garbage: it is never used.)
+    const unsigned gmask = 0xffu << group_base;
+    const bool is_nan = depth != depth;
+    const double key = (active && !is_nan) ? fadd(depth, 0.0) : __longlong_as_double(0x7ff0000000000000ll);
+    const unsigned hi = (unsigned)__double2hiint(key), lo = (unsigned)__double2loint(key);
+    const unsigned hmin = __reduce_min_sync(gmask, hi);
+    const unsigned lmin = __reduce_min_sync(gmask, hi == hmin ? lo : 0xffffffffu);
+    const unsigned holders = (__ballot_sync(0xffffffffu, active && hi == hmin && lo == lmin) >> group_base) & 0xffu;
+#else
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const bool is_nan = depth != depth;
     const double key = (active && !is_nan) ? depth : inf;
@@ -1342,19 +1436,22 @@ __device__ __forceinline__ int fold_min_overlap(bool active, double depth, int g
         kmin = (k2 < kmin) ? k2 : kmin;
     }
     const unsigned holders = (__ballot_sync(0xffffffffu, active && key == kmin) >> group_base) & 0xffu;
+#endif
     const unsigned nans = (__ballot_sync(0xffffffffu, active && is_nan) >> group_base) & 0xffu;
     if ((nans & 1u) || holders == 0u) return 0;
     return __ffs((int)holders) - 1;
 }
 
-struct __align__(16) CoopRes { double depth; int edge_pen; int flags; };   // per (pair, direction): minOverlap's winner
-enum { CO_F_SEP = 1, CO_F_FALLBACK = 2 };
+struct __align__(16) CoopRes { double depth; int edge_pen; int sep; };   // per (pair, direction): minOverlap's winner
 
 // SORTED: the tile's 32 pairs come from the cell-ordered work list (w_i / w_j / w_a), so neighbouring tiles touch
 // the same hulls whatever the slot numbering; results go to the pair's place in the reference order, off[r(i)] + a,
 // and pair_i / pair_j are written here.  Otherwise the tile is 32 consecutive pairs of the reference order.
+#ifndef COOP_MIN_BLOCKS
+#define COOP_MIN_BLOCKS 6
+#endif
 template <bool SORTED>
-__global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
+__global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_coop(Params P)
 {
     __shared__ int4 s_meta[CO_WARPS][32];                 // per pair of the tile: offset / count of hull A, of hull B
     __shared__ ulonglong2 s_ext[CO_WARPS][32];            // packed extents of both hulls
@@ -1377,11 +1474,9 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
     auto stage = [&](int t) {
         const int src = 2 * t + half;
         const int4 m = s_meta[warp][src];
-        const int k = idx16 & 7;
-        if (m.y >= 1 && m.w >= 1 && m.y <= MAX_STAGED_VERTS && m.w <= MAX_STAGED_VERTS) {
-            if (k < m.y) cp_async16(&s_hull[warp][t & 1][half][idx16], src_arr + m.x + k);
-            if (k < m.w) cp_async16(&s_hull[warp][t & 1][half][16 + idx16], src_arr + m.z + k);
-        }
+        const int k = idx16 & 7;         // (pairs left to the per-thread pass carry vertex counts 0: nothing is copied)
+        if (k < m.y) cp_async16(&s_hull[warp][t & 1][half][idx16], src_arr + (unsigned)(m.x + k));
+        if (k < m.w) cp_async16(&s_hull[warp][t & 1][half][16 + idx16], src_arr + (unsigned)(m.z + k));
         cp_async_commit();
     };
 
@@ -1392,6 +1487,7 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
         int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
         long long my_dst = base + lane;
         unsigned long long my_xa = 0, my_xb = 0;
+        bool fallback = false;
         if (base + lane < n_pairs) {
             if (SORTED) {
                 my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane];
@@ -1402,9 +1498,10 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
             my_xa = (unsigned long long)ha.z | ((unsigned long long)ha.w << 32);
             my_xb = (unsigned long long)hb.z | ((unsigned long long)hb.w << 32);
             const bool own = my_i >= P.own_lo && my_i < P.own_hi && my_j >= P.own_lo && my_j < P.own_hi;
-            if (!own || my_na > MAX_STAGED_VERTS || my_nb > MAX_STAGED_VERTS) my_na = MAX_STAGED_VERTS + 1;
+            fallback = !own || my_na < 1 || my_nb < 1 || my_na > MAX_STAGED_VERTS || my_nb > MAX_STAGED_VERTS;
         }
-        s_meta[warp][lane] = make_int4(my_oa, my_na, my_ob, my_nb);
+        // phase 1 sees vertex counts 0 for pairs it must not touch (no pair / per-thread pass)
+        s_meta[warp][lane] = make_int4(my_oa, fallback ? 0 : my_na, my_ob, fallback ? 0 : my_nb);
         s_ext[warp][lane] = make_ulonglong2(my_xa, my_xb);
         __syncwarp();
         // ---- phase 1: SAT, two pairs per step, operands staged one step ahead
@@ -1417,13 +1514,11 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
             const int src = 2 * t + half;
             const int4 m = s_meta[warp][src];
             const int na = m.y, nb = m.w;
-            const bool valid = na >= 1;
-            const bool coop = valid && nb >= 1 && na <= MAX_STAGED_VERTS && nb <= MAX_STAGED_VERTS;
             // my direction: E = penetrated hull (its edge normals are the axes), Pn = the other hull
             const int e_n = dir ? nb : na, pn_n = dir ? na : nb;
             const double2 *const rec = s_hull[warp][t & 1][half];
             const double2 *const ev = rec + (dir ? 16 : 0), *const pvs = rec + (dir ? 0 : 16);
-            const bool active = coop && e < e_n;
+            const bool active = e < e_n;
             bool sep = false;
             double depth = 0.0;
             int pen = 0;
@@ -1465,7 +1560,7 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
                 CoopRes r;
                 r.depth = best;
                 r.edge_pen = edge | (bpen << 8);
-                r.flags = (((sep_mask >> (16 * half)) & 0xffffu) ? CO_F_SEP : 0) | ((valid && !coop) ? CO_F_FALLBACK : 0);
+                r.sep = (int)((sep_mask >> (16 * half)) & 0xffffu);
                 s_res[warp][src][dir] = r;
             }
             __syncwarp();       // buffer t & 1 is free again before stage(t + 2) refills it
@@ -1476,8 +1571,8 @@ __global__ void __launch_bounds__(CO_WARPS * 32, 6) k_manifolds_coop(Params P)
             if (SORTED) { P.pair_i[p] = my_i; P.pair_j[p] = my_j; }
             const CoopRes r0 = s_res[warp][lane][0], r1 = s_res[warp][lane][1];
             unsigned cnt = 0;
-            if (r0.flags & CO_F_FALLBACK) cnt = CCNT_FALLBACK;          // finished by k_manifolds<.., FLAGGED_ONLY>
-            else if (!(r0.flags & CO_F_SEP)) {
+            if (fallback) cnt = CCNT_FALLBACK;                          // finished by k_manifolds<.., FLAGGED_ONLY>
+            else if (!r0.sep) {
                 const bool same = r0.depth < r1.depth;                  // depth_ab < depth_ba ? Same : Flip (ties: Flip)
                 const int ep = same ? r0.edge_pen : r1.edge_pen;
                 cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
@@ -1760,7 +1855,7 @@ static NcclApi &nccl_api()
 }
 
 struct FrameKey {   // everything a captured frame graph bakes in
-    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote, sorted; int64_t geometry, n_prev; unsigned cell_limit;
+    int64_t n; const double *in[7]; double dt, baumgarte, slop, cell; bool world, profiling, warm, p2p, remote, sorted; int64_t geometry, n_prev; unsigned cell_limit, big_limit;
 };
 
 struct WorldStep;   // device-resident world (world_step.cuh)
@@ -1790,6 +1885,9 @@ struct shapes_ctx {
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
+    bool use_plan_ahead = true;   // single rank: grid planned from the previous frame's bounds, K0 keys and bins (SHAPES_B200_NO_PLAN_AHEAD=1: plan inside the frame)
+    bool plan_valid = false;      // the bounds in FrameState describe the last completed frame of the current geometry
+    int64_t big_seen = 0;         // big-list length of the last frame that ran on an exactly seeded plan
     bool use_sorted = true;       // general polygons: single-pass sweep + SAT work list in cell order (SHAPES_B200_NO_SORTED=1: two-pass sweep, SAT in the reference's pair order)
     uint4 *d_hh = nullptr;        // static hull headers (Params::hh)
     bool has_circles = false;
@@ -1948,6 +2046,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.wn, V));
     TRY_CREATE(dev_alloc(c, &P.circ, N));
     c->use_sorted = std::getenv("SHAPES_B200_NO_SORTED") == nullptr;
+    c->use_plan_ahead = std::getenv("SHAPES_B200_NO_PLAN_AHEAD") == nullptr;
     TRY_CREATE(dev_alloc(c, &c->d_hh, N));
     P.hh = c->d_hh;
     TRY_CREATE(dev_alloc(c, &P.w_i, c->use_sorted ? max_pairs : 1));
@@ -2060,6 +2159,10 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     P.cell_size = c->user_cell > 0.0 ? c->user_cell : c->auto_cell;
     // general polygon worlds on one rank: hull records and the SAT work list in cell order
     P.sorted_mode = (c->use_sorted && c->use_coop && c->world == 1 && !c->has_circles && c->max_hull_verts > 4) ? 1 : 0;
+    P.plan_ahead = (c->use_plan_ahead && c->world == 1) ? 1 : 0;
+    const bool seed_plan = P.plan_ahead && !c->plan_valid;
+    // a freshly seeded plan is exact: whatever is on the big list then belongs there
+    P.big_limit = seed_plan ? 0xffffffffu : (unsigned)std::max<int64_t>(std::max<int64_t>(1024, n_slots / 256), 2 * c->big_seen + 64);
     // the previous frame's key columns become the join's "that" side; this frame writes the other set
     if (c->have_frame) {
         std::swap(P.key_i, c->alt_key[0]); std::swap(P.key_j, c->alt_key[1]);
@@ -2106,10 +2209,13 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         int stage = 0;
     #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
         STAGE_MARK(); // 0: transform
-        k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
+        if (P.plan_ahead) {
+            k_begin_frame<<<1, 1, 0, s>>>(P); ++c->launches;
+            CU_TRY(c, cudaMemsetAsync(P.cell_count, 0, sizeof(uint32_t) * ((size_t)P.cell_limit + 2), s));
+        } else { k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches; }
         if (N > 0) {
             CU_TRY(c, cudaMemsetAsync(P.cnt, 0, sizeof(unsigned long long) * (size_t)std::max(n_query, 1), s));
-            k_transform_aabb<<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
+            k_transform_aabb<false><<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches;
         }
         STAGE_MARK(); // 1: allgather
         if (N > 0 && c->world > 1 && p2p) {
@@ -2126,8 +2232,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             NCCL_TRY(c, nccl_api().AllGather(P.rank_bounds + 4 * c->rank, P.rank_bounds, 4, ncclUint64, c->comm, s));
             NCCL_TRY(c, nccl_api().GroupEnd());
         }
-        STAGE_MARK(); // 2: grid keys
-        if (N > 0) {
+        STAGE_MARK(); // 2: grid keys (plan-ahead frames: done by K0)
+        if (N > 0 && !P.plan_ahead) {
             k_plan_grid<<<1, 1, 0, s>>>(P, c->world); ++c->launches;
             k_clear_cells<<<sms * 4, 256, 0, s>>>(P); ++c->launches;
             if (p2p) {
@@ -2209,8 +2315,14 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     key.dt = dt; key.baumgarte = baumgarte; key.slop = slop; key.cell = P.cell_size;
     key.world = want_world; key.profiling = c->profiling; key.geometry = c->geometry_version;
     key.warm = warm; key.n_prev = 0; key.p2p = p2p; key.cell_limit = P.cell_limit; key.remote = P.remote_inputs != 0; key.sorted = P.sorted_mode != 0;
+    key.big_limit = P.big_limit;
     CU_TRY(c, cudaEventRecord(c->ev0, s));
     if (warm) { k_set_i64<<<1, 1, 0, s>>>(c->d_n_prev, n_prev_now); ++c->launches; }   // outside the graph: varies per frame
+    if (seed_plan) {
+        // first frame of a geometry (or after a failed frame): a bounds-only pass seeds the grid plan
+        k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
+        if (N > 0) { k_transform_aabb<true><<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, 0, N); ++c->launches; }
+    }
     const int64_t launches_before = c->launches;
     // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
     if (!c->use_graph || c->profiling || c->world > 1) { // per-stage events cannot be timed from inside a graph
@@ -2236,6 +2348,22 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     CU_TRY(c, cudaEventRecord(c->ev1, s));
     CU_TRY(c, cudaStreamSynchronize(s));
     const FrameState &st = *c->h_state;
+    if (st.error & ERR_REPLAN) {
+        // the plan was stale (the world moved further than the grid's margin since the last frame): seed it from
+        // this frame's positions and run the frame again -- nothing of the aborted attempt is visible
+        c->plan_valid = false;
+        if (c->have_frame) {   // undo the key-column swap of this attempt
+            std::swap(P.key_i, c->alt_key[0]); std::swap(P.key_j, c->alt_key[1]);
+            std::swap(P.feat_a, c->alt_key[2]); std::swap(P.feat_b, c->alt_key[3]);
+            c->parity ^= 1;
+        }
+        --c->frame_no;
+        const bool had_cache = warm;
+        c->cache_valid = had_cache;
+        return run_frame(c, n_slots, in, dt, baumgarte, slop, want_world, out, own_slots_only);
+    }
+    c->plan_valid = P.plan_ahead && st.error == 0;
+    if (seed_plan) c->big_seen = st.n_big;
     c->last_pairs = st.n_pairs;
     c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
     c->have_frame = (st.error == 0);
@@ -2419,6 +2547,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     c->P.radius = any_circle ? c->d_radius : nullptr;
     c->hulls_set = true;
     c->have_frame = false;
+    c->plan_valid = false;
     ++c->geometry_version;
     return SHAPES_OK;
 }
@@ -2427,6 +2556,7 @@ int shapes_set_cell_size(shapes_ctx *c, double cell_size)
 {
     if (!c) return SHAPES_E_ARG;
     c->user_cell = (cell_size > 0.0 && std::isfinite(cell_size)) ? cell_size : 0.0;
+    c->plan_valid = false;
     return SHAPES_OK;
 }
 

@@ -655,7 +655,7 @@ int shapes_world_upload(shapes_ctx *c, int64_t n_slots, const double *vel_x, con
     CU_TRY(c, cudaStreamSynchronize(s));
     w->uploaded = true; w->n = n_slots; w->steps = 0;
     // a new world state starts with an empty EngineCache (initEngine, Engine/Main.hs:43-46)
-    c->have_frame = false; c->cache_valid = false;
+    c->have_frame = false; c->cache_valid = false; c->plan_valid = false;
     return SHAPES_OK;
 }
 

@@ -346,3 +346,46 @@ def test_compact_wire_format_expands_to_the_full_rows(oracle):
             full = eng.frame(cos_sin=(c, s))
             assert full.d2h_bytes > fr.d2h_bytes + 12 * 8 * fr.n_contacts
             assert_frames_match(full.cols, want)
+
+
+# ---- plan-ahead grid (the grid of a frame is planned from the previous frame's bounds) -----------------------
+
+@pytest.mark.parametrize("kind", ["polygons", "pile"])
+def test_plan_ahead_follows_a_moving_world_and_survives_teleports(oracle, kind):
+    """Frames on one ctx: small drifts stay inside the planned grid's margin, a jump of 5000 units makes the plan
+    stale (ERR_REPLAN: seeded again inside the same call), a jump of part of the world lands those shapes on the
+    exact big-shape path.  Every frame bit-identical to the oracle, warm-start join included."""
+    from shapes_b200.engine import Engine
+    w = scenes.random_polygons(20_000, density=1.5, config=46) if kind == "polygons" else scenes.box_pile(150, 100)
+    want = ("pairs", "contacts", "constraints", "warm")
+    rng = np.random.default_rng(7)
+    with Engine(w) as eng:
+        prev = None
+        for step, move in enumerate(["none", "drift", "drift", "teleport", "drift", "scatter_few", "drift"]):
+            if move == "drift":
+                w.pos_x += rng.uniform(-0.05, 0.05, w.n_slots); w.pos_y += rng.uniform(-0.05, 0.05, w.n_slots)
+            elif move == "teleport":
+                w.pos_x += 5000.0; w.pos_y -= 3000.0
+            elif move == "scatter_few":
+                far = rng.choice(w.n_slots, 40, replace=False)
+                w.pos_x[far] += rng.uniform(50.0, 400.0, 40)
+            c, s = oracle.cos_sin(w.rot)
+            ref = oracle.frame(w, c, s, broadphase="sweep")
+            if prev is not None:
+                eng.set_lagrangian_cache(prev[1], prev[2])
+            fr = eng.frame_grow(cos_sin=(c, s), want=want)
+            assert_frames_match(fr.cols, ref)
+            cur = {k: np.array(fr[k]) for k in ("key_i", "key_j", "feat_a", "feat_b")}
+            if prev is not None:
+                o_np, o_f, o_hit = oracle.warm_join(cur, prev[0], prev[1], prev[2])
+                assert np.array_equal(fr["warm_hit"], o_hit) and np.array_equal(fr["warm_np"], o_np)
+            if move == "scatter_few":
+                assert fr.n_big >= 30
+            prev = (cur, 0.5 + (cur["key_i"] % 97).astype(np.float64), 1.0 + (cur["feat_a"] % 5).astype(np.float64))
+
+
+def test_plan_inside_the_frame_still_matches(oracle, monkeypatch):
+    """SHAPES_B200_NO_PLAN_AHEAD=1: bounds -> plan -> keys inside the frame (the r1 path, what multi-rank ctxs run)."""
+    monkeypatch.setenv("SHAPES_B200_NO_PLAN_AHEAD", "1")
+    check_world(oracle, scenes.random_polygons(10_000), broadphase="sweep")
+    check_world(oracle, scenes.box_pile(120, 90))
