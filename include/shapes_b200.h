@@ -228,6 +228,37 @@ int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
 int  shapes_ipc_export(shapes_ctx *, void *out_blob /* SHAPES_IPC_BYTES */);
 int  shapes_ipc_import(shapes_ctx *, const void *all_blobs /* world_size x SHAPES_IPC_BYTES */);
 
+/* ---- one process, several GPUs ----------------------------------------------------------------
+ *
+ * The reference's host is one single-threaded ST computation (Engine/Main.hs:38,71-86): it cannot run one process
+ * per GPU.  shapes_create_multi builds one ctx per listed GPU of an NVSwitch box inside THIS process (peer access
+ * instead of CUDA IPC, no NCCL), and shapes_multi_frame is shapes_frame over all of them from one host thread:
+ * every GPU uploads only its slot range of the body columns over its own PCIe link, the sweep / SAT work is split by
+ * grid rows balanced on the pair counts of the previous frame, every pair is delivered to the GPU that owns its
+ * larger key, and each GPU's slice of the result is copied straight to its global row offset in `out` -- which
+ * therefore holds the whole frame in the reference's descending order, exactly what a single-GPU shapes_frame
+ * returns.  Array pointers in `out` must hold n_gpus x max_pairs_per_gpu pairs / n_gpus x max_contacts_per_gpu
+ * rows.  The aabb / world debug outputs are not gathered (use shapes_multi_rank + shapes_fetch). */
+typedef struct shapes_multi shapes_multi;
+int  shapes_create_multi(shapes_multi **out, int n_gpus, const int *device_ids /* NULL: 0..n_gpus-1 */,
+                         int64_t max_shapes, int64_t max_verts,
+                         int64_t max_pairs_per_gpu, int64_t max_contacts_per_gpu);
+void shapes_multi_destroy(shapes_multi *);
+const char *shapes_multi_last_error(const shapes_multi *);   /* NULL: last create error */
+int  shapes_multi_set_shapes(shapes_multi *, int64_t n_slots, const uint8_t *alive,
+                             const int32_t *vert_offset,
+                             const double *local_x, const double *local_y,
+                             const int32_t *ext_min, const int32_t *ext_max,
+                             const double *radius);
+int  shapes_multi_frame(shapes_multi *, int64_t n_slots,
+                        const double *pos_x, const double *pos_y,
+                        const double *rot, const double *cos_rot, const double *sin_rot,
+                        const double *inv_lin, const double *inv_rot,
+                        double dt, double baumgarte, double slop,
+                        shapes_frame_out *out);
+/* The ctx of one GPU (stage timing, shapes_rank_info, shapes_fetch of its slice, ...). */
+shapes_ctx *shapes_multi_rank(shapes_multi *, int rank);
+
 /* ---- device-resident world ---------------------------- */
 
 /* The rest of Physics.Engine.Main.updateWorld (Engine/Main.hs:71-86) on the GPU: the body state

@@ -113,6 +113,12 @@ SYMBOLS = {
     "shapes_set_lagrangian_cache_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "shapes_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "shapes_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "shapes_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "shapes_multi_destroy": (None, [C.c_void_p]),
+    "shapes_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "shapes_multi_set_shapes": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+    "shapes_multi_frame": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
+    "shapes_multi_rank": (C.c_void_p, [C.c_void_p, C.c_int]),
     "shapes_rank_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "shapes_world_upload": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 12),

@@ -33,6 +33,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -133,6 +134,8 @@ __device__ __forceinline__ double dec_ordered(unsigned long long u)
 }
 
 constexpr int SHAPES_MAX_RANKS = 16;
+constexpr int ROW_BINS = 4096;       // rows mode: resolution of the per-row work histogram that balances the row cuts
+enum { RW_PHASE_SEED = 0, RW_PHASE_KEYS = 1, RW_PHASE_RESULTS = 2, RW_PHASE_COUNTS = 3, RW_PHASES = 4 };
 constexpr int ERR_PAIR_CAP = 1;
 constexpr int ERR_PEER_TIMEOUT = 4;
 constexpr int ERR_CONTACT_CAP = 2;
@@ -152,6 +155,13 @@ struct FrameState {
     long long n_contacts;
     unsigned long long work_cursor; // sorted mode: next free entry of the cell-ordered SAT work list
     unsigned long long n_pairs_hit; // pairs with at least one contact (statistics: the roofline accounting)
+    // rows mode (multi-rank): the frame counter lives here so that frames replay as CUDA graphs
+    unsigned long long frame_no;
+    int row_lo, row_hi;         // grid rows this rank sweeps, [lo, hi)
+    unsigned cell_lo, cell_end; // cells it keeps: rows [row_lo - 1, row_hi + 1); every other mode: [0, n_cells)
+    int cut[SHAPES_MAX_RANKS + 1]; // row cuts of all ranks: rank g sweeps rows [cut[g], cut[g + 1])
+    unsigned n_kept;            // shapes in this rank's grid
+    int peer_error;             // OR of every rank's error word (exchanged at the results barrier)
 };
 
 struct Params;
@@ -244,6 +254,27 @@ struct Params {
     double *warm_np, *warm_f;
     uint8_t *warm_hit;
     FrameState *st;
+    // ---- rows mode (multi-rank with mapped peers): the SWEEP / SAT work is partitioned by grid rows (cuts balanced by
+    // the pair counts the rows produced in the previous frame), results are delivered to the slot-range HOME of the
+    // pair's larger key, so the global order stays "rank G-1's rows, then G-2's, ..." with no merge.
+    int work_mode;              // 0: SAT walks the pairs in reference order; 1: cell-ordered work list, results at
+                                // off[r(i)] + a; 2: rows mode -- results stay in work order on the sweeping rank
+    uint32_t *sat_ccnt;         // where the SAT stage writes its contact counts / manifolds
+    ManRec *sat_man;
+    uint32_t *pair_src;         // rows mode, per home pair: sweeping rank << 28 | index into that rank's work-order arrays
+    uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
+    uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
+    uint32_t *rw_cnt[SHAPES_MAX_RANKS];      // every rank's per-slot partner counts (home arrays, pushed by the sweeping rank)
+    uint32_t *rw_wstart[SHAPES_MAX_RANKS];   // ... and sweeping rank << 28 | first work-list index of the slot's partners
+    const uint32_t *rw_wj[SHAPES_MAX_RANKS]; // every rank's work-order results (read by the homes after the results barrier)
+    const uint32_t *rw_ccnt[SHAPES_MAX_RANKS];
+    const ManRec *rw_man[SHAPES_MAX_RANKS];
+    Xf *rw_xf[SHAPES_MAX_RANKS];             // every rank's packed transforms (its own slot range is valid)
+    uint32_t *rw_weights[SHAPES_MAX_RANKS];  // every rank's [G][ROW_BINS] inbox of row weights (this frame's parity)
+    const uint32_t *rw_weights_prev;         // my inbox of the previous frame
+    const unsigned long long *rw_bounds_prev;// bounds every rank pushed in the previous frame [4 G]
+    long long *rw_counts[SHAPES_MAX_RANKS];  // every rank's [2 G] inbox of (pairs, contacts)
+    int *rw_err[SHAPES_MAX_RANKS];           // every rank's [G] inbox of error words
 };
 
 // Body column k (0 pos_x, 1 pos_y, 2 rot, 3 cos, 4 sin, 5 inv_lin, 6 inv_rot) of ANY slot.  When every
@@ -263,6 +294,7 @@ __device__ __forceinline__ bool slot_static(const Params &P, int s)
 __device__ __forceinline__ Xf slot_xf(const Params &P, int s)
 {
     if (s >= P.own_lo && s < P.own_hi) return P.xf[s];
+    if (P.work_mode == 2) return P.rw_xf[s / P.chunk][s];
     double c, sn;
     if (P.cos_rot) { c = in_col(P, 3, P.cos_rot, s); sn = in_col(P, 4, P.sin_rot, s); }
     else sincos(in_col(P, 2, P.rot, s), &sn, &c);
@@ -281,6 +313,8 @@ __device__ __forceinline__ Box box_of(const Params &P, int s)
     if (P.n_peers > 0) return P.peer_box[s / P.chunk][s];
     return P.box[s];
 }
+
+constexpr uint32_t KEY_STATIC_BIT = 0x80000000u;   // rows mode: pushed cell keys carry isStatic in bit 31
 
 // ---------------------------------------------------------------------------------------------
 // K0: moveShapes + toAabb
@@ -303,6 +337,8 @@ __global__ void k_reset_state(FrameState *st)
     st->n_contacts = 0;
     st->work_cursor = 0ull;
     st->n_pairs_hit = 0ull;
+    st->peer_error = 0;
+    st->cell_lo = 0u; st->cell_end = 1u; st->row_lo = 0; st->row_hi = 1;
 }
 
 // Choose origin, cell edge and grid extent for finite world bounds [bmin, bmax] (ordered-uint encodings in st).
@@ -313,6 +349,7 @@ __device__ void plan_grid_from_bounds(FrameState *st, double cell_size, unsigned
 {
     if (st->bmax_x == 0ull) { // no finite shape
         st->ox = st->oy = 0.0; st->h = cell_size; st->W = st->H = 1; st->n_cells = 1;
+        st->cell_lo = 0u; st->cell_end = 1u; st->row_lo = 0; st->row_hi = 1;
         return;
     }
     const double bx = dec_ordered(st->bmin_x), by = dec_ordered(st->bmin_y);
@@ -332,6 +369,8 @@ __device__ void plan_grid_from_bounds(FrameState *st, double cell_size, unsigned
     st->ox = isfinite(ox) ? ox : bx; st->oy = isfinite(oy) ? oy : by; st->h = h;
     st->W = (int)wx; st->H = (int)wy;
     st->n_cells = (unsigned)(st->W * st->H);
+    st->cell_lo = 0u; st->cell_end = st->n_cells;
+    st->row_lo = 0; st->row_hi = st->H;
 }
 
 // Plan-ahead frames (single rank): first kernel of the frame, one thread.  The bounds K0 reduced in the PREVIOUS
@@ -351,6 +390,7 @@ __global__ void k_begin_frame(Params P)
     st->n_contacts = 0;
     st->work_cursor = 0ull;
     st->n_pairs_hit = 0ull;
+    st->peer_error = 0;
 }
 
 __device__ __forceinline__ double warp_min(double v)
@@ -660,7 +700,8 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
         if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
         P.sbox[p] = box_of(P, s);
-        P.smeta[p] = (uint32_t)s | ((uint32_t)slot_static(P, s) << 31);
+        const bool st_flag = P.work_mode == 2 ? (P.gkeys[s] & KEY_STATIC_BIT) != 0u : slot_static(P, s);
+        P.smeta[p] = (uint32_t)s | ((uint32_t)st_flag << 31);
         P.keys_sorted[p] = key;
     }
 }
@@ -724,8 +765,8 @@ __device__ __forceinline__ unsigned long long sweep_test_all(const Params &P, co
     for (unsigned b = 0; b < n_big; ++b, ++cand) {
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
-        if (si && slot_static(P, j)) continue;
-        const Box bj = box_of(P, j);
+        if (si && (P.work_mode == 2 ? (P.gkeys[j] & KEY_STATIC_BIT) != 0u : slot_static(P, j))) continue;
+        const Box bj = P.work_mode == 2 ? P.sbox[P.cell_begin[st->cell_end] + b] : box_of(P, j);
         if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
     }
     return (cand > 63u) ? (1ull << 63) : mask;
@@ -779,7 +820,8 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
     constexpr bool EMIT = MODE == SWEEP_EMIT, FUSED = MODE == SWEEP_FUSED;
     const FrameState *st = P.st;
     if ((EMIT && st->error) || (st->error & ERR_REPLAN)) return;
-    const unsigned n_sorted = P.cell_begin[st->n_cells]; // shapes in this rank's grid
+    const unsigned n_sorted = P.cell_begin[st->cell_end]; // shapes in this rank's grid
+    const bool rows = P.work_mode == 2;
     __shared__ unsigned long long s_wbase;
     // blocks walk whole 128-position tiles, so that the work-list reservation below is block uniform
     for (unsigned tile = blockIdx.x * 128u; tile < n_sorted; tile += gridDim.x * 128u) {
@@ -787,24 +829,30 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
         uint32_t meta = 0;
         int i = -1;
         bool query = false;
+        int cx = 0, cy = 0;
         if (p < n_sorted) {
             meta = P.smeta[p];
             i = (int)(meta & 0x7fffffffu);
-            query = i >= P.own_lo && i < P.own_hi;
+            if (rows) {   // rows mode: a query belongs to the rank that sweeps its grid row
+                const uint32_t key = P.keys_sorted[p];
+                cy = (int)(key / (uint32_t)st->W); cx = (int)(key % (uint32_t)st->W);
+                query = cy >= st->row_lo && cy < st->row_hi;
+            } else query = i >= P.own_lo && i < P.own_hi;
         }
         const int r = P.own_hi - 1 - i;
         const bool si = (meta >> 31) != 0;
         Box bi{ 0.0, 0.0, 0.0, 0.0 };
-        int cx = 0, cy = 0;
         if (query) {
             bi = P.sbox[p];
-            const uint32_t key = P.keys_sorted[p];
-            cy = (int)(key / (uint32_t)st->W); cx = (int)(key % (uint32_t)st->W);
+            if (!rows) {
+                const uint32_t key = P.keys_sorted[p];
+                cy = (int)(key / (uint32_t)st->W); cx = (int)(key % (uint32_t)st->W);
+            }
         }
         unsigned long long count = 0, mask = 0;
         if (query && !EMIT) {
             mask = sweep_test_all(P, st, i, si, bi, cx, cy, [&](int) { ++count; });
-            P.cnt[r] = count;
+            if (!rows) P.cnt[r] = count;
             if (!FUSED) P.hitmask[p] = mask;
         }
         if (MODE == SWEEP_COUNT) continue;
@@ -818,6 +866,16 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             __syncthreads();
             base = s_wbase + before;
             room = s_wbase + total <= (unsigned long long)P.max_pairs;   // else k_finish_pairs raises the capacity error
+            if (rows) {
+                if (!room && threadIdx.x == 0) atomicOr(&P.st->error, ERR_PAIR_CAP);   // this rank's work list is full
+                if (query) {
+                    // the slot-range HOME of i learns how many partners i has and where this rank keeps them
+                    const int home = i / P.chunk;
+                    P.rw_cnt[home][i] = (uint32_t)count;
+                    P.rw_wstart[home][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)base;
+                    if (count) atomicAdd(&P.roww[(unsigned)(((unsigned long long)cy * ROW_BINS) / (unsigned)st->H)], (uint32_t)count);
+                }
+            }
         } else if (query) {
             base = P.off[r];
             mask = P.hitmask[p];
@@ -875,22 +933,33 @@ __global__ void __launch_bounds__(256) k_big(Params P)
     for (unsigned b = blockIdx.x; b < n_big; b += gridDim.x) {
         const int i = (int)P.big_idx[b];
         if (i < P.own_lo || i >= P.own_hi) continue;
+        const bool rows = P.work_mode == 2;       // rows mode: big queries stay with their slot-range home
+        const bool listed = P.sorted_mode || rows; // results go to the SAT work list
         const Box bi = P.box[i];
-        const bool si = slot_static(P, i);
+        const bool si = rows ? (P.gkeys[i] & KEY_STATIC_BIT) != 0u : slot_static(P, i);
         const int r = P.own_hi - 1 - i;
-        const unsigned long long base = EMIT ? P.off[r] : 0ull;
+        const unsigned long long base = (EMIT && !rows) ? P.off[r] : 0ull;
         if (threadIdx.x == 0) {
             s_run = 0;
-            // sorted mode: this query's run of the SAT work list (see k_sweep)
-            if (EMIT && P.sorted_mode) { const unsigned long long n = P.cnt[r]; s_wbase = n ? atomicAdd(&P.st->work_cursor, n) : 0ull; }
+            // this query's run of the SAT work list (see k_sweep)
+            if (EMIT && listed) {
+                const unsigned long long n = rows ? (unsigned long long)P.rw_cnt[P.my_rank][i] : P.cnt[r];
+                s_wbase = n ? atomicAdd(&P.st->work_cursor, n) : 0ull;
+                if (rows) {
+                    P.rw_wstart[P.my_rank][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)s_wbase;
+                    if (s_wbase + n > (unsigned long long)P.max_pairs) atomicOr(&P.st->error, ERR_PAIR_CAP);
+                }
+            }
         }
         __syncthreads();
-        const unsigned long long wbase = (EMIT && P.sorted_mode) ? s_wbase : 0ull;
-        const bool room = wbase + (P.sorted_mode ? P.cnt[r] : 0ull) <= (unsigned long long)P.max_pairs;
+        const unsigned long long wbase = (EMIT && listed) ? s_wbase : 0ull;
+        const unsigned long long n_mine = !listed ? 0ull : rows ? (unsigned long long)P.rw_cnt[P.my_rank][i] : P.cnt[r];
+        const bool room = wbase + n_mine <= (unsigned long long)P.max_pairs;
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
-            if (j >= 0 && P.alive[j] && !(si && slot_static(P, j))) pred = aabb_check(bi, box_of(P, j));
+            if (j >= 0 && P.alive[j] && !(si && (rows ? (P.gkeys[j] & KEY_STATIC_BIT) != 0u : slot_static(P, j))))
+                pred = aabb_check(bi, box_of(P, j));
             const unsigned bal = __ballot_sync(0xffffffffu, pred);
             if (lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
@@ -899,7 +968,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             const unsigned long long run = s_run;
             if (EMIT && pred) {
                 const unsigned long long pos = base + run + before + __popc(bal & ((1u << lane) - 1u));
-                if (P.sorted_mode) {   // work-list entry; the SAT stage writes pair_i / pair_j at off[r] + a
+                if (listed) {   // work-list entry; single rank: the SAT stage writes pair_i / pair_j at off[r] + a
                     const unsigned long long a = pos - base, w = wbase + a;
                     if (room) { P.w_i[w] = (uint32_t)i; P.w_j[w] = (uint32_t)j; P.w_a[w] = (uint32_t)a; }
                 } else {
@@ -911,7 +980,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             if (threadIdx.x == 0) s_run = run + total;
             __syncthreads();
         }
-        if (!EMIT && threadIdx.x == 0) P.cnt[r] = s_run;
+        if (!EMIT && threadIdx.x == 0) { if (rows) P.rw_cnt[P.my_rank][i] = (uint32_t)s_run; else P.cnt[r] = s_run; }
         __syncthreads();
     }
 }
@@ -972,7 +1041,8 @@ struct ContactKernel {
     }
     __device__ __forceinline__ void stage(HullAcc &h) const
     {
-        h.owned = h.slot >= P.own_lo && h.slot < P.own_hi;
+        // rows mode: the hulls this rank keeps were materialised by k_rw_hulls (a big query's partners may not be)
+        h.owned = P.work_mode == 2 ? P.mat_stamp[h.slot] == (uint32_t)P.st->frame_no : (h.slot >= P.own_lo && h.slot < P.own_hi);
         if (h.n <= MAXV) {
             if (h.owned) {
                 if (MAXV > 4) {
@@ -1085,7 +1155,9 @@ struct ContactKernel {
     // world centre of a circle slot: K0's value for owned slots, else setCircleTransform here
     __device__ __forceinline__ V2 circle_center(int slot) const
     {
-        if (slot >= P.own_lo && slot < P.own_hi) { const double2 c = P.circ[slot]; return V2{ c.x, c.y }; }
+        if (P.work_mode == 2 ? P.mat_stamp[slot] == (uint32_t)P.st->frame_no : (slot >= P.own_lo && slot < P.own_hi)) {
+            const double2 c = P.circ[slot]; return V2{ c.x, c.y };
+        }
         const Xf x = slot_xf(P, slot);
         return afmul(to_transform(x.px, x.py, x.c, x.s), V2{ 0.0, 0.0 });
     }
@@ -1270,7 +1342,7 @@ __device__ __forceinline__ unsigned emit_manifold(const Params &P, long long p, 
             rec.c0x = c0.x; rec.c0y = c0.y; rec.c1x = c1.x; rec.c1y = c1.y;
             rec.bits = (unsigned long long)(unsigned)edge | ((unsigned long long)(unsigned)p0 << 20) |
                        ((unsigned long long)(unsigned)p1 << 40) | ((unsigned long long)(same ? 0 : 1) << 60);
-            P.man[p] = rec;
+            P.sat_man[p] = rec;
         }
     }
     return cnt;
@@ -1320,14 +1392,15 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
 
     const FrameState *st = P.st;
     if (st->error) return;
-    const long long n_pairs = st->n_pairs;
+    const bool rows = P.work_mode == 2;   // rows mode: p walks this rank's work list, results stay in work order
+    const long long n_pairs = rows ? (long long)st->work_cursor : st->n_pairs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     ContactKernel<MAXV> K{ P, s_verts[warp], lane };
 
     for (long long p = (long long)blockIdx.x * CT_THREADS + threadIdx.x; p < n_pairs;
          p += (long long)gridDim.x * CT_THREADS) {
-        if (FLAGGED_ONLY && P.ccnt[p] != CCNT_FALLBACK) continue;   // second pass after k_manifolds_coop
-        const int i = P.pair_i[p], j = P.pair_j[p];
+        if (FLAGGED_ONLY && P.sat_ccnt[p] != CCNT_FALLBACK) continue;   // second pass after k_manifolds_coop
+        const int i = rows ? (int)P.w_i[p] : P.pair_i[p], j = rows ? (int)P.w_j[p] : P.pair_j[p];
         HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
         A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
         B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
@@ -1357,13 +1430,13 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
                     rec.ref_d = depth;                    // explicit depth (bit 61): not derived from a reference edge
                     rec.c0x = center.x; rec.c0y = center.y; rec.c1x = 0.0; rec.c1y = 0.0;
                     rec.bits = ((unsigned long long)(unsigned)feature << 20) | ((unsigned long long)flip << 60) | (1ull << 61);
-                    P.man[p] = rec;
+                    P.sat_man[p] = rec;
                 }
-                P.ccnt[p] = hit ? 1u : 0u;
+                P.sat_ccnt[p] = hit ? 1u : 0u;
                 continue;
             }
         }
-        P.ccnt[p] = hull_pair_manifold<MAXV>(K, P, p, A, B);
+        P.sat_ccnt[p] = hull_pair_manifold<MAXV>(K, P, p, A, B);
     }
 }
 
@@ -1450,7 +1523,7 @@ struct __align__(16) CoopRes { double depth; int edge_pen; int sep; };   // per 
 #ifndef COOP_MIN_BLOCKS
 #define COOP_MIN_BLOCKS 6
 #endif
-template <bool SORTED>
+template <int WMODE>   // = Params::work_mode
 __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_coop(Params P)
 {
     __shared__ int4 s_meta[CO_WARPS][32];                 // per pair of the tile: offset / count of hull A, of hull B
@@ -1458,9 +1531,10 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
     __shared__ double2 s_hull[CO_WARPS][2][2][32];        // [buffer][pair of the step][A verts, A normals, B verts, B normals]
     __shared__ CoopRes s_res[CO_WARPS][32][2];            // phase 1 -> phase 2
 
+    constexpr bool SORTED = WMODE == 1, ROWS = WMODE == 2;
     const FrameState *st = P.st;
     if (st->error) return;
-    const long long n_pairs = st->n_pairs;
+    const long long n_pairs = ROWS ? (long long)st->work_cursor : st->n_pairs;
     const double2 *const WV = P.wv;
     const double2 *const WN = P.wn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1492,12 +1566,14 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
             if (SORTED) {
                 my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane];
                 my_dst = (long long)(P.off[P.own_hi - 1 - my_i] + P.w_a[base + lane]);
-            } else { my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane]; }
+            } else if (ROWS) { my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane]; }
+            else { my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane]; }
             const uint4 ha = __ldg(&P.hh[my_i]), hb = __ldg(&P.hh[my_j]);
             my_oa = (int)ha.x; my_na = (int)ha.y; my_ob = (int)hb.x; my_nb = (int)hb.y;
             my_xa = (unsigned long long)ha.z | ((unsigned long long)ha.w << 32);
             my_xb = (unsigned long long)hb.z | ((unsigned long long)hb.w << 32);
-            const bool own = my_i >= P.own_lo && my_i < P.own_hi && my_j >= P.own_lo && my_j < P.own_hi;
+            const bool own = ROWS ? (P.mat_stamp[my_i] == (uint32_t)st->frame_no && P.mat_stamp[my_j] == (uint32_t)st->frame_no)
+                                  : (my_i >= P.own_lo && my_i < P.own_hi && my_j >= P.own_lo && my_j < P.own_hi);
             fallback = !own || my_na < 1 || my_nb < 1 || my_na > MAX_STAGED_VERTS || my_nb > MAX_STAGED_VERTS;
         }
         // phase 1 sees vertex counts 0 for pairs it must not touch (no pair / per-thread pass)
@@ -1578,7 +1654,7 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
                 cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
                                     same ? my_na : my_nb, same ? my_nb : my_na, ep & 0xff, (ep >> 8) & 0xff, same);
             }
-            P.ccnt[p] = cnt;
+            P.sat_ccnt[p] = cnt;
         }
         __syncwarp();
     }
@@ -1623,7 +1699,8 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const long long q = m >> 1;
         const int k = m & 1;
         const int i = P.pair_i[q], j = P.pair_j[q];
-        const ManRec rec = P.man[q];
+        // rows mode: the manifold still lives on the rank that swept the pair -- pulled over NVLink, once per row
+        const ManRec rec = P.work_mode == 2 ? P.rw_man[P.pair_src[q] >> 28][P.pair_src[q] & 0x0fffffffu] : P.man[q];
         // i is always an owned slot; j may belong to another rank (raw input columns)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
         const bool j_own = j >= P.own_lo && j < P.own_hi;
@@ -1754,6 +1831,349 @@ __global__ void __launch_bounds__(256) k_warm_join(Params P)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rows mode: one frame on G ranks with mapped peer memory.
+//
+//   home(s)  = rank whose slot range holds s: owns s's body columns, computes its AABB / key, and ends up with the
+//              pairs whose LARGER key is s (so the global descending order is rank G-1's slice, then G-2's, ...);
+//   sweeper  = rank whose grid-row range holds the cell of the pair's larger key: finds the pair and runs SAT on it.
+//              Rows are cut so that every rank gets the same number of pairs, measured per row in the previous frame.
+//
+//   K0 (home slots): AABB + cell key, key pushed to every rank (4 B)         k_rw_transform
+//   -- barrier KEYS --
+//   keep the keys of my rows + one halo row, counting sort                   k_rw_bin, k_scan_cells_*, k_scatter_sorted
+//   world vertices / normals of the kept hulls (transform pulled, 32 B)      k_rw_hulls
+//   single-pass sweep of my rows -> local work list; per query its count and
+//   list position are pushed to home(i)                                      k_sweep<FUSED>, k_big
+//   SAT over the local work list, results in work order                      k_manifolds*
+//   -- barrier RESULTS (row weights and error words ride along) --
+//   home: scan the counts, pull (j, contact count) of every pair into place  k_rw_home_counts, scan, k_rw_gather
+//   rows: manifolds pulled from the sweeping rank by k_rows (64 B per pair with contacts)
+//   -- barrier COUNTS (every rank's pair / contact totals) --
+// The grid and the row cuts of frame f come from what frame f-1 exchanged (bounds, row weights), so no barrier
+// sits between K0 and the keys.
+// ---------------------------------------------------------------------------------------------
+
+// Barrier, arrive side: payload stores, system fence, then this frame's number into every peer's flag word.
+__global__ void k_rw_publish(Params P, int phase)
+{
+    FrameState *st = P.st;
+    const int G = P.n_peers, me = P.my_rank;
+    if (phase == RW_PHASE_SEED || phase == RW_PHASE_KEYS) {
+        // my finite bounds of this frame: frame f + 1 plans its grid from them (SEED: this frame does)
+        for (int r = threadIdx.x; r < G; r += blockDim.x) {
+            unsigned long long *dst = P.peer_bounds[r] + 4 * me;
+            dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+        }
+    } else if (phase == RW_PHASE_RESULTS) {
+        // pairs per row bin (balances the next frame's cuts) and my error word
+        for (int k = threadIdx.x; k < G * ROW_BINS; k += blockDim.x) {
+            const int r = k / ROW_BINS, b = k % ROW_BINS;
+            P.rw_weights[r][(size_t)me * ROW_BINS + b] = P.roww[b];
+        }
+        for (int r = threadIdx.x; r < G; r += blockDim.x) P.rw_err[r][me] = st->error;
+    } else {
+        for (int r = threadIdx.x; r < G; r += blockDim.x) {
+            P.rw_counts[r][2 * me] = st->n_pairs;
+            P.rw_counts[r][2 * me + 1] = (st->error & ERR_PAIR_CAP) ? 2 * st->n_pairs : st->n_contacts;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int r = threadIdx.x; r < G; r += blockDim.x)
+        *reinterpret_cast<volatile unsigned long long *>(P.peer_flags[r] + phase * SHAPES_MAX_RANKS + me) = st->frame_no;
+}
+
+// Barrier, wait side.  Bounded spin: a missing peer turns into an error, not a hang.
+__global__ void k_rw_wait(Params P, int phase)
+{
+    FrameState *st = P.st;
+    const int r = threadIdx.x;
+    if (r < P.n_peers) {
+        const volatile unsigned long long *flag = P.flags + phase * SHAPES_MAX_RANKS + r;
+        const long long t0 = clock64();
+        while (*flag < st->frame_no) {
+            if (clock64() - t0 > 8000000000ll) { atomicOr(&st->error, ERR_PEER_TIMEOUT); break; } // ~4 s
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (phase == RW_PHASE_RESULTS && threadIdx.x == 0) {
+        int e = 0;
+        for (int q = 0; q < P.n_peers; ++q) e |= reinterpret_cast<volatile int *>(P.rw_err[P.my_rank])[q];
+        st->peer_error = e;
+        if (e) st->error |= e & (ERR_PAIR_CAP | ERR_PEER_TIMEOUT);   // a full work list anywhere voids every home's slice
+    }
+}
+
+// First kernel of a rows-mode frame (one block).  Frame counter, the grid from the bounds every rank pushed in the
+// previous frame (two cells of margin: whatever moved further goes to the exact big-shape path), the row cuts from
+// the row weights of the previous frame, and the per-frame counters.
+__global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
+{
+    FrameState *st = P.st;
+    __shared__ unsigned long long s_pre[1024];
+    const int G = P.n_peers, t = threadIdx.x;
+    if (t == 0) {
+        if (advance) st->frame_no += 1;
+        st->bmin_x = st->bmin_y = ~0ull;
+        st->bmax_x = st->bmax_y = 0ull;
+        for (int r = 0; r < G; ++r) {
+            const unsigned long long *b = P.rw_bounds_prev + 4 * r;
+            if (b[0] < st->bmin_x) st->bmin_x = b[0];
+            if (b[1] < st->bmin_y) st->bmin_y = b[1];
+            if (b[2] > st->bmax_x) st->bmax_x = b[2];
+            if (b[3] > st->bmax_y) st->bmax_y = b[3];
+        }
+        plan_grid_from_bounds(st, P.cell_size, P.cell_limit, 2.0);
+        st->bmin_x = st->bmin_y = ~0ull;       // K0 reduces this frame's bounds into them
+        st->bmax_x = st->bmax_y = 0ull;
+        st->n_big = 0; st->n_small = 0; st->error = 0; st->peer_error = 0;
+        st->n_pairs = 0; st->n_contacts = 0; st->work_cursor = 0ull; st->n_pairs_hit = 0ull; st->n_kept = 0u;
+    }
+    // row weights: ROW_BINS bins over the rows, summed over the ranks that measured them; 4 bins per thread
+    unsigned long long mine = 0;
+    for (int b = 4 * t; b < 4 * t + 4 && b < ROW_BINS; ++b)
+        for (int r = 0; r < G; ++r) mine += P.rw_weights_prev[(size_t)r * ROW_BINS + b];
+    s_pre[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {       // inclusive scan (Hillis-Steele; one block, once per frame)
+        const unsigned long long v = t >= o ? s_pre[t - o] : 0ull;
+        __syncthreads();
+        s_pre[t] += v;
+        __syncthreads();
+    }
+    if (t == 0) {
+        const int H = st->H;
+        const unsigned long long total = s_pre[1023];
+        st->cut[0] = 0;
+        for (int g = 1; g < G; ++g) {
+            int row;
+            if (total < (unsigned long long)(64 * G)) row = (int)(((long long)H * g) / G);   // nothing measured yet: equal rows
+            else {
+                // first group of 4 bins whose running total reaches g / G of the work
+                const unsigned long long want = (total * (unsigned long long)g) / (unsigned long long)G;
+                int lo = 0, hi = 1023;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_pre[mid] >= want) hi = mid; else lo = mid + 1; }
+                row = (int)(((long long)(4 * lo + 2) * H) / ROW_BINS);
+            }
+            if (row < st->cut[g - 1]) row = st->cut[g - 1];
+            if (row > H) row = H;
+            st->cut[g] = row;
+        }
+        st->cut[G] = H;
+        st->row_lo = st->cut[P.my_rank]; st->row_hi = st->cut[P.my_rank + 1];
+        const int k_lo = st->row_lo > 0 ? st->row_lo - 1 : 0, k_hi = st->row_hi < H ? st->row_hi + 1 : H;
+        st->cell_lo = (unsigned)k_lo * (unsigned)st->W;
+        st->cell_end = (st->row_hi > st->row_lo) ? (unsigned)k_hi * (unsigned)st->W : st->cell_lo;   // no rows: keep nothing
+    }
+    for (int b = t; b < ROW_BINS; b += blockDim.x) P.roww[b] = 0u;
+}
+
+// K0 of a rows-mode frame, one thread per HOME slot: packed transform / inverse masses (pulled later by the ranks
+// that keep the shape), AABB, this rank's finite bounds, and the cell key -- bit 31 = isStatic, key_none = no cell,
+// key_none + 1 = big-shape path -- pushed to every rank.  World vertices are not materialised here: that is the
+// sweeping rank's job (k_rw_hulls).
+template <bool BOUNDS_ONLY>
+__global__ void __launch_bounds__(256) k_rw_transform(Params P, int lo, int hi)
+{
+    const FrameState *st = P.st;
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
+        const double px = P.pos_x[s], py = P.pos_y[s];
+        const double il = P.inv_lin[s], ir = P.inv_rot[s];
+        const bool live = P.alive[s] != 0;
+        const int o = P.vert_offset[s];
+        const int n = P.vert_offset[s + 1] - o;
+        const double rad = P.radius ? P.radius[s] : -1.0;
+        double c, sn;
+        if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
+        else sincos(P.rot[s], &sn, &c);
+        uint32_t key = P.key_none;
+        if (!BOUNDS_ONLY) { P.xf[s] = Xf{ px, py, c, sn }; P.mass[s] = make_double2(il, ir); }
+        if (live) {
+            const Aff m = to_transform(px, py, c, sn);
+            Box b{ 0.0, 0.0, 0.0, 0.0 };
+            if (rad >= 0.0) {   // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
+                const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
+                b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
+                b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+            }
+            for (int k = 0; k < n; ++k) {   // hullToAabb (Aabb.hs:81-84): foldl1 mergeAabb
+                const double2 l = __ldg(&P.local[o + k]);
+                const V2 w = afmul(m, V2{ l.x, l.y });
+                if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                else {
+                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                }
+            }
+            if (finite4(b)) {
+                mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
+                mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+            }
+            if (!BOUNDS_ONLY) {
+                P.box[s] = b;
+                int cx, cy;
+                key = small_cell(b, st, cx, cy) ? (uint32_t)cy * (uint32_t)st->W + (uint32_t)cx : P.key_none + 1u;
+                if (il == 0.0 && ir == 0.0) key |= KEY_STATIC_BIT;      // isStatic (Constraint.hs:123-125)
+            }
+        }
+        if (!BOUNDS_ONLY) for (int r = 0; r < P.n_peers; ++r) P.peer_keys[r][s] = key;
+    }
+    __shared__ double s_red[4][8];
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
+    __syncthreads();
+    if (warp == 0) {
+        mnx = lane < 8 ? s_red[0][lane] : INFINITY; mny = lane < 8 ? s_red[1][lane] : INFINITY;
+        mxx = lane < 8 ? s_red[2][lane] : -INFINITY; mxy = lane < 8 ? s_red[3][lane] : -INFINITY;
+        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+        if (lane == 0 && mnx <= mxx) {
+            atomicMin(&P.st->bmin_x, enc_ordered(mnx)); atomicMin(&P.st->bmin_y, enc_ordered(mny));
+            atomicMax(&P.st->bmax_x, enc_ordered(mxx)); atomicMax(&P.st->bmax_y, enc_ordered(mxy));
+        }
+    }
+}
+
+// Keep the shapes whose cell lies in my rows or the halo row on either side (histogram of the cell table; the
+// arrival order is the counting sort's scatter slot); every rank lists every big shape.
+__global__ void __launch_bounds__(256) k_rw_bin(Params P)
+{
+    const FrameState *st = P.st;
+    const unsigned c_lo = st->cell_lo, c_end = st->cell_end;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        const uint32_t key = P.gkeys[s] & ~KEY_STATIC_BIT;
+        uint32_t kept = P.key_none;
+        if (key == P.key_none + 1u) {
+            const unsigned pos = atomicAdd(&P.st->n_big, 1u);
+            P.big_idx[pos] = (uint32_t)s;
+            if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);
+        } else if (key >= c_lo && key < c_end) {
+            P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
+            kept = key;
+        }
+        P.keys[s] = kept;
+    }
+}
+
+// Exclusive scan of cell_count over the kept cell range [cell_lo, cell_end) (device side bounds) into cell_begin,
+// cell_begin[cell_end] = total.  Two passes over a small table: chunk sums, then each block scans its chunk.
+constexpr int SCAN_BLOCKS = 296, SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_sums(Params P, unsigned *chunk_sum)
+{
+    const FrameState *st = P.st;
+    const unsigned lo = st->cell_lo, len = st->cell_end - st->cell_lo;
+    const unsigned chunk = (len + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
+    const unsigned a = min(len, blockIdx.x * chunk), b = min(len, a + chunk);
+    unsigned sum = 0;
+    for (unsigned k = a + threadIdx.x; k < b; k += SCAN_THREADS) sum += P.cell_count[lo + k];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ unsigned s_w[SCAN_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int w = 0; w < SCAN_THREADS / 32; ++w) t += s_w[w]; chunk_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, const unsigned *chunk_sum)
+{
+    FrameState *st = P.st;
+    const unsigned lo = st->cell_lo, len = st->cell_end - st->cell_lo;
+    const unsigned chunk = (len + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
+    const unsigned a = min(len, blockIdx.x * chunk), b = min(len, a + chunk);
+    __shared__ unsigned s_w[SCAN_THREADS / 32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (unsigned q = 0; q < blockIdx.x; ++q) t += chunk_sum[q];
+        s_carry = t;
+        if (blockIdx.x == SCAN_BLOCKS - 1) { P.cell_begin[lo + len] = t + chunk_sum[blockIdx.x]; st->n_kept = t + chunk_sum[blockIdx.x]; }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned base = a; base < b; base += SCAN_THREADS) {
+        const unsigned k = base + threadIdx.x;
+        const unsigned v = k < b ? P.cell_count[lo + k] : 0u;
+        unsigned inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) { if (w < warp) before += s_w[w]; total += s_w[w]; }
+        const unsigned carry = s_carry;
+        if (k < b) P.cell_begin[lo + k] = carry + before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+// moveShapes (World.hs:132-140) for the hulls this rank keeps (its rows, the halo rows, the big list): world
+// vertices and the unit edge normals recomputed from them (setHullTransform, ConvexHull.hs:184-195), from the packed
+// transform of the shape's home (32 B pulled over NVLink).  One thread per kept shape.
+__global__ void __launch_bounds__(256) k_rw_hulls(Params P)
+{
+    const FrameState *st = P.st;
+    if (st->error & ERR_REPLAN) return;
+    const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_all; p += gridDim.x * blockDim.x) {
+        const int s = p < n_kept ? (int)(P.smeta[p] & 0x7fffffffu) : (int)P.big_idx[p - n_kept];
+        const Xf x = P.rw_xf[s / P.chunk][s];
+        P.mat_stamp[s] = (uint32_t)st->frame_no;
+        if (p >= n_kept) P.sbox[p] = P.peer_box[s / P.chunk][s];     // big shapes: AABB record next to the grid's (local reads in the sweep)
+        const Aff m = to_transform(x.px, x.py, x.c, x.s);
+        const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
+        if (P.radius && P.radius[s] >= 0.0) {
+            const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
+            P.circ[s] = make_double2(ctr.x, ctr.y);
+            continue;
+        }
+        V2 w0{ 0.0, 0.0 }, prev{ 0.0, 0.0 };
+        for (int k = 0; k < n; ++k) {
+            const double2 l = __ldg(&P.local[o + k]);
+            const V2 w = afmul(m, V2{ l.x, l.y });
+            P.wv[o + k] = make_double2(w.x, w.y);
+            if (k == 0) w0 = w;
+            else { const V2 nn = unit_edge_normal(prev, w); P.wn[o + k - 1] = make_double2(nn.x, nn.y); }
+            prev = w;
+        }
+        if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
+    }
+}
+
+// Home side, after the results barrier: the counts the sweeping ranks pushed for my slots, in the descending order
+// the scan runs in.
+__global__ void __launch_bounds__(256) k_rw_home_counts(Params P, int n_query)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x)
+        P.cnt[r] = (unsigned long long)P.rw_cnt[P.my_rank][P.own_hi - 1 - r];
+}
+
+// Home side: every pair of my slice into its place of the reference order -- the partner and the contact count are
+// pulled from the sweeping rank's work-order arrays (8 B per pair); the manifold itself stays there until k_rows.
+__global__ void __launch_bounds__(256) k_rw_gather(Params P, int n_query)
+{
+    const FrameState *st = P.st;
+    if (st->error) return;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x) {
+        const unsigned n = (unsigned)P.cnt[r];
+        if (n == 0) continue;
+        const int i = P.own_hi - 1 - r;
+        const uint32_t ws = P.rw_wstart[P.my_rank][i];
+        const int src_rank = (int)(ws >> 28);
+        const uint32_t w0 = ws & 0x0fffffffu;
+        const unsigned long long off = P.off[r];
+        const uint32_t *wj = P.rw_wj[src_rank], *wc = P.rw_ccnt[src_rank];
+        for (unsigned a = 0; a < n; ++a) {
+            P.pair_i[off + a] = i;
+            P.pair_j[off + a] = (int32_t)wj[w0 + a];
+            P.ccnt[off + a] = wc[w0 + a];
+            P.pair_src[off + a] = ((uint32_t)src_rank << 28) | (w0 + a);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // static geometry kernels
 // ---------------------------------------------------------------------------------------------
 
@@ -1876,8 +2296,8 @@ struct shapes_ctx {
     int64_t chunk = 0;          // slots per rank (all-gather granule)
     bool hulls_set = false;
     bool use_graph = true;
-    cudaGraphExec_t graph_exec[2] = { nullptr, nullptr }; // one per key-buffer parity
-    FrameKey graph_key[2] = {};
+    cudaGraphExec_t graph_exec[4] = { nullptr, nullptr, nullptr, nullptr }; // per key-buffer parity (x frame parity in rows mode)
+    FrameKey graph_key[4] = {};
     int64_t graph_launches = 0;
     int64_t geometry_version = 0;
     int max_hull_verts = 0;
@@ -1885,6 +2305,19 @@ struct shapes_ctx {
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
+    // rows mode (multi-rank with mapped peers): one exchange arena per rank, same layout everywhere
+    bool use_rows = true;         // SHAPES_B200_NO_ROWS=1: slot-range ownership of the whole path (the r1 exchange)
+    bool rows_ready = false;      // every peer's arena is mapped
+    char *rw_arena = nullptr;
+    char *peer_arena[SHAPES_MAX_RANKS] = {};
+    struct RowsLayout {
+        size_t gkeys, box, xf, in[7], cnt, wstart, bounds[2], weights[2], counts, err, flags, wj, ccnt_w, man_w, total;
+    } rwl{};
+    uint32_t *d_roww = nullptr, *d_pair_src = nullptr, *d_w_j = nullptr;
+    Xf *d_xf = nullptr;
+    unsigned *d_chunk_sum = nullptr;
+    uint32_t *d_mat_stamp = nullptr;
+    bool pending_warm = false, pending_seed = false, pending_rows = false, pending_plan_ahead = false;
     bool use_plan_ahead = true;   // single rank: grid planned from the previous frame's bounds, K0 keys and bins (SHAPES_B200_NO_PLAN_AHEAD=1: plan inside the frame)
     bool plan_valid = false;      // the bounds in FrameState describe the last completed frame of the current geometry
     int64_t big_seen = 0;         // big-list length of the last frame that ran on an exactly seeded plan
@@ -1980,12 +2413,12 @@ inline int grid_for(int64_t n, int threads, int cap)
 }
 
 int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void *nccl_id,
-                int64_t max_shapes, int64_t max_verts, int64_t max_pairs, int64_t max_contacts)
+                int64_t max_shapes, int64_t max_verts, int64_t max_pairs, int64_t max_contacts, bool need_nccl = true)
 {
     if (!out || max_shapes < 0 || max_verts < 0 || max_pairs < 0 || max_contacts < 0 ||
         max_shapes > 0x7ffffff0ll || max_verts > 0x7ffffff0ll || max_pairs > 0x7ffffff0ll ||
         max_contacts > 0xfffffff0ll || world < 1 || world > SHAPES_MAX_RANKS || rank < 0 || rank >= world ||
-        (world > 1 && !nccl_id)) {
+        (world > 1 && need_nccl && !nccl_id)) {
         g_create_error = "shapes_create: bad argument";
         return SHAPES_E_ARG;
     }
@@ -2009,7 +2442,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(cu(cudaEventCreate(&c->ev0), "cudaEventCreate"));
     TRY_CREATE(cu(cudaEventCreate(&c->ev1), "cudaEventCreate"));
     for (int k = 0; k <= SHAPES_N_STAGES; ++k) TRY_CREATE(cu(cudaEventCreate(&c->stage_ev[k]), "cudaEventCreate"));
-    if (world > 1) {
+    if (world > 1 && nccl_id) {
         ncclUniqueId id;
         static_assert(sizeof(ncclUniqueId) <= SHAPES_NCCL_ID_BYTES, "nccl id size");
         std::memcpy(&id, nccl_id, sizeof(id));
@@ -2033,7 +2466,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         c->d_in2[0][k] = c->d_in[k];
         TRY_CREATE(dev_alloc(c, &c->d_in2[1][k], world > 1 ? N : 1));
     }
-    TRY_CREATE(dev_alloc(c, &P.xf, N));
+    TRY_CREATE(dev_alloc(c, &c->d_xf, N));
+    P.xf = c->d_xf;
     TRY_CREATE(dev_alloc(c, &P.mass, N));
     TRY_CREATE(dev_alloc(c, &c->d_box2[0], Npad));
     TRY_CREATE(dev_alloc(c, &c->d_box2[1], world > 1 ? Npad : 1));
@@ -2049,9 +2483,10 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     c->use_plan_ahead = std::getenv("SHAPES_B200_NO_PLAN_AHEAD") == nullptr;
     TRY_CREATE(dev_alloc(c, &c->d_hh, N));
     P.hh = c->d_hh;
-    TRY_CREATE(dev_alloc(c, &P.w_i, c->use_sorted ? max_pairs : 1));
-    TRY_CREATE(dev_alloc(c, &P.w_j, c->use_sorted ? max_pairs : 1));
-    TRY_CREATE(dev_alloc(c, &P.w_a, c->use_sorted ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_i, (c->use_sorted || world > 1) ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &c->d_w_j, (c->use_sorted || world > 1) ? max_pairs : 1));
+    TRY_CREATE(dev_alloc(c, &P.w_a, (c->use_sorted || world > 1) ? max_pairs : 1));
+    P.w_j = c->d_w_j;
     TRY_CREATE(dev_alloc(c, &c->d_radius, N));
     TRY_CREATE(dev_alloc(c, &P.keys, N));
     TRY_CREATE(dev_alloc(c, &P.keys_sorted, N));
@@ -2095,6 +2530,33 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     for (double **col : cols) TRY_CREATE(dev_alloc(c, col, C));
     for (int q = 0; q < 6; ++q) { TRY_CREATE(dev_alloc(c, &P.j_np[q], C)); TRY_CREATE(dev_alloc(c, &P.j_f[q], C)); }
     TRY_CREATE(dev_alloc(c, &P.st, 1));
+    TRY_CREATE(cu(cudaMemset(P.st, 0, sizeof(FrameState)), "cudaMemset"));
+    c->use_rows = std::getenv("SHAPES_B200_NO_ROWS") == nullptr;
+    if (world > 1 && c->use_rows && max_pairs < (1ll << 28)) {
+        // the exchange arena of rows mode: one allocation, identical layout on every rank (the capacities are the
+        // same everywhere), so a peer's buffer is its arena base + the local offset
+        shapes_ctx::RowsLayout &L = c->rwl;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~size_t(255); return at; };
+        L.gkeys = take(sizeof(uint32_t) * Npad); L.box = take(sizeof(Box) * Npad); L.xf = take(sizeof(Xf) * Npad);
+        for (int k = 0; k < 7; ++k) L.in[k] = take(sizeof(double) * Npad);
+        L.cnt = take(sizeof(uint32_t) * Npad); L.wstart = take(sizeof(uint32_t) * Npad);
+        for (int q = 0; q < 2; ++q) { L.bounds[q] = take(sizeof(unsigned long long) * 4 * world); L.weights[q] = take(sizeof(uint32_t) * ROW_BINS * world); }
+        L.counts = take(sizeof(long long) * 2 * world); L.err = take(sizeof(int) * world);
+        L.flags = take(sizeof(unsigned long long) * RW_PHASES * SHAPES_MAX_RANKS);
+        L.wj = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
+        L.ccnt_w = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
+        L.man_w = take(sizeof(ManRec) * std::max<int64_t>(max_pairs, 1));
+        L.total = off;
+        TRY_CREATE(dev_alloc(c, &c->rw_arena, L.total));
+        TRY_CREATE(cu(cudaMemset(c->rw_arena, 0, L.total), "cudaMemset"));
+        TRY_CREATE(dev_alloc(c, &c->d_roww, ROW_BINS));
+        TRY_CREATE(dev_alloc(c, &c->d_pair_src, max_pairs));
+        TRY_CREATE(dev_alloc(c, &c->d_chunk_sum, SCAN_BLOCKS));
+        TRY_CREATE(dev_alloc(c, &c->d_mat_stamp, N));
+        TRY_CREATE(cu(cudaMemset(c->d_mat_stamp, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(N, 1)), "cudaMemset"));
+        c->peer_arena[rank] = c->rw_arena;
+    }
     TRY_CREATE(dev_alloc(c, &c->d_counts, 2 * world));
     TRY_CREATE(dev_alloc(c, &c->d_n_prev, 1));
     TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
@@ -2120,7 +2582,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bc, k_manifolds<MAX_STAGED_VERTS, true>, CT_THREADS, 0), "occupancy"));
         c->ct_blocks[0] = std::max(b4, 1); c->ct_blocks[1] = std::max(b8, 1); c->ct_blocks[2] = std::max(bc, 1);
         int bco = 0;
-        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop<true>, CO_WARPS * 32, 0), "occupancy"));
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop<1>, CO_WARPS * 32, 0), "occupancy"));
         c->coop_blocks = std::max(bco, 1);
         c->use_coop = std::getenv("SHAPES_B200_NO_COOP") == nullptr;
         int br = 0;
@@ -2137,8 +2599,12 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
 }
 
 // Issue one frame on the ctx stream.  `in` = device pointers (pos_x, pos_y, rot, cos, sin, inv_lin, inv_rot).
-int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double dt, double baumgarte,
-              double slop, bool want_world, shapes_frame_out *out, bool own_slots_only = false)
+constexpr int SHAPES_I_REPLAN = 1;   // internal: the frame ran on a stale grid plan and must be issued again
+
+// Enqueue one frame on the ctx stream (no host synchronisation).  `in` = device pointers (pos_x, pos_y, rot, cos,
+// sin, inv_lin, inv_rot).  frame_finish() waits for it and does the bookkeeping.
+int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], double dt, double baumgarte,
+                 double slop, bool want_world, bool own_slots_only)
 {
     if (!c->hulls_set) { c->err = "shapes_frame: shapes_set_hulls has not been called"; return SHAPES_E_ARG; }
     if (n_slots != c->n_slots) { c->err = "shapes_frame: n_slots differs from shapes_set_hulls"; return SHAPES_E_ARG; }
@@ -2188,15 +2654,47 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     ++c->frame_no;
     P.frame_no = c->frame_no;
     const int fpar = (int)(c->frame_no & 1);
-    const bool p2p = c->world > 1 && c->peers_ready && c->use_p2p;
+    const bool rows = c->world > 1 && c->rows_ready && c->use_rows;
+    const bool p2p = rows || (c->world > 1 && c->peers_ready && c->use_p2p);
     if (c->world > 1) { P.box = c->d_box2[fpar]; P.rank_bounds = c->d_bounds2[fpar]; P.gkeys = c->d_gkeys2[fpar]; }
     P.n_peers = p2p ? c->world : 0;
     P.remote_inputs = (p2p && own_slots_only) ? 1 : 0;
-    for (int r = 0; r < c->world && p2p; ++r) {
+    for (int r = 0; r < c->world && p2p && !rows; ++r) {
         P.peer_box[r] = c->peer_box2[fpar][r]; P.peer_bounds[r] = c->peer_bounds2[fpar][r]; P.peer_flags[r] = c->peer_flags[r];
         P.peer_keys[r] = c->peer_keys2[fpar][r];
         for (int k = 0; k < 7; ++k) P.peer_in[k][r] = c->peer_in2[fpar][k][r];
     }
+    P.work_mode = rows ? 2 : (P.sorted_mode ? 1 : 0);
+    P.sat_ccnt = P.ccnt; P.sat_man = P.man; P.xf = c->d_xf; P.w_j = c->d_w_j;
+    const bool seed_rows = rows && !c->plan_valid;
+    if (rows) {
+        // every exchanged buffer lives in the ranks' arenas: peer pointer = that rank's arena base + my offset
+        const shapes_ctx::RowsLayout &L = c->rwl;
+        char *mine = c->rw_arena;
+        P.sorted_mode = 0; P.plan_ahead = 0;
+        P.big_limit = seed_rows ? 0xffffffffu : (unsigned)std::max<int64_t>(std::max<int64_t>(1024, n_slots / 256), 2 * c->big_seen + 64);
+        P.box = reinterpret_cast<Box *>(mine + L.box); P.gkeys = reinterpret_cast<uint32_t *>(mine + L.gkeys);
+        P.xf = reinterpret_cast<Xf *>(mine + L.xf);
+        P.flags = reinterpret_cast<unsigned long long *>(mine + L.flags);
+        P.sat_ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt_w); P.sat_man = reinterpret_cast<ManRec *>(mine + L.man_w);
+        P.w_j = reinterpret_cast<uint32_t *>(mine + L.wj);
+        P.pair_src = c->d_pair_src; P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp;
+        P.rw_weights_prev = reinterpret_cast<const uint32_t *>(mine + L.weights[fpar ^ 1]);
+        P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
+        for (int r = 0; r < c->world; ++r) {
+            char *a = c->peer_arena[r];
+            P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys);
+            P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf);
+            for (int k = 0; k < 7; ++k) P.peer_in[k][r] = reinterpret_cast<const double *>(a + L.in[k]);
+            P.rw_cnt[r] = reinterpret_cast<uint32_t *>(a + L.cnt); P.rw_wstart[r] = reinterpret_cast<uint32_t *>(a + L.wstart);
+            P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
+            P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
+            P.rw_counts[r] = reinterpret_cast<long long *>(a + L.counts); P.rw_err[r] = reinterpret_cast<int *>(a + L.err);
+            P.peer_flags[r] = reinterpret_cast<unsigned long long *>(a + L.flags);
+            P.rw_wj[r] = reinterpret_cast<const uint32_t *>(a + L.wj); P.rw_ccnt[r] = reinterpret_cast<const uint32_t *>(a + L.ccnt_w);
+            P.rw_man[r] = reinterpret_cast<const ManRec *>(a + L.man_w);
+        }
+    } else P.flags = c->d_flags;
     P.world_x = want_world ? c->d_world_x : nullptr;
     P.world_y = want_world ? c->d_world_y : nullptr;
     cudaStream_t s = c->stream;
@@ -2205,7 +2703,80 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     // The launch sequence of a frame is fixed for given buffers and scalars (all counts live in
     // device memory), so it is captured once into a CUDA graph and replayed: one cudaGraphLaunch
     // instead of ~25 launches per frame.
+    // rows mode (multi-rank, peers mapped): see the k_rw_* kernels
+    auto issue_rows = [&](bool advance) -> int {
+        int stage = 0;
+    #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
+        const int gq = grid_for(n_query, 256, sms * 8), gn = grid_for(N, 256, sms * 8);
+        STAGE_MARK(); // 0: transform (home slots) + key push
+        k_rw_begin<<<1, 1024, 0, s>>>(P, advance ? 1 : 0); ++c->launches;
+        CU_TRY(c, cudaMemsetAsync(P.cell_count, 0, sizeof(uint32_t) * ((size_t)P.cell_limit + 2), s));
+        if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches; }
+        STAGE_MARK(); // 1: barrier KEYS (this frame's bounds ride along, for the next frame's grid)
+        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
+        STAGE_MARK(); // 2: keep my rows' keys
+        if (N > 0) { k_rw_bin<<<gn, 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 3: cell offsets
+        k_scan_cells_sums<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
+        k_scan_cells_apply<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
+        STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
+        if (N > 0) {
+            k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
+            k_rw_hulls<<<grid_for(n_query + n_query / 2 + 4096, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 5: single-pass sweep of my rows; counts / list positions pushed to the homes
+        if (N > 0) {
+            k_sweep<SWEEP_FUSED><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
+            k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 6
+        STAGE_MARK(); // 7
+        STAGE_MARK(); // 8: manifolds over my work list, results in work order; then barrier RESULTS
+        if (N > 0) {
+            if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
+            else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
+            else if (c->use_coop) {
+                k_manifolds_coop<2><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                {   // hulls with more than 8 vertices, partners of big queries this rank does not keep
+                    k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
+                }
+            }
+            else k_manifolds<MAX_STAGED_VERTS, false><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
+            ++c->launches;
+        }
+        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
+        STAGE_MARK(); // 9: home -- offsets of my slice, (j, contact count) of every pair pulled into place, row offsets
+        if (n_query > 0) {
+            k_rw_home_counts<<<gq, 256, 0, s>>>(P, n_query); ++c->launches;
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+        }
+        k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+        if (n_query > 0) { k_rw_gather<<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
+        if (c->max_pairs > 0) {
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
+            k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
+        }
+        STAGE_MARK(); // 10: contact rows (manifolds pulled from the sweeping ranks)
+        if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // 11: warm-start cache join
+        if (N > 0 && warm) { k_warm_join<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
+        STAGE_MARK(); // end
+    #undef STAGE_MARK
+        // barrier COUNTS: every rank learns every rank's pair / contact totals (global row offsets of the slices)
+        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 2 * c->world, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+        return SHAPES_OK;
+    };
     auto issue = [&]() -> int {
+        if (rows) return issue_rows(true);
         int stage = 0;
     #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
         STAGE_MARK(); // 0: transform
@@ -2277,8 +2848,8 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
             else if (c->use_coop) {
-                if (P.sorted_mode) k_manifolds_coop<true><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
-                else k_manifolds_coop<false><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                if (P.sorted_mode) k_manifolds_coop<1><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                else k_manifolds_coop<0><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
                 // hulls with more than 8 vertices / foreign hulls (multi-rank): per-thread pass over the flagged pairs
                 if (c->max_hull_verts > MAX_STAGED_VERTS || c->world > 1) {
                     k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
@@ -2323,14 +2894,30 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
         k_reset_state<<<1, 1, 0, s>>>(P.st); ++c->launches;
         if (N > 0) { k_transform_aabb<true><<<grid_for(N, 256, sms * 8), 256, 0, s>>>(P, 0, N); ++c->launches; }
     }
+    c->pending_warm = warm; c->pending_seed = seed_plan || seed_rows; c->pending_rows = rows; c->pending_plan_ahead = P.plan_ahead != 0;
     const int64_t launches_before = c->launches;
-    // (multi-rank frames carry the frame number in their kernel arguments: no replay there)
-    if (!c->use_graph || c->profiling || c->world > 1) { // per-stage events cannot be timed from inside a graph
+    if (seed_rows) {
+        // rows mode, first frame of a geometry: every rank reduces the bounds of its home slots and pushes them into
+        // the inbox the frame's k_rw_begin reads (the "previous frame" one); barrier SEED; then the frame itself,
+        // without advancing the frame counter again.  Not replayed from a graph.
+        Params Ps = P;
+        for (int r = 0; r < c->world; ++r)
+            Ps.peer_bounds[r] = reinterpret_cast<unsigned long long *>(c->peer_arena[r] + c->rwl.bounds[fpar ^ 1]);
+        k_rw_begin<<<1, 1024, 0, s>>>(P, 1); ++c->launches;      // advances the counter, resets the bounds accumulators
+        if (n_query > 0) { k_rw_transform<true><<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches; }
+        k_rw_publish<<<1, 1024, 0, s>>>(Ps, RW_PHASE_SEED); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_SEED); ++c->launches;
+        const int rc = issue_rows(false);
+        if (rc != SHAPES_OK) return rc;
+    } else if (!c->use_graph || c->profiling || (c->world > 1 && !rows)) {
+        // per-stage events cannot be timed from inside a graph; the r1 multi-rank exchange carries the frame number
+        // in its kernel arguments (rows mode keeps it in device memory and replays)
         const int rc = issue();
         if (rc != SHAPES_OK) return rc;
     } else {
-        cudaGraphExec_t &gexec = c->graph_exec[c->parity];
-        if (!gexec || std::memcmp(&key, &c->graph_key[c->parity], sizeof(key)) != 0) {
+        const int gi = c->parity + (rows ? 2 * fpar : 0);
+        cudaGraphExec_t &gexec = c->graph_exec[gi];
+        if (!gexec || std::memcmp(&key, &c->graph_key[gi], sizeof(key)) != 0) {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             cudaGraph_t g = nullptr;
             CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -2340,14 +2927,25 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             CU_TRY(c, ce);
             CU_TRY(c, cudaGraphInstantiate(&gexec, g, 0));
             cudaGraphDestroy(g);
-            c->graph_key[c->parity] = key;
+            c->graph_key[gi] = key;
             c->graph_launches = c->launches - launches_before;
         } else c->launches += c->graph_launches;
         CU_TRY(c, cudaGraphLaunch(gexec, s));
     }
     CU_TRY(c, cudaEventRecord(c->ev1, s));
-    CU_TRY(c, cudaStreamSynchronize(s));
+    return SHAPES_OK;
+}
+
+// Wait for the frame frame_launch() enqueued and do the bookkeeping.  SHAPES_I_REPLAN: the grid plan was stale,
+// everything of the attempt has been undone and the caller must launch the frame again (every rank of a multi-rank
+// job takes the same decision: the condition only depends on data all of them hold).
+int frame_finish(shapes_ctx *c, shapes_frame_out *out)
+{
+    CU_TRY(c, cudaSetDevice(c->device));
+    Params &P = c->P;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     const FrameState &st = *c->h_state;
+    const bool warm = c->pending_warm;
     if (st.error & ERR_REPLAN) {
         // the plan was stale (the world moved further than the grid's margin since the last frame): seed it from
         // this frame's positions and run the frame again -- nothing of the aborted attempt is visible
@@ -2357,13 +2955,11 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
             std::swap(P.feat_a, c->alt_key[2]); std::swap(P.feat_b, c->alt_key[3]);
             c->parity ^= 1;
         }
-        --c->frame_no;
-        const bool had_cache = warm;
-        c->cache_valid = had_cache;
-        return run_frame(c, n_slots, in, dt, baumgarte, slop, want_world, out, own_slots_only);
+        c->cache_valid = warm;
+        return SHAPES_I_REPLAN;
     }
-    c->plan_valid = P.plan_ahead && st.error == 0;
-    if (seed_plan) c->big_seen = st.n_big;
+    c->plan_valid = (c->pending_plan_ahead || c->pending_rows) && st.error == 0;
+    if (c->pending_seed) c->big_seen = st.n_big;
     c->last_pairs = st.n_pairs;
     c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
     c->have_frame = (st.error == 0);
@@ -2382,13 +2978,26 @@ int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double 
     }
     if (c->profiling)
         for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
-    if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its AABB records"; c->have_frame = false; return SHAPES_E_NCCL; }
+    if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its records"; c->have_frame = false; return SHAPES_E_NCCL; }
     if (st.error) {
-        c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs)"
+        c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs; rows mode: on this or another rank)"
                                            : "capacity: max_contacts too small (required count in n_contacts)";
         return SHAPES_E_CAPACITY;
     }
     return SHAPES_OK;
+}
+
+// One frame: launch, wait, and once more if the grid plan turned out stale.
+int run_frame(shapes_ctx *c, int64_t n_slots, const double *const in[7], double dt, double baumgarte,
+              double slop, bool want_world, shapes_frame_out *out, bool own_slots_only = false)
+{
+    for (int attempt = 0;; ++attempt) {
+        int rc = frame_launch(c, n_slots, in, dt, baumgarte, slop, want_world, own_slots_only);
+        if (rc != SHAPES_OK) return rc;
+        rc = frame_finish(c, out);
+        if (rc != SHAPES_I_REPLAN) return rc;
+        if (attempt >= 2) { c->err = "grid plan did not settle"; return SHAPES_E_CUDA; }
+    }
 }
 
 template <typename T>
@@ -2439,7 +3048,7 @@ void shapes_destroy(shapes_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (int q = 0; q < 2; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
+    for (int q = 0; q < 4; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     world_free(c);
@@ -2545,6 +3154,8 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     c->max_hull_verts = max_verts_seen;
     c->has_circles = any_circle;
     c->P.radius = any_circle ? c->d_radius : nullptr;
+    if (c->rw_arena)   // rows mode: slots nobody sweeps (dead ones) must read as "no partners"
+        CU_TRY(c, cudaMemset(c->rw_arena + c->rwl.cnt, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1)));
     c->hulls_set = true;
     c->have_frame = false;
     c->plan_valid = false;
@@ -2570,7 +3181,7 @@ int shapes_frame_device(shapes_ctx *c, int64_t n_slots, const double *pos_x, con
     return run_frame(c, n_slots, in, dt, baumgarte, slop, false, out);
 }
 
-int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
+static int fetch_enqueue(shapes_ctx *c, shapes_frame_out *out)
 {
     if (!c || !out) return SHAPES_E_ARG;
     if (!c->have_frame) { c->err = "shapes_fetch: no completed frame"; return SHAPES_E_ARG; }
@@ -2603,6 +3214,12 @@ int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
     }
     if (out->world_x && c->d_world_x) { FETCH(out->world_x, c->d_world_x, c->n_verts); FETCH(out->world_y, c->d_world_y, c->n_verts); }
 #undef FETCH
+    return SHAPES_OK;
+}
+
+static int fetch_complete(shapes_ctx *c, shapes_frame_out *out)
+{
+    const int64_t nc = c->last_contacts;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (out->b_f && nc > 0) std::memset(out->b_f, 0, sizeof(double) * (size_t)nc); // Friction.toConstraint: b = 0 (Friction.hs:26-29)
     if (!c->warm_done && nc > 0) { // no cache was supplied: every contact is a newCache (ContactLagrangian 0 0)
@@ -2611,6 +3228,12 @@ int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
         if (out->warm_hit) std::memset(out->warm_hit, 0, (size_t)nc);
     }
     return SHAPES_OK;
+}
+
+int shapes_fetch(shapes_ctx *c, shapes_frame_out *out)
+{
+    const int rc = fetch_enqueue(c, out);
+    return rc != SHAPES_OK ? rc : fetch_complete(c, out);
 }
 
 int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const double *pos_y,
@@ -2629,13 +3252,14 @@ int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const doub
     const double *dev[7];
     // With the peer exchange every rank uploads only ITS slots (kernels pull foreign bodies from
     // their owners' columns); otherwise the whole world is uploaded on every rank.
-    const bool own_only = c->world > 1 && c->peers_ready && c->use_p2p;
+    const bool rows = c->world > 1 && c->rows_ready && c->use_rows;
+    const bool own_only = rows || (c->world > 1 && c->peers_ready && c->use_p2p);
     const int fpar = (int)((c->frame_no + 1) & 1);
     const int64_t lo = own_only ? std::min<int64_t>(c->rank * c->chunk, n_slots) : 0;
     const int64_t hi = own_only ? std::min<int64_t>((c->rank + 1) * c->chunk, n_slots) : n_slots;
     for (int k = 0; k < 7; ++k) {
         dev[k] = nullptr;
-        double *dst = c->world > 1 ? c->d_in2[fpar][k] : c->d_in[k];
+        double *dst = rows ? reinterpret_cast<double *>(c->rw_arena + c->rwl.in[k]) : c->world > 1 ? c->d_in2[fpar][k] : c->d_in[k];
         if (host[k] && hi > lo)
             CU_TRY(c, cudaMemcpyAsync(dst + lo, host[k] + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
         if (host[k]) dev[k] = dst;
@@ -2709,7 +3333,9 @@ int shapes_ipc_export(shapes_ctx *c, void *out)
 {
     if (!c || !out) return SHAPES_E_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
-    cudaIpcMemHandle_t h[21];
+    cudaIpcMemHandle_t h[22];
+    std::memset(h, 0, sizeof(h));
+    if (c->rw_arena) CU_TRY(c, cudaIpcGetMemHandle(&h[21], c->rw_arena));
     for (int par = 0; par < 2; ++par)
         for (int k = 0; k < 7; ++k) CU_TRY(c, cudaIpcGetMemHandle(&h[7 + par * 7 + k], c->d_in2[par][k]));
     CU_TRY(c, cudaIpcGetMemHandle(&h[0], c->d_box2[0]));
@@ -2739,13 +3365,15 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
                 for (int k = 0; k < 7; ++k) c->peer_in2[par][k][r] = c->d_in2[par][k];
             continue;
         }
-        cudaIpcMemHandle_t h[21];
+        cudaIpcMemHandle_t h[22];
         std::memcpy(h, static_cast<const char *>(all_blobs) + (size_t)r * SHAPES_IPC_BYTES, sizeof(h));
-        void *p[21];
-        for (int q = 0; q < 21; ++q) {
+        void *p[22];
+        for (int q = 0; q < 22; ++q) {
+            if (q == 21 && !c->rw_arena) { p[q] = nullptr; continue; }
             CU_TRY(c, cudaIpcOpenMemHandle(&p[q], h[q], cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened.push_back(p[q]);
         }
+        c->peer_arena[r] = static_cast<char *>(p[21]);
         c->peer_box2[0][r] = static_cast<Box *>(p[0]); c->peer_box2[1][r] = static_cast<Box *>(p[1]);
         c->peer_bounds2[0][r] = static_cast<unsigned long long *>(p[2]);
         c->peer_bounds2[1][r] = static_cast<unsigned long long *>(p[3]);
@@ -2755,6 +3383,8 @@ int shapes_ipc_import(shapes_ctx *c, const void *all_blobs)
             for (int k = 0; k < 7; ++k) c->peer_in2[par][k][r] = static_cast<const double *>(p[7 + par * 7 + k]);
     }
     c->peers_ready = true;
+    c->rows_ready = c->rw_arena != nullptr;
+    c->plan_valid = false;
     return SHAPES_OK;
 }
 
@@ -2767,6 +3397,171 @@ int shapes_rank_info(shapes_ctx *c, int64_t *own_lo, int64_t *own_hi, int64_t *a
         if (all_pairs) all_pairs[r] = c->h_counts[2 * r];
         if (all_contacts) all_contacts[r] = c->h_counts[2 * r + 1];
     }
+    return SHAPES_OK;
+}
+
+/* ---- one process, several GPUs (the host is ONE single-threaded ST computation) ---- */
+
+struct shapes_multi {
+    int n = 0;
+    std::vector<shapes_ctx *> rank;
+    std::string err;
+};
+
+static thread_local std::string g_multi_error;
+
+void shapes_multi_destroy(shapes_multi *m)
+{
+    if (!m) return;
+    for (shapes_ctx *c : m->rank) shapes_destroy(c);
+    delete m;
+}
+
+const char *shapes_multi_last_error(const shapes_multi *m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
+
+int shapes_create_multi(shapes_multi **out, int n_gpus, const int *device_ids, int64_t max_shapes, int64_t max_verts,
+                        int64_t max_pairs_per_gpu, int64_t max_contacts_per_gpu)
+{
+    if (!out || n_gpus < 1 || n_gpus > SHAPES_MAX_RANKS) { g_multi_error = "shapes_create_multi: bad argument"; return SHAPES_E_ARG; }
+    shapes_multi *m = new shapes_multi();
+    m->n = n_gpus;
+    auto fail = [&](int rc, const std::string &why) { g_multi_error = why; shapes_multi_destroy(m); return rc; };
+    for (int r = 0; r < n_gpus; ++r) {
+        shapes_ctx *c = nullptr;
+        const int dev = device_ids ? device_ids[r] : r;
+        const int rc = create_impl(&c, dev, r, n_gpus, nullptr, max_shapes, max_verts, max_pairs_per_gpu, max_contacts_per_gpu, false);
+        if (rc != SHAPES_OK) return fail(rc, g_create_error);
+        m->rank.push_back(c);
+    }
+    if (n_gpus > 1) {
+        // peers are plain pointers inside one process: enable peer access both ways and hand every rank the others' arenas
+        for (int a = 0; a < n_gpus; ++a) {
+            if (cudaSetDevice(m->rank[a]->device) != cudaSuccess) return fail(SHAPES_E_CUDA, "cudaSetDevice");
+            for (int b = 0; b < n_gpus; ++b) {
+                if (a == b || m->rank[a]->device == m->rank[b]->device) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, m->rank[a]->device, m->rank[b]->device);
+                if (!can) return fail(SHAPES_E_CUDA, "shapes_create_multi: the GPUs cannot access each other's memory");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(m->rank[b]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SHAPES_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        }
+        for (int a = 0; a < n_gpus; ++a) {
+            shapes_ctx *c = m->rank[a];
+            if (!c->rw_arena) return fail(SHAPES_E_ARG, "shapes_create_multi: rows mode is disabled (SHAPES_B200_NO_ROWS) or max_pairs_per_gpu >= 2^28");
+            for (int b = 0; b < n_gpus; ++b) c->peer_arena[b] = m->rank[b]->rw_arena;
+            c->peers_ready = true; c->rows_ready = true; c->plan_valid = false;
+        }
+    }
+    *out = m;
+    return SHAPES_OK;
+}
+
+shapes_ctx *shapes_multi_rank(shapes_multi *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->rank[rank] : nullptr; }
+
+int shapes_multi_set_shapes(shapes_multi *m, int64_t n_slots, const uint8_t *alive, const int32_t *vert_offset,
+                            const double *local_x, const double *local_y, const int32_t *ext_min, const int32_t *ext_max,
+                            const double *radius)
+{
+    if (!m) return SHAPES_E_ARG;
+    for (shapes_ctx *c : m->rank) {
+        const int rc = shapes_set_shapes(c, n_slots, alive, vert_offset, local_x, local_y, ext_min, ext_max, radius);
+        if (rc != SHAPES_OK) { m->err = c->err; return rc; }
+    }
+    return SHAPES_OK;
+}
+
+// One frame on all GPUs from ONE host thread: every rank's slice of the body columns goes up over its own PCIe link,
+// the frames are enqueued back to back (their device-side barriers meet on the GPUs), and every rank's slice of the
+// result comes down, again over its own link, straight to its global row offset in the caller's buffers.
+int shapes_multi_frame(shapes_multi *m, int64_t n_slots, const double *pos_x, const double *pos_y,
+                       const double *rot, const double *cos_rot, const double *sin_rot,
+                       const double *inv_lin, const double *inv_rot, double dt, double baumgarte,
+                       double slop, shapes_frame_out *out)
+{
+    if (!m || !out) return SHAPES_E_ARG;
+    const int G = m->n;
+    if (G == 1) return shapes_frame(m->rank[0], n_slots, pos_x, pos_y, rot, cos_rot, sin_rot, inv_lin, inv_rot, dt, baumgarte, slop, out);
+    const double *host[7] = { pos_x, pos_y, rot, cos_rot, sin_rot, inv_lin, inv_rot };
+    std::vector<std::array<const double *, 7>> dev((size_t)G);
+    auto fail = [&](shapes_ctx *c, int rc) { m->err = c->err; return rc; };
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaSetDevice(m->rank[0]->device);
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, m->rank[0]->stream);
+    for (int r = 0; r < G; ++r) {
+        shapes_ctx *c = m->rank[r];
+        if (n_slots != c->n_slots || !c->hulls_set) { c->err = "shapes_multi_frame: n_slots differs from shapes_multi_set_shapes"; return fail(c, SHAPES_E_ARG); }
+        CU_TRY(c, cudaSetDevice(c->device));
+        const int64_t lo = std::min<int64_t>(c->rank * c->chunk, n_slots), hi = std::min<int64_t>((c->rank + 1) * c->chunk, n_slots);
+        for (int k = 0; k < 7; ++k) {
+            dev[r][k] = nullptr;
+            double *dst = reinterpret_cast<double *>(c->rw_arena + c->rwl.in[k]);
+            if (host[k] && hi > lo)
+                CU_TRY(c, cudaMemcpyAsync(dst + lo, host[k] + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+            if (host[k]) dev[r][k] = dst;
+        }
+    }
+    std::vector<shapes_frame_out> part((size_t)G, *out);
+    for (int attempt = 0;; ++attempt) {
+        for (int r = 0; r < G; ++r) {
+            const int rc = frame_launch(m->rank[r], n_slots, dev[r].data(), dt, baumgarte, slop, false, true);
+            if (rc != SHAPES_OK) return fail(m->rank[r], rc);
+        }
+        bool replan = false;
+        int bad = SHAPES_OK;
+        shapes_ctx *bad_ctx = nullptr;
+        for (int r = 0; r < G; ++r) {
+            const int rc = frame_finish(m->rank[r], &part[r]);
+            if (rc == SHAPES_I_REPLAN) replan = true;
+            else if (rc != SHAPES_OK && bad == SHAPES_OK) { bad = rc; bad_ctx = m->rank[r]; }
+        }
+        if (bad != SHAPES_OK) {
+            out->n_pairs = 0; out->n_contacts = 0;
+            for (int r = 0; r < G; ++r) { out->n_pairs = std::max(out->n_pairs, part[r].n_pairs); out->n_contacts = std::max(out->n_contacts, part[r].n_contacts); }
+            return fail(bad_ctx, bad);   // capacity: the largest per-GPU requirement is reported
+        }
+        if (!replan) break;
+        if (attempt >= 2) { m->err = "grid plan did not settle"; return SHAPES_E_CUDA; }
+    }
+    // the global descending order is rank G-1's rows, then G-2's, ...
+    int64_t pair_off = 0, row_off = 0;
+    for (int r = G - 1; r >= 0; --r) {
+        shapes_ctx *c = m->rank[r];
+        shapes_frame_out &po = part[r];
+#define SHIFT(field, by) do { if (po.field) po.field += (by); } while (0)
+        SHIFT(pair_i, pair_off); SHIFT(pair_j, pair_off);
+        SHIFT(key_i, row_off); SHIFT(key_j, row_off); SHIFT(feat_a, row_off); SHIFT(feat_b, row_off); SHIFT(flip, row_off);
+        SHIFT(normal_x, row_off); SHIFT(normal_y, row_off); SHIFT(center_x, row_off); SHIFT(center_y, row_off); SHIFT(depth, row_off);
+        for (int q = 0; q < 6; ++q) { SHIFT(j_np[q], row_off); SHIFT(j_f[q], row_off); }
+        SHIFT(b_np, row_off); SHIFT(b_f, row_off);
+        SHIFT(ra_x, row_off); SHIFT(ra_y, row_off); SHIFT(rb_x, row_off); SHIFT(rb_y, row_off); SHIFT(rn_x, row_off); SHIFT(rn_y, row_off);
+        SHIFT(inv_eff_np, row_off); SHIFT(inv_eff_f, row_off);
+        SHIFT(warm_np, row_off); SHIFT(warm_f, row_off); SHIFT(warm_hit, row_off);
+#undef SHIFT
+        po.aabb_min_x = po.aabb_max_x = po.aabb_min_y = po.aabb_max_y = nullptr;   // debug outputs: per-rank calls only
+        po.world_x = po.world_y = nullptr;
+        const int rc = fetch_enqueue(c, &po);
+        if (rc != SHAPES_OK) return fail(c, rc);
+        pair_off += c->last_pairs; row_off += c->last_contacts;
+    }
+    for (int r = 0; r < G; ++r) {
+        const int rc = fetch_complete(m->rank[r], &part[r]);
+        if (rc != SHAPES_OK) return fail(m->rank[r], rc);
+    }
+    out->n_pairs = pair_off; out->n_contacts = row_off;
+    out->n_big = part[0].n_big; out->grid_w = part[0].grid_w; out->grid_h = part[0].grid_h; out->cell_size = part[0].cell_size;
+    float dev_ms = 0.f;
+    for (int r = 0; r < G; ++r) dev_ms = std::max(dev_ms, part[r].device_ms);
+    out->device_ms = dev_ms;
+    cudaSetDevice(m->rank[0]->device);
+    cudaEventRecord(t1, m->rank[0]->stream);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    out->total_ms = ms;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
     return SHAPES_OK;
 }
 

@@ -425,6 +425,113 @@ class Engine:
         return int(self.lib.shapes_launch_count(self.ctx))
 
 
+class MultiEngine:
+    """Owns one shapes_multi: several GPUs of one box driven from THIS process (shapes_create_multi) -- the form a
+    single-threaded host like the reference's ST engine can use.  frame() returns the whole frame, in the reference's
+    global descending order, exactly like Engine.frame on one GPU."""
+
+    def __init__(self, world: World, n_gpus: int, device_ids: Optional[list[int]] = None,
+                 max_pairs_per_gpu: Optional[int] = None, max_contacts_per_gpu: Optional[int] = None,
+                 ext: Optional[tuple[np.ndarray, np.ndarray]] = None):
+        self.lib = _lib.load()
+        self.n_gpus = int(n_gpus)
+        n = world.n_slots
+        own = (n + self.n_gpus - 1) // self.n_gpus
+        self.max_pairs = int(max_pairs_per_gpu if max_pairs_per_gpu is not None else max(4096, 8 * own))
+        self.max_contacts = int(max_contacts_per_gpu if max_contacts_per_gpu is not None else 2 * self.max_pairs)
+        self.ctx = C.c_void_p()
+        ids = None
+        if device_ids is not None:
+            ids = (C.c_int * self.n_gpus)(*device_ids)
+        rc = self.lib.shapes_create_multi(C.byref(self.ctx), self.n_gpus, ids, max(n, 1), max(world.n_verts, 1),
+                                          self.max_pairs, self.max_contacts)
+        if rc != _lib.OK:
+            msg = self.lib.shapes_multi_last_error(None)
+            self.ctx = C.c_void_p()
+            raise ShapesError(rc, msg.decode() if msg else "")
+        self._bufs: Optional[_HostBuffers] = None
+        self._bufs_key = None
+        self.world = None
+        self.set_hulls(world, ext)
+
+    def _check(self, rc: int, out: Optional[FrameOut] = None):
+        if rc == _lib.OK:
+            return
+        msg = self.lib.shapes_multi_last_error(self.ctx if self.ctx else None)
+        msg = msg.decode() if msg else ""
+        if rc == _lib.E_CAPACITY and out is not None:
+            raise CapacityError(msg, int(out.n_pairs), int(out.n_contacts))
+        raise ShapesError(rc, msg)
+
+    def close(self):
+        if self._bufs is not None:
+            self._bufs.free()
+            self._bufs = None
+        if self.ctx:
+            self.lib.shapes_multi_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_hulls(self, world: World, ext=None):
+        world.validate()
+        emin = emax = None
+        if ext is not None:
+            emin = np.ascontiguousarray(ext[0], np.int32); emax = np.ascontiguousarray(ext[1], np.int32)
+        radius = getattr(world, "radius", None)
+        self._check(self.lib.shapes_multi_set_shapes(self.ctx, world.n_slots, _ptr(world.alive), _ptr(world.vert_offset),
+                                                     _ptr(world.local_x), _ptr(world.local_y), _ptr(emin), _ptr(emax),
+                                                     _ptr(radius)))
+        self.world = world
+
+    def frame(self, dt: float = 0.01, baumgarte: float = 0.01, slop: float = 0.02,
+              cos_sin: Optional[tuple[np.ndarray, np.ndarray]] = None,
+              want=("pairs", "contacts", "constraints"), pinned: bool = False,
+              compact: bool = False, expand: bool = True) -> Frame:
+        """shapes_multi_frame: one frame on all GPUs, the whole result in host buffers."""
+        w = self.world
+        if compact and "constraints" in want:
+            want = tuple(dict.fromkeys(tuple(k for k in want if k != "constraints") + ("contacts", "constraints_compact")))
+        else:
+            compact = False
+        key = (tuple(sorted(want)), pinned, w.n_slots, w.n_verts)
+        if self._bufs is None or self._bufs_key != key:
+            if self._bufs is not None:
+                self._bufs.free()
+            self._bufs = _HostBuffers(self.lib, self.max_pairs * self.n_gpus, self.max_contacts * self.n_gpus,
+                                      w.n_slots, w.n_verts, want, pinned)
+            self._bufs_key = key
+        out = FrameOut()
+        self._bufs.fill(out)
+        cos_rot = sin_rot = None
+        if cos_sin is not None:
+            cos_rot = np.ascontiguousarray(cos_sin[0], np.float64)
+            sin_rot = np.ascontiguousarray(cos_sin[1], np.float64)
+        rc = self.lib.shapes_multi_frame(self.ctx, w.n_slots, _ptr(w.pos_x), _ptr(w.pos_y), _ptr(w.rot),
+                                         _ptr(cos_rot), _ptr(sin_rot), _ptr(w.inv_lin), _ptr(w.inv_rot),
+                                         dt, baumgarte, slop, C.byref(out))
+        self._check(rc, out)
+        fr = Frame(out, self._bufs, w.n_slots, w.n_verts)
+        if compact and expand:
+            expand_rows(fr.cols, w.pos_x, w.pos_y)
+        return fr
+
+    def rank_pairs(self) -> list[int]:
+        """Pairs each GPU holds as a home after the last frame."""
+        n = self.n_gpus
+        pairs = (C.c_int64 * n)(); contacts = (C.c_int64 * n)()
+        lo, hi = C.c_int64(), C.c_int64()
+        ctx0 = self.lib.shapes_multi_rank(self.ctx, 0)
+        rc = self.lib.shapes_rank_info(ctx0, C.byref(lo), C.byref(hi), pairs, contacts)
+        if rc != _lib.OK:
+            raise ShapesError(rc, "shapes_rank_info")
+        return list(pairs)
+
+
 def nccl_unique_id() -> bytes:
     lib = _lib.load()
     buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)

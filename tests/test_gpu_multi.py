@@ -1,5 +1,7 @@
-"""Multi-GPU parity: 2 ranks, one per GPU, NCCL all-gather of the AABB records; the slices,
-concatenated from the highest rank down, must be bit-identical to the oracle's global result.
+"""Multi-GPU parity, one PROCESS per GPU (2 ranks): the slices, concatenated from the highest rank down, must be
+bit-identical to the oracle's global result, for every exchange the library has -- "rows" (default with mapped peers:
+work split by grid rows, results delivered to the slot-range homes), "p2p" (SHAPES_B200_NO_ROWS=1: the r1 key push /
+box pull with slot-range ownership of the whole path) and "nccl" (no peer mapping: all-gather of the AABB records).
 Skipped on boxes with fewer than 2 GPUs."""
 import os
 import socket
@@ -16,7 +18,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world_size, nccl_id, q, kind, p2p, port):
+def _worker(rank, world_size, nccl_id, q, kind, mode, port):
+    p2p = mode != "nccl"
+    if mode == "p2p":
+        os.environ["SHAPES_B200_NO_ROWS"] = "1"
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -46,9 +51,9 @@ def _worker(rank, world_size, nccl_id, q, kind, p2p, port):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "rows"])
 @pytest.mark.parametrize("kind", ["pile", "polygons"])
-def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind, p2p):
+def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -61,7 +66,7 @@ def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind, p2p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world_size, nccl_id, q, kind, p2p, port)) for r in range(world_size)]
+    procs = [ctx.Process(target=_worker, args=(r, world_size, nccl_id, q, kind, mode, port)) for r in range(world_size)]
     for p in procs:
         p.start()
     got = {}
