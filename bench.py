@@ -367,7 +367,12 @@ def run_leg(R: Ranks, workload: str, world, desc: str, steps: int, warmup: int, 
             blobs = [None] * ws
             R.dist.all_gather_object(blobs, eng.ipc_export())
             eng.ipc_import(blobs)
-            exchange = "4 B cell keys pushed to every peer + needed AABB / body records pulled through peer pointers (CUDA IPC over NVLink), flag barriers"
+            if os.environ.get("SHAPES_B200_NO_ROWS") is None:
+                exchange = ("rows mode: home ranks push 4 B cell keys; the sweep / SAT work is split by grid rows (cuts balanced on the "
+                            "previous frame's per-row pair counts), sweeping ranks pull AABB + transform records and push per-slot counts; "
+                            "homes pull (j, contact count) and the manifolds (CUDA IPC over NVLink, 3 flag barriers, CUDA-graph replay)")
+            else:
+                exchange = "4 B cell keys pushed to every peer + needed AABB / body records pulled through peer pointers (CUDA IPC over NVLink), flag barriers"
     cos_rot, sin_rot = np.cos(world.rot), np.sin(world.rot)
     cols = [world.pos_x, world.pos_y, world.rot, cos_rot, sin_rot, world.inv_lin, world.inv_rot]
     d_in = [torch.from_numpy(np.ascontiguousarray(a)).to(R.dev) for a in cols]
@@ -467,7 +472,7 @@ def run_leg(R: Ranks, workload: str, world, desc: str, steps: int, warmup: int, 
             R.bracket(multi)
             e_elapsed = R.max_over_ranks(time.perf_counter() - t0) if multi else time.perf_counter() - t0
             # 7 body columns; with the peer exchange each rank uploads only its own slot range
-            n_up = (eng.rank_info()[1] - eng.rank_info()[0]) if exchange.startswith("4 B") else n
+            n_up = (eng.rank_info()[1] - eng.rank_info()[0]) if not exchange.startswith("NCCL") and ws > 1 else n
             res[mode] = {"value": tot_pairs / (e_elapsed / e_steps), "unit": UNIT, "ms_per_step": e_elapsed / e_steps * 1e3,
                          "steps": e_steps, "h2d_bytes_per_step": int(7 * 8 * n_up), "d2h_bytes_per_step": int(fr.d2h_bytes),
                          "api": "shapes_frame (pinned host buffers, %s result columns fetched)" %

@@ -217,6 +217,16 @@ int  shapes_fetch(shapes_ctx *, shapes_frame_out *out);
 int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
                       int64_t *all_pairs, int64_t *all_contacts);
 
+/* Rows mode (the default once the peers are mapped: shapes_ipc_import, or shapes_create_multi) splits the slot space
+ * into 2 x world_size blocks and makes rank g the home of blocks g and 2 world_size - 1 - g: whatever the host's slot
+ * numbering, every rank then holds the same number of slots and of pairs.  A rank's arrays hold the rows of its HIGH
+ * block first (run 0), then those of its low block (run 1); the global descending order is run 0 of ranks 0, 1, ...,
+ * world_size - 1 followed by run 1 of ranks world_size - 1, ..., 0.  For any rank of the job: the slot range and the
+ * pair / contact counts of its two runs after the last frame (the other exchanges have one slot range per rank: run 0 is
+ * empty, and the rule above reads "rank world_size - 1's rows, then world_size - 2's, ..."). */
+int  shapes_rank_segments(shapes_ctx *, int rank, int64_t seg_lo[2], int64_t seg_hi[2],
+                          int64_t seg_pairs[2], int64_t seg_contacts[2]);
+
 /* Peer-to-peer AABB exchange (optional, replaces the NCCL all-gather): K0 stores every AABB record
  * straight into all ranks' arrays over NVLink (fused compute + collective), with per-frame flags as
  * the cross-GPU barrier.  Each rank exports SHAPES_IPC_BYTES (CUDA IPC handles of its exchange

@@ -113,6 +113,7 @@ SYMBOLS = {
     "shapes_set_lagrangian_cache_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "shapes_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "shapes_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "shapes_rank_segments": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_int64)] * 4),
     "shapes_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "shapes_multi_destroy": (None, [C.c_void_p]),
     "shapes_multi_last_error": (C.c_char_p, [C.c_void_p]),

@@ -264,8 +264,14 @@ struct Params {
     uint32_t *pair_src;         // rows mode, per home pair: sweeping rank << 28 | index into that rank's work-order arrays
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
-    uint32_t *rw_cnt[SHAPES_MAX_RANKS];      // every rank's per-slot partner counts (home arrays, pushed by the sweeping rank)
-    uint32_t *rw_wstart[SHAPES_MAX_RANKS];   // ... and sweeping rank << 28 | first work-list index of the slot's partners
+    // homes: the slot space is cut into 2G blocks of rw_blk slots, rank g is home to blocks g and 2G-1-g.  Whatever the
+    // host's numbering, each home then holds the same number of slots AND (the larger key of a pair being uniform or
+    // linear in the slot index) the same number of pairs; its slice of the result is two runs of the global order.
+    int rw_blk;
+    int rw_lo_lo, rw_lo_hi, rw_hi_lo, rw_hi_hi;   // my low block [lo_lo, lo_hi), my high block [hi_lo, hi_hi)
+    unsigned long long *rw_cw[SHAPES_MAX_RANKS]; // every rank's per-slot word, pushed by the sweeping rank:
+                                                 // (sweeping rank << 28 | first work-list index) << 32 | partner count
+    double2 *rw_mass[SHAPES_MAX_RANKS];          // every rank's inverse masses (its home slots are valid)
     const uint32_t *rw_wj[SHAPES_MAX_RANKS]; // every rank's work-order results (read by the homes after the results barrier)
     const uint32_t *rw_ccnt[SHAPES_MAX_RANKS];
     const ManRec *rw_man[SHAPES_MAX_RANKS];
@@ -291,10 +297,11 @@ __device__ __forceinline__ bool slot_static(const Params &P, int s)
     return in_col(P, 5, P.inv_lin, s) == 0.0 && in_col(P, 6, P.inv_rot, s) == 0.0;
 }
 // (px, py, cos, sin): K0 packs it for the rank's own slots; other slots are read from the raw columns
+__device__ __forceinline__ int rw_home(const Params &P, int s);
 __device__ __forceinline__ Xf slot_xf(const Params &P, int s)
 {
+    if (P.work_mode == 2) return P.rw_xf[rw_home(P, s)][s];      // rows mode: its home's record (mine: local)
     if (s >= P.own_lo && s < P.own_hi) return P.xf[s];
-    if (P.work_mode == 2) return P.rw_xf[s / P.chunk][s];
     double c, sn;
     if (P.cos_rot) { c = in_col(P, 3, P.cos_rot, s); sn = in_col(P, 4, P.sin_rot, s); }
     else sincos(in_col(P, 2, P.rot, s), &sn, &c);
@@ -302,6 +309,7 @@ __device__ __forceinline__ Xf slot_xf(const Params &P, int s)
 }
 __device__ __forceinline__ double2 slot_mass(const Params &P, int s)
 {
+    if (P.work_mode == 2) return P.rw_mass[rw_home(P, s)][s];
     if (s >= P.own_lo && s < P.own_hi) return P.mass[s];
     return make_double2(in_col(P, 5, P.inv_lin, s), in_col(P, 6, P.inv_rot, s));
 }
@@ -310,11 +318,30 @@ __device__ __forceinline__ double2 slot_mass(const Params &P, int s)
 // the records of other ranks are PULLED through the peer pointers (NVLink loads) where needed.
 __device__ __forceinline__ Box box_of(const Params &P, int s)
 {
+    if (P.work_mode == 2) return P.peer_box[rw_home(P, s)][s];
     if (P.n_peers > 0) return P.peer_box[s / P.chunk][s];
     return P.box[s];
 }
 
 constexpr uint32_t KEY_STATIC_BIT = 0x80000000u;   // rows mode: pushed cell keys carry isStatic in bit 31
+// rows mode key encoding (so that a cleared key array reads "nothing here"): 0 = no cell, 1 = big-shape path, cell + 2
+constexpr uint32_t RW_KEY_NONE = 0u, RW_KEY_BIG = 1u, RW_KEY_BASE = 2u;
+
+__device__ __forceinline__ int rw_home(const Params &P, int s)
+{
+    const int b = s / P.rw_blk;
+    return b < P.n_peers ? b : 2 * P.n_peers - 1 - b;
+}
+__device__ __forceinline__ bool rw_mine(const Params &P, int s)
+{
+    return (s >= P.rw_lo_lo && s < P.rw_lo_hi) || (s >= P.rw_hi_lo && s < P.rw_hi_hi);
+}
+// my home slots in the order my slice lists them: descending through the high block, then through the low block
+__device__ __forceinline__ int rw_qslot(const Params &P, int r)
+{
+    const int n_hi = P.rw_hi_hi - P.rw_hi_lo;
+    return r < n_hi ? P.rw_hi_hi - 1 - r : P.rw_lo_hi - 1 - (r - n_hi);
+}
 
 // ---------------------------------------------------------------------------------------------
 // K0: moveShapes + toAabb
@@ -699,7 +726,7 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
         const uint32_t key = P.keys[s];
         if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
-        P.sbox[p] = box_of(P, s);
+        P.sbox[p] = P.work_mode == 2 ? P.box[s] : box_of(P, s);     // rows mode: the home pushed the record into my array
         const bool st_flag = P.work_mode == 2 ? (P.gkeys[s] & KEY_STATIC_BIT) != 0u : slot_static(P, s);
         P.smeta[p] = (uint32_t)s | ((uint32_t)st_flag << 31);
         P.keys_sorted[p] = key;
@@ -868,12 +895,13 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             room = s_wbase + total <= (unsigned long long)P.max_pairs;   // else k_finish_pairs raises the capacity error
             if (rows) {
                 if (!room && threadIdx.x == 0) atomicOr(&P.st->error, ERR_PAIR_CAP);   // this rank's work list is full
-                if (query) {
-                    // the slot-range HOME of i learns how many partners i has and where this rank keeps them
-                    const int home = i / P.chunk;
-                    P.rw_cnt[home][i] = (uint32_t)count;
-                    P.rw_wstart[home][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)base;
-                    if (count) atomicAdd(&P.roww[(unsigned)(((unsigned long long)cy * ROW_BINS) / (unsigned)st->H)], (uint32_t)count);
+                if (query)   // the HOME of i learns how many partners i has and where this rank keeps them
+                    P.rw_cw[rw_home(P, i)][i] = ((unsigned long long)(((uint32_t)P.my_rank << 28) | (uint32_t)base) << 32) | (uint32_t)count;
+                // pairs per row bin, for the next frame's cuts: the tile's total goes to the bin of its first row
+                // (a tile of 128 consecutive cell-sorted positions spans a row or two)
+                if (threadIdx.x == 0 && total) {
+                    const unsigned row0 = P.keys_sorted[tile] / (uint32_t)st->W;
+                    atomicAdd(&P.roww[(unsigned)(((unsigned long long)row0 * ROW_BINS) / (unsigned)st->H)], (uint32_t)total);
                 }
             }
         } else if (query) {
@@ -932,8 +960,8 @@ __global__ void __launch_bounds__(256) k_big(Params P)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (unsigned b = blockIdx.x; b < n_big; b += gridDim.x) {
         const int i = (int)P.big_idx[b];
-        if (i < P.own_lo || i >= P.own_hi) continue;
-        const bool rows = P.work_mode == 2;       // rows mode: big queries stay with their slot-range home
+        const bool rows = P.work_mode == 2;       // rows mode: big queries stay with their home
+        if (rows ? !rw_mine(P, i) : (i < P.own_lo || i >= P.own_hi)) continue;
         const bool listed = P.sorted_mode || rows; // results go to the SAT work list
         const Box bi = P.box[i];
         const bool si = rows ? (P.gkeys[i] & KEY_STATIC_BIT) != 0u : slot_static(P, i);
@@ -943,22 +971,22 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             s_run = 0;
             // this query's run of the SAT work list (see k_sweep)
             if (EMIT && listed) {
-                const unsigned long long n = rows ? (unsigned long long)P.rw_cnt[P.my_rank][i] : P.cnt[r];
+                const unsigned long long n = rows ? (P.rw_cw[P.my_rank][i] & 0xffffffffull) : P.cnt[r];
                 s_wbase = n ? atomicAdd(&P.st->work_cursor, n) : 0ull;
                 if (rows) {
-                    P.rw_wstart[P.my_rank][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)s_wbase;
+                    P.rw_cw[P.my_rank][i] = ((unsigned long long)(((uint32_t)P.my_rank << 28) | (uint32_t)s_wbase) << 32) | n;
                     if (s_wbase + n > (unsigned long long)P.max_pairs) atomicOr(&P.st->error, ERR_PAIR_CAP);
                 }
             }
         }
         __syncthreads();
         const unsigned long long wbase = (EMIT && listed) ? s_wbase : 0ull;
-        const unsigned long long n_mine = !listed ? 0ull : rows ? (unsigned long long)P.rw_cnt[P.my_rank][i] : P.cnt[r];
+        const unsigned long long n_mine = !listed ? 0ull : rows ? (P.rw_cw[P.my_rank][i] & 0xffffffffull) : P.cnt[r];
         const bool room = wbase + n_mine <= (unsigned long long)P.max_pairs;
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
             bool pred = false;
-            if (j >= 0 && P.alive[j] && !(si && (rows ? (P.gkeys[j] & KEY_STATIC_BIT) != 0u : slot_static(P, j))))
+            if (j >= 0 && P.alive[j] && !(si && (rows ? (P.peer_keys[rw_home(P, j)][j] & KEY_STATIC_BIT) != 0u : slot_static(P, j))))
                 pred = aabb_check(bi, box_of(P, j));
             const unsigned bal = __ballot_sync(0xffffffffu, pred);
             if (lane == 0) s_warp[warp] = __popc(bal);
@@ -980,7 +1008,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             if (threadIdx.x == 0) s_run = run + total;
             __syncthreads();
         }
-        if (!EMIT && threadIdx.x == 0) { if (rows) P.rw_cnt[P.my_rank][i] = (uint32_t)s_run; else P.cnt[r] = s_run; }
+        if (!EMIT && threadIdx.x == 0) { if (rows) P.rw_cw[P.my_rank][i] = s_run; else P.cnt[r] = s_run; }
         __syncthreads();
     }
 }
@@ -1701,12 +1729,13 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const int i = P.pair_i[q], j = P.pair_j[q];
         // rows mode: the manifold still lives on the rank that swept the pair -- pulled over NVLink, once per row
         const ManRec rec = P.work_mode == 2 ? P.rw_man[P.pair_src[q] >> 28][P.pair_src[q] & 0x0fffffffu] : P.man[q];
-        // i is always an owned slot; j may belong to another rank (raw input columns)
+        // i is always an owned slot; j may belong to another rank (raw input columns; rows mode: its home's records)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
-        const bool j_own = j >= P.own_lo && j < P.own_hi;
+        const bool j_own = P.work_mode == 2 ? rw_mine(P, j) : (j >= P.own_lo && j < P.own_hi);
         const double2 xj = j_own ? *reinterpret_cast<const double2 *>(&P.xf[j])
-                                 : make_double2(in_col(P, 0, P.pos_x, j), in_col(P, 1, P.pos_y, j));
-        const double2 mi = P.mass[i], mj = slot_mass(P, j);
+                         : P.work_mode == 2 ? *reinterpret_cast<const double2 *>(&P.rw_xf[rw_home(P, j)][j])
+                                            : make_double2(in_col(P, 0, P.pos_x, j), in_col(P, 1, P.pos_y, j));
+        const double2 mi = P.mass[i], mj = j_own ? P.mass[j] : slot_mass(P, j);
         const int flip = (int)((rec.bits >> 60) & 1u);
         const int edge = (int)(rec.bits & 0xfffffu);
         const int pen = (int)((rec.bits >> (k ? 40 : 20)) & 0xfffffu);
@@ -1872,9 +1901,17 @@ __global__ void k_rw_publish(Params P, int phase)
         }
         for (int r = threadIdx.x; r < G; r += blockDim.x) P.rw_err[r][me] = st->error;
     } else {
+        // (pairs, contacts) of my high block's run and of my low block's run
+        const int n_hi = P.rw_hi_hi - P.rw_hi_lo, n_q = n_hi + (P.rw_lo_hi - P.rw_lo_lo);
+        long long p_hi = 0, c_hi = 0;
+        if (!st->error && n_q > 0) {
+            p_hi = n_hi < n_q ? (long long)P.off[n_hi] : st->n_pairs;
+            if (n_hi == 0) p_hi = 0;
+            c_hi = p_hi < st->n_pairs ? (long long)P.coff[p_hi] : st->n_contacts;
+        }
         for (int r = threadIdx.x; r < G; r += blockDim.x) {
-            P.rw_counts[r][2 * me] = st->n_pairs;
-            P.rw_counts[r][2 * me + 1] = (st->error & ERR_PAIR_CAP) ? 2 * st->n_pairs : st->n_contacts;
+            long long *dst = P.rw_counts[r] + 4 * me;
+            dst[0] = p_hi; dst[1] = st->n_pairs - p_hi; dst[2] = c_hi; dst[3] = st->n_contacts - c_hi;
         }
     }
     __threadfence_system();
@@ -1970,16 +2007,19 @@ __global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
     for (int b = t; b < ROW_BINS; b += blockDim.x) P.roww[b] = 0u;
 }
 
-// K0 of a rows-mode frame, one thread per HOME slot: packed transform / inverse masses (pulled later by the ranks
-// that keep the shape), AABB, this rank's finite bounds, and the cell key -- bit 31 = isStatic, key_none = no cell,
-// key_none + 1 = big-shape path -- pushed to every rank.  World vertices are not materialised here: that is the
-// sweeping rank's job (k_rw_hulls).
+// K0 of a rows-mode frame, one thread per HOME slot (my low block, then my high block): packed transform, inverse
+// masses, AABB, this rank's finite bounds, and the cell key -- bit 31 = isStatic, RW_KEY_* encoding.  The records stay
+// in my arena (k_rows and k_big read them) and are PUSHED, 4 + 32 + 32 bytes, to the ranks whose rows (plus halo)
+// contain the shape's cell -- to every rank for big shapes: after the KEYS barrier a sweeping rank finds everything it
+// keeps in its own memory.  World vertices are not materialised here: that is the sweeping rank's job (k_rw_hulls).
 template <bool BOUNDS_ONLY>
-__global__ void __launch_bounds__(256) k_rw_transform(Params P, int lo, int hi)
+__global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
 {
     const FrameState *st = P.st;
+    const int n_lo = P.rw_lo_hi - P.rw_lo_lo;
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (int s = lo + blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += gridDim.x * blockDim.x) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_home; t += gridDim.x * blockDim.x) {
+        const int s = t < n_lo ? P.rw_lo_lo + t : P.rw_hi_lo + (t - n_lo);
         const double px = P.pos_x[s], py = P.pos_y[s];
         const double il = P.inv_lin[s], ir = P.inv_rot[s];
         const bool live = P.alive[s] != 0;
@@ -1989,11 +2029,13 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int lo, int hi)
         double c, sn;
         if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
         else sincos(P.rot[s], &sn, &c);
-        uint32_t key = P.key_none;
-        if (!BOUNDS_ONLY) { P.xf[s] = Xf{ px, py, c, sn }; P.mass[s] = make_double2(il, ir); }
+        const Xf x{ px, py, c, sn };
+        uint32_t key = RW_KEY_NONE;
+        int cy = -1;
+        Box b{ 0.0, 0.0, 0.0, 0.0 };
+        if (!BOUNDS_ONLY) { P.xf[s] = x; P.mass[s] = make_double2(il, ir); }
         if (live) {
             const Aff m = to_transform(px, py, c, sn);
-            Box b{ 0.0, 0.0, 0.0, 0.0 };
             if (rad >= 0.0) {   // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
                 const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
                 b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
@@ -2013,13 +2055,25 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int lo, int hi)
                 mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
             }
             if (!BOUNDS_ONLY) {
-                P.box[s] = b;
-                int cx, cy;
-                key = small_cell(b, st, cx, cy) ? (uint32_t)cy * (uint32_t)st->W + (uint32_t)cx : P.key_none + 1u;
+                int cx;
+                key = small_cell(b, st, cx, cy) ? RW_KEY_BASE + (uint32_t)cy * (uint32_t)st->W + (uint32_t)cx : RW_KEY_BIG;
+                if (key == RW_KEY_BIG) cy = -1;
                 if (il == 0.0 && ir == 0.0) key |= KEY_STATIC_BIT;      // isStatic (Constraint.hs:123-125)
             }
         }
-        if (!BOUNDS_ONLY) for (int r = 0; r < P.n_peers; ++r) P.peer_keys[r][s] = key;
+        if (BOUNDS_ONLY) continue;
+        P.box[s] = b;
+        P.gkeys[s] = key;
+        if (!live) continue;
+        for (int g = 0; g < P.n_peers; ++g) {
+            if (g == P.my_rank) continue;
+            // rank g keeps rows [cut[g] - 1, cut[g + 1]] when it sweeps any row at all
+            const bool wants = cy < 0 ? true : (st->cut[g + 1] > st->cut[g] && cy >= st->cut[g] - 1 && cy <= st->cut[g + 1]);
+            if (!wants) continue;
+            P.peer_keys[g][s] = key;
+            P.peer_box[g][s] = b;
+            P.rw_xf[g][s] = x;
+        }
     }
     __shared__ double s_red[4][8];
     mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
@@ -2044,15 +2098,18 @@ __global__ void __launch_bounds__(256) k_rw_bin(Params P)
     const FrameState *st = P.st;
     const unsigned c_lo = st->cell_lo, c_end = st->cell_end;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        const uint32_t key = P.gkeys[s] & ~KEY_STATIC_BIT;
+        const uint32_t enc = P.gkeys[s] & ~KEY_STATIC_BIT;
         uint32_t kept = P.key_none;
-        if (key == P.key_none + 1u) {
+        if (enc == RW_KEY_BIG) {
             const unsigned pos = atomicAdd(&P.st->n_big, 1u);
             P.big_idx[pos] = (uint32_t)s;
             if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);
-        } else if (key >= c_lo && key < c_end) {
-            P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
-            kept = key;
+        } else if (enc >= RW_KEY_BASE) {
+            const uint32_t key = enc - RW_KEY_BASE;
+            if (key >= c_lo && key < c_end) {
+                P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
+                kept = key;
+            }
         }
         P.keys[s] = kept;
     }
@@ -2110,7 +2167,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, con
 
 // moveShapes (World.hs:132-140) for the hulls this rank keeps (its rows, the halo rows, the big list): world
 // vertices and the unit edge normals recomputed from them (setHullTransform, ConvexHull.hs:184-195), from the packed
-// transform of the shape's home (32 B pulled over NVLink).  One thread per kept shape.
+// transform its home pushed.  One thread per kept shape.
 __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
 {
     const FrameState *st = P.st;
@@ -2118,9 +2175,9 @@ __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
     const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_all; p += gridDim.x * blockDim.x) {
         const int s = p < n_kept ? (int)(P.smeta[p] & 0x7fffffffu) : (int)P.big_idx[p - n_kept];
-        const Xf x = P.rw_xf[s / P.chunk][s];
+        const Xf x = P.xf[s];                      // pushed by its home (or mine)
         P.mat_stamp[s] = (uint32_t)st->frame_no;
-        if (p >= n_kept) P.sbox[p] = P.peer_box[s / P.chunk][s];     // big shapes: AABB record next to the grid's (local reads in the sweep)
+        if (p >= n_kept) P.sbox[p] = P.box[s];     // big shapes: AABB record next to the grid's
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
         if (P.radius && P.radius[s] >= 0.0) {
@@ -2146,7 +2203,7 @@ __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
 __global__ void __launch_bounds__(256) k_rw_home_counts(Params P, int n_query)
 {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x)
-        P.cnt[r] = (unsigned long long)P.rw_cnt[P.my_rank][P.own_hi - 1 - r];
+        P.cnt[r] = P.rw_cw[P.my_rank][rw_qslot(P, r)] & 0xffffffffull;
 }
 
 // Home side: every pair of my slice into its place of the reference order -- the partner and the contact count are
@@ -2158,17 +2215,22 @@ __global__ void __launch_bounds__(256) k_rw_gather(Params P, int n_query)
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x) {
         const unsigned n = (unsigned)P.cnt[r];
         if (n == 0) continue;
-        const int i = P.own_hi - 1 - r;
-        const uint32_t ws = P.rw_wstart[P.my_rank][i];
+        const int i = rw_qslot(P, r);
+        const uint32_t ws = (uint32_t)(P.rw_cw[P.my_rank][i] >> 32);
         const int src_rank = (int)(ws >> 28);
         const uint32_t w0 = ws & 0x0fffffffu;
         const unsigned long long off = P.off[r];
         const uint32_t *wj = P.rw_wj[src_rank], *wc = P.rw_ccnt[src_rank];
-        for (unsigned a = 0; a < n; ++a) {
-            P.pair_i[off + a] = i;
-            P.pair_j[off + a] = (int32_t)wj[w0 + a];
-            P.ccnt[off + a] = wc[w0 + a];
-            P.pair_src[off + a] = ((uint32_t)src_rank << 28) | (w0 + a);
+        for (unsigned a0 = 0; a0 < n; a0 += 4) {       // four pairs' remote loads in flight together
+            uint32_t vj[4], vc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (a0 + q < n) { vj[q] = wj[w0 + a0 + q]; vc[q] = wc[w0 + a0 + q]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (a0 + q < n) {
+                const unsigned long long d = off + a0 + q;
+                P.pair_i[d] = i; P.pair_j[d] = (int32_t)vj[q]; P.ccnt[d] = vc[q];
+                P.pair_src[d] = ((uint32_t)src_rank << 28) | (w0 + a0 + q);
+            }
         }
     }
 }
@@ -2311,10 +2373,11 @@ struct shapes_ctx {
     char *rw_arena = nullptr;
     char *peer_arena[SHAPES_MAX_RANKS] = {};
     struct RowsLayout {
-        size_t gkeys, box, xf, in[7], cnt, wstart, bounds[2], weights[2], counts, err, flags, wj, ccnt_w, man_w, total;
+        size_t gkeys[2], box, xf, mass, in[7], cw, bounds[2], weights[2], counts, err, flags, wj, ccnt_w, man_w, total;
     } rwl{};
     uint32_t *d_roww = nullptr, *d_pair_src = nullptr, *d_w_j = nullptr;
     Xf *d_xf = nullptr;
+    double2 *d_mass = nullptr;
     unsigned *d_chunk_sum = nullptr;
     uint32_t *d_mat_stamp = nullptr;
     bool pending_warm = false, pending_seed = false, pending_rows = false, pending_plan_ahead = false;
@@ -2468,7 +2531,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     }
     TRY_CREATE(dev_alloc(c, &c->d_xf, N));
     P.xf = c->d_xf;
-    TRY_CREATE(dev_alloc(c, &P.mass, N));
+    TRY_CREATE(dev_alloc(c, &c->d_mass, N));
+    P.mass = c->d_mass;
     TRY_CREATE(dev_alloc(c, &c->d_box2[0], Npad));
     TRY_CREATE(dev_alloc(c, &c->d_box2[1], world > 1 ? Npad : 1));
     P.box = c->d_box2[0];
@@ -2538,11 +2602,12 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         shapes_ctx::RowsLayout &L = c->rwl;
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~size_t(255); return at; };
-        L.gkeys = take(sizeof(uint32_t) * Npad); L.box = take(sizeof(Box) * Npad); L.xf = take(sizeof(Xf) * Npad);
+        L.gkeys[0] = take(sizeof(uint32_t) * Npad); L.gkeys[1] = take(sizeof(uint32_t) * Npad);
+        L.box = take(sizeof(Box) * Npad); L.xf = take(sizeof(Xf) * Npad); L.mass = take(sizeof(double2) * Npad);
         for (int k = 0; k < 7; ++k) L.in[k] = take(sizeof(double) * Npad);
-        L.cnt = take(sizeof(uint32_t) * Npad); L.wstart = take(sizeof(uint32_t) * Npad);
+        L.cw = take(sizeof(unsigned long long) * Npad);
         for (int q = 0; q < 2; ++q) { L.bounds[q] = take(sizeof(unsigned long long) * 4 * world); L.weights[q] = take(sizeof(uint32_t) * ROW_BINS * world); }
-        L.counts = take(sizeof(long long) * 2 * world); L.err = take(sizeof(int) * world);
+        L.counts = take(sizeof(long long) * 4 * world); L.err = take(sizeof(int) * world);
         L.flags = take(sizeof(unsigned long long) * RW_PHASES * SHAPES_MAX_RANKS);
         L.wj = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
         L.ccnt_w = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
@@ -2560,7 +2625,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &c->d_counts, 2 * world));
     TRY_CREATE(dev_alloc(c, &c->d_n_prev, 1));
     TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
-    TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 2 * world), "cudaMallocHost"));
+    TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 4 * world), "cudaMallocHost"));
     // library scratch: radix sort of (cell key, slot) and the offset scan
     size_t cb = 0;
     TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb, P.cnt, P.off, (int)std::max<int64_t>(N, 1), c->stream),
@@ -2599,6 +2664,14 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
 }
 
 // Issue one frame on the ctx stream.  `in` = device pointers (pos_x, pos_y, rot, cos, sin, inv_lin, inv_rot).
+// rows mode: the two home blocks of a rank, [lo[0], hi[0]) = low block, [lo[1], hi[1]) = high block
+inline void rows_home_blocks(const shapes_ctx *c, int rank, int64_t n_slots, int64_t lo[2], int64_t hi[2])
+{
+    const int64_t blk = std::max<int64_t>((c->chunk + 1) / 2, 1);
+    lo[0] = std::min<int64_t>(rank * blk, n_slots); hi[0] = std::min<int64_t>((rank + 1) * blk, n_slots);
+    lo[1] = std::min<int64_t>((2 * c->world - 1 - rank) * blk, n_slots); hi[1] = std::min<int64_t>((2 * c->world - rank) * blk, n_slots);
+}
+
 constexpr int SHAPES_I_REPLAN = 1;   // internal: the frame ran on a stale grid plan and must be issued again
 
 // Enqueue one frame on the ctx stream (no host synchronisation).  `in` = device pointers (pos_x, pos_y, rot, cos,
@@ -2665,16 +2738,25 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         for (int k = 0; k < 7; ++k) P.peer_in[k][r] = c->peer_in2[fpar][k][r];
     }
     P.work_mode = rows ? 2 : (P.sorted_mode ? 1 : 0);
-    P.sat_ccnt = P.ccnt; P.sat_man = P.man; P.xf = c->d_xf; P.w_j = c->d_w_j;
+    P.sat_ccnt = P.ccnt; P.sat_man = P.man; P.xf = c->d_xf; P.w_j = c->d_w_j; P.mass = c->d_mass;
     const bool seed_rows = rows && !c->plan_valid;
+    int n_home = 0;
     if (rows) {
         // every exchanged buffer lives in the ranks' arenas: peer pointer = that rank's arena base + my offset
         const shapes_ctx::RowsLayout &L = c->rwl;
         char *mine = c->rw_arena;
         P.sorted_mode = 0; P.plan_ahead = 0;
         P.big_limit = seed_rows ? 0xffffffffu : (unsigned)std::max<int64_t>(std::max<int64_t>(1024, n_slots / 256), 2 * c->big_seen + 64);
-        P.box = reinterpret_cast<Box *>(mine + L.box); P.gkeys = reinterpret_cast<uint32_t *>(mine + L.gkeys);
-        P.xf = reinterpret_cast<Xf *>(mine + L.xf);
+        P.box = reinterpret_cast<Box *>(mine + L.box); P.gkeys = reinterpret_cast<uint32_t *>(mine + L.gkeys[fpar]);
+        P.xf = reinterpret_cast<Xf *>(mine + L.xf); P.mass = reinterpret_cast<double2 *>(mine + L.mass);
+        // homes: blocks g and 2G-1-g of the slot space
+        const int64_t blk = std::max<int64_t>((c->chunk + 1) / 2, 1);
+        P.rw_blk = (int)blk;
+        P.rw_lo_lo = (int)std::min<int64_t>(c->rank * blk, N); P.rw_lo_hi = (int)std::min<int64_t>((c->rank + 1) * blk, N);
+        P.rw_hi_lo = (int)std::min<int64_t>((2 * c->world - 1 - c->rank) * blk, N);
+        P.rw_hi_hi = (int)std::min<int64_t>((2 * c->world - c->rank) * blk, N);
+        P.own_lo = P.rw_lo_lo; P.own_hi = P.rw_lo_hi;
+        n_home = (P.rw_lo_hi - P.rw_lo_lo) + (P.rw_hi_hi - P.rw_hi_lo);
         P.flags = reinterpret_cast<unsigned long long *>(mine + L.flags);
         P.sat_ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt_w); P.sat_man = reinterpret_cast<ManRec *>(mine + L.man_w);
         P.w_j = reinterpret_cast<uint32_t *>(mine + L.wj);
@@ -2683,10 +2765,9 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
         for (int r = 0; r < c->world; ++r) {
             char *a = c->peer_arena[r];
-            P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys);
-            P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf);
-            for (int k = 0; k < 7; ++k) P.peer_in[k][r] = reinterpret_cast<const double *>(a + L.in[k]);
-            P.rw_cnt[r] = reinterpret_cast<uint32_t *>(a + L.cnt); P.rw_wstart[r] = reinterpret_cast<uint32_t *>(a + L.wstart);
+            P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys[fpar]);
+            P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf); P.rw_mass[r] = reinterpret_cast<double2 *>(a + L.mass);
+            P.rw_cw[r] = reinterpret_cast<unsigned long long *>(a + L.cw);
             P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
             P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
             P.rw_counts[r] = reinterpret_cast<long long *>(a + L.counts); P.rw_err[r] = reinterpret_cast<int *>(a + L.err);
@@ -2707,11 +2788,14 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
     auto issue_rows = [&](bool advance) -> int {
         int stage = 0;
     #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
+        const int n_query = n_home;     // my slice: both home blocks
         const int gq = grid_for(n_query, 256, sms * 8), gn = grid_for(N, 256, sms * 8);
-        STAGE_MARK(); // 0: transform (home slots) + key push
+        STAGE_MARK(); // 0: transform (home slots) + record push
         k_rw_begin<<<1, 1024, 0, s>>>(P, advance ? 1 : 0); ++c->launches;
         CU_TRY(c, cudaMemsetAsync(P.cell_count, 0, sizeof(uint32_t) * ((size_t)P.cell_limit + 2), s));
-        if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches; }
+        // the key array the NEXT frame's homes push into must read "nothing here" wherever nobody pushes
+        CU_TRY(c, cudaMemsetAsync(c->rw_arena + c->rwl.gkeys[fpar ^ 1], 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1), s));
+        if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
         STAGE_MARK(); // 1: barrier KEYS (this frame's bounds ride along, for the next frame's grid)
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
@@ -2771,7 +2855,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
         CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 2 * c->world, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 4 * c->world, cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
         return SHAPES_OK;
     };
@@ -2904,7 +2988,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         for (int r = 0; r < c->world; ++r)
             Ps.peer_bounds[r] = reinterpret_cast<unsigned long long *>(c->peer_arena[r] + c->rwl.bounds[fpar ^ 1]);
         k_rw_begin<<<1, 1024, 0, s>>>(P, 1); ++c->launches;      // advances the counter, resets the bounds accumulators
-        if (n_query > 0) { k_rw_transform<true><<<grid_for(n_query, 256, sms * 8), 256, 0, s>>>(P, P.own_lo, P.own_hi); ++c->launches; }
+        if (n_home > 0) { k_rw_transform<true><<<grid_for(n_home, 256, sms * 8), 256, 0, s>>>(P, n_home); ++c->launches; }
         k_rw_publish<<<1, 1024, 0, s>>>(Ps, RW_PHASE_SEED); ++c->launches;
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_SEED); ++c->launches;
         const int rc = issue_rows(false);
@@ -3155,7 +3239,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     c->has_circles = any_circle;
     c->P.radius = any_circle ? c->d_radius : nullptr;
     if (c->rw_arena)   // rows mode: slots nobody sweeps (dead ones) must read as "no partners"
-        CU_TRY(c, cudaMemset(c->rw_arena + c->rwl.cnt, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1)));
+        CU_TRY(c, cudaMemset(c->rw_arena + c->rwl.cw, 0, sizeof(unsigned long long) * (size_t)std::max<int64_t>(c->chunk * c->world, 1)));
     c->hulls_set = true;
     c->have_frame = false;
     c->plan_valid = false;
@@ -3255,13 +3339,15 @@ int shapes_frame(shapes_ctx *c, int64_t n_slots, const double *pos_x, const doub
     const bool rows = c->world > 1 && c->rows_ready && c->use_rows;
     const bool own_only = rows || (c->world > 1 && c->peers_ready && c->use_p2p);
     const int fpar = (int)((c->frame_no + 1) & 1);
-    const int64_t lo = own_only ? std::min<int64_t>(c->rank * c->chunk, n_slots) : 0;
-    const int64_t hi = own_only ? std::min<int64_t>((c->rank + 1) * c->chunk, n_slots) : n_slots;
+    int64_t lo[2] = { own_only ? std::min<int64_t>(c->rank * c->chunk, n_slots) : 0, 0 };
+    int64_t hi[2] = { own_only ? std::min<int64_t>((c->rank + 1) * c->chunk, n_slots) : n_slots, 0 };
+    if (rows) rows_home_blocks(c, c->rank, n_slots, lo, hi);      // my two home blocks
     for (int k = 0; k < 7; ++k) {
         dev[k] = nullptr;
         double *dst = rows ? reinterpret_cast<double *>(c->rw_arena + c->rwl.in[k]) : c->world > 1 ? c->d_in2[fpar][k] : c->d_in[k];
-        if (host[k] && hi > lo)
-            CU_TRY(c, cudaMemcpyAsync(dst + lo, host[k] + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+        for (int q = 0; q < 2; ++q)
+            if (host[k] && hi[q] > lo[q])
+                CU_TRY(c, cudaMemcpyAsync(dst + lo[q], host[k] + lo[q], sizeof(double) * (size_t)(hi[q] - lo[q]), cudaMemcpyHostToDevice, c->stream));
         if (host[k]) dev[k] = dst;
     }
     const bool want_world = out->world_x && out->world_y;
@@ -3393,9 +3479,33 @@ int shapes_rank_info(shapes_ctx *c, int64_t *own_lo, int64_t *own_hi, int64_t *a
     if (!c) return SHAPES_E_ARG;
     if (own_lo) *own_lo = std::min<int64_t>(c->rank * c->chunk, c->n_slots);
     if (own_hi) *own_hi = std::min<int64_t>((c->rank + 1) * c->chunk, c->n_slots);
+    const bool rows = c->world > 1 && c->rows_ready && c->use_rows;
     for (int r = 0; r < c->world; ++r) {
-        if (all_pairs) all_pairs[r] = c->h_counts[2 * r];
-        if (all_contacts) all_contacts[r] = c->h_counts[2 * r + 1];
+        if (all_pairs) all_pairs[r] = rows ? c->h_counts[4 * r] + c->h_counts[4 * r + 1] : c->h_counts[2 * r];
+        if (all_contacts) all_contacts[r] = rows ? c->h_counts[4 * r + 2] + c->h_counts[4 * r + 3] : c->h_counts[2 * r + 1];
+    }
+    return SHAPES_OK;
+}
+
+int shapes_rank_segments(shapes_ctx *c, int rank, int64_t seg_lo[2], int64_t seg_hi[2], int64_t seg_pairs[2], int64_t seg_contacts[2])
+{
+    if (!c || rank < 0 || rank >= c->world) return SHAPES_E_ARG;
+    const bool rows = c->world > 1 && c->rows_ready && c->use_rows;
+    if (rows) {
+        int64_t lo[2], hi[2];
+        rows_home_blocks(c, rank, c->n_slots, lo, hi);
+        // run 0 = the high block (first in the rank's arrays), run 1 = the low block
+        if (seg_lo) { seg_lo[0] = lo[1]; seg_lo[1] = lo[0]; }
+        if (seg_hi) { seg_hi[0] = hi[1]; seg_hi[1] = hi[0]; }
+        if (seg_pairs) { seg_pairs[0] = c->h_counts[4 * rank]; seg_pairs[1] = c->h_counts[4 * rank + 1]; }
+        if (seg_contacts) { seg_contacts[0] = c->h_counts[4 * rank + 2]; seg_contacts[1] = c->h_counts[4 * rank + 3]; }
+    } else {
+        // one slot range per rank: everything is "run 1" (the global order is then rank G-1's rows, G-2's, ...)
+        if (seg_lo) { seg_lo[1] = std::min<int64_t>(rank * c->chunk, c->n_slots); seg_lo[0] = 0; }
+        if (seg_hi) { seg_hi[1] = std::min<int64_t>((rank + 1) * c->chunk, c->n_slots); seg_hi[0] = 0; }
+        const int64_t *h = c->h_counts;
+        if (seg_pairs) { seg_pairs[1] = c->world == 1 ? h[0] : h[2 * rank]; seg_pairs[0] = 0; }
+        if (seg_contacts) { seg_contacts[1] = c->world == 1 ? h[1] : h[2 * rank + 1]; seg_contacts[0] = 0; }
     }
     return SHAPES_OK;
 }
@@ -3494,12 +3604,14 @@ int shapes_multi_frame(shapes_multi *m, int64_t n_slots, const double *pos_x, co
         shapes_ctx *c = m->rank[r];
         if (n_slots != c->n_slots || !c->hulls_set) { c->err = "shapes_multi_frame: n_slots differs from shapes_multi_set_shapes"; return fail(c, SHAPES_E_ARG); }
         CU_TRY(c, cudaSetDevice(c->device));
-        const int64_t lo = std::min<int64_t>(c->rank * c->chunk, n_slots), hi = std::min<int64_t>((c->rank + 1) * c->chunk, n_slots);
+        int64_t lo[2], hi[2];
+        rows_home_blocks(c, c->rank, n_slots, lo, hi);
         for (int k = 0; k < 7; ++k) {
             dev[r][k] = nullptr;
             double *dst = reinterpret_cast<double *>(c->rw_arena + c->rwl.in[k]);
-            if (host[k] && hi > lo)
-                CU_TRY(c, cudaMemcpyAsync(dst + lo, host[k] + lo, sizeof(double) * (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+            for (int q = 0; q < 2; ++q)
+                if (host[k] && hi[q] > lo[q])
+                    CU_TRY(c, cudaMemcpyAsync(dst + lo[q], host[k] + lo[q], sizeof(double) * (size_t)(hi[q] - lo[q]), cudaMemcpyHostToDevice, c->stream));
             if (host[k]) dev[r][k] = dst;
         }
     }
@@ -3525,30 +3637,43 @@ int shapes_multi_frame(shapes_multi *m, int64_t n_slots, const double *pos_x, co
         if (!replan) break;
         if (attempt >= 2) { m->err = "grid plan did not settle"; return SHAPES_E_CUDA; }
     }
-    // the global descending order is rank G-1's rows, then G-2's, ...
+    // The global descending order walks the 2G home blocks from the top: block 2G-1 (rank 0's high block), 2G-2 (rank
+    // 1's), ..., G (rank G-1's), then the low blocks G-1 (rank G-1) ... 0 (rank 0).  Every rank holds its high block's
+    // rows first, then its low block's: two copies per column and rank, each to its global offset.
+    const int64_t *cnts = m->rank[0]->h_counts;      // per rank: pairs hi, pairs lo, contacts hi, contacts lo
+    std::vector<int64_t> pair_at((size_t)2 * G), row_at((size_t)2 * G);   // [2 r + 0] = rank r's high run, [2 r + 1] = its low run
     int64_t pair_off = 0, row_off = 0;
-    for (int r = G - 1; r >= 0; --r) {
-        shapes_ctx *c = m->rank[r];
-        shapes_frame_out &po = part[r];
-#define SHIFT(field, by) do { if (po.field) po.field += (by); } while (0)
-        SHIFT(pair_i, pair_off); SHIFT(pair_j, pair_off);
-        SHIFT(key_i, row_off); SHIFT(key_j, row_off); SHIFT(feat_a, row_off); SHIFT(feat_b, row_off); SHIFT(flip, row_off);
-        SHIFT(normal_x, row_off); SHIFT(normal_y, row_off); SHIFT(center_x, row_off); SHIFT(center_y, row_off); SHIFT(depth, row_off);
-        for (int q = 0; q < 6; ++q) { SHIFT(j_np[q], row_off); SHIFT(j_f[q], row_off); }
-        SHIFT(b_np, row_off); SHIFT(b_f, row_off);
-        SHIFT(ra_x, row_off); SHIFT(ra_y, row_off); SHIFT(rb_x, row_off); SHIFT(rb_y, row_off); SHIFT(rn_x, row_off); SHIFT(rn_y, row_off);
-        SHIFT(inv_eff_np, row_off); SHIFT(inv_eff_f, row_off);
-        SHIFT(warm_np, row_off); SHIFT(warm_f, row_off); SHIFT(warm_hit, row_off);
-#undef SHIFT
-        po.aabb_min_x = po.aabb_max_x = po.aabb_min_y = po.aabb_max_y = nullptr;   // debug outputs: per-rank calls only
-        po.world_x = po.world_y = nullptr;
-        const int rc = fetch_enqueue(c, &po);
-        if (rc != SHAPES_OK) return fail(c, rc);
-        pair_off += c->last_pairs; row_off += c->last_contacts;
-    }
+    for (int r = 0; r < G; ++r) { pair_at[2 * r] = pair_off; row_at[2 * r] = row_off; pair_off += cnts[4 * r]; row_off += cnts[4 * r + 2]; }
+    for (int r = G - 1; r >= 0; --r) { pair_at[2 * r + 1] = pair_off; row_at[2 * r + 1] = row_off; pair_off += cnts[4 * r + 1]; row_off += cnts[4 * r + 3]; }
     for (int r = 0; r < G; ++r) {
-        const int rc = fetch_complete(m->rank[r], &part[r]);
-        if (rc != SHAPES_OK) return fail(m->rank[r], rc);
+        shapes_ctx *c = m->rank[r];
+        const Params &P = c->P;
+        const int64_t np[2] = { cnts[4 * r], cnts[4 * r + 1] }, nc[2] = { cnts[4 * r + 2], cnts[4 * r + 3] };
+        CU_TRY(c, cudaSetDevice(c->device));
+        for (int q = 0; q < 2; ++q) {
+            const int64_t ps = q ? np[0] : 0, cs = q ? nc[0] : 0;         // where the run starts in the rank's arrays
+            const int64_t pd = pair_at[2 * r + q], cd = row_at[2 * r + q]; // ... and in the caller's
+            int rc = SHAPES_OK;
+#define RUNP(field, src) do { if (out->field) { rc = fetch_col(c, out->field + pd, src + ps, np[q]); if (rc) return fail(c, rc); } } while (0)
+#define RUNC(field, src) do { if (out->field) { rc = fetch_col(c, out->field + cd, src + cs, nc[q]); if (rc) return fail(c, rc); } } while (0)
+            RUNP(pair_i, P.pair_i); RUNP(pair_j, P.pair_j);
+            RUNC(key_i, P.key_i); RUNC(key_j, P.key_j); RUNC(feat_a, P.feat_a); RUNC(feat_b, P.feat_b); RUNC(flip, P.flip);
+            RUNC(normal_x, P.normal_x); RUNC(normal_y, P.normal_y); RUNC(center_x, P.center_x); RUNC(center_y, P.center_y); RUNC(depth, P.depth);
+            for (int k = 0; k < 6; ++k) { RUNC(j_np[k], P.j_np[k]); RUNC(j_f[k], P.j_f[k]); }
+            RUNC(b_np, P.b_np);
+            RUNC(ra_x, P.ra_x); RUNC(ra_y, P.ra_y); RUNC(rb_x, P.rb_x); RUNC(rb_y, P.rb_y); RUNC(rn_x, P.rn_x); RUNC(rn_y, P.rn_y);
+            RUNC(inv_eff_np, P.inv_eff_np); RUNC(inv_eff_f, P.inv_eff_f);
+            if (c->warm_done) { RUNC(warm_np, P.warm_np); RUNC(warm_f, P.warm_f); RUNC(warm_hit, P.warm_hit); }
+#undef RUNP
+#undef RUNC
+        }
+    }
+    for (int r = 0; r < G; ++r) { shapes_ctx *c = m->rank[r]; CU_TRY(c, cudaSetDevice(c->device)); CU_TRY(c, cudaStreamSynchronize(c->stream)); }
+    if (out->b_f && row_off > 0) std::memset(out->b_f, 0, sizeof(double) * (size_t)row_off);   // Friction.toConstraint: b = 0
+    if (!m->rank[0]->warm_done && row_off > 0) {
+        if (out->warm_np) std::memset(out->warm_np, 0, sizeof(double) * (size_t)row_off);
+        if (out->warm_f) std::memset(out->warm_f, 0, sizeof(double) * (size_t)row_off);
+        if (out->warm_hit) std::memset(out->warm_hit, 0, (size_t)row_off);
     }
     out->n_pairs = pair_off; out->n_contacts = row_off;
     out->n_big = part[0].n_big; out->grid_w = part[0].grid_w; out->grid_h = part[0].grid_h; out->cell_size = part[0].cell_size;

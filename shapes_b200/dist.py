@@ -40,3 +40,22 @@ def assemble_descending(slices: Sequence[dict]) -> dict:
     """Concatenate per-rank column dicts (index = rank) into the global descending order."""
     keys = slices[0].keys()
     return {k: np.concatenate([np.asarray(slices[r][k]) for r in range(len(slices) - 1, -1, -1)]) for k in keys}
+
+
+def assemble_runs(slices: Sequence[dict], segments: Sequence[tuple], pair_cols=("pair_i", "pair_j")) -> dict:
+    """Global descending order from per-rank column dicts and their shapes_rank_segments: run 0 of ranks 0, 1, ...,
+    G-1, then run 1 of ranks G-1, ..., 0 (a rank's arrays hold run 0 first).  `segments[r]` =
+    ((lo0, hi0, pairs0, contacts0), (lo1, hi1, pairs1, contacts1)); exchanges with one slot range per rank have an empty
+    run 0, which makes this the plain "highest rank first" concatenation."""
+    G = len(slices)
+    out = {}
+    for k in slices[0].keys():
+        which = 2 if k in pair_cols else 3
+        parts = []
+        for r in range(G):
+            parts.append(np.asarray(slices[r][k])[: segments[r][0][which]])
+        for r in range(G - 1, -1, -1):
+            n0 = segments[r][0][which]
+            parts.append(np.asarray(slices[r][k])[n0: n0 + segments[r][1][which]])
+        out[k] = np.concatenate(parts)
+    return out

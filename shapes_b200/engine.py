@@ -354,6 +354,12 @@ class Engine:
         self._check(self.lib.shapes_rank_info(self.ctx, C.byref(lo), C.byref(hi), pairs, contacts))
         return lo.value, hi.value, list(pairs), list(contacts)
 
+    def rank_segments(self, rank: Optional[int] = None):
+        """shapes_rank_segments: ((lo0, hi0, pairs0, contacts0), (lo1, hi1, pairs1, contacts1)) of a rank's two runs."""
+        a = [(C.c_int64 * 2)() for _ in range(4)]
+        self._check(self.lib.shapes_rank_segments(self.ctx, self.rank if rank is None else rank, *a))
+        return tuple((int(a[0][q]), int(a[1][q]), int(a[2][q]), int(a[3][q])) for q in range(2))
+
     def grow(self, n_pairs: int, n_contacts: int):
         """Re-create the ctx with larger capacities (the caller's answer to E_CAPACITY)."""
         world = self.world

@@ -46,7 +46,7 @@ def _worker(rank, world_size, nccl_id, q, kind, mode, port):
         for _ in range(3):   # frames alternate exchange buffers: results must not change
             fr3 = eng.frame(cos_sin=(c, s))
             assert fr3.n_pairs == fr.n_pairs and fr3.n_contacts == fr.n_contacts
-        q.put((rank, {k: np.array(v) for k, v in fr3.cols.items()}, (lo, hi), pairs, contacts))
+        q.put((rank, {k: np.array(v) for k, v in fr3.cols.items()}, eng.rank_segments(), pairs, contacts))
         dist.barrier()
     dist.destroy_process_group()
 
@@ -69,16 +69,17 @@ def test_two_rank_slices_reassemble_to_the_oracle(oracle, kind, mode):
     procs = [ctx.Process(target=_worker, args=(r, world_size, nccl_id, q, kind, mode, port)) for r in range(world_size)]
     for p in procs:
         p.start()
-    got = {}
+    got, segs = {}, {}
     for _ in range(world_size):
-        rank, cols, rng, pairs, contacts = q.get(timeout=300)
+        rank, cols, seg, pairs, contacts = q.get(timeout=300)
         got[rank] = cols
+        segs[rank] = seg
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     w = scenes.box_pile(150, 120) if kind == "pile" else scenes.random_polygons(40_000, density=1.5, config=71)
     c, s = oracle.cos_sin(w.rot)
     want = oracle.frame(w, c, s, broadphase="sweep")
-    glob = sdist.assemble_descending([got[r] for r in range(world_size)])
+    glob = sdist.assemble_runs([got[r] for r in range(world_size)], [segs[r] for r in range(world_size)])
     assert_frames_match(glob, want)
     assert sum(pairs) == len(want["pair_i"]) and sum(contacts) == len(want["key_i"])
