@@ -135,7 +135,7 @@ __device__ __forceinline__ double dec_ordered(unsigned long long u)
 
 constexpr int SHAPES_MAX_RANKS = 16;
 constexpr int ROW_BINS = 4096;       // rows mode: resolution of the per-row work histogram that balances the row cuts
-enum { RW_PHASE_SEED = 0, RW_PHASE_KEYS = 1, RW_PHASE_RESULTS = 2, RW_PHASE_COUNTS = 3, RW_PHASES = 4 };
+enum { RW_PHASE_SEED = 0, RW_PHASE_KEYS = 1, RW_PHASE_CNT = 2, RW_PHASE_OFF = 3, RW_PHASE_RESULTS = 4, RW_PHASE_COUNTS = 5, RW_PHASES = 6 };
 constexpr int ERR_PAIR_CAP = 1;
 constexpr int ERR_PEER_TIMEOUT = 4;
 constexpr int ERR_CONTACT_CAP = 2;
@@ -162,6 +162,8 @@ struct FrameState {
     int cut[SHAPES_MAX_RANKS + 1]; // row cuts of all ranks: rank g sweeps rows [cut[g], cut[g + 1])
     unsigned n_kept;            // shapes in this rank's grid
     int peer_error;             // OR of every rank's error word (exchanged at the results barrier)
+    unsigned long long loc_fold, loc_contig;   // rows mode: work entries whose home would be this rank under the folded /
+                                               // the contiguous home layout (decides which one the next frames use)
 };
 
 struct Params;
@@ -259,22 +261,27 @@ struct Params {
     // pair's larger key, so the global order stays "rank G-1's rows, then G-2's, ..." with no merge.
     int work_mode;              // 0: SAT walks the pairs in reference order; 1: cell-ordered work list, results at
                                 // off[r(i)] + a; 2: rows mode -- results stay in work order on the sweeping rank
-    uint32_t *sat_ccnt;         // where the SAT stage writes its contact counts / manifolds
-    ManRec *sat_man;
-    uint32_t *pair_src;         // rows mode, per home pair: sweeping rank << 28 | index into that rank's work-order arrays
+    uint32_t *sat_ccnt;         // rows mode: per work entry, the SAT stage's contact count (local copy: marks the pairs
+                                // left to the per-thread pass); otherwise = ccnt
+    uint32_t *q_off;            // rows mode, per slot i this rank sweeps: first index of i's pairs in its home's arrays
+    double4 *pj;                // rows mode, per home pair with contacts: (pos_j, inverse masses of j), pushed by the sweeping rank
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
     // homes: the slot space is cut into 2G blocks of rw_blk slots, rank g is home to blocks g and 2G-1-g.  Whatever the
     // host's numbering, each home then holds the same number of slots AND (the larger key of a pair being uniform or
     // linear in the slot index) the same number of pairs; its slice of the result is two runs of the global order.
-    int rw_blk;
+    // (rw_fold 0: one contiguous block per rank, the high block is empty -- chosen after the first frames when the slot
+    // numbering turns out to follow the geometry, so that a slot's home is also the rank that sweeps it and its results
+    // stay on the GPU; the decision is taken from counters every rank holds, so all ranks switch in the same frame.)
+    int rw_blk, rw_fold;
     int rw_lo_lo, rw_lo_hi, rw_hi_lo, rw_hi_hi;   // my low block [lo_lo, lo_hi), my high block [hi_lo, hi_hi)
-    unsigned long long *rw_cw[SHAPES_MAX_RANKS]; // every rank's per-slot word, pushed by the sweeping rank:
-                                                 // (sweeping rank << 28 | first work-list index) << 32 | partner count
+    uint32_t *rw_cq[SHAPES_MAX_RANKS];           // every rank's per-slot word, pushed by the sweeping rank: rank << 28 | partner count
+    uint32_t *rw_qoff[SHAPES_MAX_RANKS];         // every rank's q_off (pushed by the homes after their scan)
+    int32_t *rw_pair_i[SHAPES_MAX_RANKS], *rw_pair_j[SHAPES_MAX_RANKS];   // every rank's result arrays (home side): the sweeping
+    uint32_t *rw_ccnt[SHAPES_MAX_RANKS];                                  // rank stores each pair straight into its final place
+    ManRec *rw_man[SHAPES_MAX_RANKS];
+    double4 *rw_pj[SHAPES_MAX_RANKS];
     double2 *rw_mass[SHAPES_MAX_RANKS];          // every rank's inverse masses (its home slots are valid)
-    const uint32_t *rw_wj[SHAPES_MAX_RANKS]; // every rank's work-order results (read by the homes after the results barrier)
-    const uint32_t *rw_ccnt[SHAPES_MAX_RANKS];
-    const ManRec *rw_man[SHAPES_MAX_RANKS];
     Xf *rw_xf[SHAPES_MAX_RANKS];             // every rank's packed transforms (its own slot range is valid)
     uint32_t *rw_weights[SHAPES_MAX_RANKS];  // every rank's [G][ROW_BINS] inbox of row weights (this frame's parity)
     const uint32_t *rw_weights_prev;         // my inbox of the previous frame
@@ -330,7 +337,7 @@ constexpr uint32_t RW_KEY_NONE = 0u, RW_KEY_BIG = 1u, RW_KEY_BASE = 2u;
 __device__ __forceinline__ int rw_home(const Params &P, int s)
 {
     const int b = s / P.rw_blk;
-    return b < P.n_peers ? b : 2 * P.n_peers - 1 - b;
+    return (!P.rw_fold || b < P.n_peers) ? b : 2 * P.n_peers - 1 - b;
 }
 __device__ __forceinline__ bool rw_mine(const Params &P, int s)
 {
@@ -895,8 +902,18 @@ __global__ void __launch_bounds__(128) k_sweep(Params P)
             room = s_wbase + total <= (unsigned long long)P.max_pairs;   // else k_finish_pairs raises the capacity error
             if (rows) {
                 if (!room && threadIdx.x == 0) atomicOr(&P.st->error, ERR_PAIR_CAP);   // this rank's work list is full
-                if (query)   // the HOME of i learns how many partners i has and where this rank keeps them
-                    P.rw_cw[rw_home(P, i)][i] = ((unsigned long long)(((uint32_t)P.my_rank << 28) | (uint32_t)base) << 32) | (uint32_t)count;
+                if (query) {  // the HOME of i learns how many partners i has and who found them
+                    P.rw_cq[rw_home(P, i)][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)count;
+                    if (count) {   // would i's results stay on this GPU? (under either home layout; sampled: one query in 16)
+                        if ((p & 15u) == 0u) {
+                            const int G = P.n_peers;
+                            const int chunk_blk = P.rw_fold ? 2 * P.rw_blk : P.rw_blk, half_blk = P.rw_fold ? P.rw_blk : (P.rw_blk + 1) / 2;
+                            const int bf = i / half_blk;
+                            if ((bf < G ? bf : 2 * G - 1 - bf) == P.my_rank) atomicAdd(&P.st->loc_fold, count);
+                            if (i / chunk_blk == P.my_rank) atomicAdd(&P.st->loc_contig, count);
+                        }
+                    }
+                }
                 // pairs per row bin, for the next frame's cuts: the tile's total goes to the bin of its first row
                 // (a tile of 128 consecutive cell-sorted positions spans a row or two)
                 if (threadIdx.x == 0 && total) {
@@ -971,17 +988,14 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             s_run = 0;
             // this query's run of the SAT work list (see k_sweep)
             if (EMIT && listed) {
-                const unsigned long long n = rows ? (P.rw_cw[P.my_rank][i] & 0xffffffffull) : P.cnt[r];
+                const unsigned long long n = rows ? (unsigned long long)(P.rw_cq[P.my_rank][i] & 0x0fffffffu) : P.cnt[r];
                 s_wbase = n ? atomicAdd(&P.st->work_cursor, n) : 0ull;
-                if (rows) {
-                    P.rw_cw[P.my_rank][i] = ((unsigned long long)(((uint32_t)P.my_rank << 28) | (uint32_t)s_wbase) << 32) | n;
-                    if (s_wbase + n > (unsigned long long)P.max_pairs) atomicOr(&P.st->error, ERR_PAIR_CAP);
-                }
+                if (rows && s_wbase + n > (unsigned long long)P.max_pairs) atomicOr(&P.st->error, ERR_PAIR_CAP);
             }
         }
         __syncthreads();
         const unsigned long long wbase = (EMIT && listed) ? s_wbase : 0ull;
-        const unsigned long long n_mine = !listed ? 0ull : rows ? (P.rw_cw[P.my_rank][i] & 0xffffffffull) : P.cnt[r];
+        const unsigned long long n_mine = !listed ? 0ull : rows ? (unsigned long long)(P.rw_cq[P.my_rank][i] & 0x0fffffffu) : P.cnt[r];
         const bool room = wbase + n_mine <= (unsigned long long)P.max_pairs;
         for (int top = i - 1; top >= 0; top -= (int)blockDim.x) {
             const int j = top - (int)threadIdx.x;
@@ -1008,7 +1022,7 @@ __global__ void __launch_bounds__(256) k_big(Params P)
             if (threadIdx.x == 0) s_run = run + total;
             __syncthreads();
         }
-        if (!EMIT && threadIdx.x == 0) { if (rows) P.rw_cw[P.my_rank][i] = s_run; else P.cnt[r] = s_run; }
+        if (!EMIT && threadIdx.x == 0) { if (rows) P.rw_cq[P.my_rank][i] = ((uint32_t)P.my_rank << 28) | (uint32_t)s_run; else P.cnt[r] = s_run; }
         __syncthreads();
     }
 }
@@ -1317,7 +1331,7 @@ __device__ __forceinline__ int clip_segment(V2 bp, V2 bn, V2 in, double ib, V2 a
 // (SAT.hs:181-187).  E = penetrated hull, Pn = penetrating hull; `acc` supplies their world vertices and
 // the unit normal of E's edge.  Writes the ManRec when the pair has contacts; returns their number.
 template <typename Acc>
-__device__ __forceinline__ unsigned emit_manifold(const Params &P, long long p, const Acc &acc, int e_n, int pn_n,
+__device__ __forceinline__ unsigned emit_manifold(ManRec *out_rec, const Acc &acc, int e_n, int pn_n,
                                                   int edge, int pen, bool same)
 {
     unsigned cnt = 0;
@@ -1370,7 +1384,7 @@ __device__ __forceinline__ unsigned emit_manifold(const Params &P, long long p, 
             rec.c0x = c0.x; rec.c0y = c0.y; rec.c1x = c1.x; rec.c1y = c1.y;
             rec.bits = (unsigned long long)(unsigned)edge | ((unsigned long long)(unsigned)p0 << 20) |
                        ((unsigned long long)(unsigned)p1 << 40) | ((unsigned long long)(same ? 0 : 1) << 60);
-            P.sat_man[p] = rec;
+            if (out_rec) *out_rec = rec;      // null: the home's arrays are full (it raises the capacity error itself)
         }
     }
     return cnt;
@@ -1388,7 +1402,7 @@ struct StagedAcc {
 
 // One hull pair on ONE thread: stage both hulls, SAT both ways, clip.  Returns the contact count.
 template <int MAXV>
-__device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV> &K, const Params &P, long long p, HullAcc &A, HullAcc &B)
+__device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV> &K, ManRec *out_rec, HullAcc &A, HullAcc &B)
 {
     K.stage(A);
     K.stage(B);
@@ -1403,7 +1417,44 @@ __device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV>
     const HullAcc &E = same ? A : B;
     const HullAcc &Pn = same ? B : A;
     const SatRes ov = same ? ab : ba;
-    return emit_manifold(P, p, StagedAcc<MAXV>{ K, E, Pn }, E.n, Pn.n, ov.edge, ov.pen, same);
+    return emit_manifold(out_rec, StagedAcc<MAXV>{ K, E, Pn }, E.n, Pn.n, ov.edge, ov.pen, same);
+}
+
+// Where a pair's results go.  work_mode 0: SAT walks the pairs in reference order, results at the pair's own index.
+// 1: cell-ordered work list, results at off[r(i)] + a of this rank's arrays, pair_i / pair_j written too.
+// 2 (rows mode): results at q_off[i] + a of the arrays of i's HOME (stores over NVLink), plus the partner's position
+// and inverse masses for k_rows there; `ok` false = beyond the home's capacity (it raises the error itself).
+struct PairOut {
+    long long idx;
+    uint32_t *ccnt; ManRec *man; int32_t *pair_i, *pair_j; double4 *pj;
+    bool ok;
+};
+__device__ __forceinline__ PairOut pair_out(const Params &P, long long w, int i)
+{
+    PairOut o{ w, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+    if (P.work_mode == 1) { o.idx = (long long)(P.off[P.own_hi - 1 - i] + P.w_a[w]); o.pair_i = P.pair_i; o.pair_j = P.pair_j; }
+    else if (P.work_mode == 2) {
+        const int h = rw_home(P, i);
+        o.idx = (long long)P.q_off[i] + (long long)P.w_a[w];
+        o.ccnt = P.rw_ccnt[h]; o.man = P.rw_man[h]; o.pair_i = P.rw_pair_i[h]; o.pair_j = P.rw_pair_j[h]; o.pj = P.rw_pj[h];
+        o.ok = o.idx < P.max_pairs;
+    }
+    return o;
+}
+// the pair's index entries and, in rows mode when it has contacts, the partner's body record
+__device__ __forceinline__ void pair_out_finish(const Params &P, const PairOut &o, int i, int j, unsigned cnt)
+{
+    if (!o.ok) return;
+    o.ccnt[o.idx] = cnt;
+    if (o.pair_i) { o.pair_i[o.idx] = i; o.pair_j[o.idx] = j; }
+    if (o.pj && cnt != 0u && cnt != 0xffffffffu) {
+        // j's records were pushed here if this rank keeps j; a big query's far partner is read from its home
+        const bool here = P.mat_stamp[j] == (uint32_t)P.st->frame_no;
+        const int hj = here ? P.my_rank : rw_home(P, j);
+        const Xf x = here ? P.xf[j] : P.rw_xf[hj][j];
+        const double2 m = here ? P.mass[j] : P.rw_mass[hj][j];
+        o.pj[o.idx] = make_double4(x.px, x.py, m.x, m.y);
+    }
 }
 
 // K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
@@ -1429,6 +1480,10 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
          p += (long long)gridDim.x * CT_THREADS) {
         if (FLAGGED_ONLY && P.sat_ccnt[p] != CCNT_FALLBACK) continue;   // second pass after k_manifolds_coop
         const int i = rows ? (int)P.w_i[p] : P.pair_i[p], j = rows ? (int)P.w_j[p] : P.pair_j[p];
+        // (work_mode 1 reaches this kernel only as the flagged pass, which walks the reference order: like mode 0)
+        PairOut o{ p, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+        if (rows) o = pair_out(P, p, i);
+        ManRec *const out_rec = o.ok ? &o.man[o.idx] : nullptr;
         HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
         A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
         B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
@@ -1458,13 +1513,16 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
                     rec.ref_d = depth;                    // explicit depth (bit 61): not derived from a reference edge
                     rec.c0x = center.x; rec.c0y = center.y; rec.c1x = 0.0; rec.c1y = 0.0;
                     rec.bits = ((unsigned long long)(unsigned)feature << 20) | ((unsigned long long)flip << 60) | (1ull << 61);
-                    P.sat_man[p] = rec;
+                    if (out_rec) *out_rec = rec;
                 }
-                P.sat_ccnt[p] = hit ? 1u : 0u;
+                pair_out_finish(P, o, i, j, hit ? 1u : 0u);
+                if (rows) P.sat_ccnt[p] = hit ? 1u : 0u;
                 continue;
             }
         }
-        P.sat_ccnt[p] = hull_pair_manifold<MAXV>(K, P, p, A, B);
+        const unsigned cnt = hull_pair_manifold<MAXV>(K, out_rec, A, B);
+        pair_out_finish(P, o, i, j, cnt);
+        if (rows) P.sat_ccnt[p] = cnt;
     }
 }
 
@@ -1587,14 +1645,10 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
         // ---- prologue: lane L reads the header of pair base + L into shared memory (vertex count 0 = no pair,
         // MAX_STAGED_VERTS + 1 = leave it to the per-thread pass)
         int my_i = 0, my_j = 0, my_oa = 0, my_na = 0, my_ob = 0, my_nb = 0;
-        long long my_dst = base + lane;
         unsigned long long my_xa = 0, my_xb = 0;
         bool fallback = false;
         if (base + lane < n_pairs) {
-            if (SORTED) {
-                my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane];
-                my_dst = (long long)(P.off[P.own_hi - 1 - my_i] + P.w_a[base + lane]);
-            } else if (ROWS) { my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane]; }
+            if (SORTED || ROWS) { my_i = (int)P.w_i[base + lane]; my_j = (int)P.w_j[base + lane]; }
             else { my_i = P.pair_i[base + lane]; my_j = P.pair_j[base + lane]; }
             const uint4 ha = __ldg(&P.hh[my_i]), hb = __ldg(&P.hh[my_j]);
             my_oa = (int)ha.x; my_na = (int)ha.y; my_ob = (int)hb.x; my_nb = (int)hb.y;
@@ -1671,18 +1725,19 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
         }
         // ---- phase 2: one pair per lane
         if (base + lane < n_pairs) {
-            const long long p = my_dst;     // the pair's index in the reference order
-            if (SORTED) { P.pair_i[p] = my_i; P.pair_j[p] = my_j; }
+            PairOut o{ base + lane, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+            if (SORTED || ROWS) o = pair_out(P, base + lane, my_i);     // the pair's place in the reference order
             const CoopRes r0 = s_res[warp][lane][0], r1 = s_res[warp][lane][1];
             unsigned cnt = 0;
             if (fallback) cnt = CCNT_FALLBACK;                          // finished by k_manifolds<.., FLAGGED_ONLY>
             else if (!r0.sep) {
                 const bool same = r0.depth < r1.depth;                  // depth_ab < depth_ba ? Same : Flip (ties: Flip)
                 const int ep = same ? r0.edge_pen : r1.edge_pen;
-                cnt = emit_manifold(P, p, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
+                cnt = emit_manifold(o.ok ? &o.man[o.idx] : nullptr, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
                                     same ? my_na : my_nb, same ? my_nb : my_na, ep & 0xff, (ep >> 8) & 0xff, same);
             }
-            P.sat_ccnt[p] = cnt;
+            if (ROWS) { P.sat_ccnt[base + lane] = cnt; if (cnt != CCNT_FALLBACK) pair_out_finish(P, o, my_i, my_j, cnt); }
+            else pair_out_finish(P, o, my_i, my_j, cnt);
         }
         __syncwarp();
     }
@@ -1727,15 +1782,17 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const long long q = m >> 1;
         const int k = m & 1;
         const int i = P.pair_i[q], j = P.pair_j[q];
-        // rows mode: the manifold still lives on the rank that swept the pair -- pulled over NVLink, once per row
-        const ManRec rec = P.work_mode == 2 ? P.rw_man[P.pair_src[q] >> 28][P.pair_src[q] & 0x0fffffffu] : P.man[q];
+        const ManRec rec = P.man[q];
         // i is always an owned slot; j may belong to another rank (raw input columns; rows mode: its home's records)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
-        const bool j_own = P.work_mode == 2 ? rw_mine(P, j) : (j >= P.own_lo && j < P.own_hi);
-        const double2 xj = j_own ? *reinterpret_cast<const double2 *>(&P.xf[j])
-                         : P.work_mode == 2 ? *reinterpret_cast<const double2 *>(&P.rw_xf[rw_home(P, j)][j])
-                                            : make_double2(in_col(P, 0, P.pos_x, j), in_col(P, 1, P.pos_y, j));
-        const double2 mi = P.mass[i], mj = j_own ? P.mass[j] : slot_mass(P, j);
+        // rows mode: the rank that swept the pair stored the partner's position / inverse masses next to the manifold
+        const bool rows = P.work_mode == 2;
+        const double4 pjr = rows ? P.pj[q] : make_double4(0.0, 0.0, 0.0, 0.0);
+        const bool j_own = j >= P.own_lo && j < P.own_hi;
+        const double2 xj = rows ? make_double2(pjr.x, pjr.y)
+                         : j_own ? *reinterpret_cast<const double2 *>(&P.xf[j])
+                                 : make_double2(in_col(P, 0, P.pos_x, j), in_col(P, 1, P.pos_y, j));
+        const double2 mi = P.mass[i], mj = rows ? make_double2(pjr.z, pjr.w) : slot_mass(P, j);
         const int flip = (int)((rec.bits >> 60) & 1u);
         const int edge = (int)(rec.bits & 0xfffffu);
         const int pen = (int)((rec.bits >> (k ? 40 : 20)) & 0xfffffu);
@@ -1893,13 +1950,14 @@ __global__ void k_rw_publish(Params P, int phase)
             unsigned long long *dst = P.peer_bounds[r] + 4 * me;
             dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
         }
-    } else if (phase == RW_PHASE_RESULTS) {
-        // pairs per row bin (balances the next frame's cuts) and my error word
+    } else if (phase == RW_PHASE_CNT) {
+        // pairs per row bin (balances the next frame's cuts)
         for (int k = threadIdx.x; k < G * ROW_BINS; k += blockDim.x) {
             const int r = k / ROW_BINS, b = k % ROW_BINS;
             P.rw_weights[r][(size_t)me * ROW_BINS + b] = P.roww[b];
         }
-        for (int r = threadIdx.x; r < G; r += blockDim.x) P.rw_err[r][me] = st->error;
+    } else if (phase == RW_PHASE_OFF || phase == RW_PHASE_RESULTS) {
+        for (int r = threadIdx.x; r < G; r += blockDim.x) P.rw_err[r][(phase == RW_PHASE_OFF ? 0 : G) + me] = st->error;
     } else {
         // (pairs, contacts) of my high block's run and of my low block's run
         const int n_hi = P.rw_hi_hi - P.rw_hi_lo, n_q = n_hi + (P.rw_lo_hi - P.rw_lo_lo);
@@ -1912,6 +1970,8 @@ __global__ void k_rw_publish(Params P, int phase)
         for (int r = threadIdx.x; r < G; r += blockDim.x) {
             long long *dst = P.rw_counts[r] + 4 * me;
             dst[0] = p_hi; dst[1] = st->n_pairs - p_hi; dst[2] = c_hi; dst[3] = st->n_contacts - c_hi;
+            long long *loc = P.rw_counts[r] + 4 * G + 2 * me;
+            loc[0] = (long long)st->loc_fold; loc[1] = (long long)st->loc_contig;
         }
     }
     __threadfence_system();
@@ -1935,11 +1995,11 @@ __global__ void k_rw_wait(Params P, int phase)
     }
     __threadfence_system();
     __syncthreads();
-    if (phase == RW_PHASE_RESULTS && threadIdx.x == 0) {
+    if ((phase == RW_PHASE_OFF || phase == RW_PHASE_RESULTS) && threadIdx.x == 0) {
         int e = 0;
-        for (int q = 0; q < P.n_peers; ++q) e |= reinterpret_cast<volatile int *>(P.rw_err[P.my_rank])[q];
-        st->peer_error = e;
-        if (e) st->error |= e & (ERR_PAIR_CAP | ERR_PEER_TIMEOUT);   // a full work list anywhere voids every home's slice
+        for (int q = 0; q < P.n_peers; ++q) e |= reinterpret_cast<volatile int *>(P.rw_err[P.my_rank])[(phase == RW_PHASE_OFF ? 0 : P.n_peers) + q];
+        st->peer_error |= e;
+        if (e) st->error |= e & (ERR_PAIR_CAP | ERR_PEER_TIMEOUT);   // a full list anywhere voids the frame everywhere
     }
 }
 
@@ -1967,6 +2027,7 @@ __global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
         st->bmax_x = st->bmax_y = 0ull;
         st->n_big = 0; st->n_small = 0; st->error = 0; st->peer_error = 0;
         st->n_pairs = 0; st->n_contacts = 0; st->work_cursor = 0ull; st->n_pairs_hit = 0ull; st->n_kept = 0u;
+        st->loc_fold = 0ull; st->loc_contig = 0ull;
     }
     // row weights: ROW_BINS bins over the rows, summed over the ranks that measured them; 4 bins per thread
     unsigned long long mine = 0;
@@ -2009,7 +2070,7 @@ __global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
 
 // K0 of a rows-mode frame, one thread per HOME slot (my low block, then my high block): packed transform, inverse
 // masses, AABB, this rank's finite bounds, and the cell key -- bit 31 = isStatic, RW_KEY_* encoding.  The records stay
-// in my arena (k_rows and k_big read them) and are PUSHED, 4 + 32 + 32 bytes, to the ranks whose rows (plus halo)
+// in my arena (k_rows and k_big read them) and are PUSHED, 4 + 32 + 16 bytes, to the ranks whose rows (plus halo)
 // contain the shape's cell -- to every rank for big shapes: after the KEYS barrier a sweeping rank finds everything it
 // keeps in its own memory.  World vertices are not materialised here: that is the sweeping rank's job (k_rw_hulls).
 template <bool BOUNDS_ONLY>
@@ -2070,9 +2131,9 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
             // rank g keeps rows [cut[g] - 1, cut[g + 1]] when it sweeps any row at all
             const bool wants = cy < 0 ? true : (st->cut[g + 1] > st->cut[g] && cy >= st->cut[g] - 1 && cy <= st->cut[g + 1]);
             if (!wants) continue;
-            P.peer_keys[g][s] = key;
-            P.peer_box[g][s] = b;
+            P.peer_keys[g][s] = key;      // (the AABB is not sent: the sweeping rank folds it again from the same vertices)
             P.rw_xf[g][s] = x;
+            P.rw_mass[g][s] = make_double2(il, ir);
         }
     }
     __shared__ double s_red[4][8];
@@ -2165,73 +2226,107 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, con
     }
 }
 
-// moveShapes (World.hs:132-140) for the hulls this rank keeps (its rows, the halo rows, the big list): world
-// vertices and the unit edge normals recomputed from them (setHullTransform, ConvexHull.hs:184-195), from the packed
-// transform its home pushed.  One thread per kept shape.
-__global__ void __launch_bounds__(256) k_rw_hulls(Params P)
+// Scatter into cell order + moveShapes (World.hs:132-140) for the shapes this rank keeps, one thread per SLOT (slot
+// order: the static geometry and the pushed records are read in streams, whatever the cell order is).  Kept shapes
+// get their AABB record / slot id / key at their sorted position; kept and big shapes get their world vertices and
+// the unit edge normals recomputed from them (setHullTransform, ConvexHull.hs:184-195) from the packed transform
+// their home pushed.
+__global__ void __launch_bounds__(256) k_rw_scatter_hulls(Params P)
 {
     const FrameState *st = P.st;
     if (st->error & ERR_REPLAN) return;
-    const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n_all; p += gridDim.x * blockDim.x) {
-        const int s = p < n_kept ? (int)(P.smeta[p] & 0x7fffffffu) : (int)P.big_idx[p - n_kept];
-        const Xf x = P.xf[s];                      // pushed by its home (or mine)
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
+        const uint32_t key = P.keys[s];
+        const uint32_t enc = P.gkeys[s];
+        const bool kept = key < P.key_none, big = (enc & ~KEY_STATIC_BIT) == RW_KEY_BIG;
+        if (!kept && !big) continue;
         P.mat_stamp[s] = (uint32_t)st->frame_no;
-        if (p >= n_kept) P.sbox[p] = P.box[s];     // big shapes: AABB record next to the grid's
+        const Xf x = P.xf[s];                      // pushed by its home (or mine)
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
+        Box b{ 0.0, 0.0, 0.0, 0.0 };               // hullToAabb (Aabb.hs:81-84): the fold K0 ran at the shape's home, same bits
         if (P.radius && P.radius[s] >= 0.0) {
+            const double rad = P.radius[s];
             const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
             P.circ[s] = make_double2(ctr.x, ctr.y);
-            continue;
+            b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
+            b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+        } else if (n <= MAX_STAGED_VERTS) {
+            double2 l[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < n) l[k] = __ldg(&P.local[o + k]);
+            V2 w[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                w[k] = afmul(m, V2{ l[k].x, l[k].y });
+                P.wv[o + k] = make_double2(w[k].x, w[k].y);
+                if (k == 0) { b.min_x = b.max_x = w[k].x; b.min_y = b.max_y = w[k].y; }
+                else {
+                    b.min_x = (b.min_x < w[k].x) ? b.min_x : w[k].x; b.max_x = (b.max_x > w[k].x) ? b.max_x : w[k].x;
+                    b.min_y = (b.min_y < w[k].y) ? b.min_y : w[k].y; b.max_y = (b.max_y > w[k].y) ? b.max_y : w[k].y;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                const V2 nxt = (k + 1 < MAX_STAGED_VERTS && k + 1 < n) ? w[(k + 1) & (MAX_STAGED_VERTS - 1)] : w[0];
+                const V2 nn = unit_edge_normal(w[k], nxt);
+                P.wn[o + k] = make_double2(nn.x, nn.y);
+            }
+        } else {
+            V2 w0{ 0.0, 0.0 }, prev{ 0.0, 0.0 };
+            for (int k = 0; k < n; ++k) {
+                const double2 l = __ldg(&P.local[o + k]);
+                const V2 w = afmul(m, V2{ l.x, l.y });
+                P.wv[o + k] = make_double2(w.x, w.y);
+                if (k == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                else {
+                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                    const V2 nn = unit_edge_normal(prev, w); P.wn[o + k - 1] = make_double2(nn.x, nn.y);
+                }
+                prev = w;
+            }
+            if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
         }
-        V2 w0{ 0.0, 0.0 }, prev{ 0.0, 0.0 };
-        for (int k = 0; k < n; ++k) {
-            const double2 l = __ldg(&P.local[o + k]);
-            const V2 w = afmul(m, V2{ l.x, l.y });
-            P.wv[o + k] = make_double2(w.x, w.y);
-            if (k == 0) w0 = w;
-            else { const V2 nn = unit_edge_normal(prev, w); P.wn[o + k - 1] = make_double2(nn.x, nn.y); }
-            prev = w;
-        }
-        if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
+        if (kept) {
+            const uint32_t p = P.cell_begin[key] + P.rank[s];
+            P.sbox[p] = b;
+            P.smeta[p] = (uint32_t)s | (enc & KEY_STATIC_BIT);
+            P.keys_sorted[p] = key;
+        } else P.box[s] = b;                       // big shape: k_rw_big_boxes lists it next to the grid's records
     }
 }
 
-// Home side, after the results barrier: the counts the sweeping ranks pushed for my slots, in the descending order
-// the scan runs in.
+// The big shapes' AABB records go next to the grid's (positions n_kept + b): local reads in the sweep.
+__global__ void __launch_bounds__(256) k_rw_big_boxes(Params P)
+{
+    const FrameState *st = P.st;
+    if (st->error & ERR_REPLAN) return;
+    const unsigned n_kept = P.cell_begin[st->cell_end], n_big = st->n_big;
+    for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < n_big; b += gridDim.x * blockDim.x)
+        P.sbox[n_kept + b] = P.box[P.big_idx[b]];
+}
+
+// Home side, after the CNT barrier: the counts the sweeping ranks pushed for my slots, in the descending order the
+// scan runs in.
 __global__ void __launch_bounds__(256) k_rw_home_counts(Params P, int n_query)
 {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x)
-        P.cnt[r] = P.rw_cw[P.my_rank][rw_qslot(P, r)] & 0xffffffffull;
+        P.cnt[r] = (unsigned long long)(P.rw_cq[P.my_rank][rw_qslot(P, r)] & 0x0fffffffu);
 }
 
-// Home side: every pair of my slice into its place of the reference order -- the partner and the contact count are
-// pulled from the sweeping rank's work-order arrays (8 B per pair); the manifold itself stays there until k_rows.
-__global__ void __launch_bounds__(256) k_rw_gather(Params P, int n_query)
+// Home side, after the scan: every slot's first pair index goes back to the rank that swept it (4 B over NVLink), so
+// that its SAT stage stores each pair straight into its final place here.
+__global__ void __launch_bounds__(256) k_rw_push_offsets(Params P, int n_query)
 {
-    const FrameState *st = P.st;
-    if (st->error) return;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_query; r += gridDim.x * blockDim.x) {
-        const unsigned n = (unsigned)P.cnt[r];
-        if (n == 0) continue;
         const int i = rw_qslot(P, r);
-        const uint32_t ws = (uint32_t)(P.rw_cw[P.my_rank][i] >> 32);
-        const int src_rank = (int)(ws >> 28);
-        const uint32_t w0 = ws & 0x0fffffffu;
+        const uint32_t w = P.rw_cq[P.my_rank][i];
+        if ((w & 0x0fffffffu) == 0u) continue;
         const unsigned long long off = P.off[r];
-        const uint32_t *wj = P.rw_wj[src_rank], *wc = P.rw_ccnt[src_rank];
-        for (unsigned a0 = 0; a0 < n; a0 += 4) {       // four pairs' remote loads in flight together
-            uint32_t vj[4], vc[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (a0 + q < n) { vj[q] = wj[w0 + a0 + q]; vc[q] = wc[w0 + a0 + q]; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (a0 + q < n) {
-                const unsigned long long d = off + a0 + q;
-                P.pair_i[d] = i; P.pair_j[d] = (int32_t)vj[q]; P.ccnt[d] = vc[q];
-                P.pair_src[d] = ((uint32_t)src_rank << 28) | (w0 + a0 + q);
-            }
-        }
+        P.rw_qoff[w >> 28][i] = off < 0xffffffffull ? (uint32_t)off : 0xffffffffu;
     }
 }
 
@@ -2370,12 +2465,15 @@ struct shapes_ctx {
     // rows mode (multi-rank with mapped peers): one exchange arena per rank, same layout everywhere
     bool use_rows = true;         // SHAPES_B200_NO_ROWS=1: slot-range ownership of the whole path (the r1 exchange)
     bool rows_ready = false;      // every peer's arena is mapped
+    bool rows_fold = true;        // home layout: folded blocks (any slot numbering) / contiguous chunks (numbering follows the geometry)
+    int rows_frames = 0;          // rows-mode frames since the geometry was set (the layout decision is taken after the second)
     char *rw_arena = nullptr;
     char *peer_arena[SHAPES_MAX_RANKS] = {};
     struct RowsLayout {
-        size_t gkeys[2], box, xf, mass, in[7], cw, bounds[2], weights[2], counts, err, flags, wj, ccnt_w, man_w, total;
+        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, pair_i, pair_j, ccnt, man, pj, total;
     } rwl{};
-    uint32_t *d_roww = nullptr, *d_pair_src = nullptr, *d_w_j = nullptr;
+    uint32_t *d_roww = nullptr, *d_ccnt_w = nullptr, *d_w_j = nullptr;
+    int32_t *d_pair_i = nullptr, *d_pair_j = nullptr; uint32_t *d_ccnt = nullptr; ManRec *d_man = nullptr;   // single-rank homes of the result arrays
     Xf *d_xf = nullptr;
     double2 *d_mass = nullptr;
     unsigned *d_chunk_sum = nullptr;
@@ -2579,6 +2677,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.pair_j, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.man, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.ccnt, max_pairs));
+    c->d_pair_i = P.pair_i; c->d_pair_j = P.pair_j; c->d_man = P.man; c->d_ccnt = P.ccnt;
     TRY_CREATE(dev_alloc(c, &P.coff, max_pairs));
     TRY_CREATE(dev_alloc(c, &P.row_map, max_contacts));
     TRY_CREATE(cu(cudaMemset(P.ccnt, 0, std::max<int64_t>(max_pairs, 1) * sizeof(uint32_t)), "cudaMemset"));
@@ -2596,6 +2695,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &P.st, 1));
     TRY_CREATE(cu(cudaMemset(P.st, 0, sizeof(FrameState)), "cudaMemset"));
     c->use_rows = std::getenv("SHAPES_B200_NO_ROWS") == nullptr;
+    if (const char *lay = std::getenv("SHAPES_B200_ROWS_LAYOUT")) c->rows_fold = std::strcmp(lay, "contiguous") != 0;   // pin the home layout
     if (world > 1 && c->use_rows && max_pairs < (1ll << 28)) {
         // the exchange arena of rows mode: one allocation, identical layout on every rank (the capacities are the
         // same everywhere), so a peer's buffer is its arena base + the local offset
@@ -2605,18 +2705,18 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         L.gkeys[0] = take(sizeof(uint32_t) * Npad); L.gkeys[1] = take(sizeof(uint32_t) * Npad);
         L.box = take(sizeof(Box) * Npad); L.xf = take(sizeof(Xf) * Npad); L.mass = take(sizeof(double2) * Npad);
         for (int k = 0; k < 7; ++k) L.in[k] = take(sizeof(double) * Npad);
-        L.cw = take(sizeof(unsigned long long) * Npad);
+        L.cq = take(sizeof(uint32_t) * Npad); L.qoff = take(sizeof(uint32_t) * Npad);
         for (int q = 0; q < 2; ++q) { L.bounds[q] = take(sizeof(unsigned long long) * 4 * world); L.weights[q] = take(sizeof(uint32_t) * ROW_BINS * world); }
-        L.counts = take(sizeof(long long) * 4 * world); L.err = take(sizeof(int) * world);
+        L.counts = take(sizeof(long long) * 6 * world); L.err = take(sizeof(int) * 2 * world);
         L.flags = take(sizeof(unsigned long long) * RW_PHASES * SHAPES_MAX_RANKS);
-        L.wj = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
-        L.ccnt_w = take(sizeof(uint32_t) * std::max<int64_t>(max_pairs, 1));
-        L.man_w = take(sizeof(ManRec) * std::max<int64_t>(max_pairs, 1));
+        const size_t MP = (size_t)std::max<int64_t>(max_pairs, 1);
+        L.pair_i = take(sizeof(int32_t) * MP); L.pair_j = take(sizeof(int32_t) * MP); L.ccnt = take(sizeof(uint32_t) * MP);
+        L.man = take(sizeof(ManRec) * MP); L.pj = take(sizeof(double4) * MP);
         L.total = off;
         TRY_CREATE(dev_alloc(c, &c->rw_arena, L.total));
         TRY_CREATE(cu(cudaMemset(c->rw_arena, 0, L.total), "cudaMemset"));
         TRY_CREATE(dev_alloc(c, &c->d_roww, ROW_BINS));
-        TRY_CREATE(dev_alloc(c, &c->d_pair_src, max_pairs));
+        TRY_CREATE(dev_alloc(c, &c->d_ccnt_w, max_pairs));
         TRY_CREATE(dev_alloc(c, &c->d_chunk_sum, SCAN_BLOCKS));
         TRY_CREATE(dev_alloc(c, &c->d_mat_stamp, N));
         TRY_CREATE(cu(cudaMemset(c->d_mat_stamp, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(N, 1)), "cudaMemset"));
@@ -2625,7 +2725,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(dev_alloc(c, &c->d_counts, 2 * world));
     TRY_CREATE(dev_alloc(c, &c->d_n_prev, 1));
     TRY_CREATE(cu(cudaMallocHost(&c->h_state, sizeof(FrameState)), "cudaMallocHost"));
-    TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 4 * world), "cudaMallocHost"));
+    TRY_CREATE(cu(cudaMallocHost(&c->h_counts, sizeof(int64_t) * 6 * world), "cudaMallocHost"));
     // library scratch: radix sort of (cell key, slot) and the offset scan
     size_t cb = 0;
     TRY_CREATE(cu(cub::DeviceScan::ExclusiveSum(nullptr, cb, P.cnt, P.off, (int)std::max<int64_t>(N, 1), c->stream),
@@ -2667,6 +2767,11 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
 // rows mode: the two home blocks of a rank, [lo[0], hi[0]) = low block, [lo[1], hi[1]) = high block
 inline void rows_home_blocks(const shapes_ctx *c, int rank, int64_t n_slots, int64_t lo[2], int64_t hi[2])
 {
+    if (!c->rows_fold) {     // contiguous homes: one block per rank
+        lo[0] = std::min<int64_t>(rank * c->chunk, n_slots); hi[0] = std::min<int64_t>((rank + 1) * c->chunk, n_slots);
+        lo[1] = hi[1] = n_slots;
+        return;
+    }
     const int64_t blk = std::max<int64_t>((c->chunk + 1) / 2, 1);
     lo[0] = std::min<int64_t>(rank * blk, n_slots); hi[0] = std::min<int64_t>((rank + 1) * blk, n_slots);
     lo[1] = std::min<int64_t>((2 * c->world - 1 - rank) * blk, n_slots); hi[1] = std::min<int64_t>((2 * c->world - rank) * blk, n_slots);
@@ -2738,7 +2843,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         for (int k = 0; k < 7; ++k) P.peer_in[k][r] = c->peer_in2[fpar][k][r];
     }
     P.work_mode = rows ? 2 : (P.sorted_mode ? 1 : 0);
-    P.sat_ccnt = P.ccnt; P.sat_man = P.man; P.xf = c->d_xf; P.w_j = c->d_w_j; P.mass = c->d_mass;
+    P.pair_i = c->d_pair_i; P.pair_j = c->d_pair_j; P.man = c->d_man; P.ccnt = c->d_ccnt;
+    P.sat_ccnt = P.ccnt; P.xf = c->d_xf; P.mass = c->d_mass;
     const bool seed_rows = rows && !c->plan_valid;
     int n_home = 0;
     if (rows) {
@@ -2750,30 +2856,35 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         P.box = reinterpret_cast<Box *>(mine + L.box); P.gkeys = reinterpret_cast<uint32_t *>(mine + L.gkeys[fpar]);
         P.xf = reinterpret_cast<Xf *>(mine + L.xf); P.mass = reinterpret_cast<double2 *>(mine + L.mass);
         // homes: blocks g and 2G-1-g of the slot space
-        const int64_t blk = std::max<int64_t>((c->chunk + 1) / 2, 1);
-        P.rw_blk = (int)blk;
-        P.rw_lo_lo = (int)std::min<int64_t>(c->rank * blk, N); P.rw_lo_hi = (int)std::min<int64_t>((c->rank + 1) * blk, N);
-        P.rw_hi_lo = (int)std::min<int64_t>((2 * c->world - 1 - c->rank) * blk, N);
-        P.rw_hi_hi = (int)std::min<int64_t>((2 * c->world - c->rank) * blk, N);
+        int64_t hlo[2], hhi[2];
+        rows_home_blocks(c, c->rank, N, hlo, hhi);
+        P.rw_fold = c->rows_fold ? 1 : 0;
+        P.rw_blk = (int)std::max<int64_t>(c->rows_fold ? (c->chunk + 1) / 2 : c->chunk, 1);
+        P.rw_lo_lo = (int)hlo[0]; P.rw_lo_hi = (int)hhi[0]; P.rw_hi_lo = (int)hlo[1]; P.rw_hi_hi = (int)hhi[1];
         P.own_lo = P.rw_lo_lo; P.own_hi = P.rw_lo_hi;
         n_home = (P.rw_lo_hi - P.rw_lo_lo) + (P.rw_hi_hi - P.rw_hi_lo);
         P.flags = reinterpret_cast<unsigned long long *>(mine + L.flags);
-        P.sat_ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt_w); P.sat_man = reinterpret_cast<ManRec *>(mine + L.man_w);
-        P.w_j = reinterpret_cast<uint32_t *>(mine + L.wj);
-        P.pair_src = c->d_pair_src; P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp;
+        // the result arrays of a home live in its arena: the sweeping ranks store into them
+        P.pair_i = reinterpret_cast<int32_t *>(mine + L.pair_i); P.pair_j = reinterpret_cast<int32_t *>(mine + L.pair_j);
+        P.ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt); P.man = reinterpret_cast<ManRec *>(mine + L.man);
+        P.pj = reinterpret_cast<double4 *>(mine + L.pj); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
+        P.sat_ccnt = c->d_ccnt_w;
+        P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp;
         P.rw_weights_prev = reinterpret_cast<const uint32_t *>(mine + L.weights[fpar ^ 1]);
         P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
         for (int r = 0; r < c->world; ++r) {
             char *a = c->peer_arena[r];
             P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys[fpar]);
             P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf); P.rw_mass[r] = reinterpret_cast<double2 *>(a + L.mass);
-            P.rw_cw[r] = reinterpret_cast<unsigned long long *>(a + L.cw);
+            P.rw_cq[r] = reinterpret_cast<uint32_t *>(a + L.cq); P.rw_qoff[r] = reinterpret_cast<uint32_t *>(a + L.qoff);
+            P.rw_pair_i[r] = reinterpret_cast<int32_t *>(a + L.pair_i); P.rw_pair_j[r] = reinterpret_cast<int32_t *>(a + L.pair_j);
+            P.rw_ccnt[r] = reinterpret_cast<uint32_t *>(a + L.ccnt); P.rw_man[r] = reinterpret_cast<ManRec *>(a + L.man);
+            P.rw_pj[r] = reinterpret_cast<double4 *>(a + L.pj);
             P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
             P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
             P.rw_counts[r] = reinterpret_cast<long long *>(a + L.counts); P.rw_err[r] = reinterpret_cast<int *>(a + L.err);
             P.peer_flags[r] = reinterpret_cast<unsigned long long *>(a + L.flags);
-            P.rw_wj[r] = reinterpret_cast<const uint32_t *>(a + L.wj); P.rw_ccnt[r] = reinterpret_cast<const uint32_t *>(a + L.ccnt_w);
-            P.rw_man[r] = reinterpret_cast<const ManRec *>(a + L.man_w);
+
         }
     } else P.flags = c->d_flags;
     P.world_x = want_world ? c->d_world_x : nullptr;
@@ -2806,18 +2917,29 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         k_scan_cells_apply<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
         STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
         if (N > 0) {
-            k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
-            k_rw_hulls<<<grid_for(n_query + n_query / 2 + 4096, 256, sms * 8), 256, 0, s>>>(P); ++c->launches;
+            k_rw_scatter_hulls<<<gn, 256, 0, s>>>(P); ++c->launches;
+            k_rw_big_boxes<<<8, 256, 0, s>>>(P); ++c->launches;
         }
-        STAGE_MARK(); // 5: single-pass sweep of my rows; counts / list positions pushed to the homes
+        STAGE_MARK(); // 5: single-pass sweep of my rows; every query's count is pushed to its home; barrier CNT
         if (N > 0) {
             k_sweep<SWEEP_FUSED><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
             k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
             k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
         }
-        STAGE_MARK(); // 6
+        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
+        STAGE_MARK(); // 6: home -- offsets of my slice, sent back to the sweeping ranks; barrier OFF
+        if (n_query > 0) {
+            k_rw_home_counts<<<gq, 256, 0, s>>>(P, n_query); ++c->launches;
+            size_t cb = c->scan_tmp_bytes;
+            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+        }
+        k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+        if (n_query > 0) { k_rw_push_offsets<<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
+        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
+        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
         STAGE_MARK(); // 7
-        STAGE_MARK(); // 8: manifolds over my work list, results in work order; then barrier RESULTS
+        STAGE_MARK(); // 8: manifolds over my work list, every pair stored into its final place at its home; barrier RESULTS
         if (N > 0) {
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
@@ -2832,20 +2954,13 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         }
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
-        STAGE_MARK(); // 9: home -- offsets of my slice, (j, contact count) of every pair pulled into place, row offsets
-        if (n_query > 0) {
-            k_rw_home_counts<<<gq, 256, 0, s>>>(P, n_query); ++c->launches;
-            size_t cb = c->scan_tmp_bytes;
-            CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
-        }
-        k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
-        if (n_query > 0) { k_rw_gather<<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
+        STAGE_MARK(); // 9: home -- row offsets
         if (c->max_pairs > 0) {
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
             k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
         }
-        STAGE_MARK(); // 10: contact rows (manifolds pulled from the sweeping ranks)
+        STAGE_MARK(); // 10: contact rows
         if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
         STAGE_MARK(); // 11: warm-start cache join
         if (N > 0 && warm) { k_warm_join<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
@@ -2855,7 +2970,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
         CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 4 * c->world, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 6 * c->world, cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
         return SHAPES_OK;
     };
@@ -3043,6 +3158,22 @@ int frame_finish(shapes_ctx *c, shapes_frame_out *out)
         return SHAPES_I_REPLAN;
     }
     c->plan_valid = (c->pending_plan_ahead || c->pending_rows) && st.error == 0;
+    if (c->pending_rows && st.error == 0) {
+        // Home layout for the next frames, from the locality counters every rank received with the counts: if most
+        // pairs would stay on the GPU that sweeps them with contiguous homes (slot numbering follows the geometry) use
+        // those; otherwise the folded blocks, which balance slots and pairs for any numbering.  Hysteresis 0.45 / 0.55.
+        ++c->rows_frames;
+        long long lf = 0, lc = 0, tot = 0;
+        for (int r = 0; r < c->world; ++r) { lf += c->h_counts[4 * c->world + 2 * r]; lc += c->h_counts[4 * c->world + 2 * r + 1]; }
+        for (int r = 0; r < c->world; ++r) tot += c->h_counts[4 * r] + c->h_counts[4 * r + 1];
+        (void)lf;
+        const double f_contig = tot > 0 ? 16.0 * (double)lc / (double)tot : 0.0;   // one query in 16 is sampled
+        const bool want_fold = c->rows_fold ? !(f_contig > 0.55) : (f_contig < 0.45);
+        if (want_fold != c->rows_fold && std::getenv("SHAPES_B200_ROWS_LAYOUT") == nullptr) {
+            c->rows_fold = want_fold;
+            for (int q = 0; q < 4; ++q) if (c->graph_exec[q]) { cudaGraphExecDestroy(c->graph_exec[q]); c->graph_exec[q] = nullptr; }
+        }
+    }
     if (c->pending_seed) c->big_seen = st.n_big;
     c->last_pairs = st.n_pairs;
     c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
@@ -3239,7 +3370,7 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
     c->has_circles = any_circle;
     c->P.radius = any_circle ? c->d_radius : nullptr;
     if (c->rw_arena)   // rows mode: slots nobody sweeps (dead ones) must read as "no partners"
-        CU_TRY(c, cudaMemset(c->rw_arena + c->rwl.cw, 0, sizeof(unsigned long long) * (size_t)std::max<int64_t>(c->chunk * c->world, 1)));
+        CU_TRY(c, cudaMemset(c->rw_arena + c->rwl.cq, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1)));
     c->hulls_set = true;
     c->have_frame = false;
     c->plan_valid = false;
