@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
         const uint32_t key = P.keys[s];
         if (key >= P.key_none) continue;
         const uint32_t p = P.cell_begin[key] + P.rank[s];
-        P.sbox[p] = P.work_mode == 2 ? P.box[s] : box_of(P, s);     // rows mode: the home pushed the record into my array
+        if (P.work_mode != 2) P.sbox[p] = box_of(P, s);     // rows mode: k_rw_hulls folds the record at the sorted position
         const bool st_flag = P.work_mode == 2 ? (P.gkeys[s] & KEY_STATIC_BIT) != 0u : slot_static(P, s);
         P.smeta[p] = (uint32_t)s | ((uint32_t)st_flag << 31);
         P.keys_sorted[p] = key;
@@ -2226,87 +2226,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, con
     }
 }
 
-// Scatter into cell order + moveShapes (World.hs:132-140) for the shapes this rank keeps, one thread per SLOT (slot
-// order: the static geometry and the pushed records are read in streams, whatever the cell order is).  Kept shapes
-// get their AABB record / slot id / key at their sorted position; kept and big shapes get their world vertices and
-// the unit edge normals recomputed from them (setHullTransform, ConvexHull.hs:184-195) from the packed transform
-// their home pushed.
-__global__ void __launch_bounds__(256) k_rw_scatter_hulls(Params P)
+// moveShapes (World.hs:132-140) for the shapes this rank keeps (its rows, the halo rows, the big list), 8 lanes per
+// shape in CELL order (dense whatever share of the world this rank keeps): lane k transforms vertex k and its
+// successor with the packed transform the shape's home pushed and emits the world vertex and the unit normal of the
+// edge that starts there (setHullTransform, ConvexHull.hs:184-195: normals recomputed from the NEW vertices); lane 0
+// also folds the AABB over the vertices in order (hullToAabb, Aabb.hs:81-84 -- the fold K0 ran at the home, same bits)
+// and stores it at the shape's sorted position.  Hulls of more than 8 vertices are walked by lane 0 alone.
+__global__ void __launch_bounds__(256) k_rw_hulls(Params P)
 {
     const FrameState *st = P.st;
     if (st->error & ERR_REPLAN) return;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        const uint32_t key = P.keys[s];
-        const uint32_t enc = P.gkeys[s];
-        const bool kept = key < P.key_none, big = (enc & ~KEY_STATIC_BIT) == RW_KEY_BIG;
-        if (!kept && !big) continue;
-        P.mat_stamp[s] = (uint32_t)st->frame_no;
+    const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
+    const int k = threadIdx.x & 7;
+    for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < n_all; p += (gridDim.x * blockDim.x) >> 3) {
+        const int s = p < n_kept ? (int)(P.smeta[p] & 0x7fffffffu) : (int)P.big_idx[p - n_kept];
         const Xf x = P.xf[s];                      // pushed by its home (or mine)
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
-        Box b{ 0.0, 0.0, 0.0, 0.0 };               // hullToAabb (Aabb.hs:81-84): the fold K0 ran at the shape's home, same bits
-        if (P.radius && P.radius[s] >= 0.0) {
-            const double rad = P.radius[s];
+        const double rad = P.radius ? P.radius[s] : -1.0;
+        if (k == 0) P.mat_stamp[s] = (uint32_t)st->frame_no;
+        if (rad < 0.0 && n <= MAX_STAGED_VERTS && k < n) {
+            const double2 la = __ldg(&P.local[o + k]), lb = __ldg(&P.local[o + ((k + 1 < n) ? k + 1 : 0)]);
+            const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
+            const V2 nn = unit_edge_normal(wa, wb);
+            P.wv[o + k] = make_double2(wa.x, wa.y);
+            P.wn[o + k] = make_double2(nn.x, nn.y);
+        }
+        if (k != 0) continue;
+        Box b{ 0.0, 0.0, 0.0, 0.0 };
+        if (rad >= 0.0) {      // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
             const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
             P.circ[s] = make_double2(ctr.x, ctr.y);
             b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
             b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
-        } else if (n <= MAX_STAGED_VERTS) {
-            double2 l[MAX_STAGED_VERTS];
-#pragma unroll
-            for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < n) l[k] = __ldg(&P.local[o + k]);
-            V2 w[MAX_STAGED_VERTS];
-#pragma unroll
-            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
-                if (k >= n) break;
-                w[k] = afmul(m, V2{ l[k].x, l[k].y });
-                P.wv[o + k] = make_double2(w[k].x, w[k].y);
-                if (k == 0) { b.min_x = b.max_x = w[k].x; b.min_y = b.max_y = w[k].y; }
-                else {
-                    b.min_x = (b.min_x < w[k].x) ? b.min_x : w[k].x; b.max_x = (b.max_x > w[k].x) ? b.max_x : w[k].x;
-                    b.min_y = (b.min_y < w[k].y) ? b.min_y : w[k].y; b.max_y = (b.max_y > w[k].y) ? b.max_y : w[k].y;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
-                if (k >= n) break;
-                const V2 nxt = (k + 1 < MAX_STAGED_VERTS && k + 1 < n) ? w[(k + 1) & (MAX_STAGED_VERTS - 1)] : w[0];
-                const V2 nn = unit_edge_normal(w[k], nxt);
-                P.wn[o + k] = make_double2(nn.x, nn.y);
-            }
         } else {
+            const bool long_hull = n > MAX_STAGED_VERTS;
             V2 w0{ 0.0, 0.0 }, prev{ 0.0, 0.0 };
-            for (int k = 0; k < n; ++k) {
-                const double2 l = __ldg(&P.local[o + k]);
+            for (int q = 0; q < n; ++q) {
+                const double2 l = __ldg(&P.local[o + q]);
                 const V2 w = afmul(m, V2{ l.x, l.y });
-                P.wv[o + k] = make_double2(w.x, w.y);
-                if (k == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                if (q == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
                 else {
                     b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
                     b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
-                    const V2 nn = unit_edge_normal(prev, w); P.wn[o + k - 1] = make_double2(nn.x, nn.y);
                 }
-                prev = w;
+                if (long_hull) {
+                    P.wv[o + q] = make_double2(w.x, w.y);
+                    if (q > 0) { const V2 nn = unit_edge_normal(prev, w); P.wn[o + q - 1] = make_double2(nn.x, nn.y); }
+                    prev = w;
+                }
             }
-            if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
+            if (long_hull && n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
         }
-        if (kept) {
-            const uint32_t p = P.cell_begin[key] + P.rank[s];
-            P.sbox[p] = b;
-            P.smeta[p] = (uint32_t)s | (enc & KEY_STATIC_BIT);
-            P.keys_sorted[p] = key;
-        } else P.box[s] = b;                       // big shape: k_rw_big_boxes lists it next to the grid's records
+        P.sbox[p] = b;      // big shapes: positions n_kept + b, next to the grid's records
     }
-}
-
-// The big shapes' AABB records go next to the grid's (positions n_kept + b): local reads in the sweep.
-__global__ void __launch_bounds__(256) k_rw_big_boxes(Params P)
-{
-    const FrameState *st = P.st;
-    if (st->error & ERR_REPLAN) return;
-    const unsigned n_kept = P.cell_begin[st->cell_end], n_big = st->n_big;
-    for (unsigned b = blockIdx.x * blockDim.x + threadIdx.x; b < n_big; b += gridDim.x * blockDim.x)
-        P.sbox[n_kept + b] = P.box[P.big_idx[b]];
 }
 
 // Home side, after the CNT barrier: the counts the sweeping ranks pushed for my slots, in the descending order the
@@ -2917,8 +2890,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         k_scan_cells_apply<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
         STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
         if (N > 0) {
-            k_rw_scatter_hulls<<<gn, 256, 0, s>>>(P); ++c->launches;
-            k_rw_big_boxes<<<8, 256, 0, s>>>(P); ++c->launches;
+            k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
+            k_rw_hulls<<<sms * 16, 256, 0, s>>>(P); ++c->launches;
         }
         STAGE_MARK(); // 5: single-pass sweep of my rows; every query's count is pushed to its home; barrier CNT
         if (N > 0) {
