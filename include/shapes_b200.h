@@ -167,6 +167,15 @@ int  shapes_set_shapes(shapes_ctx *, int64_t n_slots, const uint8_t *alive,
  * shapes_set_hulls.  Performance only: results do not depend on it. */
 int  shapes_set_cell_size(shapes_ctx *, double cell_size);
 
+/* Grow max_pairs / max_contacts IN PLACE (values below the current capacity are ignored): the caller's answer to
+ * SHAPES_E_CAPACITY.  A frame that returned SHAPES_E_CAPACITY left the ctx as it was before the call -- the previous
+ * frame's ObjectFeatureKey columns, the Lagrangian cache supplied for them (the reference's EngineCache,
+ * Engine/Main.hs:32,60-68) and an uploaded world all stay valid -- and shapes_grow keeps them, so the retried frame
+ * (or world step) warm-starts exactly as the reference's applyCachedSlns would (Solvers/Contact.hs:84-121).
+ * Only the result arrays of the last frame become unavailable (shapes_fetch / shapes_device_view_get fail until the
+ * next completed frame).  Single-GPU ctxs only: ranks of a multi-GPU job re-create their ctxs collectively. */
+int  shapes_grow(shapes_ctx *, int64_t max_pairs, int64_t max_contacts);
+
 /* ---- per frame -------------------------------------------------------- */
 
 /* Inputs are the reference's own SoA columns of _wPhysObjs (World.hs:47,

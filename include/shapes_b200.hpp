@@ -13,7 +13,7 @@
 //   shapes::constraintGen    Constraints.Contact.constraintGen   (Constraints/Contact.hs:60-72)
 //
 // Errors: the replaced functions are total; every non-zero C-ABI code is thrown as shapes::Error
-// (SHAPES_E_CAPACITY is handled by growing the ctx and retrying, the frame being side-effect free).
+// (SHAPES_E_CAPACITY is handled by shapes_grow and retrying, the failed frame being side-effect free).
 // There is no CPU fallback: without the CUDA library/device the constructor throws.
 #pragma once
 
@@ -170,20 +170,15 @@ public:
         if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
         uploaded_ = &w;
     }
-    // shapes_world_step: one updateWorld; grows the ctx and re-uploads on SHAPES_E_CAPACITY (the step
-    // leaves the world untouched in that case, so the last downloaded/uploaded state is still current)
+    // shapes_world_step: one updateWorld; on SHAPES_E_CAPACITY (the step leaves the world and the EngineCache
+    // untouched) the capacities grow in place and the step is issued again
     shapes_step_stats worldStep(World &w, const shapes_step_config &cfg)
     {
         if (uploaded_ != &w) worldUpload(w);
         for (int attempt = 0;; ++attempt) {
             shapes_step_stats st{};
             const int rc = shapes_world_step(ctx_, &cfg, &st);
-            if (rc == SHAPES_E_CAPACITY && attempt < 4) {
-                worldDownload(w);
-                grow(w, st.n_pairs, st.n_contacts);
-                worldUpload(w);
-                continue;
-            }
+            if (rc == SHAPES_E_CAPACITY && attempt < 4) { grow(w, st.n_pairs, st.n_contacts); continue; }
             if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
             return st;
         }
@@ -276,13 +271,14 @@ private:
             w.geometry_dirty = false;
         }
     }
+    // shapes_grow: capacities grow in place; key columns, EngineCache and an uploaded world survive
     void grow(World &w, int64_t need_pairs, int64_t need_contacts)
     {
+        (void)w;
         max_pairs_ = std::max(max_pairs_, need_pairs + need_pairs / 4 + 1024);
         max_contacts_ = std::max(max_contacts_, need_contacts + need_contacts / 4 + 1024);
-        create(w);
-        w.geometry_dirty = true;
-        ensure(w);
+        const int rc = shapes_grow(ctx_, max_pairs_, max_contacts_);
+        if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
     }
 
     shapes_ctx *ctx_ = nullptr;

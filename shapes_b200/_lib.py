@@ -105,6 +105,7 @@ SYMBOLS = {
     "shapes_set_shapes": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "shapes_set_cell_size": (C.c_int, [C.c_void_p, C.c_double]),
+    "shapes_grow": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "shapes_frame": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
     "shapes_frame_device": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_double] * 3 + [C.POINTER(FrameOut)]),
     "shapes_device_view_get": (C.c_int, [C.c_void_p, C.POINTER(DeviceView)]),

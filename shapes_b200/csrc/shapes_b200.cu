@@ -39,6 +39,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -2503,7 +2504,8 @@ struct shapes_ctx {
     int parity = 0;
     // last frame
     int64_t last_pairs = 0, last_contacts = 0;
-    bool have_frame = false;
+    bool have_frame = false;      // key columns (and counts) of a completed frame exist: the join's "previous frame"
+    bool results_valid = false;   // the result arrays hold that frame (false after a failed attempt until the next success)
 };
 
 namespace {
@@ -3148,15 +3150,32 @@ int frame_finish(shapes_ctx *c, shapes_frame_out *out)
         }
     }
     if (c->pending_seed) c->big_seen = st.n_big;
-    c->last_pairs = st.n_pairs;
-    c->last_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
-    c->have_frame = (st.error == 0);
-    c->warm_done = warm && c->have_frame;
-    c->cache_valid = false; // a cache describes exactly one previous frame
-    if (c->world == 1) { c->h_counts[0] = c->last_pairs; c->h_counts[1] = c->last_contacts; }
+    const int64_t now_pairs = st.n_pairs;
+    const int64_t now_contacts = (st.error & ERR_PAIR_CAP) ? 2 * st.n_pairs : st.n_contacts;
+    const bool capacity = st.error != 0 && !(st.error & ERR_PEER_TIMEOUT);
+    if (capacity) {
+        // SHAPES_E_CAPACITY leaves the ctx as it was before the call: the previous frame's key columns go back to the
+        // "current" side, its Lagrangian cache stays valid, so after shapes_grow the retried frame joins against the
+        // same EngineCache the failed attempt saw (Solvers/Contact.hs:84-121).  Only the result arrays are stale.
+        if (c->have_frame) {
+            std::swap(P.key_i, c->alt_key[0]); std::swap(P.key_j, c->alt_key[1]);
+            std::swap(P.feat_a, c->alt_key[2]); std::swap(P.feat_b, c->alt_key[3]);
+            c->parity ^= 1;
+        }
+        c->cache_valid = warm;
+        c->results_valid = false;
+    } else {
+        c->last_pairs = now_pairs;
+        c->last_contacts = now_contacts;
+        c->have_frame = (st.error == 0);
+        c->results_valid = c->have_frame;
+        c->warm_done = warm && c->have_frame;
+        c->cache_valid = false; // a cache describes exactly one previous frame
+        if (c->world == 1) { c->h_counts[0] = c->last_pairs; c->h_counts[1] = c->last_contacts; }
+    }
     if (out) {
-        out->n_pairs = c->last_pairs;
-        out->n_contacts = c->last_contacts;
+        out->n_pairs = now_pairs;
+        out->n_contacts = now_contacts;
         out->n_big = st.n_big;
         out->grid_w = st.W; out->grid_h = st.H; out->cell_size = st.h;
         float ms = 0.f;
@@ -3166,7 +3185,7 @@ int frame_finish(shapes_ctx *c, shapes_frame_out *out)
     }
     if (c->profiling)
         for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
-    if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its records"; c->have_frame = false; return SHAPES_E_NCCL; }
+    if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its records"; c->have_frame = false; c->results_valid = false; return SHAPES_E_NCCL; }
     if (st.error) {
         c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs; rows mode: on this or another rank)"
                                            : "capacity: max_contacts too small (required count in n_contacts)";
@@ -3197,6 +3216,7 @@ int fetch_col(shapes_ctx *c, T *dst, const T *src, int64_t n)
 }
 
 void world_free(shapes_ctx *c);
+int world_grow(shapes_ctx *c, bool pairs, bool contacts);
 
 } // namespace
 
@@ -3323,9 +3343,15 @@ int shapes_set_shapes(shapes_ctx *c, int64_t n_slots, const uint8_t *alive, cons
         if (n_verts > 0) CU_TRY(c, cudaMemcpyAsync(c->d_local, inter.data(), sizeof(double2) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
         if (any_circle) CU_TRY(c, cudaMemcpyAsync(c->d_radius, radius, sizeof(double) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
         if (ext_min) {
-            for (int64_t v = 0; v < n_verts; ++v) {
-                // _hullExtents entries index the hull's own vertices
-                if (ext_min[v] < 0 || ext_max[v] < 0) { c->err = "shapes_set_hulls: negative extent index"; return SHAPES_E_ARG; }
+            for (int64_t sl = 0; sl < n_slots; ++sl) {
+                // _hullExtents entries index the hull's own vertices (ConvexHull.hs:63-77): anything else would be an
+                // out-of-bounds read of the staged hull
+                const int32_t o = vert_offset[sl], n = vert_offset[sl + 1] - o;
+                for (int32_t k = 0; k < n; ++k)
+                    if (ext_min[o + k] < 0 || ext_max[o + k] < 0 || ext_min[o + k] >= n || ext_max[o + k] >= n) {
+                        c->err = "shapes_set_hulls: extent index outside its hull";
+                        return SHAPES_E_ARG;
+                    }
             }
             CU_TRY(c, cudaMemcpyAsync(c->d_ext_min, ext_min, sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
             CU_TRY(c, cudaMemcpyAsync(c->d_ext_max, ext_max, sizeof(int32_t) * (size_t)n_verts, cudaMemcpyHostToDevice, s));
@@ -3359,6 +3385,77 @@ int shapes_set_cell_size(shapes_ctx *c, double cell_size)
     return SHAPES_OK;
 }
 
+// Grow the pair / contact capacities in place.  Everything that describes the world between frames survives: the
+// previous frame's key columns (both halves of the double buffer), the Lagrangian cache supplied for them, the
+// uploaded world (world_step.cuh) and the grid plan -- i.e. the reference's EngineCache (Engine/Main.hs:32,60-68) is
+// NOT dropped, which re-creating the ctx would do.  Per-frame result arrays are simply re-allocated.
+int shapes_grow(shapes_ctx *c, int64_t max_pairs, int64_t max_contacts)
+{
+    if (!c) return SHAPES_E_ARG;
+    if (c->world != 1) { c->err = "shapes_grow: single-GPU ctx only (a multi-rank job re-creates its ctxs collectively)"; return SHAPES_E_ARG; }
+    max_pairs = std::max(max_pairs, c->max_pairs); max_contacts = std::max(max_contacts, c->max_contacts);
+    if (max_pairs > 0x7ffffff0ll || max_contacts > 0xfffffff0ll || (c->ws && max_pairs >= (int64_t)SOLVE_NODE_MASK)) {
+        c->err = "shapes_grow: capacity out of range";
+        return SHAPES_E_ARG;
+    }
+    if (max_pairs == c->max_pairs && max_contacts == c->max_contacts) return SHAPES_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    Params &P = c->P;
+    const size_t oldP = (size_t)std::max<int64_t>(c->max_pairs, 1), newP = (size_t)std::max<int64_t>(max_pairs, 1);
+    const size_t oldC = (size_t)std::max<int64_t>(c->max_contacts, 1), newC = (size_t)std::max<int64_t>(max_contacts, 1);
+    // one buffer: new allocation, the first `keep` elements copied over, old one released
+    auto regrow = [&](auto **p, size_t count, size_t keep) -> int {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+        T *q = nullptr;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&q), count * sizeof(T)));
+        if (keep > 0 && *p) CU_TRY(c, cudaMemcpy(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice));
+        bool tracked = false;
+        for (void *&a : c->allocs) if (a == static_cast<void *>(*p)) { cudaFree(a); a = q; tracked = true; }
+        if (!tracked) c->allocs.push_back(q);
+        *p = q;
+        return SHAPES_OK;
+    };
+#define GROW(ptr, count, keep) do { int rc__ = regrow(ptr, count, keep); if (rc__ != SHAPES_OK) return rc__; } while (0)
+    if (newP != oldP) {
+        const bool lists = c->use_sorted;
+        if (lists) { GROW(&P.w_i, newP, 0); GROW(&c->d_w_j, newP, 0); GROW(&P.w_a, newP, 0); P.w_j = c->d_w_j; }
+        GROW(&c->d_pair_i, newP, 0); GROW(&c->d_pair_j, newP, 0); GROW(&c->d_man, newP, 0); GROW(&c->d_ccnt, newP, 0);
+        P.pair_i = c->d_pair_i; P.pair_j = c->d_pair_j; P.man = c->d_man; P.ccnt = c->d_ccnt; P.sat_ccnt = P.ccnt;
+        GROW(&P.coff, newP, 0);
+        CU_TRY(c, cudaMemset(P.ccnt, 0, newP * sizeof(uint32_t)));
+        size_t cb = 0;
+        CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, cb, P.ccnt, P.coff, (int)newP, c->stream));
+        if (cb > c->scan_tmp_bytes) {
+            uint8_t *tmp = static_cast<uint8_t *>(c->d_scan_tmp);
+            GROW(&tmp, cb, 0);
+            c->d_scan_tmp = tmp; c->scan_tmp_bytes = cb;
+        }
+    }
+    if (newC != oldC) {
+        GROW(&P.row_map, newC, 0);
+        // the key columns of the last completed frame and the cache given for them must survive
+        const size_t keep = c->have_frame ? (size_t)std::min<int64_t>(c->last_contacts, (int64_t)oldC) : 0;
+        GROW(&P.key_i, newC, keep); GROW(&P.key_j, newC, keep); GROW(&P.feat_a, newC, keep); GROW(&P.feat_b, newC, keep);
+        for (int q = 0; q < 4; ++q) GROW(&c->alt_key[q], newC, keep);
+        GROW(&c->d_cache_np, newC, keep); GROW(&c->d_cache_f, newC, keep);
+        GROW(&P.flip, newC, 0); GROW(&P.warm_np, newC, 0); GROW(&P.warm_f, newC, 0); GROW(&P.warm_hit, newC, 0);
+        double **cols[] = { &P.normal_x, &P.normal_y, &P.center_x, &P.center_y, &P.depth, &P.b_np,
+                            &P.ra_x, &P.ra_y, &P.rb_x, &P.rb_y, &P.rn_x, &P.rn_y, &P.inv_eff_np, &P.inv_eff_f };
+        for (double **col : cols) GROW(col, newC, 0);
+        for (int q = 0; q < 6; ++q) { GROW(&P.j_np[q], newC, 0); GROW(&P.j_f[q], newC, 0); }
+    }
+    c->max_pairs = max_pairs; c->max_contacts = max_contacts;
+    P.max_pairs = max_pairs; P.max_contacts = max_contacts;
+    const int rc = world_grow(c, newP != oldP, newC != oldC);
+    if (rc != SHAPES_OK) return rc;
+#undef GROW
+    // captured frames bake the old pointers in
+    for (int q = 0; q < 4; ++q) if (c->graph_exec[q]) { cudaGraphExecDestroy(c->graph_exec[q]); c->graph_exec[q] = nullptr; }
+    c->results_valid = false;
+    return SHAPES_OK;
+}
+
 int shapes_frame_device(shapes_ctx *c, int64_t n_slots, const double *pos_x, const double *pos_y,
                         const double *rot, const double *cos_rot, const double *sin_rot,
                         const double *inv_lin, const double *inv_rot, double dt, double baumgarte,
@@ -3372,7 +3469,7 @@ int shapes_frame_device(shapes_ctx *c, int64_t n_slots, const double *pos_x, con
 static int fetch_enqueue(shapes_ctx *c, shapes_frame_out *out)
 {
     if (!c || !out) return SHAPES_E_ARG;
-    if (!c->have_frame) { c->err = "shapes_fetch: no completed frame"; return SHAPES_E_ARG; }
+    if (!c->have_frame || !c->results_valid) { c->err = "shapes_fetch: no completed frame"; return SHAPES_E_ARG; }
     CU_TRY(c, cudaSetDevice(c->device));
     const Params &P = c->P;
     const int64_t np = c->last_pairs, nc = c->last_contacts;
@@ -3501,7 +3598,7 @@ int shapes_set_lagrangian_cache_device(shapes_ctx *c, int64_t n_prev, const doub
 int shapes_device_view_get(shapes_ctx *c, shapes_device_view *v)
 {
     if (!c || !v) return SHAPES_E_ARG;
-    if (!c->have_frame) { c->err = "shapes_device_view_get: no completed frame"; return SHAPES_E_ARG; }
+    if (!c->have_frame || !c->results_valid) { c->err = "shapes_device_view_get: no completed frame"; return SHAPES_E_ARG; }
     const Params &P = c->P;
     v->n_pairs = c->last_pairs; v->n_contacts = c->last_contacts;
     v->pair_i = P.pair_i; v->pair_j = P.pair_j;
@@ -3810,7 +3907,7 @@ int64_t shapes_launch_count(const shapes_ctx *c) { return c ? c->launches : 0; }
 int shapes_last_frame_info(shapes_ctx *c, shapes_frame_info *info)
 {
     if (!c || !info) return SHAPES_E_ARG;
-    if (!c->have_frame) { c->err = "shapes_last_frame_info: no completed frame"; return SHAPES_E_ARG; }
+    if (!c->have_frame || !c->results_valid) { c->err = "shapes_last_frame_info: no completed frame"; return SHAPES_E_ARG; }
     info->pairs_with_contacts = (int64_t)c->h_state->n_pairs_hit;
     info->sorted_mode = c->P.sorted_mode;
     info->sat_kernel = c->has_circles ? SHAPES_SAT_PER_THREAD_CIRCLES : c->max_hull_verts <= 4 ? SHAPES_SAT_PER_THREAD_BOXES

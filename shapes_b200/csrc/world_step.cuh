@@ -604,6 +604,39 @@ int world_alloc(shapes_ctx *c)
     return SHAPES_OK;
 }
 
+// shapes_grow: the pair / contact sized buffers of the device-resident world (all of them per-step scratch; the body
+// columns, velocities and materials are sized by slots and stay where they are).
+int world_grow(shapes_ctx *c, bool pairs, bool contacts)
+{
+    WorldStep *w = c->ws;
+    if (!w) return SHAPES_OK;
+    const size_t P = (size_t)std::max<int64_t>(c->max_pairs, 1);
+    auto fresh = [&](auto **p, size_t count) -> int {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+        T *q = nullptr;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void **>(&q), count * sizeof(T)));
+        for (void *&a : c->allocs) if (a == static_cast<void *>(*p)) { cudaFree(a); a = q; }
+        *p = q;
+        return SHAPES_OK;
+    };
+#define WS_FRESH(ptr, count) do { int rc__ = fresh(ptr, count); if (rc__ != SHAPES_OK) return rc__; } while (0)
+    if (pairs) {
+        WS_FRESH(&w->next_i, P); WS_FRESH(&w->next_j, P); WS_FRESH(&w->cnt, P); WS_FRESH(&w->node, P);
+        for (int k = 0; k < 2; ++k) { WS_FRESH(&w->sort_key[k], P); WS_FRESH(&w->sort_val[k], P); }
+        size_t tb = 0;
+        CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, w->sort_key[0], w->sort_key[1], w->sort_val[0], w->sort_val[1],
+                                                  (int)P, 0, 32, c->stream));
+        if (tb > w->sort_tmp_bytes) {
+            uint8_t *tmp = static_cast<uint8_t *>(w->sort_tmp);
+            WS_FRESH(&tmp, tb);
+            w->sort_tmp = tmp; w->sort_tmp_bytes = tb;
+        }
+    }
+    if (contacts) WS_FRESH(&w->rows, (size_t)std::max<int64_t>(c->max_contacts, 1) * ROW_DOUBLES);
+#undef WS_FRESH
+    return SHAPES_OK;
+}
+
 void world_free(shapes_ctx *c)
 {
     WorldStep *w = c->ws;

@@ -361,11 +361,19 @@ class Engine:
         return tuple((int(a[0][q]), int(a[1][q]), int(a[2][q]), int(a[3][q])) for q in range(2))
 
     def grow(self, n_pairs: int, n_contacts: int):
-        """Re-create the ctx with larger capacities (the caller's answer to E_CAPACITY)."""
-        world = self.world
-        self.close()
+        """The caller's answer to E_CAPACITY.  Single GPU: shapes_grow, in place -- the previous frame's key columns,
+        the Lagrangian cache (EngineCache) and an uploaded world survive, so the retried frame warm-starts exactly as
+        the failed attempt would have.  Multi-rank: the ctx is re-created (a collective decision of all ranks; the
+        next frame starts cold)."""
         self.max_pairs = max(self.max_pairs, int(n_pairs * 1.25) + 1024)
         self.max_contacts = max(self.max_contacts, int(n_contacts * 1.25) + 1024)
+        if self.world_size == 1:
+            self._check(self.lib.shapes_grow(self.ctx, self.max_pairs, self.max_contacts))
+            return          # host buffers are keyed on the capacities and follow on the next frame
+        world = self.world
+        max_pairs, max_contacts = self.max_pairs, self.max_contacts
+        self.close()
+        self.max_pairs, self.max_contacts = max_pairs, max_contacts
         self._create(world.n_slots, world.n_verts)
         self.set_hulls(world)
 

@@ -190,6 +190,21 @@ def test_host_supplied_extents_are_used(oracle):
     assert len(base["key_i"]) != len(want["key_i"]) or not np.array_equal(base["depth"], want["depth"])
 
 
+def test_out_of_range_extent_indices_are_rejected(oracle):
+    """An extent index must name a vertex of its own hull; anything else is SHAPES_E_ARG, not an out-of-bounds read."""
+    from shapes_b200.engine import Engine, ShapesError
+    w = scenes.random_polygons(200, density=1.0, config=36)
+    emin, emax = oracle.hull_extents(w)
+    nv = np.diff(w.vert_offset)
+    for which in (0, 1):
+        bad = [emin.copy(), emax.copy()]
+        bad[which][w.vert_offset[7]] = nv[7]              # one past the last vertex of hull 7
+        with pytest.raises(ShapesError):
+            Engine(w, ext=(bad[0], bad[1])).close()
+    with Engine(w, ext=(emin, emax)) as eng:               # the exact table is accepted
+        eng.frame_grow()
+
+
 def test_cell_size_does_not_change_results(oracle):
     w = scenes.random_polygons(4000, density=2.0, config=35)
     c, s = oracle.cos_sin(w.rot)

@@ -65,3 +65,36 @@ def test_cache_size_must_match_previous_frame(oracle):
         eng.set_lagrangian_cache(np.ones(f0.n_contacts), np.ones(f0.n_contacts))
         f1 = eng.frame(want=("contacts", "warm"))
         assert f1["warm_hit"].all() and (f1["warm_np"] == 1.0).all()   # nothing moved: every key persists
+
+
+def test_capacity_error_keeps_keys_and_cache_for_the_retry(oracle):
+    """A frame that fails with SHAPES_E_CAPACITY leaves the previous frame's keys and the supplied cache in place;
+    after Engine.grow (shapes_grow, in place) the retried frame joins against them as if nothing had happened."""
+    from shapes_b200.engine import CapacityError, Engine, ShapesError
+    w = scenes.random_polygons(20_000, density=2.0, config=83)
+    half = np.arange(w.n_slots) % 2 == 1
+    home_x = w.pos_x.copy()
+    w.pos_x[half] += 1.0e4                                   # every second shape far away: few pairs
+    c, s = oracle.cos_sin(w.rot)
+    want = ("pairs", "contacts", "warm")
+    small = oracle.frame(w, c, s, broadphase="aabb")
+    with Engine(w, max_pairs=len(small["pair_i"]) + 8, max_contacts=len(small["key_i"]) + 8) as eng:
+        f0 = eng.frame(cos_sin=(c, s), want=want)
+        prev = {k: np.array(f0[k]) for k in ("key_i", "key_j", "feat_a", "feat_b")}
+        lam_np, lam_f = _lagr(prev)
+        eng.set_lagrangian_cache(lam_np, lam_f)
+        w.pos_x[:] = home_x                                   # everybody comes back: the lists overflow
+        with pytest.raises(CapacityError) as e:
+            eng.frame(cos_sin=(c, s), want=want)
+        assert e.value.n_pairs > eng.max_pairs
+        with pytest.raises(ShapesError):
+            eng.fetch(want=want)                              # the failed attempt left no results to fetch
+        eng.grow(e.value.n_pairs, e.value.n_contacts)
+        f1 = eng.frame(cos_sin=(c, s), want=want)             # no second set_lagrangian_cache: the first one is still valid
+        cur = {k: np.array(f1[k]) for k in ("key_i", "key_j", "feat_a", "feat_b")}
+        o_np, o_f, o_hit = oracle.warm_join(cur, prev, lam_np, lam_f)
+        assert 0 < o_hit.sum() < len(o_hit)
+        assert np.array_equal(f1["warm_hit"], o_hit)
+        assert np.array_equal(f1["warm_np"], o_np) and np.array_equal(f1["warm_f"], o_f)
+        full = oracle.frame(w, c, s, broadphase="aabb")
+        assert np.array_equal(f1["pair_i"], full["pair_i"]) and np.array_equal(f1["key_j"], full["key_j"])

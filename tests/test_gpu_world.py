@@ -127,6 +127,49 @@ def test_capacity_error_leaves_the_world_untouched(oracle):
             assert same(before[k], after[k]), k
 
 
+def test_capacity_growth_mid_run_keeps_the_engine_cache(oracle):
+    """growing after SHAPES_E_CAPACITY must not drop the EngineCache.  The stacks land on the floor while
+    the capacities are those of the first frame: a later step overflows, shapes_grow enlarges the ctx in place and the
+    retried step still applies the cached Lagrangians (warm == 1) -- every step stays bit-identical to the oracle."""
+    from shapes_b200 import engine
+    from shapes_b200.engine import CapacityError, Engine
+    w = scenes.stacks_scene((12, 8), 0.0)
+    w.pos_y[1:] -= 0.895                       # a hair above the floor: the floor contacts appear after a few frames
+    bodies = Bodies.at_rest(w.n_slots, 0.2, 0.0)
+    wo, bo = copy.deepcopy(w), bodies.copy()
+    c, s = engine.sincos(wo.rot)
+    first = oracle.frame(wo, c, s, broadphase="aabb")
+    n_pairs0, n_contacts0 = len(first["pair_i"]), len(first["key_i"])
+    cache, grown_warm = None, 0
+    with Engine(w, max_pairs=n_pairs0 + 2, max_contacts=n_contacts0 + 2) as eng:
+        eng.world_upload(bodies)
+        for step in range(40):
+            for attempt in range(4):
+                try:
+                    st = eng.world_step(external=(1, 0.0, -2.0))
+                    break
+                except CapacityError as e:
+                    assert step > 0, "the first frame must fit (capacities were taken from it)"
+                    before = eng.world_download()
+                    eng.grow(e.n_pairs, e.n_contacts)
+                    after = eng.world_download()
+                    for k in STATE:
+                        assert same(before[k], after[k]), k          # the uploaded world survives the growth
+                    grown_warm += 1
+            fr, cache, c, s = oracle.update_world(wo, bo, cache, c, s, external=(1, 0.0, -2.0), sincos=engine.sincos)
+            assert st.n_pairs == len(fr["pair_i"]) and st.n_contacts == len(fr["key_i"]), step
+            assert st.warm == (1 if step > 0 else 0), step
+            d = eng.world_download()
+            want = dict(vel_x=bo.vel_x, vel_y=bo.vel_y, rot_vel=bo.rot_vel, pos_x=wo.pos_x, pos_y=wo.pos_y, rot=wo.rot,
+                        cos_rot=c, sin_rot=s)
+            for k in STATE:
+                assert same(d[k], want[k]), (step, k)
+            got = eng.fetch(want=("contacts", "warm"))
+            assert same(got["warm_hit"], fr["warm_hit"]), step
+            assert same(got["warm_np"], cache[1]) and same(got["warm_f"], cache[2]), step
+        assert grown_warm >= 1, "the scenario never overflowed: the test did not exercise shapes_grow"
+
+
 def test_step_needs_an_uploaded_world():
     from shapes_b200.engine import Engine, ShapesError
     w = scenes.box_pile(10, 10)
