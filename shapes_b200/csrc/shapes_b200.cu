@@ -2504,6 +2504,12 @@ struct shapes_ctx {
     int parity = 0;
     // last frame
     int64_t last_pairs = 0, last_contacts = 0;
+    // SHAPES_B200_KERNEL_TIMES=1: per-kernel CUDA events inside profiled rows-mode frames, averages printed by shapes_destroy
+    bool dbg_times = false;
+    std::vector<cudaEvent_t> dbg_ev;
+    std::vector<const char *> dbg_name;
+    std::vector<double> dbg_sum;
+    int dbg_marks = 0, dbg_frames = 0;
     bool have_frame = false;      // key columns (and counts) of a completed frame exist: the join's "previous frame"
     bool results_valid = false;   // the result arrays hold that frame (false after a failed attempt until the next success)
 };
@@ -2563,6 +2569,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     c->max_shapes = max_shapes; c->max_verts = max_verts;
     c->max_pairs = max_pairs; c->max_contacts = max_contacts;
     c->use_graph = std::getenv("SHAPES_B200_NO_GRAPH") == nullptr;
+    c->dbg_times = std::getenv("SHAPES_B200_KERNEL_TIMES") != nullptr;
     auto fail = [&](int code) { g_create_error = c->err; shapes_destroy(c); return code; };
 #define TRY_CREATE(expr) do { int rc__ = (expr); if (rc__ != SHAPES_OK) return fail(rc__); } while (0)
     auto cu = [&](cudaError_t e, const char *what) {
@@ -2873,46 +2880,76 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
     // rows mode (multi-rank, peers mapped): see the k_rw_* kernels
     auto issue_rows = [&](bool advance) -> int {
         int stage = 0;
+        c->dbg_marks = 0;
+        auto kt = [&](const char *name) {      // per-kernel timing marks (debug aid, profiled frames only)
+            if (!c->dbg_times || !c->profiling) return;
+            if ((int)c->dbg_ev.size() <= c->dbg_marks) { cudaEvent_t e; cudaEventCreate(&e); c->dbg_ev.push_back(e); c->dbg_name.push_back(name); c->dbg_sum.push_back(0.0); }
+            c->dbg_name[c->dbg_marks] = name;
+            cudaEventRecord(c->dbg_ev[c->dbg_marks++], s);
+        };
+        kt("start");
     #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
         const int n_query = n_home;     // my slice: both home blocks
         const int gq = grid_for(n_query, 256, sms * 8), gn = grid_for(N, 256, sms * 8);
         STAGE_MARK(); // 0: transform (home slots) + record push
         k_rw_begin<<<1, 1024, 0, s>>>(P, advance ? 1 : 0); ++c->launches;
+        kt("k_rw_begin");
         CU_TRY(c, cudaMemsetAsync(P.cell_count, 0, sizeof(uint32_t) * ((size_t)P.cell_limit + 2), s));
+        kt("memset");
         // the key array the NEXT frame's homes push into must read "nothing here" wherever nobody pushes
         CU_TRY(c, cudaMemsetAsync(c->rw_arena + c->rwl.gkeys[fpar ^ 1], 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1), s));
+        kt("memset");
         if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
+        kt("k_rw_transform");
         STAGE_MARK(); // 1: barrier KEYS (this frame's bounds ride along, for the next frame's grid)
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
+        kt("k_rw_publish:KEYS");
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
+        kt("k_rw_wait:KEYS");
         STAGE_MARK(); // 2: keep my rows' keys
         if (N > 0) { k_rw_bin<<<gn, 256, 0, s>>>(P); ++c->launches; }
+        kt("k_rw_bin");
         STAGE_MARK(); // 3: cell offsets
         k_scan_cells_sums<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
+        kt("k_scan_cells_sums");
         k_scan_cells_apply<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
+        kt("k_scan_cells_apply");
         STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
         if (N > 0) {
             k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
+            kt("k_scatter_sorted");
             k_rw_hulls<<<sms * 16, 256, 0, s>>>(P); ++c->launches;
+            kt("k_rw_hulls");
         }
         STAGE_MARK(); // 5: single-pass sweep of my rows; every query's count is pushed to its home; barrier CNT
         if (N > 0) {
             k_sweep<SWEEP_FUSED><<<grid_for(n_query + n_query / 2 + 4096, 128, 1 << 30), 128, 0, s>>>(P); ++c->launches;
+            kt("k_sweep");
             k_big<false><<<64, 256, 0, s>>>(P); ++c->launches;
+            kt("k_big");
             k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
+            kt("k_big");
         }
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
+        kt("k_rw_publish:CNT");
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
+        kt("k_rw_wait:CNT");
         STAGE_MARK(); // 6: home -- offsets of my slice, sent back to the sweeping ranks; barrier OFF
         if (n_query > 0) {
             k_rw_home_counts<<<gq, 256, 0, s>>>(P, n_query); ++c->launches;
+            kt("k_rw_home_counts");
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.cnt, P.off, n_query, s));
+            kt("cub_scan");
         }
         k_finish_pairs<<<1, 1, 0, s>>>(P, n_query); ++c->launches;
+        kt("k_finish_pairs");
         if (n_query > 0) { k_rw_push_offsets<<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
+        kt("k_rw_push_offsets");
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
+        kt("k_rw_publish:OFF");
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
+        kt("k_rw_wait:OFF");
         STAGE_MARK(); // 7
         STAGE_MARK(); // 8: manifolds over my work list, every pair stored into its final place at its home; barrier RESULTS
         if (N > 0) {
@@ -2920,30 +2957,40 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
             else if (c->use_coop) {
                 k_manifolds_coop<2><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                kt("k_manifolds_coop");
                 {   // hulls with more than 8 vertices, partners of big queries this rank does not keep
                     k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
                 }
             }
             else k_manifolds<MAX_STAGED_VERTS, false><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P);
+            kt("k_manifolds");
             ++c->launches;
         }
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
+        kt("k_rw_publish:RESULTS");
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
+        kt("k_rw_wait:RESULTS");
         STAGE_MARK(); // 9: home -- row offsets
         if (c->max_pairs > 0) {
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
+            kt("cub_scan");
             k_row_map<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
+            kt("k_row_map");
         }
         STAGE_MARK(); // 10: contact rows
         if (N > 0) { k_rows<<<sms * c->rows_blocks, 256, 0, s>>>(P); ++c->launches; }
+        kt("k_rows");
         STAGE_MARK(); // 11: warm-start cache join
         if (N > 0 && warm) { k_warm_join<<<sms * 8, 256, 0, s>>>(P); ++c->launches; }
+        kt("k_warm_join");
         STAGE_MARK(); // end
     #undef STAGE_MARK
         // barrier COUNTS: every rank learns every rank's pair / contact totals (global row offsets of the slices)
         k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
+        kt("k_rw_publish:COUNTS");
         k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
+        kt("k_rw_wait:COUNTS");
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 6 * c->world, cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
@@ -3185,6 +3232,10 @@ int frame_finish(shapes_ctx *c, shapes_frame_out *out)
     }
     if (c->profiling)
         for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
+    if (c->profiling && c->dbg_times && c->pending_rows && c->dbg_marks > 1) {
+        for (int k = 1; k < c->dbg_marks; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, c->dbg_ev[k - 1], c->dbg_ev[k]); c->dbg_sum[k] += ms; }
+        ++c->dbg_frames;
+    }
     if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its records"; c->have_frame = false; c->results_valid = false; return SHAPES_E_NCCL; }
     if (st.error) {
         c->err = (st.error & ERR_PAIR_CAP) ? "capacity: max_pairs too small (required count in n_pairs; rows mode: on this or another rank)"
@@ -3257,6 +3308,12 @@ void shapes_destroy(shapes_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int q = 0; q < 4; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
+    if (c->dbg_times && c->dbg_frames > 0) {
+        std::string line = "[shapes_b200 rank " + std::to_string(c->rank) + "] rows-mode kernel ms (mean of " + std::to_string(c->dbg_frames) + " profiled frames):";
+        for (int k = 1; k < c->dbg_marks; ++k) { char buf[96]; std::snprintf(buf, sizeof(buf), " %s %.4f", c->dbg_name[k], c->dbg_sum[k] / c->dbg_frames); line += buf; }
+        std::fprintf(stderr, "%s\n", line.c_str());
+    }
+    for (cudaEvent_t e : c->dbg_ev) cudaEventDestroy(e);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     world_free(c);

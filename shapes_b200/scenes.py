@@ -146,6 +146,24 @@ def test_opt_boxes() -> World:
     return w
 
 
+def kat_triangle_on_box(triangle_is_a: bool = False, lift: float = 0.0):
+    """KAT-6 / KAT-7 / KAT-8 (tests/golden/README.md): a 32x16 box at (1,-2) and a small right triangle (sides
+    2.5 / 4.6875 / 5.3125, every edge a Pythagorean direction) turned by a quarter turn with cos = 0, sin = 1 given
+    exactly, its tip poking through the box's top edge next to the top-left corner.  Every coordinate is a dyadic
+    rational, so moveShapes, the clip points, depths, Jacobians and inverse effective masses are exact.
+    Returns (world, cos, sin): the triangle is slot 0 (shape b) unless triangle_is_a; `lift` raises it."""
+    tri = ([(-0.5, 1.5), (-2.0, -0.5), (1.75, -3.3125)], (-14.0, 6.0 + lift), 0.0, (0.5, 4.0))      # inverse masses (2, 0.25)
+    box = (rectangle_vertices(32.0, 16.0), (1.0, -2.0), 0.0, (2.0, 8.0))                            # inverse masses (0.5, 0.125)
+    objs = [box, tri] if triangle_is_a else [tri, box]
+    w = World.from_objects(objs, name="kat_triangle_on_box")
+    w.meta.update(dt=0.25, baumgarte=0.5, slop=0.25)
+    t = 1 if triangle_is_a else 0
+    c = np.ones(2); s = np.zeros(2)
+    c[t], s[t] = 0.0, 1.0
+    w.rot[t] = math.pi / 2        # informative only: the frame is evaluated with the exact (cos, sin) returned here
+    return w, c, s
+
+
 # ---------------------------------------------------------------------------
 # BASELINE.json configs 2-5
 # ---------------------------------------------------------------------------

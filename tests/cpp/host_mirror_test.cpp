@@ -58,6 +58,34 @@ int main()
                 CHECK(c0.normal.x == -0.0 && c0.normal.y == 1.0);         // Restitution: -n for Flip
             }
         }
+        {   // KAT-6 (tests/golden/README.md): right triangle into the top edge of a 32x16 box next to its corner --
+            // Same, ClipLeft, two points, depth > slop.  The C++ host takes cos/sin from libm, so the triangle is given
+            // unrotated here (local = world - position): the same world vertices as the fixture's quarter turn.
+            World w;
+            w.append(makePhysicalObj({ -14.0, 6.0 }, 0.0, { 0.5, 4.0 }), makeHull({ { -1.5, -0.5 }, { 0.5, -2.0 }, { 3.3125, 1.75 } }));
+            w.append(makePhysicalObj({ 1.0, -2.0 }, 0.0, { 2.0, 8.0 }), makeRectangleHull(32.0, 16.0));
+            Frame f = constraintGen(eng, ContactBehavior{ 0.5, 0.25 }, 0.25, w);
+            CHECK(f.keys.size() == 1 && f.contacts.size() == 2 && f.constraints.size() == 2);
+            if (f.contacts.size() == 2 && f.constraints.size() == 2) {
+                CHECK(f.contacts[0].featA == 0 && f.contacts[0].featB == 1 && !f.contacts[0].flip);
+                CHECK(f.contacts[1].featA == 0 && f.contacts[1].featB == 0 && !f.contacts[1].flip);
+                CHECK(f.contacts[0].normal.x == 0.0 && f.contacts[0].normal.y == 1.0);
+                CHECK(f.contacts[0].center.x == -13.5 && f.contacts[0].center.y == 4.0 && f.contacts[0].depth == 2.0);
+                CHECK(f.contacts[1].center.x == -15.0 && f.contacts[1].center.y == 5.125 && f.contacts[1].depth == 0.875);
+                const ContactConstraint &c0 = f.constraints[0], &c1 = f.constraints[1];
+                const double jn0[6] = { -0.0, -1.0, 14.5, 0.0, 1.0, 0.5 }, jf0[6] = { -1.0, 0.0, 6.0, 1.0, -0.0, 2.0 };
+                const double jn1[6] = { -0.0, -1.0, 16.0, 0.0, 1.0, -1.0 }, jf1[6] = { -1.0, 0.0, 7.125, 1.0, -0.0, 0.875 };
+                for (int q = 0; q < 6; ++q) {
+                    CHECK(c0.nonPen.j[q] == jn0[q] && std::signbit(c0.nonPen.j[q]) == std::signbit(jn0[q]));
+                    CHECK(c0.friction.j[q] == jf0[q] && std::signbit(c0.friction.j[q]) == std::signbit(jf0[q]));
+                    CHECK(c1.nonPen.j[q] == jn1[q] && c1.friction.j[q] == jf1[q]);
+                }
+                CHECK(c0.nonPen.b == -3.5 && c1.nonPen.b == -1.25 && c0.friction.b == 0.0);     // (0.5 / 0.25) * (0.25 - depth)
+                CHECK(c0.radiusA.x == -14.5 && c0.radiusA.y == 6.0 && c0.radiusB.x == 0.5 && c0.radiusB.y == -2.0);
+                CHECK(c1.radiusA.x == -16.0 && c1.radiusA.y == 7.125 && c1.radiusB.x == -1.0 && c1.radiusB.y == -0.875);
+                CHECK(c0.normal.x == 0.0 && c0.normal.y == 1.0);
+            }
+        }
         {   // KAT-4 / KAT-5: circles (Circle.contact; CircleVsHull through GJK)
             World w;
             w.append(makePhysicalObj({ 3.0, 0.0 }, 0.0, { 1.0, 1.0 }), makeCircle(1.5));

@@ -69,6 +69,42 @@ def test_kat2_jacobian_through_generator(oracle):
         assert (r["rn_x"][k], r["rn_y"][k]) == (-0.0, -1.0)
 
 
+KAT678 = [("kat6_triangle_into_box_same", False, 0.0), ("kat7_triangle_into_box_flip", True, 0.0),
+          ("kat8_triangle_lifted_single_point", False, 1.0)]
+
+
+def assert_kat_rows(r, want, where):
+    """Every pinned column of a KAT-6/7/8 entry, signed zeros included."""
+    def bits(x):
+        return np.float64(x).tobytes()
+    assert list(zip(r["pair_i"].tolist(), r["pair_j"].tolist())) == [tuple(p) for p in want["pairs"]], where
+    assert len(r["key_i"]) == len(want["contacts"]), where
+    for k, c in enumerate(want["contacts"]):
+        assert [int(r["key_i"][k]), int(r["key_j"][k])] == c["key"] and [int(r["feat_a"][k]), int(r["feat_b"][k])] == c["feat"], (where, k)
+        assert int(r["flip"][k]) == c["flip"], (where, k)
+        pairs = [("normal_x", c["normal"][0]), ("normal_y", c["normal"][1]), ("center_x", c["center"][0]),
+                 ("center_y", c["center"][1]), ("depth", c["depth"]), ("b_np", c["b_np"]),
+                 ("ra_x", c["ra"][0]), ("ra_y", c["ra"][1]), ("rb_x", c["rb"][0]), ("rb_y", c["rb"][1]),
+                 ("rn_x", c["rn"][0]), ("rn_y", c["rn"][1]), ("inv_eff_np", c["inv_eff_np"]), ("inv_eff_f", c["inv_eff_f"])]
+        pairs += [(f"j_np{q}", c["j_np"][q]) for q in range(6)] + [(f"j_f{q}", c["j_f"][q]) for q in range(6)]
+        for col, val in pairs:
+            assert bits(r[col][k]) == bits(val), (where, k, col, r[col][k], val)
+
+
+@pytest.mark.parametrize("name,triangle_is_a,lift", KAT678)
+def test_kat678_triangle_on_box(oracle, kat, name, triangle_is_a, lift):
+    """KAT-6 (Same, ClipLeft, two points, active Baumgarte, non-trivial radii), KAT-7 (the same pair with the keys
+    swapped: Flip, Jacobian halves swapped, restitution normal negated), KAT-8 (the clipped point lies above the
+    face: the third clip removes it).  Hand traces: tests/golden/README.md."""
+    want = kat[name]
+    w, c, s = scenes.kat_triangle_on_box(triangle_is_a, lift)
+    r = oracle.frame(w, c, s, broadphase="aabb", **want["behaviour"])
+    if name.startswith("kat6"):
+        t, b = want["world_vertices"]["triangle"], want["world_vertices"]["box"]
+        assert list(zip(r["world_x"].tolist(), r["world_y"].tolist())) == [tuple(v) for v in t + b]
+    assert_kat_rows(r, want, name)
+
+
 def test_kat3_broadphase_knife_edge(oracle, kat):
     """Aabb.culledKeys testWorld (bench/Physics/Broadphase/Benchmark.hs:50-52)."""
     for name, spacing in (("spacing0", 0.0), ("spacing1", 1.0)):

@@ -71,6 +71,36 @@ def test_kat1_through_the_mirror():
         assert list(c["normal"]) == want["normal"] and list(c["center"]) == want["center"] and c["depth"] == want["depth"]
 
 
+@pytest.mark.parametrize("name,triangle_is_a,lift", [("kat6_triangle_into_box_same", False, 0.0),
+                                                     ("kat7_triangle_into_box_flip", True, 0.0),
+                                                     ("kat8_triangle_lifted_single_point", False, 1.0)])
+def test_kat678_through_the_mirror(name, triangle_is_a, lift):
+    """The hand traces of KAT-6/7/8 (tests/golden/README.md) through the second restatement: ClipLeft, Same / Flip on
+    a non-box hull, the third clip removing a point, active Baumgarte term, Friction / Restitution with real radii."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")) as f:
+        want = json.load(f)[name]
+    w, c, s = scenes.kat_triangle_on_box(triangle_is_a, lift)
+    hulls = hs.hulls_of(w, c, s)
+    beh = want["behaviour"]
+    rows = hs.prepare_frame(w, hulls, [tuple(p) for p in want["pairs"]], (beh["baumgarte"], beh["slop"]), beh["dt"])
+    assert len(rows) == len(want["contacts"])
+    bits = lambda x: np.float64(x).tobytes()
+    for r, c_ in zip(rows, want["contacts"]):
+        assert r["key"] == tuple(c_["key"] + c_["feat"]) and r["flip"] == c_["flip"]
+        ct = r["contact"]
+        jn, bn = r["constraint"]["nonpen"]
+        jf, bf = r["constraint"]["friction"]
+        ra, rb, rn = r["constraint"]["restitution"]
+        got = list(ct["normal"]) + list(ct["center"]) + [ct["depth"], bn] + list(jn) + list(jf) + list(ra) + list(rb) + list(rn)
+        exp = c_["normal"] + c_["center"] + [c_["depth"], c_["b_np"]] + c_["j_np"] + c_["j_f"] + c_["ra"] + c_["rb"] + c_["rn"]
+        assert [bits(x) for x in got] == [bits(x) for x in exp], (got, exp)
+        assert bf == 0.0
+        i, j = r["key"][0], r["key"][1]
+        a = {"inv": (w.inv_lin[i], w.inv_rot[i])}
+        b = {"inv": (w.inv_lin[j], w.inv_rot[j])}
+        assert hs.effMassM2(jn, a, b) == c_["inv_eff_np"] and hs.effMassM2(jf, a, b) == c_["inv_eff_f"]
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_polygon_worlds(oracle, seed):
     w = scenes.random_polygons(260, density=2.5, config=300 + seed)
