@@ -13,8 +13,14 @@
  * Method (public-domain fdlibm scheme, restated): Cody-Waite reduction by pi/2 with a 33+33+33+53
  * bit split of pi/2 (the multiple fn is itself split so that every product is exact) carried as a
  * double-double remainder, then the degree-13 / degree-14 minimax kernels on [-pi/4, pi/4].
- * Error < 1 ulp for |x| <= 1e12 (tests/test_sincos.py measures it against libm); beyond that the
- * reduction loses accuracy gradually but stays deterministic; |x| > 2^60 or non-finite gives NaN.
+ * Error < 1 ulp for |x| <= 1e12 (tests/test_sincos.py measures it against libm).  Beyond 1e12 the multiple of
+ * pi/2 no longer splits into two 20-bit halves and the "every product is exact" argument fails, so instead of a
+ * silently inaccurate rotation |x| > 1e12 (or non-finite x) gives NaN -- visible in the very next frame (NaN bodies
+ * take the exact big-shape path) instead of a slow drift.  A body reaches 1e12 rad only after ~1.6e9 revolutions.
+ *
+ * Host bit-parity needs un-fused arithmetic: the host functions carry GCC's optimize("fp-contract=off") attribute
+ * (clang: FP_CONTRACT OFF pragma), so an includer built with contraction on -- GCC's default on targets with FMA,
+ * e.g. aarch64 -- still gets separately rounded multiplies and adds.
  */
 #ifndef SHAPES_SINCOS_H
 #define SHAPES_SINCOS_H
@@ -23,9 +29,19 @@
 
 #if defined(__CUDACC__)
 #define SHAPES_SC_FN static __host__ __device__ __forceinline__
+#define SHAPES_SC_NOFMA
 #else
 #include <string.h>
+#if defined(__clang__)
 #define SHAPES_SC_FN static inline
+#define SHAPES_SC_NOFMA _Pragma("STDC FP_CONTRACT OFF")
+#elif defined(__GNUC__)
+#define SHAPES_SC_FN static inline __attribute__((optimize("fp-contract=off")))
+#define SHAPES_SC_NOFMA
+#else
+#define SHAPES_SC_FN static inline
+#define SHAPES_SC_NOFMA
+#endif
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -45,6 +61,7 @@ SHAPES_SC_FN double shapes_sc_from_bits(uint64_t u) { double x; memcpy(&x, &u, 8
 /* sin on [-pi/4, pi/4] of the double-double x + y */
 SHAPES_SC_FN double shapes_sc_ksin(double x, double y)
 {
+    SHAPES_SC_NOFMA
     const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
                  S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
                  S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
@@ -58,6 +75,7 @@ SHAPES_SC_FN double shapes_sc_ksin(double x, double y)
 /* cos on [-pi/4, pi/4] of the double-double x + y */
 SHAPES_SC_FN double shapes_sc_kcos(double x, double y)
 {
+    SHAPES_SC_NOFMA
     const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
                  C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
                  C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
@@ -78,6 +96,7 @@ SHAPES_SC_FN double shapes_sc_kcos(double x, double y)
 /* s + e = a + b exactly (Knuth TwoSum, branch free) */
 SHAPES_SC_FN double shapes_sc_two_sum(double a, double b, double *e)
 {
+    SHAPES_SC_NOFMA
     const double s = SC_ADD(a, b);
     const double bb = SC_SUB(s, a);
     *e = SC_ADD(SC_SUB(a, SC_SUB(s, bb)), SC_SUB(b, bb));
@@ -87,9 +106,10 @@ SHAPES_SC_FN double shapes_sc_two_sum(double a, double b, double *e)
 /* cos(x), sin(x).  Same bits on host and device. */
 SHAPES_SC_FN void shapes_sincos_inline(double x, double *cos_out, double *sin_out)
 {
+    SHAPES_SC_NOFMA
     const uint64_t ux = shapes_sc_bits(x);
     const uint64_t ax = ux & 0x7fffffffffffffffull;
-    if (ax > 0x43b0000000000000ull) {           /* |x| > 2^60, inf, NaN */
+    if (ax > 0x426d1a94a2000000ull) {           /* |x| > 1e12, inf, NaN: outside the proven range of the reduction */
         const double nan = shapes_sc_from_bits(0x7ff8000000000000ull);
         *cos_out = nan; *sin_out = nan;
         return;

@@ -36,7 +36,7 @@ constexpr unsigned SOLVE_NONE = 0xffffffffu;     // "no node" / empty queue slot
 constexpr int SOLVE_PASS_SHIFT = 28;             // queue entry = node | pass << 28
 constexpr unsigned SOLVE_NODE_MASK = (1u << SOLVE_PASS_SHIFT) - 1u;
 constexpr int SOLVE_THREADS = 128;
-constexpr unsigned long long SOLVE_IDLE_LIMIT_NS = 15000000000ull;  // a warp idle for ~15 s of sleeps gives up
+constexpr unsigned long long SOLVE_IDLE_LIMIT_NS = 15000000000ull;  // a warp without work for 15 s of wall clock gives up
 
 // Shared scheduler words, one 128 B line each: the idle pollers, the pushers and the chain ends
 // must not queue up behind each other on one L2 sector.
@@ -307,6 +307,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // release fence: the velocity / lambda / counter stores before it are visible device-wide before
 // the counter decrements after it
 __device__ __forceinline__ void fence_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Consumer side of the hand-over: a thread that learned through a relaxed atomic's return value (or a polled queue
+// slot) that a node's predecessors are done must not read their results before this fence (PTX memory model:
+// release fence + relaxed write -> relaxed read + acquire fence is the synchronising pattern).
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 
 // One contact row against the pair's velocities v (improveContactSln, Solvers/Contact.hs:124-143).
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams S)
                 unsigned e = SOLVE_NONE;
                 if ((unsigned long long)my_slot < S.queue_cap) e = ld_volatile_u32(&S.queue[my_slot]);
                 if (e != SOLVE_NONE) {
+                    fence_acquire();                    // the pusher's results become visible with the slot
                     node = e & SOLVE_NODE_MASK; pass = (int)(e >> SOLVE_PASS_SHIFT);
                     rec = load_node(&S.node[node]);
                     my_slot = -1;
@@ -409,13 +415,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams S)
             if (lane == 0) {
                 if (*reinterpret_cast<volatile unsigned *>(&ss->done) >= expected) stop = 1;
                 else if (*reinterpret_cast<volatile int *>(&ss->overflow)) stop = 1;
-                else if (idle_ns > SOLVE_IDLE_LIMIT_NS) { ss->overflow = 2; stop = 1; }   // never spin forever: the host reports it
+                else {
+                    // never spin forever: wall clock (%globaltimer) since this warp last had work; the host reports it
+                    const unsigned long long now = global_ns();
+                    if (idle_ns == 0) idle_ns = now;
+                    else if (now - idle_ns > SOLVE_IDLE_LIMIT_NS) { ss->overflow = 2; stop = 1; }
+                }
             }
             stop = __shfl_sync(0xffffffffu, stop, 0);
             if (stop) break;
             idle_iters = S.claim_after;                 // an idle warp listens to the global queue
             if (S.sleep_cap) __nanosleep(backoff);
-            idle_ns += backoff;
             if (backoff < S.sleep_cap) backoff <<= 1;
             continue;
         }
@@ -488,6 +498,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveParams S)
             if (go_j) old_j = atomicSub(&S.cnt[sj], 1);
             if (end_i || end_j) atomicAdd(&ss->done, (end_i ? 1u : 0u) + (end_j ? 1u : 0u));
             const bool rdy_i = go_i && old_i == 1, rdy_j = go_j && old_j == 1;
+            if (rdy_i || rdy_j) fence_acquire();        // last arriver: the other predecessor's stores, published before its decrement
             // continue along one ready successor; a second one is offered to the warp
             node = SOLVE_NONE;
             if (rdy_i || rdy_j) {

@@ -1,8 +1,9 @@
 """BASELINE.json configs 4 (4M mixed boxes/polygons) and 5 (1M-polygon Gaussian blob) at FULL size.
 The oracle cannot walk such worlds pair by pair in test time, so the frame is checked through
 size-independent properties plus the oracle on bounded samples:
-  * pairs: i > j, strictly descending, never static/static; for sampled shapes the partner set equals a
-    brute-force overlap test of the device's own AABBs against ALL other shapes (completeness);
+  * pairs: the whole list, set and order, equals the oracle's Grid.culledKeys restatement (linear in N); also i > j,
+    strictly descending, never static/static, and for sampled shapes the partner set equals a brute-force overlap
+    test of the device's own AABBs against ALL other shapes (an oracle-independent completeness check);
   * AABBs of sampled shapes equal the oracle's (moveShapes + toAabb);
   * contact rows: keys follow the pair list in order, unit normals, the exact sign relations between the
     Jacobian halves / restitution normal / flip, b_f = 0;
@@ -48,6 +49,10 @@ def check_full_size(oracle, w, max_pairs, max_contacts, seed):
     boxes = oracle.aabbs(w, wx, wy)
     for got, ref in zip(("aabb_min_x", "aabb_max_x", "aabb_min_y", "aabb_max_y"), boxes):
         assert np.array_equal(cols[got], ref), got
+    # ---- the WHOLE pair list, set and order, against the oracle's restatement of Grid.culledKeys (Grid.hs:67-100),
+    # which is linear in the number of shapes
+    gi, gj = oracle.culled_keys_grid(w, boxes, oracle.is_static(w))
+    assert len(gi) == P and np.array_equal(gi, cols["pair_i"]) and np.array_equal(gj, cols["pair_j"])
     x0, x1, y0, y1 = boxes
     starts = np.searchsorted(-pi, -np.arange(n, -1, -1))                     # rows of shape i: pairs are grouped by i, descending
     for i in rng.integers(1, n, 60):

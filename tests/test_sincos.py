@@ -31,10 +31,12 @@ def test_sincos_within_one_ulp_of_libm(oracle, product_lib):
 
 
 def test_sincos_special_values(product_lib):
-    c, s = engine.sincos(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 2.0**61]))
+    c, s = engine.sincos(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 2.0**61, np.nextafter(1e12, np.inf), -1.0e13]))
     assert c[0] == 1.0 and s[0] == 0.0 and not np.signbit(s[0])
     assert c[1] == 1.0 and s[1] == 0.0 and np.signbit(s[1])
-    assert np.isnan(c[2:]).all() and np.isnan(s[2:]).all()
+    assert np.isnan(c[2:]).all() and np.isnan(s[2:]).all()       # beyond the proven range (|x| > 1e12): NaN, never a drift
+    c, s = engine.sincos(np.array([1e12, -1e12]))
+    assert np.isfinite(c).all() and np.isfinite(s).all()
     # unit circle to rounding, symmetric in sign
     x = np.linspace(-50, 50, 10001)
     c, s = engine.sincos(x)
