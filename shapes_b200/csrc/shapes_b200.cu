@@ -162,6 +162,7 @@ struct FrameState {
     unsigned cell_lo, cell_end; // cells it keeps: rows [row_lo - 1, row_hi + 1); every other mode: [0, n_cells)
     int cut[SHAPES_MAX_RANKS + 1]; // row cuts of all ranks: rank g sweeps rows [cut[g], cut[g + 1])
     unsigned n_kept;            // shapes in this rank's grid
+    unsigned n_list;            // rows mode: entries of the kept-slot list (k_rw_bin appends, k_rw_hulls walks it)
     int peer_error;             // OR of every rank's error word (exchanged at the results barrier)
     unsigned long long loc_fold, loc_contig;   // rows mode: work entries whose home would be this rank under the folded /
                                                // the contiguous home layout (decides which one the next frames use)
@@ -268,6 +269,7 @@ struct Params {
     double4 *pj;                // rows mode, per home pair with contacts: (pos_j, inverse masses of j), pushed by the sweeping rank
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
+    uint32_t *kept_list;        // rows mode: the slots this rank keeps, in (roughly) ascending slot order
     // homes: the slot space is cut into 2G blocks of rw_blk slots, rank g is home to blocks g and 2G-1-g.  Whatever the
     // host's numbering, each home then holds the same number of slots AND (the larger key of a pair being uniform or
     // linear in the slot index) the same number of pairs; its slice of the result is two runs of the global order.
@@ -2004,6 +2006,63 @@ __global__ void k_rw_wait(Params P, int phase)
     }
 }
 
+// Both sides of a barrier in one launch (one block of 1024 threads): payload + flags out, then the bounded spin on
+// my own flag words.  Saves a kernel boundary per barrier on the frame's critical path.
+__global__ void __launch_bounds__(1024) k_rw_sync(Params P, int phase)
+{
+    FrameState *st = P.st;
+    const int G = P.n_peers, me = P.my_rank;
+    if (phase == RW_PHASE_KEYS) {
+        for (int r = threadIdx.x; r < G; r += blockDim.x) {
+            unsigned long long *dst = P.peer_bounds[r] + 4 * me;
+            dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+        }
+    } else if (phase == RW_PHASE_CNT) {
+        for (int k = threadIdx.x; k < G * ROW_BINS; k += blockDim.x) {
+            const int r = k / ROW_BINS, b = k % ROW_BINS;
+            P.rw_weights[r][(size_t)me * ROW_BINS + b] = P.roww[b];
+        }
+    } else if (phase == RW_PHASE_OFF || phase == RW_PHASE_RESULTS) {
+        for (int r = threadIdx.x; r < G; r += blockDim.x) P.rw_err[r][(phase == RW_PHASE_OFF ? 0 : G) + me] = st->error;
+    } else {
+        const int n_hi = P.rw_hi_hi - P.rw_hi_lo, n_q = n_hi + (P.rw_lo_hi - P.rw_lo_lo);
+        long long p_hi = 0, c_hi = 0;
+        if (!st->error && n_q > 0) {
+            p_hi = n_hi < n_q ? (long long)P.off[n_hi] : st->n_pairs;
+            if (n_hi == 0) p_hi = 0;
+            c_hi = p_hi < st->n_pairs ? (long long)P.coff[p_hi] : st->n_contacts;
+        }
+        for (int r = threadIdx.x; r < G; r += blockDim.x) {
+            long long *dst = P.rw_counts[r] + 4 * me;
+            dst[0] = p_hi; dst[1] = st->n_pairs - p_hi; dst[2] = c_hi; dst[3] = st->n_contacts - c_hi;
+            long long *loc = P.rw_counts[r] + 4 * G + 2 * me;
+            loc[0] = (long long)st->loc_fold; loc[1] = (long long)st->loc_contig;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const unsigned long long frame = st->frame_no;
+    for (int r = threadIdx.x; r < G; r += blockDim.x)
+        *reinterpret_cast<volatile unsigned long long *>(P.peer_flags[r] + phase * SHAPES_MAX_RANKS + me) = frame;
+    // ---- wait side
+    if ((int)threadIdx.x < G) {
+        const volatile unsigned long long *flag = P.flags + phase * SHAPES_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while (*flag < frame) {
+            if (clock64() - t0 > 8000000000ll) { atomicOr(&st->error, ERR_PEER_TIMEOUT); break; } // ~4 s
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((phase == RW_PHASE_OFF || phase == RW_PHASE_RESULTS) && threadIdx.x == 0) {
+        int e = 0;
+        for (int q = 0; q < G; ++q) e |= reinterpret_cast<volatile int *>(P.rw_err[me])[(phase == RW_PHASE_OFF ? 0 : G) + q];
+        st->peer_error |= e;
+        if (e) st->error |= e & (ERR_PAIR_CAP | ERR_PEER_TIMEOUT);   // a full list anywhere voids the frame everywhere
+    }
+}
+
 // First kernel of a rows-mode frame (one block).  Frame counter, the grid from the bounds every rank pushed in the
 // previous frame (two cells of margin: whatever moved further goes to the exact big-shape path), the row cuts from
 // the row weights of the previous frame, and the per-frame counters.
@@ -2027,7 +2086,7 @@ __global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
         st->bmin_x = st->bmin_y = ~0ull;       // K0 reduces this frame's bounds into them
         st->bmax_x = st->bmax_y = 0ull;
         st->n_big = 0; st->n_small = 0; st->error = 0; st->peer_error = 0;
-        st->n_pairs = 0; st->n_contacts = 0; st->work_cursor = 0ull; st->n_pairs_hit = 0ull; st->n_kept = 0u;
+        st->n_pairs = 0; st->n_contacts = 0; st->work_cursor = 0ull; st->n_pairs_hit = 0ull; st->n_kept = 0u; st->n_list = 0u;
         st->loc_fold = 0ull; st->loc_contig = 0ull;
     }
     // row weights: ROW_BINS bins over the rows, summed over the ranks that measured them; 4 bins per thread
@@ -2154,26 +2213,47 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
 }
 
 // Keep the shapes whose cell lies in my rows or the halo row on either side (histogram of the cell table; the
-// arrival order is the counting sort's scatter slot); every rank lists every big shape.
+// arrival order is the counting sort's scatter slot); every rank lists every big shape.  The kept slots are also
+// appended to a list, one reservation per block and ascending inside it, so that k_rw_hulls touches the static
+// geometry and its outputs in nearly ascending address order however the cells are numbered.
 __global__ void __launch_bounds__(256) k_rw_bin(Params P)
 {
     const FrameState *st = P.st;
     const unsigned c_lo = st->cell_lo, c_end = st->cell_end;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
-        const uint32_t enc = P.gkeys[s] & ~KEY_STATIC_BIT;
-        uint32_t kept = P.key_none;
-        if (enc == RW_KEY_BIG) {
-            const unsigned pos = atomicAdd(&P.st->n_big, 1u);
-            P.big_idx[pos] = (uint32_t)s;
-            if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);
-        } else if (enc >= RW_KEY_BASE) {
-            const uint32_t key = enc - RW_KEY_BASE;
-            if (key >= c_lo && key < c_end) {
-                P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
-                kept = key;
+    __shared__ unsigned s_wsum[8];
+    __shared__ unsigned s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = blockIdx.x * blockDim.x; base < P.n_slots; base += gridDim.x * blockDim.x) {
+        const int s = base + (int)threadIdx.x;
+        bool keep = false;
+        if (s < P.n_slots) {
+            const uint32_t enc = P.gkeys[s] & ~KEY_STATIC_BIT;
+            uint32_t kept = P.key_none;
+            if (enc == RW_KEY_BIG) {
+                const unsigned pos = atomicAdd(&P.st->n_big, 1u);
+                P.big_idx[pos] = (uint32_t)s;
+                if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);
+            } else if (enc >= RW_KEY_BASE) {
+                const uint32_t key = enc - RW_KEY_BASE;
+                if (key >= c_lo && key < c_end) {
+                    P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
+                    kept = key;
+                    keep = true;
+                }
             }
+            P.keys[s] = kept;
         }
-        P.keys[s] = kept;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[warp] = (unsigned)__popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < 8; ++w) { const unsigned c = s_wsum[w]; s_wsum[w] = t; t += c; }
+            s_base = t ? atomicAdd(&P.st->n_list, t) : 0u;
+        }
+        __syncthreads();
+        if (keep) P.kept_list[s_base + s_wsum[warp] + (unsigned)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)s;
+        __syncthreads();
     }
 }
 
@@ -2227,59 +2307,78 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, con
     }
 }
 
-// moveShapes (World.hs:132-140) for the shapes this rank keeps (its rows, the halo rows, the big list), 8 lanes per
-// shape in CELL order (dense whatever share of the world this rank keeps): lane k transforms vertex k and its
-// successor with the packed transform the shape's home pushed and emits the world vertex and the unit normal of the
-// edge that starts there (setHullTransform, ConvexHull.hs:184-195: normals recomputed from the NEW vertices); lane 0
-// also folds the AABB over the vertices in order (hullToAabb, Aabb.hs:81-84 -- the fold K0 ran at the home, same bits)
-// and stores it at the shape's sorted position.  Hulls of more than 8 vertices are walked by lane 0 alone.
+// moveShapes (World.hs:132-140) for the shapes this rank keeps (its rows, the halo rows, the big list): one thread
+// per shape, walking the kept-slot list (ascending slots inside every 256-entry run: the gathers of the static
+// geometry and the stores of the world vertices / normals are as dense as K0's, whatever share of the world this
+// rank keeps).  Same body as K0 (k_transform_aabb): the hull's local vertices as one batch of loads, world vertices
+// kept in registers for the unit normals (setHullTransform, ConvexHull.hs:184-195: normals recomputed from the NEW
+// vertices), AABB folded in vertex order (hullToAabb, Aabb.hs:81-84 -- the fold the shape's home ran for its key,
+// same vertices, same bits), with the packed transform the home pushed.  The record goes to the sorted position.
 __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
 {
     const FrameState *st = P.st;
     if (st->error & ERR_REPLAN) return;
     const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
-    const int k = threadIdx.x & 7;
-    for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < n_all; p += (gridDim.x * blockDim.x) >> 3) {
-        const int s = p < n_kept ? (int)(P.smeta[p] & 0x7fffffffu) : (int)P.big_idx[p - n_kept];
-        const Xf x = P.xf[s];                      // pushed by its home (or mine)
-        const Aff m = to_transform(x.px, x.py, x.c, x.s);
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_all; q += gridDim.x * blockDim.x) {
+        int s;
+        unsigned p;
+        if (q < n_kept) { s = (int)P.kept_list[q]; p = P.cell_begin[P.keys[s]] + P.rank[s]; }
+        else { s = (int)P.big_idx[q - n_kept]; p = q; }              // big shapes: positions n_kept + b, next to the grid's records
+        const Xf x = P.xf[s];                                        // pushed by its home (or mine)
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
         const double rad = P.radius ? P.radius[s] : -1.0;
-        if (k == 0) P.mat_stamp[s] = (uint32_t)st->frame_no;
-        if (rad < 0.0 && n <= MAX_STAGED_VERTS && k < n) {
-            const double2 la = __ldg(&P.local[o + k]), lb = __ldg(&P.local[o + ((k + 1 < n) ? k + 1 : 0)]);
-            const V2 wa = afmul(m, V2{ la.x, la.y }), wb = afmul(m, V2{ lb.x, lb.y });
-            const V2 nn = unit_edge_normal(wa, wb);
-            P.wv[o + k] = make_double2(wa.x, wa.y);
-            P.wn[o + k] = make_double2(nn.x, nn.y);
-        }
-        if (k != 0) continue;
+        P.mat_stamp[s] = (uint32_t)st->frame_no;
+        const Aff m = to_transform(x.px, x.py, x.c, x.s);
         Box b{ 0.0, 0.0, 0.0, 0.0 };
         if (rad >= 0.0) {      // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
             const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
             P.circ[s] = make_double2(ctr.x, ctr.y);
             b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
             b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+        }
+        if (n <= MAX_STAGED_VERTS) {
+            double2 l[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < n) l[k] = __ldg(&P.local[o + k]);
+            V2 w[MAX_STAGED_VERTS];
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                w[k] = afmul(m, V2{ l[k].x, l[k].y });
+                P.wv[o + k] = make_double2(w[k].x, w[k].y);
+                if (k == 0) { b.min_x = b.max_x = w[k].x; b.min_y = b.max_y = w[k].y; }
+                else {
+                    b.min_x = (b.min_x < w[k].x) ? b.min_x : w[k].x;
+                    b.max_x = (b.max_x > w[k].x) ? b.max_x : w[k].x;
+                    b.min_y = (b.min_y < w[k].y) ? b.min_y : w[k].y;
+                    b.max_y = (b.max_y > w[k].y) ? b.max_y : w[k].y;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                if (k >= n) break;
+                const V2 nxt = (k + 1 < MAX_STAGED_VERTS && k + 1 < n) ? w[(k + 1) & (MAX_STAGED_VERTS - 1)] : w[0];
+                const V2 nn = unit_edge_normal(w[k], nxt);
+                P.wn[o + k] = make_double2(nn.x, nn.y);
+            }
         } else {
-            const bool long_hull = n > MAX_STAGED_VERTS;
             V2 w0{ 0.0, 0.0 }, prev{ 0.0, 0.0 };
-            for (int q = 0; q < n; ++q) {
-                const double2 l = __ldg(&P.local[o + q]);
+            for (int v = 0; v < n; ++v) {
+                const double2 l = __ldg(&P.local[o + v]);
                 const V2 w = afmul(m, V2{ l.x, l.y });
-                if (q == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                P.wv[o + v] = make_double2(w.x, w.y);
+                if (v == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
                 else {
                     b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
                     b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                    const V2 nn = unit_edge_normal(prev, w);
+                    P.wn[o + v - 1] = make_double2(nn.x, nn.y);
                 }
-                if (long_hull) {
-                    P.wv[o + q] = make_double2(w.x, w.y);
-                    if (q > 0) { const V2 nn = unit_edge_normal(prev, w); P.wn[o + q - 1] = make_double2(nn.x, nn.y); }
-                    prev = w;
-                }
+                prev = w;
             }
-            if (long_hull && n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
+            if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
         }
-        P.sbox[p] = b;      // big shapes: positions n_kept + b, next to the grid's records
+        P.sbox[p] = b;
     }
 }
 
@@ -2451,7 +2550,7 @@ struct shapes_ctx {
     Xf *d_xf = nullptr;
     double2 *d_mass = nullptr;
     unsigned *d_chunk_sum = nullptr;
-    uint32_t *d_mat_stamp = nullptr;
+    uint32_t *d_mat_stamp = nullptr, *d_kept_list = nullptr;
     bool pending_warm = false, pending_seed = false, pending_rows = false, pending_plan_ahead = false;
     bool use_plan_ahead = true;   // single rank: grid planned from the previous frame's bounds, K0 keys and bins (SHAPES_B200_NO_PLAN_AHEAD=1: plan inside the frame)
     bool plan_valid = false;      // the bounds in FrameState describe the last completed frame of the current geometry
@@ -2701,6 +2800,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         TRY_CREATE(dev_alloc(c, &c->d_ccnt_w, max_pairs));
         TRY_CREATE(dev_alloc(c, &c->d_chunk_sum, SCAN_BLOCKS));
         TRY_CREATE(dev_alloc(c, &c->d_mat_stamp, N));
+        TRY_CREATE(dev_alloc(c, &c->d_kept_list, N));
         TRY_CREATE(cu(cudaMemset(c->d_mat_stamp, 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(N, 1)), "cudaMemset"));
         c->peer_arena[rank] = c->rw_arena;
     }
@@ -2851,7 +2951,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         P.ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt); P.man = reinterpret_cast<ManRec *>(mine + L.man);
         P.pj = reinterpret_cast<double4 *>(mine + L.pj); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
         P.sat_ccnt = c->d_ccnt_w;
-        P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp;
+        P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp; P.kept_list = c->d_kept_list;
         P.rw_weights_prev = reinterpret_cast<const uint32_t *>(mine + L.weights[fpar ^ 1]);
         P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
         for (int r = 0; r < c->world; ++r) {
@@ -2902,10 +3002,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
         kt("k_rw_transform");
         STAGE_MARK(); // 1: barrier KEYS (this frame's bounds ride along, for the next frame's grid)
-        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
-        kt("k_rw_publish:KEYS");
-        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
-        kt("k_rw_wait:KEYS");
+        k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
+        kt("k_rw_sync:KEYS");
         STAGE_MARK(); // 2: keep my rows' keys
         if (N > 0) { k_rw_bin<<<gn, 256, 0, s>>>(P); ++c->launches; }
         kt("k_rw_bin");
@@ -2918,7 +3016,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         if (N > 0) {
             k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
             kt("k_scatter_sorted");
-            k_rw_hulls<<<sms * 16, 256, 0, s>>>(P); ++c->launches;
+            k_rw_hulls<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
             kt("k_rw_hulls");
         }
         STAGE_MARK(); // 5: single-pass sweep of my rows; every query's count is pushed to its home; barrier CNT
@@ -2930,10 +3028,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             k_big<true><<<64, 256, 0, s>>>(P); ++c->launches;
             kt("k_big");
         }
-        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
-        kt("k_rw_publish:CNT");
-        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
-        kt("k_rw_wait:CNT");
+        k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_CNT); ++c->launches;
+        kt("k_rw_sync:CNT");
         STAGE_MARK(); // 6: home -- offsets of my slice, sent back to the sweeping ranks; barrier OFF
         if (n_query > 0) {
             k_rw_home_counts<<<gq, 256, 0, s>>>(P, n_query); ++c->launches;
@@ -2946,10 +3042,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         kt("k_finish_pairs");
         if (n_query > 0) { k_rw_push_offsets<<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
         kt("k_rw_push_offsets");
-        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
-        kt("k_rw_publish:OFF");
-        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
-        kt("k_rw_wait:OFF");
+        k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_OFF); ++c->launches;
+        kt("k_rw_sync:OFF");
         STAGE_MARK(); // 7
         STAGE_MARK(); // 8: manifolds over my work list, every pair stored into its final place at its home; barrier RESULTS
         if (N > 0) {
@@ -2966,10 +3060,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             kt("k_manifolds");
             ++c->launches;
         }
-        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
-        kt("k_rw_publish:RESULTS");
-        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
-        kt("k_rw_wait:RESULTS");
+        k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
+        kt("k_rw_sync:RESULTS");
         STAGE_MARK(); // 9: home -- row offsets
         if (c->max_pairs > 0) {
             size_t cb = c->scan_tmp_bytes;
@@ -2987,10 +3079,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         STAGE_MARK(); // end
     #undef STAGE_MARK
         // barrier COUNTS: every rank learns every rank's pair / contact totals (global row offsets of the slices)
-        k_rw_publish<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
-        kt("k_rw_publish:COUNTS");
-        k_rw_wait<<<1, 32, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
-        kt("k_rw_wait:COUNTS");
+        k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_COUNTS); ++c->launches;
+        kt("k_rw_sync:COUNTS");
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(c->h_counts, c->rw_arena + c->rwl.counts, sizeof(int64_t) * 6 * c->world, cudaMemcpyDeviceToHost, s));
         CU_TRY(c, cudaMemcpyAsync(c->h_state, P.st, sizeof(FrameState), cudaMemcpyDeviceToHost, s));
