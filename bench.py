@@ -368,9 +368,11 @@ def run_leg(R: Ranks, workload: str, world, desc: str, steps: int, warmup: int, 
             R.dist.all_gather_object(blobs, eng.ipc_export())
             eng.ipc_import(blobs)
             if os.environ.get("SHAPES_B200_NO_ROWS") is None:
-                exchange = ("rows mode: home ranks push 4 B cell keys; the sweep / SAT work is split by grid rows (cuts balanced on the "
-                            "previous frame's per-row pair counts), sweeping ranks pull AABB + transform records and push per-slot counts; "
-                            "homes pull (j, contact count) and the manifolds (CUDA IPC over NVLink, 3 flag barriers, CUDA-graph replay)")
+                exchange = ("rows mode: home ranks push 4 B cell keys + 48 B body records only to the ranks whose grid rows need them; "
+                            "the sweep / SAT work is split by grid rows (cuts balanced on the previous frame's per-row pair counts); "
+                            "sweeping ranks re-transform the kept hulls, push per-slot pair counts, get the offsets back and store "
+                            "every pair (keys, count, manifold) into its final place at the rank that owns its larger key "
+                            "(CUDA IPC over NVLink, 5 flag barriers, CUDA-graph replay)")
             else:
                 exchange = "4 B cell keys pushed to every peer + needed AABB / body records pulled through peer pointers (CUDA IPC over NVLink), flag barriers"
     cos_rot, sin_rot = np.cos(world.rot), np.sin(world.rot)

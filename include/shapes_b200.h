@@ -236,13 +236,17 @@ int  shapes_rank_info(shapes_ctx *, int64_t *own_lo, int64_t *own_hi,
 int  shapes_rank_segments(shapes_ctx *, int rank, int64_t seg_lo[2], int64_t seg_hi[2],
                           int64_t seg_pairs[2], int64_t seg_contacts[2]);
 
-/* Peer-to-peer AABB exchange (optional, replaces the NCCL all-gather): K0 stores every AABB record
- * straight into all ranks' arrays over NVLink (fused compute + collective), with per-frame flags as
- * the cross-GPU barrier.  Each rank exports SHAPES_IPC_BYTES (CUDA IPC handles of its exchange
- * buffers); the host gathers the blobs of all ranks (rank order) and hands them to every rank.
- * Ranks live in different processes (CUDA IPC does not map a process's own handles).  Without an
- * import the exchange goes through NCCL.  With it, shapes_frame also uploads only the rank's own
- * slots of the body columns; foreign bodies are pulled from their owner's columns.  SHAPES_B200_NO_P2P=1 forces the NCCL path. */
+/* Mapped peer memory (optional, replaces the NCCL all-gather of the AABB records): each rank exports
+ * SHAPES_IPC_BYTES (CUDA IPC handles of its exchange arena); the host gathers the blobs of all ranks (rank order)
+ * and hands them to every rank.  Ranks live in different processes (CUDA IPC does not map a process's own handles;
+ * one process with several GPUs uses shapes_create_multi below).  With the peers mapped the frame runs in "rows
+ * mode": homes push 4 B cell keys + 48 B body records over NVLink only to the ranks whose grid rows need them, the
+ * sweep / SAT work is split by grid rows balanced on the previous frame's pair counts, every pair is stored straight
+ * into its final place at the rank that owns its larger key, and per-frame flag words are the cross-GPU barriers
+ * (five per frame, bounded spins).  shapes_frame then uploads only the rank's own slots of the body columns.
+ * Without an import the exchange goes through NCCL.  SHAPES_B200_NO_P2P=1 forces the NCCL path,
+ * SHAPES_B200_NO_ROWS=1 the round-1 exchange (keys pushed to every peer, AABB records pulled, slot-range ownership
+ * of the whole path). */
 #define SHAPES_IPC_BYTES 2048
 int  shapes_ipc_export(shapes_ctx *, void *out_blob /* SHAPES_IPC_BYTES */);
 int  shapes_ipc_import(shapes_ctx *, const void *all_blobs /* world_size x SHAPES_IPC_BYTES */);

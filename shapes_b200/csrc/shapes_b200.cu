@@ -6,17 +6,23 @@
 //   constraintGen per contact           (shapes/src/Physics/Constraints/Contact.hs:60-72)
 // All reference paths below are relative to /root/reference/.
 //
-// Pipeline (one stream, no host round trip between kernels):
-//   K0  k_transform_aabb  moveShapes + toAabb per slot                 (World.hs:132-140, Aabb.hs:81-110)
-//   [N>1: ncclAllGather of the AABB records over NVLink]
-//   K0b k_plan_grid / k_keys / k_bin   uniform-grid cell key of each AABB's min corner + cell histogram
+// Pipeline of one frame on one GPU (one stream, one CUDA graph, no host round trip between kernels):
+//   K0  k_begin_frame + k_transform_aabb   moveShapes + toAabb per slot (World.hs:132-140, Aabb.hs:81-110); the grid was
+//       planned from the PREVIOUS frame's bounds, so K0 also computes each shape's cell key and bins it (stale plans
+//       are detected on the device and the frame is re-seeded inside the call)
 //   K1  counting sort on the cell table: exclusive scan of the histogram + k_scatter_sorted
-//   K2  k_sweep<count> -> exclusive scan over slots in DESCENDING key order -> k_sweep<emit>
-//       (+ k_big<count/emit> for shapes spanning more than 2 cells or with non-finite bounds)
-//       => pairs come out in the reference's descending (i, j) order by construction.
-//   K3  k_contacts  SAT both directions + incident-edge clipping + NonPenetration / Friction /
-//       Restitution generators + inverse effective mass, one thread per pair, rows compacted in
-//       order by a single-pass decoupled look-back scan.
+//   K2  boxes-only worlds: k_sweep<count> -> exclusive scan over slots in DESCENDING key order -> k_sweep<emit>;
+//       general polygon worlds ("sorted mode"): ONE sweep pass that also appends every pair to a work list in grid-CELL
+//       order; (+ k_big<count/emit> for shapes spanning more than 2 cells or with non-finite bounds)
+//       => pairs come out in the reference's descending (i, j) order by construction (a pair's place is
+//       off[rank of i] + its rank among i's partners).
+//   K3a k_manifolds<4> (boxes, one thread per pair) / k_manifolds_coop (general polygons, 16 lanes per pair, walks the
+//       cell-ordered work list so that neighbouring tiles share their hulls): SAT both directions + incident-edge
+//       clipping -> per pair a contact count and a 64 B manifold record
+//   K3b exclusive scan of the counts + k_row_map, then k_rows: one lane per contact row -- NonPenetration / Friction /
+//       Restitution generators + inverse effective masses, every column store a whole number of 32 B sectors
+//   (+ k_warm_join: descZipVector of this frame's keys against the previous frame's Lagrangian cache)
+// Several GPUs: "rows mode", the k_rw_* kernels further down (the comment there describes the exchange).
 //
 // Arithmetic: IEEE binary64, every operation a separately rounded __dmul_rn/__dadd_rn/... so no
 // FMA contraction can occur whatever the compiler flags; expression trees follow the reference's
@@ -270,6 +276,7 @@ struct Params {
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
     uint32_t *kept_list;        // rows mode: the slots this rank keeps, in (roughly) ascending slot order
+    int dbg_local_stores;       // experiment (SHAPES_B200_DBG_LOCAL_STORES): SAT results stay on the sweeping rank -- WRONG results, timing only
     // homes: the slot space is cut into 2G blocks of rw_blk slots, rank g is home to blocks g and 2G-1-g.  Whatever the
     // host's numbering, each home then holds the same number of slots AND (the larger key of a pair being uniform or
     // linear in the slot index) the same number of pairs; its slice of the result is two runs of the global order.
@@ -1437,7 +1444,7 @@ __device__ __forceinline__ PairOut pair_out(const Params &P, long long w, int i)
     PairOut o{ w, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
     if (P.work_mode == 1) { o.idx = (long long)(P.off[P.own_hi - 1 - i] + P.w_a[w]); o.pair_i = P.pair_i; o.pair_j = P.pair_j; }
     else if (P.work_mode == 2) {
-        const int h = rw_home(P, i);
+        const int h = P.dbg_local_stores ? P.my_rank : rw_home(P, i);
         o.idx = (long long)P.q_off[i] + (long long)P.w_a[w];
         o.ccnt = P.rw_ccnt[h]; o.man = P.rw_man[h]; o.pair_i = P.rw_pair_i[h]; o.pair_j = P.rw_pair_j[h]; o.pj = P.rw_pj[h];
         o.ok = o.idx < P.max_pairs;
@@ -1920,26 +1927,35 @@ __global__ void __launch_bounds__(256) k_warm_join(Params P)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Rows mode: one frame on G ranks with mapped peer memory.
+// Rows mode: one frame on G ranks with mapped peer memory (CUDA IPC between processes,
+// peer access inside one process).
 //
-//   home(s)  = rank whose slot range holds s: owns s's body columns, computes its AABB / key, and ends up with the
-//              pairs whose LARGER key is s (so the global descending order is rank G-1's slice, then G-2's, ...);
-//   sweeper  = rank whose grid-row range holds the cell of the pair's larger key: finds the pair and runs SAT on it.
-//              Rows are cut so that every rank gets the same number of pairs, measured per row in the previous frame.
+//   home(s)  = rank whose slot block holds s (two folded blocks per rank, or one contiguous block when the slot
+//              numbering follows the geometry): owns s's body columns, computes its AABB / cell key, and ends up with
+//              the pairs whose LARGER key is s -- the global descending order is a fixed concatenation of the ranks'
+//              slices, no merge;
+//   sweeper  = rank whose grid-ROW range holds the cell of the pair's larger key: finds the pair and runs SAT on it.
+//              Rows are cut so that every rank gets the same number of pairs, measured per row in the previous frame
+//              (ROW_BINS bins, exchanged with the CNT barrier): a Gaussian blob is balanced like a uniform world.
 //
-//   K0 (home slots): AABB + cell key, key pushed to every rank (4 B)         k_rw_transform
-//   -- barrier KEYS --
-//   keep the keys of my rows + one halo row, counting sort                   k_rw_bin, k_scan_cells_*, k_scatter_sorted
-//   world vertices / normals of the kept hulls (transform pulled, 32 B)      k_rw_hulls
-//   single-pass sweep of my rows -> local work list; per query its count and
-//   list position are pushed to home(i)                                      k_sweep<FUSED>, k_big
-//   SAT over the local work list, results in work order                      k_manifolds*
-//   -- barrier RESULTS (row weights and error words ride along) --
-//   home: scan the counts, pull (j, contact count) of every pair into place  k_rw_home_counts, scan, k_rw_gather
-//   rows: manifolds pulled from the sweeping rank by k_rows (64 B per pair with contacts)
-//   -- barrier COUNTS (every rank's pair / contact totals) --
+//   K0 (home slots)  AABB + cell key; key (4 B), packed transform (32 B) and inverse masses (16 B) are PUSHED over
+//                    NVLink to the rank(s) whose rows + halo hold the cell (big shapes: to all)     k_rw_transform
+//   -- barrier KEYS (this frame's bounds ride along: they plan the NEXT frame's grid) --            k_rw_sync
+//   keep the keys of my rows + one halo row: histogram, kept-slot list, counting sort   k_rw_bin, k_scan_cells_*, k_scatter_sorted
+//   world vertices / normals / AABB of the kept hulls, from the pushed transforms                   k_rw_hulls
+//   single-pass sweep of my rows -> local work list in cell order; every query's partner count
+//   is pushed to home(i) (4 B)                                                                      k_sweep<FUSED>, k_big
+//   -- barrier CNT (row weights ride along) --
+//   home: scan of the counts in descending slot order; each slot's first pair index goes back to
+//   its sweeper (4 B)                                                     k_rw_home_counts, scan, k_finish_pairs, k_rw_push_offsets
+//   -- barrier OFF (error words ride along) --
+//   SAT over the local work list; every pair is STORED into its final place at its home: (i, j), contact count,
+//   64 B manifold and the partner's body record when it has contacts                                k_manifolds*
+//   -- barrier RESULTS --
+//   home: row offsets, k_rows over local memory only, cache join                                    scan, k_row_map, k_rows
+//   -- barrier COUNTS (every rank's pair / contact totals: global row offsets of the slices) --
 // The grid and the row cuts of frame f come from what frame f-1 exchanged (bounds, row weights), so no barrier
-// sits between K0 and the keys.
+// sits between K0 and the keys; the frame number lives in device memory, so frames replay as CUDA graphs.
 // ---------------------------------------------------------------------------------------------
 
 // Barrier, arrive side: payload stores, system fence, then this frame's number into every peer's flag word.
@@ -2952,6 +2968,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         P.pj = reinterpret_cast<double4 *>(mine + L.pj); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
         P.sat_ccnt = c->d_ccnt_w;
         P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp; P.kept_list = c->d_kept_list;
+        P.dbg_local_stores = std::getenv("SHAPES_B200_DBG_LOCAL_STORES") ? 1 : 0;
         P.rw_weights_prev = reinterpret_cast<const uint32_t *>(mine + L.weights[fpar ^ 1]);
         P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
         for (int r = 0; r < c->world; ++r) {
