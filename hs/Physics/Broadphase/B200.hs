@@ -22,7 +22,8 @@ Marshalling notes
 -}
 module Physics.Broadphase.B200
   ( Ctx, Frame(..), StepConfig(..)
-  , create, destroy, setShapes, frame, growAndRetry
+  , create, destroy, setShapes, frame, growAndRetry, c_grow
+  , Multi, c_createMulti, c_multiDestroy, c_multiSetShapes, c_multiFrame
   , worldUpload, worldStep, worldDownload, sincos
   ) where
 
@@ -135,6 +136,35 @@ frame ctx ContactBehavior{..} dt world = unsafeIOToST $ do
       -4 -> growAndRetry ctx out               -- SHAPES_E_CAPACITY: the required sizes are in `out`
       _  -> check ctx rc >> undefined
 
+-- | SHAPES_E_CAPACITY: the failed call left the ctx as it was (previous frame's keys, the Lagrangian cache, an
+-- uploaded world); shapes_grow enlarges the capacities in place and the same call is issued again, so the retried
+-- frame still joins against the EngineCache applyCachedSlns would have used (Physics/Solvers/Contact.hs:84-121).
+foreign import ccall unsafe "shapes_grow"
+  c_grow :: Ptr Ctx -> Int64 -> Int64 -> IO CInt
+
+-- | One process, several GPUs (the host is one single-threaded ST computation, Physics/Engine/Main.hs:38,71-86):
+-- same arguments as shapes_frame, `out` receives the whole frame in the reference's descending order.
+data Multi
+foreign import ccall unsafe "shapes_create_multi"
+  c_createMulti :: Ptr (Ptr Multi) -> CInt -> Ptr CInt -> Int64 -> Int64 -> Int64 -> Int64 -> IO CInt
+foreign import ccall unsafe "shapes_multi_destroy"
+  c_multiDestroy :: Ptr Multi -> IO ()
+foreign import ccall safe "shapes_multi_set_shapes"
+  c_multiSetShapes :: Ptr Multi -> Int64 -> Ptr Word8 -> Ptr Int32 -> Ptr Double -> Ptr Double
+                   -> Ptr Int32 -> Ptr Int32 -> Ptr Double -> IO CInt
+foreign import ccall safe "shapes_multi_frame"
+  c_multiFrame :: Ptr Multi -> Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Double
+               -> Ptr Double -> Ptr Double -> Double -> Double -> Double -> Ptr FrameOut -> IO CInt
+
+-- Compact wire format: withFrameOut leaves the pointers of the sixteen derived constraint columns NULL (nothing is
+-- copied for a NULL column) and readFrame rebuilds them, bit for bit, from what is shipped
+--   key_i key_j feat_a feat_b flip | normal_x/y center_x/y depth | j_np2 j_np5 j_f2 j_f5 | b_np | inv_eff_np inv_eff_f:
+-- with n = normal, s = if flip then n else negateV2 n, c = center
+--   _ccNonPen      = Constraint (V6 s.x s.y j_np2 (-s.x) (-s.y) j_np5) b_np      (NonPenetration.hs:34-43; flip3v3 for Flip)
+--   _ccFriction    = Constraint (V6 s.y (-s.x) j_f2 (-s.y) s.x j_f5) 0           (Friction.hs:31-44)
+--   _ccRestitution = RestitutionConstraint (c - pos i) (c - pos j) (negateV2 s)  (Restitution.hs:21-31)
+-- 113 B per contact row cross PCIe instead of 225.
+--
 -- marshalBodies / withFrameOut / readFrame / growAndRetry: buffer management and the hsc2hs
 -- peeks of shapes_frame_out; readFrame builds
 --   Descending [(i, j)]                                                 from pair_i / pair_j

@@ -155,7 +155,7 @@ public:
                                         beh.contactPenetrationSlop, &out);
             if (rc == SHAPES_E_CAPACITY && attempt < 4) { grow(w, out.n_pairs, out.n_contacts); continue; }
             if (rc != SHAPES_OK) throw Error(rc, shapes_last_error(ctx_));
-            return col.unpack(out, want_contacts, want_constraints);
+            return col.unpack(out, want_contacts, want_constraints, w);
         }
     }
 
@@ -219,15 +219,41 @@ private:
                 o.center_y = f64[3].data(); o.depth = f64[4].data();
             }
             if (has_k) {
-                for (int q = 0; q < 6; ++q) { o.j_np[q] = jn[q].data(); o.j_f[q] = jf[q].data(); }
+                // Compact wire format: of a row's 27 doubles only the 11 independent ones cross PCIe -- the contact
+                // (normal, centre, depth: above), the four cross terms, the Baumgarte bias and the two inverse
+                // effective masses.  A NULL pointer means "not wanted, nothing is copied"; unpack() rebuilds the other
+                // sixteen (sign copies of the normal / tangent, centre - position) bit for bit.
+                compact = has_c;
+                for (int q = 0; q < 6; ++q) {
+                    const bool shipped = !compact || q == 2 || q == 5;
+                    o.j_np[q] = shipped ? jn[q].data() : nullptr; o.j_f[q] = shipped ? jf[q].data() : nullptr;
+                }
                 o.b_np = bnp.data();
-                o.ra_x = r[0].data(); o.ra_y = r[1].data(); o.rb_x = r[2].data(); o.rb_y = r[3].data();
-                o.rn_x = r[4].data(); o.rn_y = r[5].data();
+                if (!compact) {
+                    o.ra_x = r[0].data(); o.ra_y = r[1].data(); o.rb_x = r[2].data(); o.rb_y = r[3].data();
+                    o.rn_x = r[4].data(); o.rn_y = r[5].data();
+                }
                 o.inv_eff_np = ie[0].data(); o.inv_eff_f = ie[1].data();
             }
         }
-        Frame unpack(const shapes_frame_out &o, bool want_c, bool want_k) const
+        bool compact = false;
+        Frame unpack(const shapes_frame_out &o, bool want_c, bool want_k, const World &w)
         {
+            if (want_k && compact)
+                for (int64_t k = 0; k < o.n_contacts; ++k) {
+                    // With n the contact normal and t = clockwiseV2 n = (n.y, -n.x): J_np = (-n, x, n, x), J_f = (-t, x, t, x)
+                    // on (penetrated, penetrator), halves swapped back for Flip (NonPenetration.hs:34-43,
+                    // Friction.hs:31-44, Constraint.hs:96-98); ra = c - pos_i, rb = c - pos_j, rn = n for Same / -n for
+                    // Flip (Restitution.hs:21-31).  Negation and one IEEE subtraction reproduce the device's bits.
+                    const size_t u = (size_t)k;
+                    const double nx = f64[0][u], ny = f64[1][u];
+                    const double sx = flip[u] ? nx : -nx, sy = flip[u] ? ny : -ny;
+                    jn[0][u] = sx; jn[1][u] = sy; jn[3][u] = -sx; jn[4][u] = -sy;
+                    jf[0][u] = sy; jf[1][u] = -sx; jf[3][u] = -sy; jf[4][u] = sx;
+                    r[4][u] = -sx; r[5][u] = -sy;
+                    r[0][u] = f64[2][u] - w.pos_x[(size_t)ki[u]]; r[1][u] = f64[3][u] - w.pos_y[(size_t)ki[u]];
+                    r[2][u] = f64[2][u] - w.pos_x[(size_t)kj[u]]; r[3][u] = f64[3][u] - w.pos_y[(size_t)kj[u]];
+                }
             Frame f;
             f.device_ms = o.device_ms;
             f.keys.reserve((size_t)o.n_pairs);

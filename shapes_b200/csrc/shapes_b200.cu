@@ -169,6 +169,7 @@ struct FrameState {
     int cut[SHAPES_MAX_RANKS + 1]; // row cuts of all ranks: rank g sweeps rows [cut[g], cut[g + 1])
     unsigned n_kept;            // shapes in this rank's grid
     unsigned n_list;            // rows mode: entries of the kept-slot list (k_rw_bin appends, k_rw_hulls walks it)
+    unsigned push_cursor[SHAPES_MAX_RANKS];   // rows mode, home side: records appended to every rank's inbox this frame
     int peer_error;             // OR of every rank's error word (exchanged at the results barrier)
     unsigned long long loc_fold, loc_contig;   // rows mode: work entries whose home would be this rank under the folded /
                                                // the contiguous home layout (decides which one the next frames use)
@@ -186,6 +187,16 @@ struct __align__(64) ManRec {
     double c0x, c0y, c1x, c1y; // manifold points, descending feature index
     unsigned long long bits;   // edge [0,20) | pen0 [20,40) | pen1 [40,60) | flip [60]
 };
+
+// Rows mode: what a home sends to a rank that sweeps one of its shapes -- one 64 B record, appended densely to the
+// receiver's inbox (a warp's records leave as whole 128 B lines, not as three scattered stores per shape).
+struct __align__(64) HomeRec {
+    Xf xf;                 // packed transform
+    double2 mass;          // inverse masses
+    uint32_t slot, key;    // key: RW_KEY_* encoding, bit 31 = isStatic
+    uint32_t pad[2];
+};
+static_assert(sizeof(HomeRec) == 64, "HomeRec layout");
 
 // Everything the kernels need, passed by value.
 struct Params {
@@ -276,6 +287,11 @@ struct Params {
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
     uint32_t *kept_list;        // rows mode: the slots this rank keeps, in (roughly) ascending slot order
+    HomeRec *rw_inbox[SHAPES_MAX_RANKS];     // every rank's inbox [G sources][inbox_cap]; I append to section my_rank
+    unsigned *rw_inbox_cnt[SHAPES_MAX_RANKS];// every rank's [G] record counts of its inbox sections (written at the KEYS barrier)
+    const HomeRec *inbox;                    // mine
+    const unsigned *inbox_cnt;
+    int inbox_cap;                           // records per section
     int dbg_local_stores;       // experiment (SHAPES_B200_DBG_LOCAL_STORES): SAT results stay on the sweeping rank -- WRONG results, timing only
     // homes: the slot space is cut into 2G blocks of rw_blk slots, rank g is home to blocks g and 2G-1-g.  Whatever the
     // host's numbering, each home then holds the same number of slots AND (the larger key of a pair being uniform or
@@ -739,6 +755,17 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
 // and keys in sorted order, contiguous per cell and per grid row.
 __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 {
+    if (P.work_mode == 2) {      // rows mode: only the kept slots have keys; their list is what this rank walks
+        const unsigned n_list = P.st->n_list;
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_list; q += gridDim.x * blockDim.x) {
+            const int s = (int)P.kept_list[q];
+            const uint32_t key = P.keys[s];
+            const uint32_t p = P.cell_begin[key] + P.rank[s];
+            P.smeta[p] = (uint32_t)s | ((P.gkeys[s] & KEY_STATIC_BIT) ? 0x80000000u : 0u);   // (k_rw_hulls folds the AABB record)
+            P.keys_sorted[p] = key;
+        }
+        return;
+    }
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_slots; s += gridDim.x * blockDim.x) {
         const uint32_t key = P.keys[s];
         if (key >= P.key_none) continue;
@@ -2032,6 +2059,7 @@ __global__ void __launch_bounds__(1024) k_rw_sync(Params P, int phase)
         for (int r = threadIdx.x; r < G; r += blockDim.x) {
             unsigned long long *dst = P.peer_bounds[r] + 4 * me;
             dst[0] = st->bmin_x; dst[1] = st->bmin_y; dst[2] = st->bmax_x; dst[3] = st->bmax_y;
+            P.rw_inbox_cnt[r][me] = st->push_cursor[r];     // how many records I appended to r's inbox
         }
     } else if (phase == RW_PHASE_CNT) {
         for (int k = threadIdx.x; k < G * ROW_BINS; k += blockDim.x) {
@@ -2103,6 +2131,7 @@ __global__ void __launch_bounds__(1024) k_rw_begin(Params P, int advance)
         st->bmax_x = st->bmax_y = 0ull;
         st->n_big = 0; st->n_small = 0; st->error = 0; st->peer_error = 0;
         st->n_pairs = 0; st->n_contacts = 0; st->work_cursor = 0ull; st->n_pairs_hit = 0ull; st->n_kept = 0u; st->n_list = 0u;
+        for (int r = 0; r < SHAPES_MAX_RANKS; ++r) st->push_cursor[r] = 0u;
         st->loc_fold = 0ull; st->loc_contig = 0ull;
     }
     // row weights: ROW_BINS bins over the rows, summed over the ranks that measured them; 4 bins per thread
@@ -2154,67 +2183,127 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
 {
     const FrameState *st = P.st;
     const int n_lo = P.rw_lo_hi - P.rw_lo_lo;
+    const int G = P.n_peers;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    __shared__ unsigned s_cnt[8][SHAPES_MAX_RANKS];     // per warp and destination: records of this tile, then their offset
+    __shared__ unsigned s_base[SHAPES_MAX_RANKS];       // per destination: the tile's first index in my section of its inbox
+    __shared__ HomeRec s_rec[8][32];                    // per warp: the records going to one destination, compacted
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_home; t += gridDim.x * blockDim.x) {
-        const int s = t < n_lo ? P.rw_lo_lo + t : P.rw_hi_lo + (t - n_lo);
-        const double px = P.pos_x[s], py = P.pos_y[s];
-        const double il = P.inv_lin[s], ir = P.inv_rot[s];
-        const bool live = P.alive[s] != 0;
-        const int o = P.vert_offset[s];
-        const int n = P.vert_offset[s + 1] - o;
-        const double rad = P.radius ? P.radius[s] : -1.0;
-        double c, sn;
-        if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
-        else sincos(P.rot[s], &sn, &c);
-        const Xf x{ px, py, c, sn };
+    // the block walks whole 256-slot tiles (block-uniform trip count: the reservation below synchronises the block)
+    for (int tile = blockIdx.x * blockDim.x; tile < n_home; tile += gridDim.x * blockDim.x) {
+        const int t = tile + (int)threadIdx.x;
+        const bool valid = t < n_home;
+        const int s = !valid ? 0 : (t < n_lo ? P.rw_lo_lo + t : P.rw_hi_lo + (t - n_lo));
         uint32_t key = RW_KEY_NONE;
         int cy = -1;
-        Box b{ 0.0, 0.0, 0.0, 0.0 };
-        if (!BOUNDS_ONLY) { P.xf[s] = x; P.mass[s] = make_double2(il, ir); }
-        if (live) {
-            const Aff m = to_transform(px, py, c, sn);
-            if (rad >= 0.0) {   // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
-                const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
-                b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
-                b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
-            }
-            for (int k = 0; k < n; ++k) {   // hullToAabb (Aabb.hs:81-84): foldl1 mergeAabb
-                const double2 l = __ldg(&P.local[o + k]);
-                const V2 w = afmul(m, V2{ l.x, l.y });
-                if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
-                else {
-                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
-                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+        bool live = false;
+        Xf x{ 0.0, 0.0, 1.0, 0.0 };
+        double2 mass = make_double2(0.0, 0.0);
+        if (valid) {
+            const double px = P.pos_x[s], py = P.pos_y[s];
+            const double il = P.inv_lin[s], ir = P.inv_rot[s];
+            live = P.alive[s] != 0;
+            const int o = P.vert_offset[s];
+            const int n = P.vert_offset[s + 1] - o;
+            const double rad = P.radius ? P.radius[s] : -1.0;
+            double c, sn;
+            if (P.cos_rot) { c = P.cos_rot[s]; sn = P.sin_rot[s]; }
+            else sincos(P.rot[s], &sn, &c);
+            x = Xf{ px, py, c, sn };
+            mass = make_double2(il, ir);
+            Box b{ 0.0, 0.0, 0.0, 0.0 };
+            if (!BOUNDS_ONLY) { P.xf[s] = x; P.mass[s] = mass; }
+            if (live) {
+                const Aff m = to_transform(px, py, c, sn);
+                if (rad >= 0.0) {   // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
+                    const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
+                    b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
+                    b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
+                }
+                // hullToAabb (Aabb.hs:81-84): foldl1 mergeAabb.  Hulls of up to 8 vertices: the local vertices as ONE batch
+                // of loads (a load per loop iteration made this kernel latency-bound: 0.15 ms for 2M slots)
+                if (n <= MAX_STAGED_VERTS) {
+                    double2 l[MAX_STAGED_VERTS];
+#pragma unroll
+                    for (int k = 0; k < MAX_STAGED_VERTS; ++k) if (k < n) l[k] = __ldg(&P.local[o + k]);
+#pragma unroll
+                    for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
+                        if (k >= n) break;
+                        const V2 w = afmul(m, V2{ l[k].x, l[k].y });
+                        if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                        else {
+                            b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                            b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                        }
+                    }
+                } else
+                for (int k = 0; k < n; ++k) {
+                    const double2 l = __ldg(&P.local[o + k]);
+                    const V2 w = afmul(m, V2{ l.x, l.y });
+                    if (k == 0) { b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
+                    else {
+                        b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
+                        b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
+                    }
+                }
+                if (finite4(b)) {
+                    mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
+                    mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
+                }
+                if (!BOUNDS_ONLY) {
+                    int cx;
+                    key = small_cell(b, st, cx, cy) ? RW_KEY_BASE + (uint32_t)cy * (uint32_t)st->W + (uint32_t)cx : RW_KEY_BIG;
+                    if (key == RW_KEY_BIG) cy = -1;
+                    if (il == 0.0 && ir == 0.0) key |= KEY_STATIC_BIT;      // isStatic (Constraint.hs:123-125)
                 }
             }
-            if (finite4(b)) {
-                mnx = fmin(mnx, b.min_x); mxx = fmax(mxx, b.max_x);
-                mny = fmin(mny, b.min_y); mxy = fmax(mxy, b.max_y);
-            }
-            if (!BOUNDS_ONLY) {
-                int cx;
-                key = small_cell(b, st, cx, cy) ? RW_KEY_BASE + (uint32_t)cy * (uint32_t)st->W + (uint32_t)cx : RW_KEY_BIG;
-                if (key == RW_KEY_BIG) cy = -1;
-                if (il == 0.0 && ir == 0.0) key |= KEY_STATIC_BIT;      // isStatic (Constraint.hs:123-125)
-            }
+            if (!BOUNDS_ONLY) { P.box[s] = b; P.gkeys[s] = key; }
         }
         if (BOUNDS_ONLY) continue;
-        P.box[s] = b;
-        P.gkeys[s] = key;
-        if (!live) continue;
-        for (int g = 0; g < P.n_peers; ++g) {
-            if (g == P.my_rank) continue;
-            // rank g keeps rows [cut[g] - 1, cut[g + 1]] when it sweeps any row at all
-            const bool wants = cy < 0 ? true : (st->cut[g + 1] > st->cut[g] && cy >= st->cut[g] - 1 && cy <= st->cut[g + 1]);
-            if (!wants) continue;
-            P.peer_keys[g][s] = key;      // (the AABB is not sent: the sweeping rank folds it again from the same vertices)
-            P.rw_xf[g][s] = x;
-            P.rw_mass[g][s] = make_double2(il, ir);
+        // ---- who sweeps this shape: rank g keeps rows [cut[g] - 1, cut[g + 1]] when it sweeps any row at all; big
+        // shapes go to every rank (mine included: the inbox is the only way into a rank's grid)
+        unsigned wants = 0;
+        if (live)
+            for (int g = 0; g < G; ++g)
+                if (cy < 0 || (st->cut[g + 1] > st->cut[g] && cy >= st->cut[g] - 1 && cy <= st->cut[g + 1])) wants |= 1u << g;
+        if (P.dbg_local_stores) wants &= 1u << P.my_rank;       // experiment: nothing leaves this GPU (WRONG results, timing only)
+        for (int g = 0; g < G; ++g) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (wants >> g) & 1u);
+            if (lane == 0) s_cnt[warp][g] = (unsigned)__popc(bal);
         }
+        __syncthreads();
+        if ((int)threadIdx.x < G) {      // one reservation per destination and tile
+            const int g = (int)threadIdx.x;
+            unsigned tot = 0;
+            for (int w = 0; w < 8; ++w) { const unsigned c = s_cnt[w][g]; s_cnt[w][g] = tot; tot += c; }
+            s_base[g] = tot ? atomicAdd(&P.st->push_cursor[g], tot) : 0u;
+        }
+        __syncthreads();
+        // ---- per destination: the warp's records compacted in shared memory, then copied out 16 B per lane, so that
+        // they leave as contiguous 512 B runs (whole lines over NVLink) -- 64 B per shape instead of three packets
+        for (int g = 0; g < G; ++g) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (wants >> g) & 1u);
+            if (bal == 0u) continue;
+            if ((wants >> g) & 1u) {
+                HomeRec r;
+                r.xf = x; r.mass = mass; r.slot = (uint32_t)s; r.key = key; r.pad[0] = 0u; r.pad[1] = 0u;
+                s_rec[warp][__popc(bal & lt_mask)] = r;
+            }
+            __syncwarp();
+            const unsigned first = s_base[g] + s_cnt[warp][g];
+            const int n_chunks = 4 * __popc(bal);
+            if (first + (unsigned)__popc(bal) <= (unsigned)P.inbox_cap) {       // (cannot overflow: a section holds a whole home)
+                int4 *dst = reinterpret_cast<int4 *>(P.rw_inbox[g] + ((size_t)P.my_rank * (size_t)P.inbox_cap + first));
+                const int4 *src = reinterpret_cast<const int4 *>(&s_rec[warp][0]);
+                for (int c = lane; c < n_chunks; c += 32) dst[c] = src[c];
+            }
+            __syncwarp();
+        }
+        __syncthreads();     // s_cnt / s_base are rewritten by the next tile
     }
     __shared__ double s_red[4][8];
     mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { s_red[0][warp] = mnx; s_red[1][warp] = mny; s_red[2][warp] = mxx; s_red[3][warp] = mxy; }
     __syncthreads();
     if (warp == 0) {
@@ -2228,23 +2317,38 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
     }
 }
 
-// Keep the shapes whose cell lies in my rows or the halo row on either side (histogram of the cell table; the
-// arrival order is the counting sort's scatter slot); every rank lists every big shape.  The kept slots are also
-// appended to a list, one reservation per block and ascending inside it, so that k_rw_hulls touches the static
-// geometry and its outputs in nearly ascending address order however the cells are numbered.
+// The records my inbox received (one section per home rank, counts published with the KEYS barrier): every shape
+// whose cell lies in my rows or the halo row on either side, and every big shape.  Histogram of the cell table (the
+// arrival order is the counting sort's scatter slot), the slot-indexed copies the later kernels read (transform,
+// inverse masses, key + static flag), the big list, and the kept-slot list (one reservation per block, the inbox
+// order inside it: sections are in ascending slot order up to the interleaving of the sender's blocks).
 __global__ void __launch_bounds__(256) k_rw_bin(Params P)
 {
     const FrameState *st = P.st;
     const unsigned c_lo = st->cell_lo, c_end = st->cell_end;
+    const int G = P.n_peers;
     __shared__ unsigned s_wsum[8];
     __shared__ unsigned s_base;
+    __shared__ unsigned s_pre[SHAPES_MAX_RANKS + 1];
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int h = 0; h < G; ++h) { s_pre[h] = t; t += min(P.inbox_cnt[h], (unsigned)P.inbox_cap); }
+        s_pre[G] = t;
+    }
+    __syncthreads();
+    const unsigned total = s_pre[G];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = blockIdx.x * blockDim.x; base < P.n_slots; base += gridDim.x * blockDim.x) {
-        const int s = base + (int)threadIdx.x;
+    for (unsigned base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const unsigned e = base + threadIdx.x;
         bool keep = false;
-        if (s < P.n_slots) {
-            const uint32_t enc = P.gkeys[s] & ~KEY_STATIC_BIT;
-            uint32_t kept = P.key_none;
+        int s = 0;
+        if (e < total) {
+            int h = 0;
+            while (e >= s_pre[h + 1]) ++h;
+            const HomeRec r = P.inbox[(size_t)h * (size_t)P.inbox_cap + (e - s_pre[h])];
+            s = (int)r.slot;
+            const uint32_t enc = r.key & ~KEY_STATIC_BIT;
+            P.xf[s] = r.xf; P.mass[s] = r.mass; P.gkeys[s] = r.key;
             if (enc == RW_KEY_BIG) {
                 const unsigned pos = atomicAdd(&P.st->n_big, 1u);
                 P.big_idx[pos] = (uint32_t)s;
@@ -2253,11 +2357,10 @@ __global__ void __launch_bounds__(256) k_rw_bin(Params P)
                 const uint32_t key = enc - RW_KEY_BASE;
                 if (key >= c_lo && key < c_end) {
                     P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
-                    kept = key;
+                    P.keys[s] = key;
                     keep = true;
                 }
             }
-            P.keys[s] = kept;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wsum[warp] = (unsigned)__popc(bal);
@@ -2559,7 +2662,7 @@ struct shapes_ctx {
     char *rw_arena = nullptr;
     char *peer_arena[SHAPES_MAX_RANKS] = {};
     struct RowsLayout {
-        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, pair_i, pair_j, ccnt, man, pj, total;
+        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, pair_i, pair_j, ccnt, man, pj, inbox, inbox_cnt, total;
     } rwl{};
     uint32_t *d_roww = nullptr, *d_ccnt_w = nullptr, *d_w_j = nullptr;
     int32_t *d_pair_i = nullptr, *d_pair_j = nullptr; uint32_t *d_ccnt = nullptr; ManRec *d_man = nullptr;   // single-rank homes of the result arrays
@@ -2809,6 +2912,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         const size_t MP = (size_t)std::max<int64_t>(max_pairs, 1);
         L.pair_i = take(sizeof(int32_t) * MP); L.pair_j = take(sizeof(int32_t) * MP); L.ccnt = take(sizeof(uint32_t) * MP);
         L.man = take(sizeof(ManRec) * MP); L.pj = take(sizeof(double4) * MP);
+        // inbox: one section per home rank, each large enough for that rank's whole home (2 folded blocks <= chunk + 1 slots)
+        L.inbox = take(sizeof(HomeRec) * (size_t)(c->chunk + 2) * (size_t)world); L.inbox_cnt = take(sizeof(unsigned) * SHAPES_MAX_RANKS);
         L.total = off;
         TRY_CREATE(dev_alloc(c, &c->rw_arena, L.total));
         TRY_CREATE(cu(cudaMemset(c->rw_arena, 0, L.total), "cudaMemset"));
@@ -2968,6 +3073,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         P.pj = reinterpret_cast<double4 *>(mine + L.pj); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
         P.sat_ccnt = c->d_ccnt_w;
         P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp; P.kept_list = c->d_kept_list;
+        P.inbox = reinterpret_cast<const HomeRec *>(mine + L.inbox); P.inbox_cnt = reinterpret_cast<const unsigned *>(mine + L.inbox_cnt);
+        P.inbox_cap = (int)(c->chunk + 2);
         P.dbg_local_stores = std::getenv("SHAPES_B200_DBG_LOCAL_STORES") ? 1 : 0;
         P.rw_weights_prev = reinterpret_cast<const uint32_t *>(mine + L.weights[fpar ^ 1]);
         P.rw_bounds_prev = reinterpret_cast<const unsigned long long *>(mine + L.bounds[fpar ^ 1]);
@@ -2979,6 +3086,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             P.rw_pair_i[r] = reinterpret_cast<int32_t *>(a + L.pair_i); P.rw_pair_j[r] = reinterpret_cast<int32_t *>(a + L.pair_j);
             P.rw_ccnt[r] = reinterpret_cast<uint32_t *>(a + L.ccnt); P.rw_man[r] = reinterpret_cast<ManRec *>(a + L.man);
             P.rw_pj[r] = reinterpret_cast<double4 *>(a + L.pj);
+            P.rw_inbox[r] = reinterpret_cast<HomeRec *>(a + L.inbox); P.rw_inbox_cnt[r] = reinterpret_cast<unsigned *>(a + L.inbox_cnt);
             P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
             P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
             P.rw_counts[r] = reinterpret_cast<long long *>(a + L.counts); P.rw_err[r] = reinterpret_cast<int *>(a + L.err);
@@ -3007,14 +3115,12 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         kt("start");
     #define STAGE_MARK() do { if (c->profiling) CU_TRY(c, cudaEventRecord(c->stage_ev[stage], s)); ++stage; } while (0)
         const int n_query = n_home;     // my slice: both home blocks
-        const int gq = grid_for(n_query, 256, sms * 8), gn = grid_for(N, 256, sms * 8);
+        const int gq = grid_for(n_query, 256, sms * 8);
+        const int gk = grid_for(2 * c->chunk + 1024, 256, sms * 8);     // the shapes a rank keeps: about a home's worth plus halo and big list
         STAGE_MARK(); // 0: transform (home slots) + record push
         k_rw_begin<<<1, 1024, 0, s>>>(P, advance ? 1 : 0); ++c->launches;
         kt("k_rw_begin");
         CU_TRY(c, cudaMemsetAsync(P.cell_count, 0, sizeof(uint32_t) * ((size_t)P.cell_limit + 2), s));
-        kt("memset");
-        // the key array the NEXT frame's homes push into must read "nothing here" wherever nobody pushes
-        CU_TRY(c, cudaMemsetAsync(c->rw_arena + c->rwl.gkeys[fpar ^ 1], 0, sizeof(uint32_t) * (size_t)std::max<int64_t>(c->chunk * c->world, 1), s));
         kt("memset");
         if (n_query > 0) { k_rw_transform<false><<<gq, 256, 0, s>>>(P, n_query); ++c->launches; }
         kt("k_rw_transform");
@@ -3022,7 +3128,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_KEYS); ++c->launches;
         kt("k_rw_sync:KEYS");
         STAGE_MARK(); // 2: keep my rows' keys
-        if (N > 0) { k_rw_bin<<<gn, 256, 0, s>>>(P); ++c->launches; }
+        if (N > 0) { k_rw_bin<<<gk, 256, 0, s>>>(P); ++c->launches; }
         kt("k_rw_bin");
         STAGE_MARK(); // 3: cell offsets
         k_scan_cells_sums<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
@@ -3031,7 +3137,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         kt("k_scan_cells_apply");
         STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
         if (N > 0) {
-            k_scatter_sorted<<<gn, 256, 0, s>>>(P); ++c->launches;
+            k_scatter_sorted<<<gk, 256, 0, s>>>(P); ++c->launches;
             kt("k_scatter_sorted");
             k_rw_hulls<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
             kt("k_rw_hulls");
