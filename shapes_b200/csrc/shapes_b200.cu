@@ -188,6 +188,18 @@ struct __align__(64) ManRec {
     unsigned long long bits;   // edge [0,20) | pen0 [20,40) | pen1 [40,60) | flip [60]
 };
 
+// Rows mode: everything a sweeping rank delivers for one pair, ONE 128 B-aligned record in the arena of the pair's
+// home, so that a pair costs one NVLink write request (its 16 B header alone when it has no contact) instead of up to
+// nine scattered stores.  [0,16) header, [32,64) the partner's body record, [64,128) the manifold.
+struct __align__(128) PairRec {
+    int32_t i, j;          // the pair (pair_i / pair_j of the home's slice are unpacked from here)
+    uint32_t cnt, pad0;    // contact count
+    double pad1[2];
+    double4 pj;            // (pos_j, inverse masses of j) when cnt != 0
+    ManRec man;            // when cnt != 0
+};
+static_assert(sizeof(PairRec) == 128, "PairRec layout");
+
 // Rows mode: what a home sends to a rank that sweeps one of its shapes -- one 64 B record, appended densely to the
 // receiver's inbox (a warp's records leave as whole 128 B lines, not as three scattered stores per shape).
 struct __align__(64) HomeRec {
@@ -283,7 +295,6 @@ struct Params {
     uint32_t *sat_ccnt;         // rows mode: per work entry, the SAT stage's contact count (local copy: marks the pairs
                                 // left to the per-thread pass); otherwise = ccnt
     uint32_t *q_off;            // rows mode, per slot i this rank sweeps: first index of i's pairs in its home's arrays
-    double4 *pj;                // rows mode, per home pair with contacts: (pos_j, inverse masses of j), pushed by the sweeping rank
     uint32_t *roww;             // rows mode: pairs produced per row bin this frame [ROW_BINS]
     uint32_t *mat_stamp;        // rows mode, per slot: frame in which k_rw_hulls materialised its world vertices / normals
     uint32_t *kept_list;        // rows mode: the slots this rank keeps, in (roughly) ascending slot order
@@ -303,10 +314,9 @@ struct Params {
     int rw_lo_lo, rw_lo_hi, rw_hi_lo, rw_hi_hi;   // my low block [lo_lo, lo_hi), my high block [hi_lo, hi_hi)
     uint32_t *rw_cq[SHAPES_MAX_RANKS];           // every rank's per-slot word, pushed by the sweeping rank: rank << 28 | partner count
     uint32_t *rw_qoff[SHAPES_MAX_RANKS];         // every rank's q_off (pushed by the homes after their scan)
-    int32_t *rw_pair_i[SHAPES_MAX_RANKS], *rw_pair_j[SHAPES_MAX_RANKS];   // every rank's result arrays (home side): the sweeping
-    uint32_t *rw_ccnt[SHAPES_MAX_RANKS];                                  // rank stores each pair straight into its final place
-    ManRec *rw_man[SHAPES_MAX_RANKS];
-    double4 *rw_pj[SHAPES_MAX_RANKS];
+    PairRec *rw_prec[SHAPES_MAX_RANKS];          // every rank's pair records (home side): the sweeping rank stores each pair
+                                                 // straight into its final place
+    PairRec *prec;                               // mine
     double2 *rw_mass[SHAPES_MAX_RANKS];          // every rank's inverse masses (its home slots are valid)
     Xf *rw_xf[SHAPES_MAX_RANKS];             // every rank's packed transforms (its own slot range is valid)
     uint32_t *rw_weights[SHAPES_MAX_RANKS];  // every rank's [G][ROW_BINS] inbox of row weights (this frame's parity)
@@ -1463,7 +1473,8 @@ __device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV>
 // and inverse masses for k_rows there; `ok` false = beyond the home's capacity (it raises the error itself).
 struct PairOut {
     long long idx;
-    uint32_t *ccnt; ManRec *man; int32_t *pair_i, *pair_j; double4 *pj;
+    uint32_t *ccnt; ManRec *man; int32_t *pair_i, *pair_j;
+    PairRec *rec;      // rows mode: the pair's record at its home (null: the home's arrays are full)
     bool ok;
 };
 __device__ __forceinline__ PairOut pair_out(const Params &P, long long w, int i)
@@ -1473,25 +1484,39 @@ __device__ __forceinline__ PairOut pair_out(const Params &P, long long w, int i)
     else if (P.work_mode == 2) {
         const int h = P.dbg_local_stores ? P.my_rank : rw_home(P, i);
         o.idx = (long long)P.q_off[i] + (long long)P.w_a[w];
-        o.ccnt = P.rw_ccnt[h]; o.man = P.rw_man[h]; o.pair_i = P.rw_pair_i[h]; o.pair_j = P.rw_pair_j[h]; o.pj = P.rw_pj[h];
         o.ok = o.idx < P.max_pairs;
+        o.rec = o.ok ? &P.rw_prec[h][o.idx] : nullptr;
+        o.ccnt = nullptr; o.man = nullptr;
     }
     return o;
+}
+// where the pair's manifold record goes (null: nowhere)
+__device__ __forceinline__ ManRec *pair_out_man(const Params &P, const PairOut &o)
+{
+    if (!o.ok) return nullptr;
+    return P.work_mode == 2 ? &o.rec->man : &o.man[o.idx];
+}
+// rows mode: (pos_j, inverse masses of j) for the home's k_rows.  j's records were pushed here if this rank keeps j;
+// a big query's far partner is read from its home
+__device__ __forceinline__ double4 partner_record(const Params &P, int j)
+{
+    const bool here = P.mat_stamp[j] == (uint32_t)P.st->frame_no;
+    const int hj = here ? P.my_rank : rw_home(P, j);
+    const Xf x = here ? P.xf[j] : P.rw_xf[hj][j];
+    const double2 m = here ? P.mass[j] : P.rw_mass[hj][j];
+    return make_double4(x.px, x.py, m.x, m.y);
 }
 // the pair's index entries and, in rows mode when it has contacts, the partner's body record
 __device__ __forceinline__ void pair_out_finish(const Params &P, const PairOut &o, int i, int j, unsigned cnt)
 {
     if (!o.ok) return;
+    if (P.work_mode == 2) {
+        *reinterpret_cast<int4 *>(o.rec) = make_int4(i, j, (int)cnt, 0);
+        if (cnt != 0u && cnt != 0xffffffffu) o.rec->pj = partner_record(P, j);
+        return;
+    }
     o.ccnt[o.idx] = cnt;
     if (o.pair_i) { o.pair_i[o.idx] = i; o.pair_j[o.idx] = j; }
-    if (o.pj && cnt != 0u && cnt != 0xffffffffu) {
-        // j's records were pushed here if this rank keeps j; a big query's far partner is read from its home
-        const bool here = P.mat_stamp[j] == (uint32_t)P.st->frame_no;
-        const int hj = here ? P.my_rank : rw_home(P, j);
-        const Xf x = here ? P.xf[j] : P.rw_xf[hj][j];
-        const double2 m = here ? P.mass[j] : P.rw_mass[hj][j];
-        o.pj[o.idx] = make_double4(x.px, x.py, m.x, m.y);
-    }
 }
 
 // K3a: one thread per pair.  SAT both ways + incident-edge clipping; writes the pair's contact
@@ -1520,7 +1545,7 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
         // (work_mode 1 reaches this kernel only as the flagged pass, which walks the reference order: like mode 0)
         PairOut o{ p, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
         if (rows) o = pair_out(P, p, i);
-        ManRec *const out_rec = o.ok ? &o.man[o.idx] : nullptr;
+        ManRec *const out_rec = pair_out_man(P, o);
         HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
         A.slot = i; A.off = P.vert_offset[i]; A.n = P.vert_offset[i + 1] - A.off; A.which = 0;
         B.slot = j; B.off = P.vert_offset[j]; B.n = P.vert_offset[j + 1] - B.off; B.which = 1;
@@ -1653,8 +1678,8 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
     __shared__ ulonglong2 s_ext[CO_WARPS][32];            // packed extents of both hulls
     __shared__ double2 s_hull[CO_WARPS][2][2][32];        // [buffer][pair of the step][A verts, A normals, B verts, B normals]
     __shared__ CoopRes s_res[CO_WARPS][32][2];            // phase 1 -> phase 2
-
     constexpr bool SORTED = WMODE == 1, ROWS = WMODE == 2;
+
     const FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = ROWS ? (long long)st->work_cursor : st->n_pairs;
@@ -1761,6 +1786,11 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
             __syncwarp();       // buffer t & 1 is free again before stage(t + 2) refills it
         }
         // ---- phase 2: one pair per lane
+        unsigned long long dst = 0ull;      // rows mode: where my pair's record goes
+        unsigned n_chunks = 0;              //            and how many of its 16 B chunks are live
+        int4 hdr = make_int4(0, 0, 0, 0);
+        double4 pj = make_double4(0.0, 0.0, 0.0, 0.0);
+        ManRec staged;                      //            the manifold on its way to shared memory
         if (base + lane < n_pairs) {
             PairOut o{ base + lane, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
             if (SORTED || ROWS) o = pair_out(P, base + lane, my_i);     // the pair's place in the reference order
@@ -1770,13 +1800,72 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
             else if (!r0.sep) {
                 const bool same = r0.depth < r1.depth;                  // depth_ab < depth_ba ? Same : Flip (ties: Flip)
                 const int ep = same ? r0.edge_pen : r1.edge_pen;
-                cnt = emit_manifold(o.ok ? &o.man[o.idx] : nullptr, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
+                ManRec *const out_rec = ROWS ? &staged : pair_out_man(P, o);
+                cnt = emit_manifold(out_rec, GlobalAcc{ WV, WN, same ? my_oa : my_ob, same ? my_ob : my_oa },
                                     same ? my_na : my_nb, same ? my_nb : my_na, ep & 0xff, (ep >> 8) & 0xff, same);
             }
-            if (ROWS) { P.sat_ccnt[base + lane] = cnt; if (cnt != CCNT_FALLBACK) pair_out_finish(P, o, my_i, my_j, cnt); }
-            else pair_out_finish(P, o, my_i, my_j, cnt);
+            if (ROWS) {
+                P.sat_ccnt[base + lane] = cnt;
+                if (cnt != CCNT_FALLBACK && o.ok) {
+                    hdr = make_int4(my_i, my_j, (int)cnt, 0);
+                    if (cnt) pj = partner_record(P, my_j);
+                    dst = (unsigned long long)o.rec;
+                    n_chunks = cnt ? 8u : 1u;
+                }
+            } else pair_out_finish(P, o, my_i, my_j, cnt);
         }
         __syncwarp();
+        if (ROWS) {
+            // The tile's records leave as whole records: staged chunk-major in the (now idle) operand buffers of phase 1
+            // -- 16 pairs at a time, no extra shared memory: the kernel lives on its L1 -- and written out 8 lanes per
+            // record, 4 records per step: ONE write request per pair (header [0,16), body [32,128)).
+            int4 *const stage4 = reinterpret_cast<int4 *>(&s_hull[warp][0][0][0]);       // 128 x 16 B = [8 chunks][16 pairs]
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if ((lane >> 4) == h && n_chunks) {
+                    const int c16 = lane & 15;
+                    stage4[0 * 16 + c16] = hdr;
+                    if (n_chunks > 1u) {
+                        stage4[2 * 16 + c16] = make_int4(__double2loint(pj.x), __double2hiint(pj.x), __double2loint(pj.y), __double2hiint(pj.y));
+                        stage4[3 * 16 + c16] = make_int4(__double2loint(pj.z), __double2hiint(pj.z), __double2loint(pj.w), __double2hiint(pj.w));
+                        const int4 *m4 = reinterpret_cast<const int4 *>(&staged);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) stage4[(4 + q) * 16 + c16] = m4[q];
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r16 = it * 4 + (lane >> 3), ch = lane & 7;
+                    const unsigned long long d = __shfl_sync(0xffffffffu, dst, h * 16 + r16);
+                    const unsigned nc = __shfl_sync(0xffffffffu, n_chunks, h * 16 + r16);
+                    if (d != 0ull && (unsigned)ch < nc && ch != 1) reinterpret_cast<int4 *>(d)[ch] = stage4[ch * 16 + r16];
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// Rows mode, home side, after the RESULTS barrier: the pair columns of my slice and the contact counts the row-offset
+// scan runs over, from the headers of the records the sweeping ranks stored.
+__global__ void __launch_bounds__(256) k_rw_unpack(Params P)
+{
+    const FrameState *st = P.st;
+    if (st->error) return;
+    const long long n_pairs = st->n_pairs < P.max_pairs ? st->n_pairs : P.max_pairs;
+    // four headers in flight per thread (each is 16 B out of its own 128 B line: latency, not bandwidth, is the cost)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += 4 * stride) {
+        int4 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (p + u * stride < n_pairs) h[u] = __ldcs(reinterpret_cast<const int4 *>(&P.prec[p + u * stride]));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (p + u * stride < n_pairs) {
+                const long long q = p + u * stride;
+                P.pair_i[q] = h[u].x; P.pair_j[q] = h[u].y; P.ccnt[q] = (uint32_t)h[u].z;
+            }
     }
 }
 
@@ -1819,12 +1908,13 @@ __global__ void __launch_bounds__(256) k_rows(Params P)
         const long long q = m >> 1;
         const int k = m & 1;
         const int i = P.pair_i[q], j = P.pair_j[q];
-        const ManRec rec = P.man[q];
+        // rows mode: the rank that swept the pair stored the manifold and the partner's position / inverse masses in
+        // the pair's record
+        const bool rows = P.work_mode == 2;
+        const ManRec rec = rows ? P.prec[q].man : P.man[q];
         // i is always an owned slot; j may belong to another rank (raw input columns; rows mode: its home's records)
         const double2 xi = *reinterpret_cast<const double2 *>(&P.xf[i]);
-        // rows mode: the rank that swept the pair stored the partner's position / inverse masses next to the manifold
-        const bool rows = P.work_mode == 2;
-        const double4 pjr = rows ? P.pj[q] : make_double4(0.0, 0.0, 0.0, 0.0);
+        const double4 pjr = rows ? P.prec[q].pj : make_double4(0.0, 0.0, 0.0, 0.0);
         const bool j_own = j >= P.own_lo && j < P.own_hi;
         const double2 xj = rows ? make_double2(pjr.x, pjr.y)
                          : j_own ? *reinterpret_cast<const double2 *>(&P.xf[j])
@@ -2653,6 +2743,7 @@ struct shapes_ctx {
     unsigned cell_limit = 0;     // sticky per-frame cell budget (0 = not chosen yet)
     int ct_blocks[3] = { 4, 4, 4 }; // resident k_manifolds blocks per SM (boxes / general / with circles)
     int coop_blocks = 4;          // resident k_manifolds_coop blocks per SM
+    int coop_blocks_rows = 4;     // ... of the rows-mode instantiation (more shared memory: the staged pair records)
     bool use_coop = true;         // general polygons: 16 lanes per pair (SHAPES_B200_NO_COOP=1: one thread per pair)
     // rows mode (multi-rank with mapped peers): one exchange arena per rank, same layout everywhere
     bool use_rows = true;         // SHAPES_B200_NO_ROWS=1: slot-range ownership of the whole path (the r1 exchange)
@@ -2662,7 +2753,7 @@ struct shapes_ctx {
     char *rw_arena = nullptr;
     char *peer_arena[SHAPES_MAX_RANKS] = {};
     struct RowsLayout {
-        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, pair_i, pair_j, ccnt, man, pj, inbox, inbox_cnt, total;
+        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, prec, inbox, inbox_cnt, total;
     } rwl{};
     uint32_t *d_roww = nullptr, *d_ccnt_w = nullptr, *d_w_j = nullptr;
     int32_t *d_pair_i = nullptr, *d_pair_j = nullptr; uint32_t *d_ccnt = nullptr; ManRec *d_man = nullptr;   // single-rank homes of the result arrays
@@ -2910,8 +3001,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         L.counts = take(sizeof(long long) * 6 * world); L.err = take(sizeof(int) * 2 * world);
         L.flags = take(sizeof(unsigned long long) * RW_PHASES * SHAPES_MAX_RANKS);
         const size_t MP = (size_t)std::max<int64_t>(max_pairs, 1);
-        L.pair_i = take(sizeof(int32_t) * MP); L.pair_j = take(sizeof(int32_t) * MP); L.ccnt = take(sizeof(uint32_t) * MP);
-        L.man = take(sizeof(ManRec) * MP); L.pj = take(sizeof(double4) * MP);
+        L.prec = take(sizeof(PairRec) * MP);
         // inbox: one section per home rank, each large enough for that rank's whole home (2 folded blocks <= chunk + 1 slots)
         L.inbox = take(sizeof(HomeRec) * (size_t)(c->chunk + 2) * (size_t)world); L.inbox_cnt = take(sizeof(unsigned) * SHAPES_MAX_RANKS);
         L.total = off;
@@ -2952,6 +3042,8 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         int bco = 0;
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop<1>, CO_WARPS * 32, 0), "occupancy"));
         c->coop_blocks = std::max(bco, 1);
+        TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bco, k_manifolds_coop<2>, CO_WARPS * 32, 0), "occupancy"));
+        c->coop_blocks_rows = std::max(bco, 1);
         c->use_coop = std::getenv("SHAPES_B200_NO_COOP") == nullptr;
         int br = 0;
         TRY_CREATE(cu(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&br, k_rows, 256, 0), "occupancy"));
@@ -3068,9 +3160,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         n_home = (P.rw_lo_hi - P.rw_lo_lo) + (P.rw_hi_hi - P.rw_hi_lo);
         P.flags = reinterpret_cast<unsigned long long *>(mine + L.flags);
         // the result arrays of a home live in its arena: the sweeping ranks store into them
-        P.pair_i = reinterpret_cast<int32_t *>(mine + L.pair_i); P.pair_j = reinterpret_cast<int32_t *>(mine + L.pair_j);
-        P.ccnt = reinterpret_cast<uint32_t *>(mine + L.ccnt); P.man = reinterpret_cast<ManRec *>(mine + L.man);
-        P.pj = reinterpret_cast<double4 *>(mine + L.pj); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
+        P.prec = reinterpret_cast<PairRec *>(mine + L.prec); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
         P.sat_ccnt = c->d_ccnt_w;
         P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp; P.kept_list = c->d_kept_list;
         P.inbox = reinterpret_cast<const HomeRec *>(mine + L.inbox); P.inbox_cnt = reinterpret_cast<const unsigned *>(mine + L.inbox_cnt);
@@ -3083,9 +3173,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys[fpar]);
             P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf); P.rw_mass[r] = reinterpret_cast<double2 *>(a + L.mass);
             P.rw_cq[r] = reinterpret_cast<uint32_t *>(a + L.cq); P.rw_qoff[r] = reinterpret_cast<uint32_t *>(a + L.qoff);
-            P.rw_pair_i[r] = reinterpret_cast<int32_t *>(a + L.pair_i); P.rw_pair_j[r] = reinterpret_cast<int32_t *>(a + L.pair_j);
-            P.rw_ccnt[r] = reinterpret_cast<uint32_t *>(a + L.ccnt); P.rw_man[r] = reinterpret_cast<ManRec *>(a + L.man);
-            P.rw_pj[r] = reinterpret_cast<double4 *>(a + L.pj);
+            P.rw_prec[r] = reinterpret_cast<PairRec *>(a + L.prec);
             P.rw_inbox[r] = reinterpret_cast<HomeRec *>(a + L.inbox); P.rw_inbox_cnt[r] = reinterpret_cast<unsigned *>(a + L.inbox_cnt);
             P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
             P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
@@ -3173,7 +3261,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
             else if (c->use_coop) {
-                k_manifolds_coop<2><<<sms * c->coop_blocks, CO_WARPS * 32, 0, s>>>(P);
+                k_manifolds_coop<2><<<sms * c->coop_blocks_rows, CO_WARPS * 32, 0, s>>>(P);
                 kt("k_manifolds_coop");
                 {   // hulls with more than 8 vertices, partners of big queries this rank does not keep
                     k_manifolds<MAX_STAGED_VERTS, false, true><<<sms * c->ct_blocks[1], CT_THREADS, 0, s>>>(P); ++c->launches;
@@ -3185,8 +3273,10 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         }
         k_rw_sync<<<1, 1024, 0, s>>>(P, RW_PHASE_RESULTS); ++c->launches;
         kt("k_rw_sync:RESULTS");
-        STAGE_MARK(); // 9: home -- row offsets
+        STAGE_MARK(); // 9: home -- pair columns and counts out of the delivered records, row offsets
         if (c->max_pairs > 0) {
+            k_rw_unpack<<<sms * 16, 256, 0, s>>>(P); ++c->launches;
+            kt("k_rw_unpack");
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
             kt("cub_scan");
