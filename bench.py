@@ -308,10 +308,41 @@ class Ranks:
         self.dist = None
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.host_binding = self.bind_near_gpu()
         if self.world_size > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
+
+    def bind_near_gpu(self) -> dict:
+        """Multi-rank runs: pin this process to the cores of the GPU's NUMA node BEFORE any pinned buffer is allocated
+        (first touch then places the staging buffers next to the GPU's PCIe root; torchrun starts every rank with the
+        whole machine as its affinity mask, so without this every rank's buffers end up wherever the allocator ran)."""
+        info = {"bound": False}
+        if self.world_size <= 1 or os.environ.get("SHAPES_B200_NO_NUMA_BIND"):
+            return info
+        try:
+            p = self.torch.cuda.get_device_properties(self.local_rank)
+            bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            base = "/sys/bus/pci/devices/" + bdf
+            with open(base + "/local_cpulist") as f:
+                cpulist = f.read().strip()
+            with open(base + "/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+            cpus = set()
+            for part in cpulist.split(","):
+                if "-" in part:
+                    a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info.update(bound=True, pci=bdf, cpus=len(cpus))
+        except Exception as e:      # containers without sysfs topology: keep the inherited mask
+            info["error"] = repr(e)[:120]
+        return info
 
     def bracket(self, group=True):
         self.torch.cuda.synchronize()
@@ -685,6 +716,7 @@ def main():
         "per_rank_sat_ms": head["per_rank_sat_ms"],
         "warm_start": head.get("warm_start"),
         "roofline": roofline, "cpu_baseline": cpu, "world_step": world_step, "configs": configs,
+        "host_binding": R.host_binding,
     }
     line.update(extras)
     emit(line)

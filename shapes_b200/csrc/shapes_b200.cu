@@ -200,15 +200,17 @@ struct __align__(128) PairRec {
 };
 static_assert(sizeof(PairRec) == 128, "PairRec layout");
 
-// Rows mode: what a home sends to a rank that sweeps one of its shapes -- one 64 B record, appended densely to the
+// Rows mode: what a home sends to a rank that sweeps one of its shapes -- one 96 B record, appended densely to the
 // receiver's inbox (a warp's records leave as whole 128 B lines, not as three scattered stores per shape).
-struct __align__(64) HomeRec {
+struct __align__(32) HomeRec {
     Xf xf;                 // packed transform
+    Box box;               // the AABB its home folded: the sweep does not wait for the sweeper's own hull pass
     double2 mass;          // inverse masses
     uint32_t slot, key;    // key: RW_KEY_* encoding, bit 31 = isStatic
     uint32_t pad[2];
 };
-static_assert(sizeof(HomeRec) == 64, "HomeRec layout");
+static_assert(sizeof(HomeRec) == 96, "HomeRec layout");
+constexpr int HOME_REC_CHUNKS = (int)(sizeof(HomeRec) / 16);
 
 // Everything the kernels need, passed by value.
 struct Params {
@@ -771,8 +773,9 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
             const int s = (int)P.kept_list[q];
             const uint32_t key = P.keys[s];
             const uint32_t p = P.cell_begin[key] + P.rank[s];
-            P.smeta[p] = (uint32_t)s | ((P.gkeys[s] & KEY_STATIC_BIT) ? 0x80000000u : 0u);   // (k_rw_hulls folds the AABB record)
+            P.smeta[p] = (uint32_t)s | ((P.gkeys[s] & KEY_STATIC_BIT) ? 0x80000000u : 0u);
             P.keys_sorted[p] = key;
+            P.sbox[p] = P.box[s];         // the AABB its home folded (delivered with the record)
         }
         return;
     }
@@ -847,7 +850,7 @@ __device__ __forceinline__ unsigned long long sweep_test_all(const Params &P, co
         const int j = (int)P.big_idx[b];
         if (j >= i) continue;
         if (si && (P.work_mode == 2 ? (P.gkeys[j] & KEY_STATIC_BIT) != 0u : slot_static(P, j))) continue;
-        const Box bj = P.work_mode == 2 ? P.sbox[P.cell_begin[st->cell_end] + b] : box_of(P, j);
+        const Box bj = P.work_mode == 2 ? P.box[j] : box_of(P, j);      // rows mode: delivered with j's record (or my own fold)
         if (aabb_check(bi, bj)) { hit(j); if (cand < 63u) mask |= 1ull << cand; }
     }
     return (cand > 63u) ? (1ull << 63) : mask;
@@ -2290,6 +2293,7 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
         bool live = false;
         Xf x{ 0.0, 0.0, 1.0, 0.0 };
         double2 mass = make_double2(0.0, 0.0);
+        Box b{ 0.0, 0.0, 0.0, 0.0 };
         if (valid) {
             const double px = P.pos_x[s], py = P.pos_y[s];
             const double il = P.inv_lin[s], ir = P.inv_rot[s];
@@ -2302,7 +2306,6 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
             else sincos(P.rot[s], &sn, &c);
             x = Xf{ px, py, c, sn };
             mass = make_double2(il, ir);
-            Box b{ 0.0, 0.0, 0.0, 0.0 };
             if (!BOUNDS_ONLY) { P.xf[s] = x; P.mass[s] = mass; }
             if (live) {
                 const Aff m = to_transform(px, py, c, sn);
@@ -2371,18 +2374,18 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
         }
         __syncthreads();
         // ---- per destination: the warp's records compacted in shared memory, then copied out 16 B per lane, so that
-        // they leave as contiguous 512 B runs (whole lines over NVLink) -- 64 B per shape instead of three packets
+        // they leave as contiguous 512 B runs (whole lines over NVLink) -- one 96 B record per shape instead of three packets
         for (int g = 0; g < G; ++g) {
             const unsigned bal = __ballot_sync(0xffffffffu, (wants >> g) & 1u);
             if (bal == 0u) continue;
             if ((wants >> g) & 1u) {
                 HomeRec r;
-                r.xf = x; r.mass = mass; r.slot = (uint32_t)s; r.key = key; r.pad[0] = 0u; r.pad[1] = 0u;
+                r.xf = x; r.box = b; r.mass = mass; r.slot = (uint32_t)s; r.key = key; r.pad[0] = 0u; r.pad[1] = 0u;
                 s_rec[warp][__popc(bal & lt_mask)] = r;
             }
             __syncwarp();
             const unsigned first = s_base[g] + s_cnt[warp][g];
-            const int n_chunks = 4 * __popc(bal);
+            const int n_chunks = HOME_REC_CHUNKS * __popc(bal);
             if (first + (unsigned)__popc(bal) <= (unsigned)P.inbox_cap) {       // (cannot overflow: a section holds a whole home)
                 int4 *dst = reinterpret_cast<int4 *>(P.rw_inbox[g] + ((size_t)P.my_rank * (size_t)P.inbox_cap + first));
                 const int4 *src = reinterpret_cast<const int4 *>(&s_rec[warp][0]);
@@ -2439,6 +2442,7 @@ __global__ void __launch_bounds__(256) k_rw_bin(Params P)
             s = (int)r.slot;
             const uint32_t enc = r.key & ~KEY_STATIC_BIT;
             P.xf[s] = r.xf; P.mass[s] = r.mass; P.gkeys[s] = r.key;
+            if (!rw_mine(P, s)) P.box[s] = r.box;       // (home slots: K0 stored it; peers read that copy)
             if (enc == RW_KEY_BIG) {
                 const unsigned pos = atomicAdd(&P.st->n_big, 1u);
                 P.big_idx[pos] = (uint32_t)s;
@@ -2519,31 +2523,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_cells_apply(Params P, con
 // moveShapes (World.hs:132-140) for the shapes this rank keeps (its rows, the halo rows, the big list): one thread
 // per shape, walking the kept-slot list (ascending slots inside every 256-entry run: the gathers of the static
 // geometry and the stores of the world vertices / normals are as dense as K0's, whatever share of the world this
-// rank keeps).  Same body as K0 (k_transform_aabb): the hull's local vertices as one batch of loads, world vertices
-// kept in registers for the unit normals (setHullTransform, ConvexHull.hs:184-195: normals recomputed from the NEW
-// vertices), AABB folded in vertex order (hullToAabb, Aabb.hs:81-84 -- the fold the shape's home ran for its key,
-// same vertices, same bits), with the packed transform the home pushed.  The record goes to the sorted position.
+// rank keeps).  Same body as K0 (k_transform_aabb) without the AABB (that came with the shape's record): the hull's
+// local vertices as one batch of loads, world vertices kept in registers for the unit normals (setHullTransform,
+// ConvexHull.hs:184-195: normals recomputed from the NEW vertices), with the packed transform the home pushed.
+// Only the SAT stage reads what this kernel writes, so it runs on a second stream next to the sweep, the CNT / OFF
+// barriers and the homes' offset scan -- a chain of small, latency-bound kernels that leaves the GPU idle otherwise.
 __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
 {
     const FrameState *st = P.st;
     if (st->error & ERR_REPLAN) return;
-    const unsigned n_kept = P.cell_begin[st->cell_end], n_all = n_kept + st->n_big;
+    const unsigned n_kept = st->n_list, n_all = n_kept + st->n_big;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_all; q += gridDim.x * blockDim.x) {
-        int s;
-        unsigned p;
-        if (q < n_kept) { s = (int)P.kept_list[q]; p = P.cell_begin[P.keys[s]] + P.rank[s]; }
-        else { s = (int)P.big_idx[q - n_kept]; p = q; }              // big shapes: positions n_kept + b, next to the grid's records
+        const int s = q < n_kept ? (int)P.kept_list[q] : (int)P.big_idx[q - n_kept];
         const Xf x = P.xf[s];                                        // pushed by its home (or mine)
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
         const double rad = P.radius ? P.radius[s] : -1.0;
         P.mat_stamp[s] = (uint32_t)st->frame_no;
         const Aff m = to_transform(x.px, x.py, x.c, x.s);
-        Box b{ 0.0, 0.0, 0.0, 0.0 };
-        if (rad >= 0.0) {      // setCircleTransform (Circle.hs:55-59), circleToAabb (Aabb.hs:86-88)
+        if (rad >= 0.0) {      // setCircleTransform (Circle.hs:55-59)
             const V2 ctr = afmul(m, V2{ 0.0, 0.0 });
             P.circ[s] = make_double2(ctr.x, ctr.y);
-            b.min_x = fsub(ctr.x, rad); b.max_x = fadd(ctr.x, rad);
-            b.min_y = fsub(ctr.y, rad); b.max_y = fadd(ctr.y, rad);
         }
         if (n <= MAX_STAGED_VERTS) {
             double2 l[MAX_STAGED_VERTS];
@@ -2555,13 +2554,6 @@ __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
                 if (k >= n) break;
                 w[k] = afmul(m, V2{ l[k].x, l[k].y });
                 P.wv[o + k] = make_double2(w[k].x, w[k].y);
-                if (k == 0) { b.min_x = b.max_x = w[k].x; b.min_y = b.max_y = w[k].y; }
-                else {
-                    b.min_x = (b.min_x < w[k].x) ? b.min_x : w[k].x;
-                    b.max_x = (b.max_x > w[k].x) ? b.max_x : w[k].x;
-                    b.min_y = (b.min_y < w[k].y) ? b.min_y : w[k].y;
-                    b.max_y = (b.max_y > w[k].y) ? b.max_y : w[k].y;
-                }
             }
 #pragma unroll
             for (int k = 0; k < MAX_STAGED_VERTS; ++k) {
@@ -2576,18 +2568,12 @@ __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
                 const double2 l = __ldg(&P.local[o + v]);
                 const V2 w = afmul(m, V2{ l.x, l.y });
                 P.wv[o + v] = make_double2(w.x, w.y);
-                if (v == 0) { w0 = w; b.min_x = b.max_x = w.x; b.min_y = b.max_y = w.y; }
-                else {
-                    b.min_x = (b.min_x < w.x) ? b.min_x : w.x; b.max_x = (b.max_x > w.x) ? b.max_x : w.x;
-                    b.min_y = (b.min_y < w.y) ? b.min_y : w.y; b.max_y = (b.max_y > w.y) ? b.max_y : w.y;
-                    const V2 nn = unit_edge_normal(prev, w);
-                    P.wn[o + v - 1] = make_double2(nn.x, nn.y);
-                }
+                if (v == 0) w0 = w;
+                else { const V2 nn = unit_edge_normal(prev, w); P.wn[o + v - 1] = make_double2(nn.x, nn.y); }
                 prev = w;
             }
             if (n > 0) { const V2 nn = unit_edge_normal(prev, w0); P.wn[o + n - 1] = make_double2(nn.x, nn.y); }
         }
-        P.sbox[p] = b;
     }
 }
 
@@ -2725,6 +2711,8 @@ struct shapes_ctx {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;      // rows mode: the hull pass runs here, next to the sweep and the offset exchange
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profiling = false;
     cudaEvent_t stage_ev[SHAPES_N_STAGES + 1] = {};
@@ -2891,6 +2879,9 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
     TRY_CREATE(cu(cudaGetDeviceProperties(&prop, device_id), "cudaGetDeviceProperties"));
     c->sm_count = prop.multiProcessorCount;
     TRY_CREATE(cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    TRY_CREATE(cu(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    TRY_CREATE(cu(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate"));
+    TRY_CREATE(cu(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming), "cudaEventCreate"));
     TRY_CREATE(cu(cudaEventCreate(&c->ev0), "cudaEventCreate"));
     TRY_CREATE(cu(cudaEventCreate(&c->ev1), "cudaEventCreate"));
     for (int k = 0; k <= SHAPES_N_STAGES; ++k) TRY_CREATE(cu(cudaEventCreate(&c->stage_ev[k]), "cudaEventCreate"));
@@ -3227,8 +3218,12 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         if (N > 0) {
             k_scatter_sorted<<<gk, 256, 0, s>>>(P); ++c->launches;
             kt("k_scatter_sorted");
-            k_rw_hulls<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
-            kt("k_rw_hulls");
+            // the hull pass only feeds the SAT stage: fork it onto the side stream (inside a captured graph this is a
+            // parallel branch), join before the manifolds
+            CU_TRY(c, cudaEventRecord(c->ev_fork, s));
+            CU_TRY(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+            k_rw_hulls<<<sms * 8, 256, 0, c->side_stream>>>(P); ++c->launches;
+            CU_TRY(c, cudaEventRecord(c->ev_join, c->side_stream));
         }
         STAGE_MARK(); // 5: single-pass sweep of my rows; every query's count is pushed to its home; barrier CNT
         if (N > 0) {
@@ -3258,6 +3253,8 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         STAGE_MARK(); // 7
         STAGE_MARK(); // 8: manifolds over my work list, every pair stored into its final place at its home; barrier RESULTS
         if (N > 0) {
+            CU_TRY(c, cudaStreamWaitEvent(s, c->ev_join, 0));      // world vertices / normals of the kept hulls are in place
+            kt("join:k_rw_hulls");
             if (c->has_circles) k_manifolds<MAX_STAGED_VERTS, true><<<sms * c->ct_blocks[2], CT_THREADS, 0, s>>>(P);
             else if (c->max_hull_verts <= 4) k_manifolds<4, false><<<sms * c->ct_blocks[0], CT_THREADS, 0, s>>>(P);
             else if (c->use_coop) {
@@ -3623,6 +3620,9 @@ void shapes_destroy(shapes_ctx *c)
     for (void *p : c->allocs) cudaFree(p);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int k = 0; k <= SHAPES_N_STAGES; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
