@@ -6,7 +6,7 @@ from collections import OrderedDict
 
 cols = OrderedDict()
 for arg in sys.argv[1:]:
-    label, path = arg.split("=", 1)
+    label, path = arg.rsplit("=", 1)
     line = next((l for l in open(path) if "[shapes_b200 rank 0]" in l and "rows-mode kernel ms" in l), None)
     if line is None:
         continue

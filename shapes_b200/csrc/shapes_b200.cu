@@ -767,15 +767,15 @@ __global__ void __launch_bounds__(256) k_bin(Params P)
 // and keys in sorted order, contiguous per cell and per grid row.
 __global__ void __launch_bounds__(256) k_scatter_sorted(Params P)
 {
-    if (P.work_mode == 2) {      // rows mode: only the kept slots have keys; their list is what this rank walks
+    if (P.work_mode == 2) {      // rows mode: the kept list of inbox records is what this rank walks (dense reads)
         const unsigned n_list = P.st->n_list;
         for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_list; q += gridDim.x * blockDim.x) {
-            const int s = (int)P.kept_list[q];
-            const uint32_t key = P.keys[s];
-            const uint32_t p = P.cell_begin[key] + P.rank[s];
-            P.smeta[p] = (uint32_t)s | ((P.gkeys[s] & KEY_STATIC_BIT) ? 0x80000000u : 0u);
+            const HomeRec &r = P.inbox[P.kept_list[q]];
+            const uint32_t key = (r.key & ~KEY_STATIC_BIT) - RW_KEY_BASE;
+            const uint32_t p = P.cell_begin[key] + P.rank[q];
+            P.smeta[p] = r.slot | ((r.key & KEY_STATIC_BIT) ? 0x80000000u : 0u);
             P.keys_sorted[p] = key;
-            P.sbox[p] = P.box[s];         // the AABB its home folded (delivered with the record)
+            P.sbox[p] = r.box;            // the AABB its home folded
         }
         return;
     }
@@ -1503,10 +1503,13 @@ __device__ __forceinline__ ManRec *pair_out_man(const Params &P, const PairOut &
 // a big query's far partner is read from its home
 __device__ __forceinline__ double4 partner_record(const Params &P, int j)
 {
-    const bool here = P.mat_stamp[j] == (uint32_t)P.st->frame_no;
-    const int hj = here ? P.my_rank : rw_home(P, j);
-    const Xf x = here ? P.xf[j] : P.rw_xf[hj][j];
-    const double2 m = here ? P.mass[j] : P.rw_mass[hj][j];
+    if (P.mat_stamp[j] == (uint32_t)P.st->frame_no) {      // kept here: its record is in my inbox (keys[] = rec_of[])
+        const HomeRec &r = P.inbox[P.keys[j]];
+        return make_double4(r.xf.px, r.xf.py, r.mass.x, r.mass.y);
+    }
+    const int hj = rw_home(P, j);
+    const Xf x = P.rw_xf[hj][j];
+    const double2 m = P.rw_mass[hj][j];
     return make_double4(x.px, x.py, m.x, m.y);
 }
 // the pair's index entries and, in rows mode when it has contacts, the partner's body record
@@ -2412,9 +2415,9 @@ __global__ void __launch_bounds__(256) k_rw_transform(Params P, int n_home)
 
 // The records my inbox received (one section per home rank, counts published with the KEYS barrier): every shape
 // whose cell lies in my rows or the halo row on either side, and every big shape.  Histogram of the cell table (the
-// arrival order is the counting sort's scatter slot), the slot-indexed copies the later kernels read (transform,
-// inverse masses, key + static flag), the big list, and the kept-slot list (one reservation per block, the inbox
-// order inside it: sections are in ascending slot order up to the interleaving of the sender's blocks).
+// arrival order is the counting sort's scatter slot), slot -> record index (rec_of, kept in keys[]), the big list,
+// and the kept list of record indices (one reservation per block, the inbox order inside it: sections are in ascending
+// slot order up to the interleaving of the sender's blocks).
 __global__ void __launch_bounds__(256) k_rw_bin(Params P)
 {
     const FrameState *st = P.st;
@@ -2435,23 +2438,29 @@ __global__ void __launch_bounds__(256) k_rw_bin(Params P)
         const unsigned e = base + threadIdx.x;
         bool keep = false;
         int s = 0;
+        unsigned at = 0, cell_rank = 0;       // the record's index in my inbox; its arrival order within its cell
         if (e < total) {
             int h = 0;
             while (e >= s_pre[h + 1]) ++h;
-            const HomeRec r = P.inbox[(size_t)h * (size_t)P.inbox_cap + (e - s_pre[h])];
-            s = (int)r.slot;
-            const uint32_t enc = r.key & ~KEY_STATIC_BIT;
-            P.xf[s] = r.xf; P.mass[s] = r.mass; P.gkeys[s] = r.key;
-            if (!rw_mine(P, s)) P.box[s] = r.box;       // (home slots: K0 stored it; peers read that copy)
+            at = (unsigned)h * (unsigned)P.inbox_cap + (e - s_pre[h]);
+            // slot and key sit in the record's last 16 B: one sector per record, nothing is copied for a small shape --
+            // the later kernels read the record itself (through the kept list, or rec_of[slot] for a pair's partner)
+            const uint4 tail = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(&P.inbox[at]) + 80);
+            s = (int)tail.x;
+            const uint32_t enc = tail.y & ~KEY_STATIC_BIT;
+            P.keys[s] = at;                   // rows mode: keys[] is rec_of[] (slot -> inbox record)
             if (enc == RW_KEY_BIG) {
+                // big shapes (few): slot-indexed copies, read by the sweep's big-candidate loop and the hull pass
+                const HomeRec r = P.inbox[at];
+                P.xf[s] = r.xf; P.mass[s] = r.mass; P.gkeys[s] = r.key;
+                if (!rw_mine(P, s)) P.box[s] = r.box;       // (home slots: K0 stored it; peers read that copy)
                 const unsigned pos = atomicAdd(&P.st->n_big, 1u);
                 P.big_idx[pos] = (uint32_t)s;
                 if (pos >= P.big_limit) atomicOr(&P.st->error, ERR_REPLAN);
             } else if (enc >= RW_KEY_BASE) {
                 const uint32_t key = enc - RW_KEY_BASE;
                 if (key >= c_lo && key < c_end) {
-                    P.rank[s] = atomicAdd(&P.cell_count[key], 1u);
-                    P.keys[s] = key;
+                    cell_rank = atomicAdd(&P.cell_count[key], 1u);
                     keep = true;
                 }
             }
@@ -2465,7 +2474,11 @@ __global__ void __launch_bounds__(256) k_rw_bin(Params P)
             s_base = t ? atomicAdd(&P.st->n_list, t) : 0u;
         }
         __syncthreads();
-        if (keep) P.kept_list[s_base + s_wsum[warp] + (unsigned)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)s;
+        if (keep) {
+            const unsigned pos = s_base + s_wsum[warp] + (unsigned)__popc(bal & ((1u << lane) - 1u));
+            P.kept_list[pos] = at;            // the kept list holds inbox indices ...
+            P.rank[pos] = cell_rank;          // ... and, next to them, each shape's scatter slot within its cell
+        }
         __syncthreads();
     }
 }
@@ -2534,8 +2547,10 @@ __global__ void __launch_bounds__(256) k_rw_hulls(Params P)
     if (st->error & ERR_REPLAN) return;
     const unsigned n_kept = st->n_list, n_all = n_kept + st->n_big;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_all; q += gridDim.x * blockDim.x) {
-        const int s = q < n_kept ? (int)P.kept_list[q] : (int)P.big_idx[q - n_kept];
-        const Xf x = P.xf[s];                                        // pushed by its home (or mine)
+        int s;
+        Xf x;
+        if (q < n_kept) { const HomeRec &r = P.inbox[P.kept_list[q]]; s = (int)r.slot; x = r.xf; }   // the record its home sent
+        else { s = (int)P.big_idx[q - n_kept]; x = P.xf[s]; }
         const int o = P.vert_offset[s], n = P.vert_offset[s + 1] - o;
         const double rad = P.radius ? P.radius[s] : -1.0;
         P.mat_stamp[s] = (uint32_t)st->frame_no;
