@@ -188,17 +188,16 @@ struct __align__(64) ManRec {
     unsigned long long bits;   // edge [0,20) | pen0 [20,40) | pen1 [40,60) | flip [60]
 };
 
-// Rows mode: everything a sweeping rank delivers for one pair, ONE 128 B-aligned record in the arena of the pair's
-// home, so that a pair costs one NVLink write request (its 16 B header alone when it has no contact) instead of up to
-// nine scattered stores.  [0,16) header, [32,64) the partner's body record, [64,128) the manifold.
+// Rows mode: what a sweeping rank delivers for one pair, into the arena of the pair's home: a 16 B header in a DENSE
+// array (the home unpacks the pair columns and the contact counts from it with fully coalesced reads) and, when the
+// pair has contacts, a 96 B body written as one request -- instead of up to nine scattered stores.
+struct __align__(16) PairHdr { int32_t i, j; uint32_t cnt, pad; };
 struct __align__(128) PairRec {
-    int32_t i, j;          // the pair (pair_i / pair_j of the home's slice are unpacked from here)
-    uint32_t cnt, pad0;    // contact count
-    double pad1[2];
-    double4 pj;            // (pos_j, inverse masses of j) when cnt != 0
-    ManRec man;            // when cnt != 0
+    ManRec man;            // the manifold
+    double4 pj;            // (pos_j, inverse masses of j)
+    double pad[4];
 };
-static_assert(sizeof(PairRec) == 128, "PairRec layout");
+static_assert(sizeof(PairRec) == 128 && sizeof(PairHdr) == 16, "pair record layout");
 
 // Rows mode: what a home sends to a rank that sweeps one of its shapes -- one 96 B record, appended densely to the
 // receiver's inbox (a warp's records leave as whole 128 B lines, not as three scattered stores per shape).
@@ -319,6 +318,8 @@ struct Params {
     PairRec *rw_prec[SHAPES_MAX_RANKS];          // every rank's pair records (home side): the sweeping rank stores each pair
                                                  // straight into its final place
     PairRec *prec;                               // mine
+    PairHdr *rw_phdr[SHAPES_MAX_RANKS];          // ... and their dense headers
+    PairHdr *phdr;
     double2 *rw_mass[SHAPES_MAX_RANKS];          // every rank's inverse masses (its home slots are valid)
     Xf *rw_xf[SHAPES_MAX_RANKS];             // every rank's packed transforms (its own slot range is valid)
     uint32_t *rw_weights[SHAPES_MAX_RANKS];  // every rank's [G][ROW_BINS] inbox of row weights (this frame's parity)
@@ -1477,18 +1478,20 @@ __device__ __forceinline__ unsigned hull_pair_manifold(const ContactKernel<MAXV>
 struct PairOut {
     long long idx;
     uint32_t *ccnt; ManRec *man; int32_t *pair_i, *pair_j;
-    PairRec *rec;      // rows mode: the pair's record at its home (null: the home's arrays are full)
+    PairRec *rec;      // rows mode: the pair's body record at its home (null: the home's arrays are full)
+    PairHdr *hdr;      //            and its header
     bool ok;
 };
 __device__ __forceinline__ PairOut pair_out(const Params &P, long long w, int i)
 {
-    PairOut o{ w, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+    PairOut o{ w, P.ccnt, P.man, nullptr, nullptr, nullptr, nullptr, true };
     if (P.work_mode == 1) { o.idx = (long long)(P.off[P.own_hi - 1 - i] + P.w_a[w]); o.pair_i = P.pair_i; o.pair_j = P.pair_j; }
     else if (P.work_mode == 2) {
         const int h = P.dbg_local_stores ? P.my_rank : rw_home(P, i);
         o.idx = (long long)P.q_off[i] + (long long)P.w_a[w];
         o.ok = o.idx < P.max_pairs;
         o.rec = o.ok ? &P.rw_prec[h][o.idx] : nullptr;
+        o.hdr = o.ok ? &P.rw_phdr[h][o.idx] : nullptr;
         o.ccnt = nullptr; o.man = nullptr;
     }
     return o;
@@ -1517,7 +1520,7 @@ __device__ __forceinline__ void pair_out_finish(const Params &P, const PairOut &
 {
     if (!o.ok) return;
     if (P.work_mode == 2) {
-        *reinterpret_cast<int4 *>(o.rec) = make_int4(i, j, (int)cnt, 0);
+        *reinterpret_cast<int4 *>(o.hdr) = make_int4(i, j, (int)cnt, 0);
         if (cnt != 0u && cnt != 0xffffffffu) o.rec->pj = partner_record(P, j);
         return;
     }
@@ -1549,7 +1552,7 @@ __global__ void __launch_bounds__(CT_THREADS, MAXV <= 4 ? CT_MIN_BLOCKS : CT_MIN
         if (FLAGGED_ONLY && P.sat_ccnt[p] != CCNT_FALLBACK) continue;   // second pass after k_manifolds_coop
         const int i = rows ? (int)P.w_i[p] : P.pair_i[p], j = rows ? (int)P.w_j[p] : P.pair_j[p];
         // (work_mode 1 reaches this kernel only as the flagged pass, which walks the reference order: like mode 0)
-        PairOut o{ p, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+        PairOut o{ p, P.ccnt, P.man, nullptr, nullptr, nullptr, nullptr, true };
         if (rows) o = pair_out(P, p, i);
         ManRec *const out_rec = pair_out_man(P, o);
         HullAcc A, B; // A = shape with the larger key (Aabb.hs:174-179, Solvers/Contact.hs:48-51)
@@ -1792,13 +1795,14 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
             __syncwarp();       // buffer t & 1 is free again before stage(t + 2) refills it
         }
         // ---- phase 2: one pair per lane
-        unsigned long long dst = 0ull;      // rows mode: where my pair's record goes
+        unsigned long long dst = 0ull;      // rows mode: where my pair's body record goes
+        unsigned long long dst_hdr = 0ull;  //            and its header
         unsigned n_chunks = 0;              //            and how many of its 16 B chunks are live
         int4 hdr = make_int4(0, 0, 0, 0);
         double4 pj = make_double4(0.0, 0.0, 0.0, 0.0);
         ManRec staged;                      //            the manifold on its way to shared memory
         if (base + lane < n_pairs) {
-            PairOut o{ base + lane, P.ccnt, P.man, nullptr, nullptr, nullptr, true };
+            PairOut o{ base + lane, P.ccnt, P.man, nullptr, nullptr, nullptr, nullptr, true };
             if (SORTED || ROWS) o = pair_out(P, base + lane, my_i);     // the pair's place in the reference order
             const CoopRes r0 = s_res[warp][lane][0], r1 = s_res[warp][lane][1];
             unsigned cnt = 0;
@@ -1816,7 +1820,8 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
                     hdr = make_int4(my_i, my_j, (int)cnt, 0);
                     if (cnt) pj = partner_record(P, my_j);
                     dst = (unsigned long long)o.rec;
-                    n_chunks = cnt ? 8u : 1u;
+                    dst_hdr = (unsigned long long)o.hdr;
+                    n_chunks = cnt ? 7u : 1u;
                 }
             } else pair_out_finish(P, o, my_i, my_j, cnt);
         }
@@ -1824,19 +1829,19 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
         if (ROWS) {
             // The tile's records leave as whole records: staged chunk-major in the (now idle) operand buffers of phase 1
             // -- 16 pairs at a time, no extra shared memory: the kernel lives on its L1 -- and written out 8 lanes per
-            // record, 4 records per step: ONE write request per pair (header [0,16), body [32,128)).
+            // pair, 4 pairs per step: lanes 0..5 the 96 B body (ONE write request), lane 6 the 16 B header.
             int4 *const stage4 = reinterpret_cast<int4 *>(&s_hull[warp][0][0][0]);       // 128 x 16 B = [8 chunks][16 pairs]
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if ((lane >> 4) == h && n_chunks) {
                     const int c16 = lane & 15;
-                    stage4[0 * 16 + c16] = hdr;
+                    stage4[6 * 16 + c16] = hdr;
                     if (n_chunks > 1u) {
-                        stage4[2 * 16 + c16] = make_int4(__double2loint(pj.x), __double2hiint(pj.x), __double2loint(pj.y), __double2hiint(pj.y));
-                        stage4[3 * 16 + c16] = make_int4(__double2loint(pj.z), __double2hiint(pj.z), __double2loint(pj.w), __double2hiint(pj.w));
                         const int4 *m4 = reinterpret_cast<const int4 *>(&staged);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) stage4[(4 + q) * 16 + c16] = m4[q];
+                        for (int q = 0; q < 4; ++q) stage4[q * 16 + c16] = m4[q];
+                        stage4[4 * 16 + c16] = make_int4(__double2loint(pj.x), __double2hiint(pj.x), __double2loint(pj.y), __double2hiint(pj.y));
+                        stage4[5 * 16 + c16] = make_int4(__double2loint(pj.z), __double2hiint(pj.z), __double2loint(pj.w), __double2hiint(pj.w));
                     }
                 }
                 __syncwarp();
@@ -1844,8 +1849,12 @@ __global__ void __launch_bounds__(CO_WARPS * 32, COOP_MIN_BLOCKS) k_manifolds_co
                 for (int it = 0; it < 4; ++it) {
                     const int r16 = it * 4 + (lane >> 3), ch = lane & 7;
                     const unsigned long long d = __shfl_sync(0xffffffffu, dst, h * 16 + r16);
+                    const unsigned long long dh = __shfl_sync(0xffffffffu, dst_hdr, h * 16 + r16);
                     const unsigned nc = __shfl_sync(0xffffffffu, n_chunks, h * 16 + r16);
-                    if (d != 0ull && (unsigned)ch < nc && ch != 1) reinterpret_cast<int4 *>(d)[ch] = stage4[ch * 16 + r16];
+                    if (nc != 0u) {
+                        if (ch == 6) *reinterpret_cast<int4 *>(dh) = stage4[6 * 16 + r16];
+                        else if (ch < 6 && nc > 1u) reinterpret_cast<int4 *>(d)[ch] = stage4[ch * 16 + r16];
+                    }
                 }
                 __syncwarp();
             }
@@ -1860,18 +1869,9 @@ __global__ void __launch_bounds__(256) k_rw_unpack(Params P)
     const FrameState *st = P.st;
     if (st->error) return;
     const long long n_pairs = st->n_pairs < P.max_pairs ? st->n_pairs : P.max_pairs;
-    // four headers in flight per thread (each is 16 B out of its own 128 B line: latency, not bandwidth, is the cost)
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += 4 * stride) {
-        int4 h[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) if (p + u * stride < n_pairs) h[u] = __ldcs(reinterpret_cast<const int4 *>(&P.prec[p + u * stride]));
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (p + u * stride < n_pairs) {
-                const long long q = p + u * stride;
-                P.pair_i[q] = h[u].x; P.pair_j[q] = h[u].y; P.ccnt[q] = (uint32_t)h[u].z;
-            }
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const int4 h = __ldcs(reinterpret_cast<const int4 *>(&P.phdr[p]));
+        P.pair_i[p] = h.x; P.pair_j[p] = h.y; P.ccnt[p] = (uint32_t)h.z;
     }
 }
 
@@ -2756,7 +2756,7 @@ struct shapes_ctx {
     char *rw_arena = nullptr;
     char *peer_arena[SHAPES_MAX_RANKS] = {};
     struct RowsLayout {
-        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, prec, inbox, inbox_cnt, total;
+        size_t gkeys[2], box, xf, mass, in[7], cq, qoff, bounds[2], weights[2], counts, err, flags, prec, phdr, inbox, inbox_cnt, total;
     } rwl{};
     uint32_t *d_roww = nullptr, *d_ccnt_w = nullptr, *d_w_j = nullptr;
     int32_t *d_pair_i = nullptr, *d_pair_j = nullptr; uint32_t *d_ccnt = nullptr; ManRec *d_man = nullptr;   // single-rank homes of the result arrays
@@ -3007,7 +3007,7 @@ int create_impl(shapes_ctx **out, int device_id, int rank, int world, const void
         L.counts = take(sizeof(long long) * 6 * world); L.err = take(sizeof(int) * 2 * world);
         L.flags = take(sizeof(unsigned long long) * RW_PHASES * SHAPES_MAX_RANKS);
         const size_t MP = (size_t)std::max<int64_t>(max_pairs, 1);
-        L.prec = take(sizeof(PairRec) * MP);
+        L.prec = take(sizeof(PairRec) * MP); L.phdr = take(sizeof(PairHdr) * MP);
         // inbox: one section per home rank, each large enough for that rank's whole home (2 folded blocks <= chunk + 1 slots)
         L.inbox = take(sizeof(HomeRec) * (size_t)(c->chunk + 2) * (size_t)world); L.inbox_cnt = take(sizeof(unsigned) * SHAPES_MAX_RANKS);
         L.total = off;
@@ -3166,7 +3166,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         n_home = (P.rw_lo_hi - P.rw_lo_lo) + (P.rw_hi_hi - P.rw_hi_lo);
         P.flags = reinterpret_cast<unsigned long long *>(mine + L.flags);
         // the result arrays of a home live in its arena: the sweeping ranks store into them
-        P.prec = reinterpret_cast<PairRec *>(mine + L.prec); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
+        P.prec = reinterpret_cast<PairRec *>(mine + L.prec); P.phdr = reinterpret_cast<PairHdr *>(mine + L.phdr); P.q_off = reinterpret_cast<uint32_t *>(mine + L.qoff);
         P.sat_ccnt = c->d_ccnt_w;
         P.roww = c->d_roww; P.mat_stamp = c->d_mat_stamp; P.kept_list = c->d_kept_list;
         P.inbox = reinterpret_cast<const HomeRec *>(mine + L.inbox); P.inbox_cnt = reinterpret_cast<const unsigned *>(mine + L.inbox_cnt);
@@ -3179,7 +3179,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
             P.peer_box[r] = reinterpret_cast<Box *>(a + L.box); P.peer_keys[r] = reinterpret_cast<uint32_t *>(a + L.gkeys[fpar]);
             P.rw_xf[r] = reinterpret_cast<Xf *>(a + L.xf); P.rw_mass[r] = reinterpret_cast<double2 *>(a + L.mass);
             P.rw_cq[r] = reinterpret_cast<uint32_t *>(a + L.cq); P.rw_qoff[r] = reinterpret_cast<uint32_t *>(a + L.qoff);
-            P.rw_prec[r] = reinterpret_cast<PairRec *>(a + L.prec);
+            P.rw_prec[r] = reinterpret_cast<PairRec *>(a + L.prec); P.rw_phdr[r] = reinterpret_cast<PairHdr *>(a + L.phdr);
             P.rw_inbox[r] = reinterpret_cast<HomeRec *>(a + L.inbox); P.rw_inbox_cnt[r] = reinterpret_cast<unsigned *>(a + L.inbox_cnt);
             P.peer_bounds[r] = reinterpret_cast<unsigned long long *>(a + L.bounds[fpar]);
             P.rw_weights[r] = reinterpret_cast<uint32_t *>(a + L.weights[fpar]);
@@ -3287,7 +3287,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         kt("k_rw_sync:RESULTS");
         STAGE_MARK(); // 9: home -- pair columns and counts out of the delivered records, row offsets
         if (c->max_pairs > 0) {
-            k_rw_unpack<<<sms * 16, 256, 0, s>>>(P); ++c->launches;
+            k_rw_unpack<<<sms * 8, 256, 0, s>>>(P); ++c->launches;
             kt("k_rw_unpack");
             size_t cb = c->scan_tmp_bytes;
             CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, cb, P.ccnt, P.coff, (int)c->max_pairs, s));
