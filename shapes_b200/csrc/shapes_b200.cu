@@ -2821,7 +2821,7 @@ struct shapes_ctx {
     std::vector<cudaEvent_t> dbg_ev;
     std::vector<const char *> dbg_name;
     std::vector<double> dbg_sum;
-    int dbg_marks = 0, dbg_frames = 0;
+    int dbg_marks = 0, dbg_marks_seen = 0, dbg_frames = 0;
     bool have_frame = false;      // key columns (and counts) of a completed frame exist: the join's "previous frame"
     bool results_valid = false;   // the result arrays hold that frame (false after a failed attempt until the next success)
 };
@@ -3549,7 +3549,7 @@ int frame_finish(shapes_ctx *c, shapes_frame_out *out)
         for (int k = 0; k < SHAPES_N_STAGES; ++k) CU_TRY(c, cudaEventElapsedTime(&c->stage_ms[k], c->stage_ev[k], c->stage_ev[k + 1]));
     if (c->profiling && c->dbg_times && c->pending_rows && c->dbg_marks > 1) {
         for (int k = 1; k < c->dbg_marks; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, c->dbg_ev[k - 1], c->dbg_ev[k]); c->dbg_sum[k] += ms; }
-        ++c->dbg_frames;
+        ++c->dbg_frames; c->dbg_marks_seen = c->dbg_marks;
     }
     if (st.error & ERR_PEER_TIMEOUT) { c->err = "peer exchange timed out: a rank did not publish its records"; c->have_frame = false; c->results_valid = false; return SHAPES_E_NCCL; }
     if (st.error) {
@@ -3625,7 +3625,7 @@ void shapes_destroy(shapes_ctx *c)
     for (int q = 0; q < 4; ++q) if (c->graph_exec[q]) cudaGraphExecDestroy(c->graph_exec[q]);
     if (c->dbg_times && c->dbg_frames > 0) {
         std::string line = "[shapes_b200 rank " + std::to_string(c->rank) + "] rows-mode kernel ms (mean of " + std::to_string(c->dbg_frames) + " profiled frames):";
-        for (int k = 1; k < c->dbg_marks; ++k) { char buf[96]; std::snprintf(buf, sizeof(buf), " %s %.4f", c->dbg_name[k], c->dbg_sum[k] / c->dbg_frames); line += buf; }
+        for (int k = 1; k < c->dbg_marks_seen; ++k) { char buf[96]; std::snprintf(buf, sizeof(buf), " %s %.4f", c->dbg_name[k], c->dbg_sum[k] / c->dbg_frames); line += buf; }
         std::fprintf(stderr, "%s\n", line.c_str());
     }
     for (cudaEvent_t e : c->dbg_ev) cudaEventDestroy(e);

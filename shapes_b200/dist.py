@@ -1,8 +1,12 @@
 """Host-side logic of the multi-GPU path.
 
-Ownership is by the LARGER key of a pair: rank r owns the pairs / contacts whose i lies in its
-slot range.  The reference order is descending (i, j), so the global result is simply the slices
-concatenated from the highest rank down -- no merge.
+Ownership is by the LARGER key of a pair: a pair's rows end up on the rank that is HOME to its i.
+Round-1 exchanges: one slot range per rank, the global descending (i, j) order is the slices concatenated from the
+highest rank down.  Rows mode: the slot space is cut into 2 G blocks and rank g is home to blocks g and 2 G - 1 - g
+(folded: equal slots and equal pairs per rank for any slot numbering); a rank's arrays hold the rows of its HIGH block
+first (run 0), then those of its low block (run 1), and the global order is run 0 of ranks 0 .. G-1 followed by run 1
+of ranks G-1 .. 0 -- still a fixed concatenation, no merge.  (The sweep / SAT work is partitioned by grid rows on the
+device; that partition does not show in the result layout.)
 """
 from __future__ import annotations
 
@@ -59,3 +63,25 @@ def assemble_runs(slices: Sequence[dict], segments: Sequence[tuple], pair_cols=(
             parts.append(np.asarray(slices[r][k])[n0: n0 + segments[r][1][which]])
         out[k] = np.concatenate(parts)
     return out
+
+
+def home_blocks(n_slots: int, rank: int, world_size: int, fold: bool = True) -> tuple[tuple[int, int], tuple[int, int]]:
+    """Rows mode: ((low block lo, hi), (high block lo, hi)) of a rank, as rows_home_blocks in the library computes them.
+    fold=False: one contiguous block per rank (the high block is empty)."""
+    c = chunk_size(n_slots, world_size)
+    if not fold:
+        return (min(rank * c, n_slots), min((rank + 1) * c, n_slots)), (n_slots, n_slots)
+    blk = max((c + 1) // 2, 1)
+    lo = (min(rank * blk, n_slots), min((rank + 1) * blk, n_slots))
+    hi = (min((2 * world_size - 1 - rank) * blk, n_slots), min((2 * world_size - rank) * blk, n_slots))
+    return lo, hi
+
+
+def home_of(i: np.ndarray, n_slots: int, world_size: int, fold: bool = True) -> np.ndarray:
+    """Rows mode: the home rank of every slot (= owner of the pairs whose larger key it is)."""
+    c = chunk_size(n_slots, world_size)
+    if not fold:
+        return np.asarray(i) // max(c, 1)
+    blk = max((c + 1) // 2, 1)
+    b = np.asarray(i) // blk
+    return np.where(b < world_size, b, 2 * world_size - 1 - b)
