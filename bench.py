@@ -389,6 +389,10 @@ def run_leg(R: Ranks, workload: str, world, desc: str, steps: int, warmup: int, 
         nccl_id = box[0]
     own = (n + ws - 1) // ws
     max_pairs = pair_capacity(workload, own)
+    if ws > 1 and workload == "blob":
+        # rows mode: the first frame of a geometry cuts the rows evenly (nothing measured yet), so the ranks that get
+        # the blob's centre list several times their steady-state share before the pair-count balancing takes over
+        max_pairs *= 4
     eng = Engine(world, max_pairs=max_pairs, max_contacts=2 * max_pairs, device=R.local_rank, rank=rank,
                  world_size=ws, nccl_id=nccl_id)
     exchange = "none"
