@@ -164,6 +164,17 @@ def kat_triangle_on_box(triangle_is_a: bool = False, lift: float = 0.0):
     return w, c, s
 
 
+def kat_box_on_hexagon():
+    """KAT-9 (tests/golden/README.md): a hexagon whose six edges are axis-parallel or 3-4-5 directions (slot 1 =
+    shape a) and a 2x2 box (slot 0 = shape b) resting 0.25 deep in its top edge.  A world with a hull of more than four
+    vertices: on the GPU this vector goes through the cell-ordered work list and k_manifolds_coop."""
+    hexagon = ([(5.0, 0.0), (2.0, 4.0), (-2.0, 4.0), (-5.0, 0.0), (-2.0, -4.0), (2.0, -4.0)], (0.0, 0.0), 0.0, (1.0, 1.0))
+    box = (rectangle_vertices(2.0, 2.0), (0.5, 4.75), 0.0, (1.0, 1.0))
+    w = World.from_objects([box, hexagon], name="kat_box_on_hexagon")
+    w.meta.update(dt=0.25, baumgarte=0.5, slop=0.125)
+    return w, np.ones(2), np.zeros(2)
+
+
 # ---------------------------------------------------------------------------
 # BASELINE.json configs 2-5
 # ---------------------------------------------------------------------------

@@ -67,7 +67,8 @@ def test_kat1_and_kat3_through_the_abi(oracle):
 
 @pytest.mark.parametrize("name,triangle_is_a,lift", [("kat6_triangle_into_box_same", False, 0.0),
                                                      ("kat7_triangle_into_box_flip", True, 0.0),
-                                                     ("kat8_triangle_lifted_single_point", False, 1.0)])
+                                                     ("kat8_triangle_lifted_single_point", False, 1.0),
+                                                     ("kat9_box_on_hexagon", None, 0.0)])
 def test_kat678_through_the_abi(oracle, name, triangle_is_a, lift):
     """The hand-derived vectors KAT-6/7/8 (tests/golden/README.md) against the CUDA path itself, every pinned column
     bit for bit (signed zeros included): rotated non-box hull through minOverlap, Same and Flip, ClipLeft, the third
@@ -75,7 +76,8 @@ def test_kat678_through_the_abi(oracle, name, triangle_is_a, lift):
     from test_oracle_kat import assert_kat_rows
     with open(os.path.join(GOLDEN, "kat.json")) as f:
         want = json.load(f)[name]
-    w, c, s = scenes.kat_triangle_on_box(triangle_is_a, lift)
+    # (KAT-9's hexagon makes its world a "general polygon" world: cell-ordered work list + k_manifolds_coop)
+    w, c, s = scenes.kat_box_on_hexagon() if triangle_is_a is None else scenes.kat_triangle_on_box(triangle_is_a, lift)
     got = gpu_frame(w, (c, s), **want["behaviour"])
     assert_kat_rows(got, want, name)
     assert_frames_match(got, oracle.frame(w, c, s, broadphase="aabb", **want["behaviour"]))

@@ -105,6 +105,15 @@ def test_kat678_triangle_on_box(oracle, kat, name, triangle_is_a, lift):
     assert_kat_rows(r, want, name)
 
 
+def test_kat9_box_on_hexagon(oracle, kat):
+    """KAT-9: a six-vertex hull with 3-4-5 edges under a box -- depth tie -> Flip, ClipRight + ClipLeft + the NaN-driven
+    ClipNone, two points, live Baumgarte term.  Hand trace: tests/golden/README.md."""
+    want = kat["kat9_box_on_hexagon"]
+    w, c, s = scenes.kat_box_on_hexagon()
+    r = oracle.frame(w, c, s, broadphase="aabb", **want["behaviour"])
+    assert_kat_rows(r, want, "kat9")
+
+
 def test_kat3_broadphase_knife_edge(oracle, kat):
     """Aabb.culledKeys testWorld (bench/Physics/Broadphase/Benchmark.hs:50-52)."""
     for name, spacing in (("spacing0", 0.0), ("spacing1", 1.0)):

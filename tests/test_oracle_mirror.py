@@ -73,13 +73,14 @@ def test_kat1_through_the_mirror():
 
 @pytest.mark.parametrize("name,triangle_is_a,lift", [("kat6_triangle_into_box_same", False, 0.0),
                                                      ("kat7_triangle_into_box_flip", True, 0.0),
-                                                     ("kat8_triangle_lifted_single_point", False, 1.0)])
+                                                     ("kat8_triangle_lifted_single_point", False, 1.0),
+                                                     ("kat9_box_on_hexagon", None, 0.0)])
 def test_kat678_through_the_mirror(name, triangle_is_a, lift):
     """The hand traces of KAT-6/7/8 (tests/golden/README.md) through the second restatement: ClipLeft, Same / Flip on
     a non-box hull, the third clip removing a point, active Baumgarte term, Friction / Restitution with real radii."""
     with open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")) as f:
         want = json.load(f)[name]
-    w, c, s = scenes.kat_triangle_on_box(triangle_is_a, lift)
+    w, c, s = scenes.kat_box_on_hexagon() if triangle_is_a is None else scenes.kat_triangle_on_box(triangle_is_a, lift)
     hulls = hs.hulls_of(w, c, s)
     beh = want["behaviour"]
     rows = hs.prepare_frame(w, hulls, [tuple(p) for p in want["pairs"]], (beh["baumgarte"], beh["slop"]), beh["dt"])
