@@ -2061,21 +2061,25 @@ __global__ void __launch_bounds__(256) k_warm_join(Params P)
 //              Rows are cut so that every rank gets the same number of pairs, measured per row in the previous frame
 //              (ROW_BINS bins, exchanged with the CNT barrier): a Gaussian blob is balanced like a uniform world.
 //
-//   K0 (home slots)  AABB + cell key; key (4 B), packed transform (32 B) and inverse masses (16 B) are PUSHED over
-//                    NVLink to the rank(s) whose rows + halo hold the cell (big shapes: to all)     k_rw_transform
-//   -- barrier KEYS (this frame's bounds ride along: they plan the NEXT frame's grid) --            k_rw_sync
-//   keep the keys of my rows + one halo row: histogram, kept-slot list, counting sort   k_rw_bin, k_scan_cells_*, k_scatter_sorted
-//   world vertices / normals / AABB of the kept hulls, from the pushed transforms                   k_rw_hulls
+//   K0 (home slots)  AABB + cell key; a 96 B record (transform, AABB, inverse masses, slot, key + static bit) is
+//                    APPENDED over NVLink to the inbox of the rank(s) whose rows + halo hold the cell (big shapes:
+//                    of every rank), a warp's records leaving as whole lines                        k_rw_transform
+//   -- barrier KEYS (inbox counts; this frame's bounds ride along: they plan the NEXT frame's grid) -- k_rw_sync
+//   my inbox: histogram, slot -> record index, big list, kept list; counting sort   k_rw_bin, k_scan_cells_*, k_scatter_sorted
+//   world vertices / normals of the kept hulls from the records' transforms -- on a SIDE STREAM,
+//   joined before the SAT stage (only SAT reads them)                                               k_rw_hulls
 //   single-pass sweep of my rows -> local work list in cell order; every query's partner count
 //   is pushed to home(i) (4 B)                                                                      k_sweep<FUSED>, k_big
 //   -- barrier CNT (row weights ride along) --
 //   home: scan of the counts in descending slot order; each slot's first pair index goes back to
 //   its sweeper (4 B)                                                     k_rw_home_counts, scan, k_finish_pairs, k_rw_push_offsets
 //   -- barrier OFF (error words ride along) --
-//   SAT over the local work list; every pair is STORED into its final place at its home: (i, j), contact count,
-//   64 B manifold and the partner's body record when it has contacts                                k_manifolds*
+//   SAT over the local work list; every pair is STORED into its final place at its home: a dense 16 B header
+//   (i, j, contact count) and, when it has contacts, a 96 B body (manifold + the partner's body record)
+//   written as one request                                                                          k_manifolds*
 //   -- barrier RESULTS --
-//   home: row offsets, k_rows over local memory only, cache join                                    scan, k_row_map, k_rows
+//   home: pair columns / counts out of the headers, row offsets, k_rows over local memory only,
+//   cache join                                                                    k_rw_unpack, scan, k_row_map, k_rows
 //   -- barrier COUNTS (every rank's pair / contact totals: global row offsets of the slices) --
 // The grid and the row cuts of frame f come from what frame f-1 exchanged (bounds, row weights), so no barrier
 // sits between K0 and the keys; the frame number lives in device memory, so frames replay as CUDA graphs.
@@ -3229,7 +3233,7 @@ int frame_launch(shapes_ctx *c, int64_t n_slots, const double *const in[7], doub
         kt("k_scan_cells_sums");
         k_scan_cells_apply<<<SCAN_BLOCKS, SCAN_THREADS, 0, s>>>(P, c->d_chunk_sum); ++c->launches;
         kt("k_scan_cells_apply");
-        STAGE_MARK(); // 4: scatter into cell order (AABB records pulled from their homes) + hulls of the kept shapes
+        STAGE_MARK(); // 4: scatter into cell order (AABBs come with the records); the hull pass of the kept shapes is forked off
         if (N > 0) {
             k_scatter_sorted<<<gk, 256, 0, s>>>(P); ++c->launches;
             kt("k_scatter_sorted");
