@@ -35,6 +35,39 @@ def test_struct_layout_matches_header(product_lib):
     assert product_lib.shapes_version().startswith(b"shapes_b200")
 
 
+def test_every_struct_field_offset_matches_the_header(tmp_path):
+    """gcc compiles a C program against include/shapes_b200.h that prints sizeof / offsetof of every field of the five
+    public structs; the ctypes mirror must agree field by field (a reordered or resized field would otherwise read
+    garbage silently)."""
+    import subprocess
+    from shapes_b200 import _lib
+    structs = {"shapes_frame_out": _lib.FrameOut, "shapes_device_view": _lib.DeviceView, "shapes_step_config": _lib.StepConfig,
+               "shapes_step_stats": _lib.StepStats, "shapes_frame_info": _lib.FrameInfo}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "shapes_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line:
+            continue
+        cname, field, value = line.split()
+        cls = structs[cname]
+        if field == "size":
+            assert C.sizeof(cls) == int(value), (cname, C.sizeof(cls), value)
+        else:
+            assert getattr(cls, field).offset == int(value), (cname, field, getattr(cls, field).offset, value)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
 def test_no_silent_fallback_without_gpu(product_lib):
     import torch
     if torch.cuda.is_available():
